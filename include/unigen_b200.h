@@ -1,0 +1,197 @@
+/* unigen_b200 — C ABI of the B200-native UniGen denoiser hot path (libunigen_b200.so).
+ *
+ * The reference (gavin-gqzhang/UniGen) has NO native boundary: its hot path sits behind a Python
+ * torch.nn.Module (`UniGenFlux.forward`, src/UniGenTransformer.py:1182-1271) and calls diffusers /
+ * deepspeed / torch library kernels.  This header is therefore the boundary a maintainer would bind
+ * (ctypes stub in INTEGRATION.md); every entry point cites the reference call site it replaces.
+ *
+ * Conventions
+ *   - plain C types only; all pointers are DEVICE pointers unless a parameter says "host".
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every function returns UG_OK (0) or a negative ug_status; the message is in ug_last_error().
+ *   - no function allocates device memory, synchronises the stream, or falls back to the CPU.
+ *   - strides are in ELEMENTS of the tensor's dtype; bf16 rows must be 16-byte aligned.
+ *   - "batch" views: a logical [batch, rows, cols] tensor is (ptr, row_stride, batch_stride), which lets the
+ *     text / image / condition streams live inside one joint buffer without concat copies.
+ */
+#ifndef UNIGEN_B200_H_
+#define UNIGEN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UG_ABI_VERSION 1
+
+typedef enum {
+  UG_OK = 0,
+  UG_ERR_INVALID = -1,     /* bad argument (shape / alignment / null) */
+  UG_ERR_UNSUPPORTED = -2, /* valid request the sm_100a kernels do not cover (never a CPU fallback) */
+  UG_ERR_CUDA = -3,        /* CUDA runtime / driver error; text in ug_last_error() */
+  UG_ERR_NO_DEVICE = -4    /* no sm_100 device */
+} ug_status;
+
+/* Thread-local message of the last failing call on this thread. */
+const char* ug_last_error(void);
+int ug_abi_version(void);
+/* UG_OK iff the current device is sm_100 (B200) and the TMA driver entry point resolves. */
+int ug_device_check(void);
+/* Number of kernels this library has launched on this thread since the last reset (bench.py's gpu_launches). */
+int64_t ug_launch_count(void);
+void ug_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Dense bf16 GEMM on tcgen05 tensor cores with a fused epilogue.
+ *   C[b,r,:] = residual[b,r,:] + alpha * gate[b,:] * act( A[b,r,:] @ W[wb]^T + bias[wb,:] )
+ * Replaces every nn.Linear on the path (diffusers FluxTransformerBlock / FluxSingleTransformerBlock /
+ * FluxAttnProcessor2_0 projections; zero-linears src/UniGenTransformer.py:755-773,1104;
+ * expert linears :956-959) together with the elementwise ops the reference runs after them
+ * (bias, GELU-tanh, `gate.unsqueeze(1) * out + residual`, `* conditioning_scale`).
+ * A: [batch, rows, k] bf16, W: [n, k] bf16 (row-major, as nn.Linear.weight), C: [batch, rows, n] bf16.
+ * ---------------------------------------------------------------------------------------------------- */
+#define UG_ACT_NONE 0
+#define UG_ACT_GELU_TANH 1
+
+typedef struct ug_gemm_args {
+  const void* a;          /* bf16 */
+  int64_t a_row_stride;
+  int64_t a_batch_stride;
+  const void* w;          /* bf16 [n,k] (or [batch,n,k] when w_batch_stride != 0) */
+  int64_t w_row_stride;
+  int64_t w_batch_stride; /* 0: weights shared by all batches */
+  void* c;                /* bf16 */
+  int64_t c_row_stride;
+  int64_t c_batch_stride;
+  int32_t batch;
+  int32_t rows; /* rows per batch */
+  int32_t n;
+  int32_t k;
+  const void* bias;       /* bf16 [n] or NULL */
+  int64_t bias_batch_stride;
+  const float* gate;      /* fp32 [batch, n] or NULL */
+  int64_t gate_batch_stride;
+  float alpha;            /* scalar factor (1.0f when unused) */
+  int32_t act;            /* UG_ACT_* */
+  const void* residual;   /* bf16 or NULL; may alias c (in-place residual update) */
+  int64_t res_row_stride;
+  int64_t res_batch_stride;
+  int32_t variant;        /* 0 = auto; 1 = 1-CTA 128x256; 2 = 2-CTA 256x256 pair; 3 = 1-CTA 128x128 */
+  int32_t reserved;
+} ug_gemm_args;
+
+int ug_gemm_bf16(const ug_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Joint attention (tcgen05 / TMEM / TMA), softmax(Q K^T * scale + mask) V per head, non-causal.
+ * Replaces F.scaled_dot_product_attention in diffusers FluxAttnProcessor2_0 (same call in
+ * src/UniGenUtils.py:601,709) and the per-segment SDPA calls of the predecessor's attn_forward
+ * (UniCombineTransformerBlock.pyc L98-110).
+ * q/k/v/o: bf16 [batch, seq, heads, head_dim] views: element (b,s,h,d) at ptr[b*batch_stride + s*row_stride + h*head_dim + d].
+ * Segment visibility (optional): tokens [seg_bounds[i], seg_bounds[i+1]) form segment i; a query in segment i
+ * attends keys of segment j iff bit j of seg_visible[i] is set. n_seg = 0 means full attention.
+ * seg_bounds / seg_visible are HOST pointers (copied into the launch parameters).
+ * ---------------------------------------------------------------------------------------------------- */
+#define UG_MAX_SEGMENTS 8
+typedef struct ug_attn_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  int64_t q_row_stride, q_batch_stride;
+  int64_t k_row_stride, k_batch_stride;
+  int64_t v_row_stride, v_batch_stride;
+  int64_t o_row_stride, o_batch_stride;
+  int32_t batch, heads, seq, head_dim; /* head_dim in {64, 128}; seq_q == seq_k == seq */
+  float scale;                         /* 1/sqrt(head_dim) in the reference */
+  int32_t n_seg;
+  const int32_t* seg_bounds;   /* host, n_seg + 1 entries, seg_bounds[0] = 0, seg_bounds[n_seg] = seq */
+  const uint32_t* seg_visible; /* host, n_seg entries */
+} ug_attn_args;
+
+int ug_attention_bf16(const ug_attn_args* args, void* stream);
+/* Bit-exact expansion of the segment rule into a dense [seq, seq] uint8 mask (1 = visible); parity helper for
+ * the "condition attention mask" construction (north_star: bit-exact mask). */
+int ug_expand_segment_mask(int32_t seq, int32_t n_seg, const int32_t* seg_bounds_host,
+                           const uint32_t* seg_visible_host, uint8_t* mask_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Fused elementwise family (HBM-bound).
+ * ---------------------------------------------------------------------------------------------------- */
+/* out[b,r,:] = LayerNorm(x[b,r,:], eps, no affine) * (1 + scale[b,:]) + shift[b,:]      (bf16 in/out, fp32 math)
+ * diffusers AdaLayerNormZero / AdaLayerNormZeroSingle / AdaLayerNormContinuous and `norm2(h)*(1+scale)+shift`
+ * (reference-owned copies src/UniGenUtils.py:345-351,360-362,370-372). */
+int ug_ln_modulate(const void* x, int64_t x_row_stride, int64_t x_batch_stride, void* out, int64_t o_row_stride,
+                   int64_t o_batch_stride, const float* shift, const float* scale, int64_t mod_batch_stride,
+                   int32_t batch, int32_t rows, int32_t d, float eps, void* stream);
+
+/* In-place per-head RMSNorm (learned weight) followed by interleaved-pair RoPE on rows of a [batch, rows, heads, dh]
+ * bf16 view: diffusers RMSNorm(dh, eps) + apply_rotary_emb (src/UniGenUtils.py:597-599).
+ * cos_sin: fp32 [rows, dh/2, 2] (cos, sin of pair i) shared by all batches/heads, or NULL for no rotation. */
+int ug_qk_rmsnorm_rope(void* x, int64_t row_stride, int64_t batch_stride, int32_t batch, int32_t rows,
+                       int32_t heads, int32_t head_dim, const void* norm_weight_bf16, float eps,
+                       const float* cos_sin, void* stream);
+
+/* RoPE table from position ids: FluxPosEmbed(theta, axes_dim)(ids), float64 angles -> fp32.
+ * ids: fp32 [rows, 3]; axes_dim: host int[3] (sum = head_dim); out: fp32 [rows, head_dim/2, 2]. */
+int ug_rope_table(const float* ids, int32_t rows, const int32_t* axes_dim_host, float theta, float* cos_sin,
+                  void* stream);
+
+/* Small-M linear (M = batch rows <= 16): out[b,n] (+)= W[n,:] . f(x[b,:]) + bias[n], f = SiLU when silu_in.
+ * fp32 x / out, bf16 W / bias. HBM-bound weight streaming. Replaces AdaLN `linear(silu(temb))`, TimestepEmbedding,
+ * PixArtAlphaTextProjection and the expert modulation linears `L^e(pooled)` (src/UniGenTransformer.py:956-959). */
+int ug_gemv(const float* x, int64_t x_stride, const void* w, const void* bias, float* out, int64_t out_stride,
+            int32_t batch, int32_t n, int32_t k, int32_t silu_in, int32_t silu_out, int32_t accumulate,
+            void* stream);
+
+/* Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0): out[b] = [cos(t*f) | sin(t*f)]. */
+int ug_timestep_embedding(const float* t, int32_t batch, int32_t dim, float* out, void* stream);
+
+/* out = a + b (bf16, same [batch, rows, d] view conventions). `hidden_states+condition_hidden_states`
+ * (src/UniGenTransformer.py:979,1089) and the weave add (:1141,1166). */
+int ug_add_bf16(const void* a, int64_t a_row_stride, int64_t a_batch_stride, const void* b, int64_t b_row_stride,
+                int64_t b_batch_stride, void* out, int64_t o_row_stride, int64_t o_batch_stride, int32_t batch,
+                int32_t rows, int32_t d, void* stream);
+/* strided 2-D copy of bf16 rows (torch.cat / slicing on the path: src/UniGenTransformer.py:1146,1174). */
+int ug_copy_bf16(const void* src, int64_t s_row_stride, int64_t s_batch_stride, void* dst, int64_t d_row_stride,
+                 int64_t d_batch_stride, int32_t batch, int32_t rows, int32_t d, void* stream);
+/* fp32 -> bf16 and bf16 -> fp32 contiguous casts (pipeline boundary dtype glue). */
+int ug_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+int ug_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * CoMoE pre-stage: DeepSpeed top-1 gate with Random-Token-Selection as sparse index work
+ * instead of dense (S,E,C) one-hot einsums (src/UniGenUtils.py:99,140,183).
+ *   x            bf16 [tokens, d]    gate input `(hidden+cond).reshape(-1, d)`
+ *   wg           fp32 [experts, d]   TopKGate.wg.weight
+ *   rts_uniform  fp32 [tokens, experts]  the uniform draw of top1gating (injected for parity)
+ * outputs
+ *   expert_idx   int32 [tokens]      argmax expert
+ *   slot         int32 [tokens]      position inside the expert's capacity buffer, -1 when dropped
+ *   prob         fp32  [tokens]      softmax probability of the chosen expert (combine weight)
+ *   slot_token   int32 [experts*capacity]  inverse map, -1 for empty slots
+ *   exp_counts   int64 [experts]     pre-capacity counts (add_outputs['expert_counts'])
+ *   l_aux        fp32  [1]
+ * workspace: fp32 [tokens*experts] (softmax gates) ; capacity = max(ceil(tokens/experts), 4) is computed by the caller.
+ * ---------------------------------------------------------------------------------------------------- */
+int ug_moe_route(const void* x, const float* wg, const float* rts_uniform, int32_t tokens, int32_t d,
+                 int32_t experts, int32_t capacity, int32_t* expert_idx, int32_t* slot, float* prob,
+                 int32_t* slot_token, int64_t* exp_counts, float* l_aux, float* workspace, void* stream);
+
+/* Gather + modulate: out[e*capacity + s, :] = mod[e, b(token), :] * (x[token, :] (+ addend[e*capacity+s, :]))
+ * with token = slot_token[e*capacity+s]; empty slots give zero rows. tokens_per_batch maps token -> b.
+ * `s ⊙ x` prologue of modulated_flatten (src/UniGenUtils.py:204-228) on the dispatched rows. */
+int ug_moe_gather_modulate(const void* x, const int32_t* slot_token, const float* mod, int64_t mod_expert_stride,
+                           int64_t mod_batch_stride, const void* addend, void* out, void* gathered_x,
+                           int32_t experts, int32_t capacity, int32_t tokens_per_batch, int32_t d, void* stream);
+/* Combine: out[token,:] = prob[token] * y[expert_idx*capacity + slot, :] or 0 when dropped (einsum sec,ecm->sm,
+ * src/UniGenUtils.py:183-185). */
+int ug_moe_combine(const void* y, const int32_t* expert_idx, const int32_t* slot, const float* prob, void* out,
+                   int32_t tokens, int32_t capacity, int32_t d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIGEN_B200_H_ */

@@ -1,0 +1,96 @@
+"""ctypes binding of libunigen_b200.so (include/unigen_b200.h). The library is mandatory: there is no Python or
+CPU fallback for any op — a missing / unloadable extension raises at first use."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libunigen_b200.so"
+
+UG_ACT_NONE = 0
+UG_ACT_GELU_TANH = 1
+UG_MAX_SEGMENTS = 8
+
+
+class UgError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("a_row_stride", C.c_int64), ("a_batch_stride", C.c_int64),
+        ("w", C.c_void_p), ("w_row_stride", C.c_int64), ("w_batch_stride", C.c_int64),
+        ("c", C.c_void_p), ("c_row_stride", C.c_int64), ("c_batch_stride", C.c_int64),
+        ("batch", C.c_int32), ("rows", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
+        ("bias", C.c_void_p), ("bias_batch_stride", C.c_int64),
+        ("gate", C.c_void_p), ("gate_batch_stride", C.c_int64),
+        ("alpha", C.c_float), ("act", C.c_int32),
+        ("residual", C.c_void_p), ("res_row_stride", C.c_int64), ("res_batch_stride", C.c_int64),
+        ("variant", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p),
+        ("q_row_stride", C.c_int64), ("q_batch_stride", C.c_int64),
+        ("k_row_stride", C.c_int64), ("k_batch_stride", C.c_int64),
+        ("v_row_stride", C.c_int64), ("v_batch_stride", C.c_int64),
+        ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64),
+        ("batch", C.c_int32), ("heads", C.c_int32), ("seq", C.c_int32), ("head_dim", C.c_int32),
+        ("scale", C.c_float), ("n_seg", C.c_int32),
+        ("seg_bounds", C.POINTER(C.c_int32)), ("seg_visible", C.POINTER(C.c_uint32)),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/unigen_b200.h declares
+_VP, _I32, _I64, _F32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+SIGNATURES = {
+    "ug_last_error": (C.c_char_p, []),
+    "ug_abi_version": (C.c_int, []),
+    "ug_device_check": (C.c_int, []),
+    "ug_launch_count": (C.c_int64, []),
+    "ug_reset_launch_count": (None, []),
+    "ug_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _VP]),
+    "ug_attention_bf16": (C.c_int, [C.POINTER(AttnArgs), _VP]),
+    "ug_expand_segment_mask": (C.c_int, [_I32, _I32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), _VP, _VP]),
+    "ug_ln_modulate": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _I64, _VP, _VP, _I64, _I32, _I32, _I32, _F32, _VP]),
+    "ug_qk_rmsnorm_rope": (C.c_int, [_VP, _I64, _I64, _I32, _I32, _I32, _I32, _VP, _F32, _VP, _VP]),
+    "ug_rope_table": (C.c_int, [_VP, _I32, C.POINTER(C.c_int32), _F32, _VP, _VP]),
+    "ug_gemv": (C.c_int, [_VP, _I64, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "ug_timestep_embedding": (C.c_int, [_VP, _I32, _I32, _VP, _VP]),
+    "ug_add_bf16": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP]),
+    "ug_copy_bf16": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP]),
+    "ug_cast_f32_to_bf16": (C.c_int, [_VP, _VP, _I64, _VP]),
+    "ug_cast_bf16_to_f32": (C.c_int, [_VP, _VP, _I64, _VP]),
+    "ug_moe_route": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "ug_moe_gather_modulate": (C.c_int, [_VP, _VP, _VP, _I64, _I64, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP]),
+    "ug_moe_combine": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (building it is `__graft_entry__.build()`'s job) and type every entry point."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise UgError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the UniGen hot path)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library drift apart
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().ug_last_error().decode(errors="replace")
+        raise UgError(f"{what or 'unigen_b200'} failed with status {status}: {msg}")

@@ -1,0 +1,421 @@
+// Fused elementwise family of the UniGen hot path (HBM-bound): LayerNorm+modulate, per-head RMSNorm+RoPE,
+// RoPE table, small-M linears (AdaLN / timestep / expert-modulation GEMVs), adds / copies / casts.
+// All kernels use 16-byte vector accesses and fp32 math; bf16 is storage only.
+#include "ug_host.h"
+#include "ug_ptx.cuh"
+
+namespace ug {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm (no affine) + (1 + scale) * x + shift.  One warp per row, row kept in registers (d <= 8*32*kMaxV).
+// Algorithmic HBM bytes per row: 2*d (read) + 2*d (write).
+// ---------------------------------------------------------------------------------------------------
+template <int kMaxV>
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long x_rs,
+                                                          long long x_bs, __nv_bfloat16* __restrict__ out,
+                                                          long long o_rs, long long o_bs,
+                                                          const float* __restrict__ shift,
+                                                          const float* __restrict__ scale, long long mod_bs, int batch,
+                                                          int rows, int d, float eps) {
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp_global >= batch * rows) return;
+  const int b = warp_global / rows, r = warp_global % rows;
+  const uint4* xp = reinterpret_cast<const uint4*>(x + (long long)b * x_bs + (long long)r * x_rs);
+  const int nvec = d >> 3;
+  uint4 buf[kMaxV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      buf[i] = xp[v];
+      float f[8];
+      unpack8(buf[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += f[j];
+    }
+  }
+  const float mean = warp_sum(sum) / (float)d;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      float f[8];
+      unpack8(buf[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { float t = f[j] - mean; var += t * t; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(var) / (float)d + eps);
+  uint4* op = reinterpret_cast<uint4*>(out + (long long)b * o_bs + (long long)r * o_rs);
+  const float* sh = shift + (long long)b * mod_bs;
+  const float* sc = scale + (long long)b * mod_bs;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      float f[8];
+      unpack8(buf[i], f);
+      const float4 s0 = *reinterpret_cast<const float4*>(sc + 8 * v), s1 = *reinterpret_cast<const float4*>(sc + 8 * v + 4);
+      const float4 h0 = *reinterpret_cast<const float4*>(sh + 8 * v), h1 = *reinterpret_cast<const float4*>(sh + 8 * v + 4);
+      const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      const float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * (1.f + s[j]) + h[j];
+      op[v] = pack8(f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Per-head RMSNorm (learned weight) + interleaved-pair RoPE, in place. One warp per token row, looping heads.
+// ---------------------------------------------------------------------------------------------------
+template <int kDh>
+__global__ void __launch_bounds__(256) qk_rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long rs, long long bs,
+                                                              int batch, int rows, int heads,
+                                                              const __nv_bfloat16* __restrict__ w, float eps,
+                                                              const float* __restrict__ cos_sin) {
+  constexpr int EPL = kDh / 32;  // elements per lane: 4 (dh=128) or 2 (dh=64)
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp_global >= batch * rows) return;
+  const int b = warp_global / rows, r = warp_global % rows;
+  __nv_bfloat16* row = x + (long long)b * bs + (long long)r * rs;
+  float wv[EPL], cs[EPL], sn[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) wv[i] = __bfloat162float(w[lane * EPL + i]);
+  if (cos_sin) {
+    const float* t = cos_sin + (long long)r * kDh + lane * EPL;  // [rows, dh/2, 2]: (cos, sin) of pair
+#pragma unroll
+    for (int i = 0; i < EPL; i += 2) { cs[i] = cs[i + 1] = t[i]; sn[i] = sn[i + 1] = t[i + 1]; }
+  }
+  for (int h = 0; h < heads; ++h) {
+    __nv_bfloat16* p = row + h * kDh + lane * EPL;
+    float f[EPL];
+    if constexpr (EPL == 4) {
+      uint2 u = *reinterpret_cast<const uint2*>(p);
+      float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y);
+      f[0] = a.x; f[1] = a.y; f[2] = c.x; f[3] = c.y;
+    } else {
+      uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+      float2 a = unpack_bf16x2(u);
+      f[0] = a.x; f[1] = a.y;
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) ss += f[i] * f[i];
+    const float rstd = rsqrtf(warp_sum(ss) / (float)kDh + eps);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) f[i] = f[i] * rstd * wv[i];
+    if (cos_sin) {
+#pragma unroll
+      for (int i = 0; i < EPL; i += 2) {
+        const float x0 = f[i], x1 = f[i + 1];
+        f[i] = x0 * cs[i] - x1 * sn[i];
+        f[i + 1] = x1 * cs[i + 1] + x0 * sn[i + 1];
+      }
+    }
+    if constexpr (EPL == 4) {
+      uint2 u;
+      u.x = pack_bf16x2(f[0], f[1]);
+      u.y = pack_bf16x2(f[2], f[3]);
+      *reinterpret_cast<uint2*>(p) = u;
+    } else {
+      *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(f[0], f[1]);
+    }
+  }
+}
+
+// FluxPosEmbed: per axis a, pair j: angle = ids[r,a] / theta^(2j/d_a) in float64; table holds (cos, sin) per pair.
+__global__ void rope_table_kernel(const float* __restrict__ ids, int rows, int d0, int d1, int d2, float theta,
+                                  float* __restrict__ cos_sin) {
+  const int half = (d0 + d1 + d2) / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * half) return;
+  const int r = idx / half;
+  int j = idx % half;
+  int axis, da;
+  if (j < d0 / 2) { axis = 0; da = d0; }
+  else if (j < (d0 + d1) / 2) { axis = 1; da = d1; j -= d0 / 2; }
+  else { axis = 2; da = d2; j -= (d0 + d1) / 2; }
+  const double pos = (double)ids[r * 3 + axis];
+  const double freq = 1.0 / pow((double)theta, (double)(2 * j) / (double)da);
+  const double ang = pos * freq;
+  cos_sin[2 * idx] = (float)cos(ang);
+  cos_sin[2 * idx + 1] = (float)sin(ang);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Small-M linear: one warp computes kRowsPerWarp output features for up to kB batch rows, streaming W once.
+// Algorithmic HBM bytes: 2*n*k (weights) — x and out are negligible.
+// ---------------------------------------------------------------------------------------------------
+template <int kB>
+__global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, long long x_stride,
+                                                   const __nv_bfloat16* __restrict__ w,
+                                                   const __nv_bfloat16* __restrict__ bias, float* __restrict__ out,
+                                                   long long out_stride, int batch0, int batch, int n, int k,
+                                                   int silu_in, int silu_out, int accumulate) {
+  constexpr int kRows = 2;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = warp_global * kRows;
+  if (n0 >= n) return;
+  float acc[kRows][kB];
+#pragma unroll
+  for (int i = 0; i < kRows; ++i)
+#pragma unroll
+    for (int b = 0; b < kB; ++b) acc[i][b] = 0.f;
+  const int nb = min(kB, batch - batch0);
+  for (int kk = lane * 8; kk < k; kk += 256) {
+    float xv[kB][8];
+#pragma unroll
+    for (int b = 0; b < kB; ++b) {
+      if (b < nb) {
+        const float* xp = x + (long long)(batch0 + b) * x_stride + kk;
+        const float4 a = *reinterpret_cast<const float4*>(xp), c = *reinterpret_cast<const float4*>(xp + 4);
+        xv[b][0] = a.x; xv[b][1] = a.y; xv[b][2] = a.z; xv[b][3] = a.w;
+        xv[b][4] = c.x; xv[b][5] = c.y; xv[b][6] = c.z; xv[b][7] = c.w;
+        if (silu_in) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xv[b][j] = xv[b][j] / (1.f + expf(-xv[b][j]));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[b][j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+      if (n0 + i < n) {
+        const uint4 wv = *reinterpret_cast<const uint4*>(w + (long long)(n0 + i) * k + kk);
+        float wf[8];
+        unpack8(wv, wf);
+#pragma unroll
+        for (int b = 0; b < kB; ++b)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][b] += wf[j] * xv[b][j];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kRows; ++i)
+#pragma unroll
+    for (int b = 0; b < kB; ++b) acc[i][b] = warp_sum(acc[i][b]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+      if (n0 + i >= n) continue;
+      const float bv = bias ? __bfloat162float(bias[n0 + i]) : 0.f;
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        if (b >= nb) continue;
+        float v = acc[i][b] + bv;
+        if (silu_out) v = v / (1.f + expf(-v));
+        float* o = out + (long long)(batch0 + b) * out_stride + n0 + i;
+        *o = accumulate ? (*o + v) : v;
+      }
+    }
+  }
+}
+
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int batch, int dim, float* __restrict__ out) {
+  const int half = dim / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= batch * half) return;
+  const int b = idx / half, j = idx % half;
+  // exponent = -ln(10000) * j / (half - downscale_freq_shift), downscale_freq_shift = 0
+  const float freq = expf(-logf(10000.f) * (float)j / (float)half);
+  const float a = t[b] * freq;
+  // flip_sin_to_cos=True -> [cos | sin]
+  out[b * dim + j] = cosf(a);
+  out[b * dim + half + j] = sinf(a);
+}
+
+template <bool kAdd>
+__global__ void __launch_bounds__(256) rows_kernel(const __nv_bfloat16* __restrict__ a, long long a_rs, long long a_bs,
+                                                   const __nv_bfloat16* __restrict__ b2, long long b_rs, long long b_bs,
+                                                   __nv_bfloat16* __restrict__ out, long long o_rs, long long o_bs,
+                                                   int batch, int rows, int d) {
+  const int nvec = d >> 3;
+  const long long total = (long long)batch * rows * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    const long long rr = i / nvec;
+    const int r = (int)(rr % rows), b = (int)(rr / rows);
+    uint4 u = *reinterpret_cast<const uint4*>(a + b * a_bs + r * a_rs + 8 * v);
+    if constexpr (kAdd) {
+      const uint4 w = *reinterpret_cast<const uint4*>(b2 + b * b_bs + r * b_rs + 8 * v);
+      float f[8], g[8];
+      unpack8(u, f);
+      unpack8(w, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += g[j];
+      u = pack8(f);
+    }
+    *reinterpret_cast<uint4*>(out + b * o_bs + r * o_rs + 8 * v) = u;
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    d[i] = __float2bfloat16(s[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, float* __restrict__ d, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    d[i] = __bfloat162float(s[i]);
+}
+
+static inline int grid_for(long long threads, int block) {
+  long long g = (threads + block - 1) / block;
+  const long long cap = (long long)num_sms() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace ug
+
+using namespace ug;
+
+extern "C" int ug_ln_modulate(const void* x, int64_t x_rs, int64_t x_bs, void* out, int64_t o_rs, int64_t o_bs,
+                              const float* shift, const float* scale, int64_t mod_bs, int32_t batch, int32_t rows,
+                              int32_t d, float eps, void* stream) {
+  UG_CHECK_ARG(x && out && shift && scale, "ln_modulate: null pointer");
+  UG_CHECK_ARG(batch >= 1 && rows >= 1 && d >= 8 && d % 8 == 0, "ln_modulate: bad shape batch %d rows %d d %d", batch, rows, d);
+  UG_CHECK_ARG(x_rs % 8 == 0 && o_rs % 8 == 0 && x_bs % 8 == 0 && o_bs % 8 == 0 && mod_bs % 4 == 0 && aligned16(x) &&
+                   aligned16(out) && aligned16(shift) && aligned16(scale),
+               "ln_modulate: operands must be 16-byte aligned");
+  if (d > 8 * 32 * 16) {
+    set_error("ln_modulate: d = %d exceeds the register-resident row limit (4096)", d);
+    return UG_ERR_UNSUPPORTED;
+  }
+  const long long warps = (long long)batch * rows;
+  const int block = 256;
+  const int grid = (int)((warps * 32 + block - 1) / block);
+  auto s = reinterpret_cast<cudaStream_t>(stream);
+  auto xp = (const __nv_bfloat16*)x;
+  auto op = (__nv_bfloat16*)out;
+  if (d <= 8 * 32 * 2) ln_modulate_kernel<2><<<grid, block, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, batch, rows, d, eps);
+  else if (d <= 8 * 32 * 6) ln_modulate_kernel<6><<<grid, block, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, batch, rows, d, eps);
+  else if (d <= 8 * 32 * 12) ln_modulate_kernel<12><<<grid, block, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, batch, rows, d, eps);
+  else ln_modulate_kernel<16><<<grid, block, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, batch, rows, d, eps);
+  UG_CHECK_LAUNCH("ln_modulate");
+  return UG_OK;
+}
+
+extern "C" int ug_qk_rmsnorm_rope(void* x, int64_t rs, int64_t bs, int32_t batch, int32_t rows, int32_t heads,
+                                  int32_t head_dim, const void* w, float eps, const float* cos_sin, void* stream) {
+  UG_CHECK_ARG(x && w, "qk_rmsnorm_rope: null pointer");
+  UG_CHECK_ARG(batch >= 1 && rows >= 1 && heads >= 1, "qk_rmsnorm_rope: bad shape");
+  UG_CHECK_ARG(rs % 4 == 0 && bs % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0, "qk_rmsnorm_rope: alignment");
+  const long long warps = (long long)batch * rows;
+  const int block = 256;
+  const int grid = (int)((warps * 32 + block - 1) / block);
+  auto s = reinterpret_cast<cudaStream_t>(stream);
+  if (head_dim == 128)
+    qk_rmsnorm_rope_kernel<128><<<grid, block, 0, s>>>((__nv_bfloat16*)x, rs, bs, batch, rows, heads, (const __nv_bfloat16*)w, eps, cos_sin);
+  else if (head_dim == 64)
+    qk_rmsnorm_rope_kernel<64><<<grid, block, 0, s>>>((__nv_bfloat16*)x, rs, bs, batch, rows, heads, (const __nv_bfloat16*)w, eps, cos_sin);
+  else {
+    set_error("qk_rmsnorm_rope: head_dim %d not supported (64 or 128)", head_dim);
+    return UG_ERR_UNSUPPORTED;
+  }
+  UG_CHECK_LAUNCH("qk_rmsnorm_rope");
+  return UG_OK;
+}
+
+extern "C" int ug_rope_table(const float* ids, int32_t rows, const int32_t* axes, float theta, float* cos_sin, void* stream) {
+  UG_CHECK_ARG(ids && axes && cos_sin && rows >= 1, "rope_table: bad arguments");
+  UG_CHECK_ARG(axes[0] % 2 == 0 && axes[1] % 2 == 0 && axes[2] % 2 == 0, "rope_table: axes dims must be even");
+  const int half = (axes[0] + axes[1] + axes[2]) / 2;
+  const long long total = (long long)rows * half;
+  rope_table_kernel<<<(int)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ids, rows, axes[0], axes[1], axes[2], theta, cos_sin);
+  UG_CHECK_LAUNCH("rope_table");
+  return UG_OK;
+}
+
+extern "C" int ug_gemv(const float* x, int64_t x_stride, const void* w, const void* bias, float* out, int64_t out_stride,
+                       int32_t batch, int32_t n, int32_t k, int32_t silu_in, int32_t silu_out, int32_t accumulate,
+                       void* stream) {
+  UG_CHECK_ARG(x && w && out, "gemv: null pointer");
+  UG_CHECK_ARG(batch >= 1 && n >= 1 && k >= 8 && k % 8 == 0, "gemv: bad shape batch %d n %d k %d", batch, n, k);
+  UG_CHECK_ARG(x_stride % 4 == 0 && aligned16(x) && aligned16(w), "gemv: x / w must be 16-byte aligned");
+  auto s = reinterpret_cast<cudaStream_t>(stream);
+  const int warps = (n + 1) / 2;
+  const int block = 256;
+  const int grid = (warps * 32 + block - 1) / block;
+  auto wp = (const __nv_bfloat16*)w;
+  auto bp = (const __nv_bfloat16*)bias;
+  for (int b0 = 0; b0 < batch; b0 += 8) {
+    const int nb = batch - b0;
+    if (nb == 1) gemv_kernel<1><<<grid, block, 0, s>>>(x, x_stride, wp, bp, out, out_stride, b0, batch, n, k, silu_in, silu_out, accumulate);
+    else if (nb == 2) gemv_kernel<2><<<grid, block, 0, s>>>(x, x_stride, wp, bp, out, out_stride, b0, batch, n, k, silu_in, silu_out, accumulate);
+    else if (nb <= 4) gemv_kernel<4><<<grid, block, 0, s>>>(x, x_stride, wp, bp, out, out_stride, b0, batch, n, k, silu_in, silu_out, accumulate);
+    else gemv_kernel<8><<<grid, block, 0, s>>>(x, x_stride, wp, bp, out, out_stride, b0, batch, n, k, silu_in, silu_out, accumulate);
+    UG_CHECK_LAUNCH("gemv");
+  }
+  return UG_OK;
+}
+
+extern "C" int ug_timestep_embedding(const float* t, int32_t batch, int32_t dim, float* out, void* stream) {
+  UG_CHECK_ARG(t && out && batch >= 1 && dim >= 2 && dim % 2 == 0, "timestep_embedding: bad arguments");
+  const int total = batch * dim / 2;
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t, batch, dim, out);
+  UG_CHECK_LAUNCH("timestep_embedding");
+  return UG_OK;
+}
+
+static int rows_op(bool add, const void* a, int64_t a_rs, int64_t a_bs, const void* b, int64_t b_rs, int64_t b_bs, void* out,
+                   int64_t o_rs, int64_t o_bs, int32_t batch, int32_t rows, int32_t d, void* stream, const char* name) {
+  UG_CHECK_ARG(a && out && (!add || b), "%s: null pointer", name);
+  UG_CHECK_ARG(batch >= 1 && rows >= 1 && d >= 8 && d % 8 == 0, "%s: bad shape", name);
+  UG_CHECK_ARG(a_rs % 8 == 0 && a_bs % 8 == 0 && o_rs % 8 == 0 && o_bs % 8 == 0 && aligned16(a) && aligned16(out), "%s: alignment", name);
+  if (add) UG_CHECK_ARG(b_rs % 8 == 0 && b_bs % 8 == 0 && aligned16(b), "%s: alignment", name);
+  const long long total = (long long)batch * rows * (d >> 3);
+  const int grid = grid_for(total, 256);
+  auto s = reinterpret_cast<cudaStream_t>(stream);
+  if (add)
+    rows_kernel<true><<<grid, 256, 0, s>>>((const __nv_bfloat16*)a, a_rs, a_bs, (const __nv_bfloat16*)b, b_rs, b_bs, (__nv_bfloat16*)out, o_rs, o_bs, batch, rows, d);
+  else
+    rows_kernel<false><<<grid, 256, 0, s>>>((const __nv_bfloat16*)a, a_rs, a_bs, nullptr, 0, 0, (__nv_bfloat16*)out, o_rs, o_bs, batch, rows, d);
+  UG_CHECK_LAUNCH(name);
+  return UG_OK;
+}
+
+extern "C" int ug_add_bf16(const void* a, int64_t a_rs, int64_t a_bs, const void* b, int64_t b_rs, int64_t b_bs, void* out,
+                           int64_t o_rs, int64_t o_bs, int32_t batch, int32_t rows, int32_t d, void* stream) {
+  return rows_op(true, a, a_rs, a_bs, b, b_rs, b_bs, out, o_rs, o_bs, batch, rows, d, stream, "add_bf16");
+}
+extern "C" int ug_copy_bf16(const void* src, int64_t s_rs, int64_t s_bs, void* dst, int64_t d_rs, int64_t d_bs, int32_t batch,
+                            int32_t rows, int32_t d, void* stream) {
+  return rows_op(false, src, s_rs, s_bs, nullptr, 0, 0, dst, d_rs, d_bs, batch, rows, d, stream, "copy_bf16");
+}
+extern "C" int ug_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  UG_CHECK_ARG(src && dst && n >= 1, "cast_f32_to_bf16: bad arguments");
+  cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, (__nv_bfloat16*)dst, n);
+  UG_CHECK_LAUNCH("cast_f32_to_bf16");
+  return UG_OK;
+}
+extern "C" int ug_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream) {
+  UG_CHECK_ARG(src && dst && n >= 1, "cast_bf16_to_f32: bad arguments");
+  cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const __nv_bfloat16*)src, dst, n);
+  UG_CHECK_LAUNCH("cast_bf16_to_f32");
+  return UG_OK;
+}

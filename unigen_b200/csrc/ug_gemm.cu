@@ -1,0 +1,347 @@
+// Dense bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (accumulators in TMEM,
+// double-buffered) -> fused epilogue from TMEM (bias / GELU-tanh / gate * alpha / residual) -> HBM.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..5 = epilogue
+// (warp w reads TMEM lanes 32*(w%4)..+31, the hardware lane-quarter rule of tcgen05.ld).
+// Persistent: grid = min(tiles, SMs); tiles are walked m-fastest so concurrently running CTAs share W tiles in L2.
+// kCta == 2 pairs two SMs on a 256 x BN tile (cta_group::2): each CTA loads its own 128 A rows and HALF of the
+// W tile; the leader CTA issues the MMAs, commits are multicast to both CTAs.
+//
+// Replaces every nn.Linear call on the reference path.
+#include "ug_host.h"
+#include "ug_ptx.cuh"
+
+namespace ug {
+
+struct GemmParams {
+  int rows, n, k, batch;
+  int m_tiles, n_tiles, k_blocks, total_tiles;
+  __nv_bfloat16* c;
+  long long c_rs, c_bs;
+  const __nv_bfloat16* bias;
+  long long bias_bs;
+  const float* gate;
+  long long gate_bs;
+  float alpha;
+  int act;
+  const __nv_bfloat16* res;
+  long long res_rs, res_bs;
+  int w_batched;
+};
+
+template <int kCta, int BN, int kStages>
+struct GemmCfg {
+  static constexpr int BM = 128;  // rows per CTA
+  static constexpr int BK = 64;   // 64 bf16 = one 128-byte swizzle row
+  static constexpr int BN_LOAD = BN / kCta;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN_LOAD * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int BAR_BYTES = (2 * kStages + 4) * 8 + 16;
+  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + BAR_BYTES + 1024;
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], int b, int r, int col0) {
+  const long long c_off = (long long)b * p.c_bs + (long long)r * p.c_rs;
+  const long long r_off = (long long)b * p.res_bs + (long long)r * p.res_rs;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = col0 + 8 * j;
+    if (c >= p.n) break;
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[8 * j + i]);
+    if (p.bias) {
+      uint4 bv = *reinterpret_cast<const uint4*>(p.bias + (long long)b * p.bias_bs + c);
+      float2 f0 = unpack_bf16x2(bv.x), f1 = unpack_bf16x2(bv.y), f2 = unpack_bf16x2(bv.z), f3 = unpack_bf16x2(bv.w);
+      x[0] += f0.x; x[1] += f0.y; x[2] += f1.x; x[3] += f1.y;
+      x[4] += f2.x; x[5] += f2.y; x[6] += f3.x; x[7] += f3.y;
+    }
+    if (p.act == UG_ACT_GELU_TANH) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = gelu_tanh(x[i]);
+    }
+    if (p.gate) {
+      const float* g = p.gate + (long long)b * p.gate_bs + c;
+      float4 g0 = *reinterpret_cast<const float4*>(g), g1 = *reinterpret_cast<const float4*>(g + 4);
+      x[0] *= g0.x * p.alpha; x[1] *= g0.y * p.alpha; x[2] *= g0.z * p.alpha; x[3] *= g0.w * p.alpha;
+      x[4] *= g1.x * p.alpha; x[5] *= g1.y * p.alpha; x[6] *= g1.z * p.alpha; x[7] *= g1.w * p.alpha;
+    } else if (p.alpha != 1.0f) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] *= p.alpha;
+    }
+    if (p.res) {
+      uint4 rv = *reinterpret_cast<const uint4*>(p.res + r_off + c);
+      float2 f0 = unpack_bf16x2(rv.x), f1 = unpack_bf16x2(rv.y), f2 = unpack_bf16x2(rv.z), f3 = unpack_bf16x2(rv.w);
+      x[0] += f0.x; x[1] += f0.y; x[2] += f1.x; x[3] += f1.y;
+      x[4] += f2.x; x[5] += f2.y; x[6] += f3.x; x[7] += f3.y;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(x[0], x[1]);
+    o.y = pack_bf16x2(x[2], x[3]);
+    o.z = pack_bf16x2(x[4], x[5]);
+    o.w = pack_bf16x2(x[6], x[7]);
+    *reinterpret_cast<uint4*>(p.c + c_off + c) = o;
+  }
+}
+
+template <int kCta, int BN, int kStages>
+__global__ void __launch_bounds__(192, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<kCta, BN, kStages>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms need 1024-byte alignment; the offset is identical in both CTAs of a pair.
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + kStages;
+  uint64_t* tmem_full = empty + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (kCta == 2) ? cluster_ctarank() : 0u;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_w);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4 * kCta);  // one arrive per epilogue warp per CTA
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kCta>(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int unit = (kCta == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+  const int num_units = (kCta == 2) ? (gridDim.x >> 1) : gridDim.x;
+  const int mb_count = p.m_tiles * p.batch;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = unit; tile < p.total_tiles; tile += num_units) {
+      const int mb = tile % mb_count, nt = tile / mb_count;
+      const int b = mb / p.m_tiles, mt = mb % p.m_tiles;
+      const int row0 = mt * (Cfg::BM * kCta) + (int)cta_rank * Cfg::BM;
+      const int wrow0 = nt * BN + (int)cta_rank * Cfg::BN_LOAD;
+      const int wb = p.w_batched ? b : 0;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (lane == 0) {
+          void* sa = smem_a + stage * Cfg::A_BYTES;
+          void* sb = smem_b + stage * Cfg::B_BYTES;
+          if constexpr (kCta == 1) {
+            mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+            tma_load_3d(sa, &tma_a, &full[stage], kb * Cfg::BK, row0, b);
+            tma_load_3d(sb, &tma_w, &full[stage], kb * Cfg::BK, wrow0, wb);
+          } else {
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_3d_2sm(sa, &tma_a, &full[stage], kb * Cfg::BK, row0, b);
+            tma_load_3d_2sm(sb, &tma_w, &full[stage], kb * Cfg::BK, wrow0, wb);
+          }
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+    if (cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(Cfg::BM * kCta, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = unit; tile < p.total_tiles; tile += num_units, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint64_t a_desc = make_sdesc_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES), 16, 1024);
+            const uint64_t b_desc = make_sdesc_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES), 16, 1024);
+#pragma unroll
+            for (int k = 0; k < Cfg::BK / 16; ++k) {
+              // +32 bytes per K=16 step inside the 128-byte swizzle row (start-address field is in 16 B units)
+              umma_ss<kCta>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            if constexpr (kCta == 1) {
+              umma_commit(&empty[stage]);
+              if (kb == p.k_blocks - 1) umma_commit(&tmem_full[as]);
+            } else {
+              umma_commit_2sm(&empty[stage], 0b11);
+              if (kb == p.k_blocks - 1) umma_commit_2sm(&tmem_full[as], 0b11);
+            }
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (warps 2..5) ------------------------------
+    const int q = warp & 3;
+    const int row_local = q * 32 + lane;
+    int it = 0;
+    for (int tile = unit; tile < p.total_tiles; tile += num_units, ++it) {
+      const int mb = tile % mb_count, nt = tile / mb_count;
+      const int b = mb / p.m_tiles, mt = mb % p.m_tiles;
+      const int r = mt * (Cfg::BM * kCta) + (int)cta_rank * Cfg::BM + row_local;
+      const int n0 = nt * BN;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + ch * 32, v);
+        tmem_ld_wait();
+        if (ch == BN / 32 - 1) {
+          // accumulator stage fully read: hand it back to the MMA warp before doing the last stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (kCta == 1 || cta_rank == 0) mbar_arrive(&tmem_empty[as]);
+            else mbar_arrive_cluster(&tmem_empty[as], 0);
+          }
+        }
+        const int col0 = n0 + ch * 32;
+        if (r < p.rows && col0 < p.n) epilogue_chunk(p, v, b, r, col0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kCta>(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int kCta, int BN, int kStages>
+static int launch_gemm(const ug_gemm_args& a, cudaStream_t stream) {
+  using Cfg = GemmCfg<kCta, BN, kStages>;
+  auto kern = gemm_bf16_kernel<kCta, BN, kStages>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("gemm: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return UG_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  CUtensorMap tma_a, tma_w;
+  {
+    uint64_t dims[3] = {(uint64_t)a.k, (uint64_t)a.rows, (uint64_t)a.batch};
+    uint64_t bs = a.batch > 1 ? (uint64_t)a.a_batch_stride : (uint64_t)a.rows * a.a_row_stride;
+    uint64_t strides[2] = {(uint64_t)a.a_row_stride * 2, bs * 2};
+    uint32_t box[3] = {(uint32_t)Cfg::BK, (uint32_t)Cfg::BM, 1};
+    int st = encode_tmap_bf16(&tma_a, a.a, 3, dims, strides, box);
+    if (st != UG_OK) return st;
+  }
+  const bool w_batched = a.w_batch_stride != 0 && a.batch > 1;
+  {
+    uint64_t dims[3] = {(uint64_t)a.k, (uint64_t)a.n, (uint64_t)(w_batched ? a.batch : 1)};
+    uint64_t bs = w_batched ? (uint64_t)a.w_batch_stride : (uint64_t)a.n * a.w_row_stride;
+    uint64_t strides[2] = {(uint64_t)a.w_row_stride * 2, bs * 2};
+    uint32_t box[3] = {(uint32_t)Cfg::BK, (uint32_t)Cfg::BN_LOAD, 1};
+    int st = encode_tmap_bf16(&tma_w, a.w, 3, dims, strides, box);
+    if (st != UG_OK) return st;
+  }
+  GemmParams p;
+  p.rows = a.rows; p.n = a.n; p.k = a.k; p.batch = a.batch;
+  p.m_tiles = (a.rows + Cfg::BM * kCta - 1) / (Cfg::BM * kCta);
+  p.n_tiles = (a.n + BN - 1) / BN;
+  p.k_blocks = (a.k + Cfg::BK - 1) / Cfg::BK;
+  p.total_tiles = p.m_tiles * p.n_tiles * a.batch;
+  p.c = (__nv_bfloat16*)a.c; p.c_rs = a.c_row_stride; p.c_bs = a.c_batch_stride;
+  p.bias = (const __nv_bfloat16*)a.bias; p.bias_bs = a.bias_batch_stride;
+  p.gate = a.gate; p.gate_bs = a.gate_batch_stride;
+  p.alpha = a.alpha; p.act = a.act;
+  p.res = (const __nv_bfloat16*)a.residual; p.res_rs = a.res_row_stride; p.res_bs = a.res_batch_stride;
+  p.w_batched = w_batched ? 1 : 0;
+
+  const int sms = num_sms();
+  int units = kCta == 2 ? sms / 2 : sms;
+  if (units > p.total_tiles) units = p.total_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(units * kCta);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tma_a, tma_w, p);
+  if (e != cudaSuccess) {
+    set_error("gemm: launch failed: %s", cudaGetErrorString(e));
+    return UG_ERR_CUDA;
+  }
+  count_launch();
+  return UG_OK;
+}
+
+}  // namespace ug
+
+extern "C" int ug_gemm_bf16(const ug_gemm_args* args, void* stream) {
+  using namespace ug;
+  UG_CHECK_ARG(args != nullptr, "gemm: null args");
+  const ug_gemm_args& a = *args;
+  UG_CHECK_ARG(a.a && a.w && a.c, "gemm: null operand pointer");
+  UG_CHECK_ARG(a.batch >= 1 && a.rows >= 1 && a.n >= 1 && a.k >= 1, "gemm: empty problem (batch %d rows %d n %d k %d)",
+               a.batch, a.rows, a.n, a.k);
+  UG_CHECK_ARG(a.k % 8 == 0 && a.n % 8 == 0, "gemm: n (%d) and k (%d) must be multiples of 8", a.n, a.k);
+  UG_CHECK_ARG(a.a_row_stride % 8 == 0 && a.w_row_stride % 8 == 0 && a.c_row_stride % 8 == 0,
+               "gemm: row strides must be multiples of 8 elements (16 bytes)");
+  UG_CHECK_ARG(a.a_row_stride >= a.k && a.w_row_stride >= a.k && a.c_row_stride >= a.n, "gemm: row stride smaller than row");
+  UG_CHECK_ARG((reinterpret_cast<uintptr_t>(a.c) & 15) == 0, "gemm: C not 16-byte aligned");
+  UG_CHECK_ARG(a.batch == 1 || (a.a_batch_stride % 8 == 0 && a.c_batch_stride % 8 == 0), "gemm: batch strides must be multiples of 8");
+  if (a.residual) {
+    UG_CHECK_ARG(a.res_row_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0, "gemm: residual alignment");
+  }
+  if (a.bias) UG_CHECK_ARG((reinterpret_cast<uintptr_t>(a.bias) & 15) == 0 && a.bias_batch_stride % 8 == 0, "gemm: bias alignment");
+  if (a.gate) UG_CHECK_ARG((reinterpret_cast<uintptr_t>(a.gate) & 15) == 0 && a.gate_batch_stride % 4 == 0, "gemm: gate alignment");
+  UG_CHECK_ARG(a.act == UG_ACT_NONE || a.act == UG_ACT_GELU_TANH, "gemm: unknown activation %d", a.act);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int variant = a.variant;
+  if (variant == 0) {
+    // auto: narrow tiles when a 128x256 grid would leave most SMs idle
+    const long long tiles256 = (long long)a.batch * ((a.rows + 127) / 128) * ((a.n + 255) / 256);
+    variant = (a.n <= 128 || tiles256 < num_sms()) ? 3 : 1;
+  }
+  switch (variant) {
+    case 1: return launch_gemm<1, 256, 4>(a, s);
+    case 2: return launch_gemm<2, 256, 6>(a, s);
+    case 3: return launch_gemm<1, 128, 6>(a, s);
+    default:
+      set_error("gemm: unknown variant %d", a.variant);
+      return UG_ERR_INVALID;
+  }
+}
