@@ -109,6 +109,8 @@ typedef struct ug_attn_args {
   int32_t n_seg;
   const int32_t* seg_bounds;   /* host, n_seg + 1 entries, seg_bounds[0] = 0, seg_bounds[n_seg] = seq */
   const uint32_t* seg_visible; /* host, n_seg entries */
+  int32_t variant;             /* 0 = auto; 1 = P operand kept in TMEM (tcgen05.mma A-from-TMEM); 2 = P staged in smem */
+  int32_t reserved;
 } ug_attn_args;
 
 int ug_attention_bf16(const ug_attn_args* args, void* stream);
@@ -184,8 +186,8 @@ int ug_moe_route(const void* x, const float* wg, const float* rts_uniform, int32
  * with token = slot_token[e*capacity+s]; empty slots give zero rows. tokens_per_batch maps token -> b.
  * `s ⊙ x` prologue of modulated_flatten (src/UniGenUtils.py:204-228) on the dispatched rows. */
 int ug_moe_gather_modulate(const void* x, const int32_t* slot_token, const float* mod, int64_t mod_expert_stride,
-                           int64_t mod_batch_stride, const void* addend, void* out, void* gathered_x,
-                           int32_t experts, int32_t capacity, int32_t tokens_per_batch, int32_t d, void* stream);
+                           int64_t mod_batch_stride, const void* addend, void* out, int32_t experts,
+                           int32_t capacity, int32_t tokens_per_batch, int32_t d, void* stream);
 /* Combine: out[token,:] = prob[token] * y[expert_idx*capacity + slot, :] or 0 when dropped (einsum sec,ecm->sm,
  * src/UniGenUtils.py:183-185). */
 int ug_moe_combine(const void* y, const int32_t* expert_idx, const int32_t* slot, const float* prob, void* out,

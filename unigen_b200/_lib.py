@@ -41,6 +41,7 @@ class AttnArgs(C.Structure):
         ("batch", C.c_int32), ("heads", C.c_int32), ("seq", C.c_int32), ("head_dim", C.c_int32),
         ("scale", C.c_float), ("n_seg", C.c_int32),
         ("seg_bounds", C.POINTER(C.c_int32)), ("seg_visible", C.POINTER(C.c_uint32)),
+        ("variant", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -65,7 +66,7 @@ SIGNATURES = {
     "ug_cast_f32_to_bf16": (C.c_int, [_VP, _VP, _I64, _VP]),
     "ug_cast_bf16_to_f32": (C.c_int, [_VP, _VP, _I64, _VP]),
     "ug_moe_route": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
-    "ug_moe_gather_modulate": (C.c_int, [_VP, _VP, _VP, _I64, _I64, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP]),
+    "ug_moe_gather_modulate": (C.c_int, [_VP, _VP, _VP, _I64, _I64, _VP, _VP, _I32, _I32, _I32, _I32, _VP]),
     "ug_moe_combine": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP]),
 }
 

@@ -1,0 +1,469 @@
+// Joint attention for sm_100a: softmax(Q K^T * scale + segment mask) V, non-causal, one (128-query tile, head, batch)
+// per CTA.  TMA feeds 128B-swizzled Q/K/V tiles; both GEMMs run on tcgen05 with accumulators in TMEM:
+//   S = Q K^T  (SS MMA, K-major operands)             -> TMEM S[2] (double buffered, 128 fp32 columns each)
+//   O += P V   (P from TMEM (variant 1) or smem (2); V is the MN-major B operand) -> TMEM O (head_dim columns)
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, warps 2..5 softmax + epilogue
+// (one query row per thread; online softmax in fp32, exp2 domain; O is rescaled in TMEM only when a row max moves).
+// The segment rule (condition tokens / image tokens visibility) is applied as whole-tile skipping plus a per-row
+// column mask on tiles that straddle a segment boundary; it is the same rule ug_expand_segment_mask materialises.
+//
+// Replaces F.scaled_dot_product_attention in diffusers FluxAttnProcessor2_0.
+#include "ug_host.h"
+#include "ug_ptx.cuh"
+
+namespace ug {
+
+constexpr int kBlockQ = 128;
+constexpr int kBlockKV = 128;
+constexpr int kMaxTiles = 512;  // seq <= 65536
+
+struct AttnParams {
+  __nv_bfloat16* o;
+  long long o_rs, o_bs;
+  int seq, heads, batch;
+  float scale_log2;  // scale * log2(e)
+  int n_seg;
+  int bounds[UG_MAX_SEGMENTS + 1];
+  unsigned int visible[UG_MAX_SEGMENTS];
+};
+
+template <int kDh, bool kPInTmem>
+struct AttnCfg {
+  static constexpr int SLABS = kDh / 64;                 // 64-column (128-byte) slabs per row
+  static constexpr int SLAB_BYTES = 128 * 128;           // 128 rows x 128 B
+  static constexpr int TILE_BYTES = SLABS * SLAB_BYTES;  // one Q / K / V tile
+  static constexpr int KV_STAGES = 2;
+  static constexpr int P_BYTES = kPInTmem ? 0 : 2 * 2 * SLAB_BYTES;  // 2 buffers x (128 keys = 2 slabs)
+  static constexpr int SMEM_TILES = TILE_BYTES * (1 + 2 * KV_STAGES) + P_BYTES;
+  static constexpr int NUM_BARS = 1 + 4 * KV_STAGES + 6;
+  static constexpr int SMEM_BYTES = SMEM_TILES + NUM_BARS * 8 + 16 + kMaxTiles * 2 + 1024;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int TMEM_S0 = 0, TMEM_S1 = 128, TMEM_O = 256;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+// Is key tile `kt` needed by query tile `qt` (any visible (query segment, key segment) pair)?  flags bit0 = needed,
+// bit1 = per-element masking required (some pair invisible, or the tile holds the sequence tail).
+__device__ __forceinline__ int classify_tile(const AttnParams& p, int qt, int kt) {
+  const int q_lo = qt * kBlockQ, q_hi = min(q_lo + kBlockQ, p.seq);
+  const int k_lo = kt * kBlockKV, k_hi_full = k_lo + kBlockKV, k_hi = min(k_hi_full, p.seq);
+  int needed = 0, partial = (k_hi_full > p.seq) ? 1 : 0;
+  if (p.n_seg == 0) return 1 | (partial << 1);
+  for (int sq = 0; sq < p.n_seg; ++sq) {
+    if (p.bounds[sq + 1] <= q_lo || p.bounds[sq] >= q_hi) continue;
+    for (int sk = 0; sk < p.n_seg; ++sk) {
+      if (p.bounds[sk + 1] <= k_lo || p.bounds[sk] >= k_hi) continue;
+      if ((p.visible[sq] >> sk) & 1u) needed = 1; else partial = 1;
+    }
+  }
+  return needed | (partial << 1);
+}
+
+template <int kDh, bool kPInTmem>
+__global__ void __launch_bounds__(192, 1)
+attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                 const __grid_constant__ CUtensorMap tma_v, const AttnParams p) {
+  using Cfg = AttnCfg<kDh, kPInTmem>;
+  constexpr int KS = Cfg::KV_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_q = smem;
+  uint8_t* smem_k = smem_q + Cfg::TILE_BYTES;
+  uint8_t* smem_v = smem_k + KS * Cfg::TILE_BYTES;
+  uint8_t* smem_p = smem_v + KS * Cfg::TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::SMEM_TILES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = q_full + 1;
+  uint64_t* k_empty = k_full + KS;
+  uint64_t* v_full = k_empty + KS;
+  uint64_t* v_empty = v_full + KS;
+  uint64_t* s_full = v_empty + KS;   // [2]
+  uint64_t* p_ready = s_full + 2;    // [2]
+  uint64_t* pv_done = p_ready + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  int* n_tiles_smem = reinterpret_cast<int*>(tmem_slot + 1);
+  uint16_t* tile_list = reinterpret_cast<uint16_t*>(tmem_slot + 4);  // entry = tile | (needs_mask << 15)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_k);
+    tma_prefetch_desc(&tma_v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KS; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_ready[s], 128);
+      mbar_init(&pv_done[s], 1);
+    }
+    fence_mbar_init();
+    // key tiles this query tile has to visit
+    const int total = (p.seq + kBlockKV - 1) / kBlockKV;
+    int n = 0;
+    for (int kt = 0; kt < total; ++kt) {
+      const int f = classify_tile(p, qt, kt);
+      if (f & 1) tile_list[n++] = (uint16_t)(kt | ((f >> 1) << 15));
+    }
+    *n_tiles_smem = n;
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_tiles = *n_tiles_smem;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, Cfg::TILE_BYTES);
+#pragma unroll
+      for (int s = 0; s < Cfg::SLABS; ++s)
+        tma_load_4d(smem_q + s * Cfg::SLAB_BYTES, &tma_q, q_full, s * 64, head, qt * kBlockQ, b);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < n_tiles; ++i) {
+      const int kt = tile_list[i] & 0x7fff;
+      mbar_wait(&k_empty[stage], phase ^ 1);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&k_full[stage], Cfg::TILE_BYTES);
+#pragma unroll
+        for (int s = 0; s < Cfg::SLABS; ++s)
+          tma_load_4d(smem_k + stage * Cfg::TILE_BYTES + s * Cfg::SLAB_BYTES, &tma_k, &k_full[stage], s * 64, head,
+                      kt * kBlockKV, b);
+      }
+      mbar_wait(&v_empty[stage], phase ^ 1);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&v_full[stage], Cfg::TILE_BYTES);
+#pragma unroll
+        for (int s = 0; s < Cfg::SLABS; ++s)
+          tma_load_4d(smem_v + stage * Cfg::TILE_BYTES + s * Cfg::SLAB_BYTES, &tma_v, &v_full[stage], s * 64, head,
+                      kt * kBlockKV, b);
+      }
+      __syncwarp();
+      if (++stage == KS) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, kBlockKV, false, false);  // S = Q K^T : 128 x 128, K = dh
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, kDh, false, true);        // O = P V   : 128 x dh, V is MN-major
+    auto issue_s = [&](int stage, int buf) {
+      const uint32_t d = tmem_base + (buf ? Cfg::TMEM_S1 : Cfg::TMEM_S0);
+#pragma unroll
+      for (int k = 0; k < kDh / 16; ++k) {
+        const uint32_t off = (k >> 2) * Cfg::SLAB_BYTES + (k & 3) * 32;
+        const uint64_t a_desc = make_sdesc_sw128(smem_u32(smem_q) + off, 16, 1024);
+        const uint64_t b_desc = make_sdesc_sw128(smem_u32(smem_k + stage * Cfg::TILE_BYTES) + off, 16, 1024);
+        umma_ss<1>(d, a_desc, b_desc, idesc_s, k != 0 ? 1u : 0u);
+      }
+    };
+    auto issue_pv = [&](int stage, int buf, bool accumulate) {
+      const uint32_t d = tmem_base + Cfg::TMEM_O;
+#pragma unroll
+      for (int k = 0; k < kBlockKV / 16; ++k) {
+        // V tile: SLABS slabs of [128 keys][64 dh]; 16 keys = 2048 B down the slab; LBO = slab stride (next 64 dh)
+        const uint64_t b_desc =
+            make_sdesc_sw128(smem_u32(smem_v + stage * Cfg::TILE_BYTES) + k * 2048, Cfg::SLAB_BYTES, 1024);
+        const uint32_t acc = (accumulate || k != 0) ? 1u : 0u;
+        if constexpr (kPInTmem) {
+          // P (bf16 pairs) aliases the first 64 columns of its S buffer; 16 keys = 8 columns per MMA
+          const uint32_t a_tmem = tmem_base + (buf ? Cfg::TMEM_S1 : Cfg::TMEM_S0) + k * 8;
+          umma_ts(d, a_tmem, b_desc, idesc_o, acc);
+        } else {
+          const uint32_t off = buf * 2 * Cfg::SLAB_BYTES + (k >> 2) * Cfg::SLAB_BYTES + (k & 3) * 32;
+          const uint64_t a_desc = make_sdesc_sw128(smem_u32(smem_p) + off, 16, 1024);
+          umma_ss<1>(d, a_desc, b_desc, idesc_o, acc);
+        }
+      }
+    };
+    if (n_tiles > 0) {
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      if (lane == 0) {
+        issue_s(0, 0);
+        umma_commit(&k_empty[0]);
+        umma_commit(&s_full[0]);
+      }
+      __syncwarp();
+      for (int i = 0; i < n_tiles; ++i) {
+        const int stage = i % KS;
+        const uint32_t phase = (i / KS) & 1;
+        if (i + 1 < n_tiles) {
+          const int nstage = (i + 1) % KS;
+          mbar_wait(&k_full[nstage], ((i + 1) / KS) & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            issue_s(nstage, (i + 1) & 1);
+            umma_commit(&k_empty[nstage]);
+            umma_commit(&s_full[(i + 1) & 1]);
+          }
+          __syncwarp();
+        }
+        mbar_wait(&p_ready[i & 1], (i >> 1) & 1);
+        mbar_wait(&v_full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          issue_pv(stage, i & 1, i > 0);
+          umma_commit(&v_empty[stage]);
+          umma_commit(&pv_done[i & 1]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------ softmax + epilogue (warps 2..5) ------------------------------
+    const int qd = warp & 3;                 // TMEM lane quarter owned by this warp
+    const int row_local = qd * 32 + lane;    // query row inside the tile
+    const int q_row = qt * kBlockQ + row_local;
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    unsigned int vis = 0xffffffffu;
+    if (p.n_seg > 0) {
+      int sq = p.n_seg - 1;
+      for (int s = 0; s < p.n_seg; ++s)
+        if (q_row >= p.bounds[s] && q_row < p.bounds[s + 1]) sq = s;
+      vis = p.visible[sq];
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int i = 0; i < n_tiles; ++i) {
+      const int entry = tile_list[i];
+      const int kt = entry & 0x7fff;
+      const int buf = i & 1;
+      const uint32_t s_addr = tmem_base + lane_off + (buf ? Cfg::TMEM_S1 : Cfg::TMEM_S0);
+      mbar_wait(&s_full[buf], (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(s_addr + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
+      tmem_ld_wait();
+      if (entry & 0x8000) {
+        // per-row column mask: invisible key segments and the sequence tail
+        unsigned int mw[4] = {0u, 0u, 0u, 0u};
+        const int k_lo = kt * kBlockKV;
+        auto mask_range = [&](int lo, int hi) {  // columns [lo, hi) of this tile
+          lo = max(lo, 0); hi = min(hi, kBlockKV);
+          for (int w = 0; w < 4; ++w) {
+            const int a = max(lo - 32 * w, 0), e = min(hi - 32 * w, 32);
+            if (a < e) mw[w] |= (e - a == 32) ? 0xffffffffu : (((1u << (e - a)) - 1u) << a);
+          }
+        };
+        if (p.seq < k_lo + kBlockKV) mask_range(p.seq - k_lo, kBlockKV);
+        for (int sk = 0; sk < p.n_seg; ++sk)
+          if (!((vis >> sk) & 1u)) mask_range(p.bounds[sk] - k_lo, p.bounds[sk + 1] - k_lo);
+#pragma unroll
+        for (int c = 0; c < 128; ++c)
+          if ((mw[c >> 5] >> (c & 31)) & 1u) s[c] = 0xff800000u;  // -inf
+      }
+      float rmax = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 128; ++c) rmax = fmaxf(rmax, __uint_as_float(s[c]));
+      const float m_new = fmaxf(m, rmax);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = exp2f((m - m_use) * p.scale_log2);  // m = -inf -> 0
+      const float neg_ms = -m_use * p.scale_log2;
+      float rsum = 0.f;
+      uint32_t pk[64];
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        const float p0 = exp2f(fmaf(__uint_as_float(s[2 * c]), p.scale_log2, neg_ms));
+        const float p1 = exp2f(fmaf(__uint_as_float(s[2 * c + 1]), p.scale_log2, neg_ms));
+        rsum += p0 + p1;
+        pk[c] = pack_bf16x2(p0, p1);
+      }
+      l = l * alpha + rsum;
+      if constexpr (kPInTmem) {
+        tmem_st_32x32(s_addr, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
+        tmem_st_32x32(s_addr + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
+      } else {
+        // K-major, 128B-swizzled: row r, 16-byte chunk c of slab (keys 64*slab ..): chunk index XOR (r & 7)
+        uint8_t* pb = smem_p + buf * 2 * Cfg::SLAB_BYTES + row_local * 128;
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) {
+          uint8_t* dst = pb + (ch >> 3) * Cfg::SLAB_BYTES + (((ch & 7) ^ (row_local & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        }
+      }
+      if (i > 0) {
+        // O must be quiescent (PV of the previous tile retired) before it is rescaled
+        mbar_wait(&pv_done[(i - 1) & 1], ((i - 1) >> 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, m_new > m)) {
+          const uint32_t o_addr = tmem_base + lane_off + Cfg::TMEM_O;
+#pragma unroll
+          for (int c = 0; c < kDh / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(o_addr + 32 * c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+            tmem_st_32x32(o_addr + 32 * c, o);
+          }
+        }
+      }
+      if constexpr (kPInTmem) {
+        tmem_st_wait();
+      } else {
+        tmem_st_wait();
+        fence_proxy_async_smem();
+      }
+      tc_fence_before();
+      mbar_arrive(&p_ready[buf]);
+      m = m_new;
+    }
+    // epilogue: O / l -> bf16 -> HBM
+    if (n_tiles > 0) {
+      mbar_wait(&pv_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
+      tc_fence_after();
+    }
+    const float inv_l = l > 0.f ? 1.f / l : 0.f;
+    __nv_bfloat16* orow = p.o + (long long)b * p.o_bs + (long long)q_row * p.o_rs + head * kDh;
+    const uint32_t o_addr = tmem_base + lane_off + Cfg::TMEM_O;
+#pragma unroll
+    for (int c = 0; c < kDh / 32; ++c) {
+      uint32_t o[32];
+      if (n_tiles > 0) {
+        tmem_ld_32x32(o_addr + 32 * c, o);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = 0u;
+      }
+      if (q_row < p.seq) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[8 * j]) * inv_l, __uint_as_float(o[8 * j + 1]) * inv_l);
+          u.y = pack_bf16x2(__uint_as_float(o[8 * j + 2]) * inv_l, __uint_as_float(o[8 * j + 3]) * inv_l);
+          u.z = pack_bf16x2(__uint_as_float(o[8 * j + 4]) * inv_l, __uint_as_float(o[8 * j + 5]) * inv_l);
+          u.w = pack_bf16x2(__uint_as_float(o[8 * j + 6]) * inv_l, __uint_as_float(o[8 * j + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + 32 * c + 8 * j) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+__global__ void expand_mask_kernel(int seq, int n_seg, AttnParams p, uint8_t* __restrict__ mask) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)seq * seq) return;
+  const int q = (int)(idx / seq), k = (int)(idx % seq);
+  int sq = 0, sk = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    if (q >= p.bounds[s] && q < p.bounds[s + 1]) sq = s;
+    if (k >= p.bounds[s] && k < p.bounds[s + 1]) sk = s;
+  }
+  mask[idx] = n_seg == 0 ? 1 : (uint8_t)((p.visible[sq] >> sk) & 1u);
+}
+
+static int fill_segments(AttnParams& p, int seq, int n_seg, const int32_t* bounds, const uint32_t* visible) {
+  UG_CHECK_ARG(n_seg >= 0 && n_seg <= UG_MAX_SEGMENTS, "attention: n_seg %d out of range [0, %d]", n_seg, UG_MAX_SEGMENTS);
+  p.n_seg = n_seg;
+  for (int i = 0; i <= UG_MAX_SEGMENTS; ++i) p.bounds[i] = seq;
+  for (int i = 0; i < UG_MAX_SEGMENTS; ++i) p.visible[i] = 0;
+  if (n_seg > 0) {
+    UG_CHECK_ARG(bounds && visible, "attention: segment arrays are null");
+    UG_CHECK_ARG(bounds[0] == 0 && bounds[n_seg] == seq, "attention: seg_bounds must start at 0 and end at seq");
+    for (int i = 0; i < n_seg; ++i) {
+      UG_CHECK_ARG(bounds[i + 1] >= bounds[i], "attention: seg_bounds must be non-decreasing");
+      p.bounds[i] = bounds[i];
+      p.visible[i] = visible[i];
+    }
+    p.bounds[n_seg] = seq;
+  }
+  return UG_OK;
+}
+
+template <int kDh, bool kPInTmem>
+static int launch_attention(const ug_attn_args& a, cudaStream_t stream) {
+  using Cfg = AttnCfg<kDh, kPInTmem>;
+  auto kern = attention_kernel<kDh, kPInTmem>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("attention: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return UG_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  CUtensorMap maps[3];
+  const void* ptrs[3] = {a.q, a.k, a.v};
+  const int64_t rs[3] = {a.q_row_stride, a.k_row_stride, a.v_row_stride};
+  const int64_t bs[3] = {a.q_batch_stride, a.k_batch_stride, a.v_batch_stride};
+  for (int i = 0; i < 3; ++i) {
+    uint64_t dims[4] = {(uint64_t)kDh, (uint64_t)a.heads, (uint64_t)a.seq, (uint64_t)a.batch};
+    uint64_t bstride = a.batch > 1 ? (uint64_t)bs[i] : (uint64_t)a.seq * rs[i];
+    uint64_t strides[3] = {(uint64_t)kDh * 2, (uint64_t)rs[i] * 2, bstride * 2};
+    uint32_t box[4] = {64, 1, 128, 1};
+    int st = encode_tmap_bf16(&maps[i], ptrs[i], 4, dims, strides, box);
+    if (st != UG_OK) return st;
+  }
+  AttnParams p;
+  p.o = (__nv_bfloat16*)a.o; p.o_rs = a.o_row_stride; p.o_bs = a.o_batch_stride;
+  p.seq = a.seq; p.heads = a.heads; p.batch = a.batch;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  int st = fill_segments(p, a.seq, a.n_seg, a.seg_bounds, a.seg_visible);
+  if (st != UG_OK) return st;
+  dim3 grid((a.seq + kBlockQ - 1) / kBlockQ, a.heads, a.batch);
+  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], p);
+  UG_CHECK_LAUNCH("attention");
+  return UG_OK;
+}
+
+}  // namespace ug
+
+using namespace ug;
+
+extern "C" int ug_attention_bf16(const ug_attn_args* args, void* stream) {
+  UG_CHECK_ARG(args != nullptr, "attention: null args");
+  const ug_attn_args& a = *args;
+  UG_CHECK_ARG(a.q && a.k && a.v && a.o, "attention: null operand pointer");
+  UG_CHECK_ARG(a.batch >= 1 && a.heads >= 1 && a.seq >= 1, "attention: empty problem");
+  UG_CHECK_ARG(a.seq <= kMaxTiles * kBlockKV, "attention: seq %d exceeds %d", a.seq, kMaxTiles * kBlockKV);
+  UG_CHECK_ARG(a.q_row_stride % 8 == 0 && a.k_row_stride % 8 == 0 && a.v_row_stride % 8 == 0 && a.o_row_stride % 8 == 0,
+               "attention: row strides must be multiples of 8 elements");
+  UG_CHECK_ARG((reinterpret_cast<uintptr_t>(a.o) & 15) == 0, "attention: O not 16-byte aligned");
+  UG_CHECK_ARG(a.batch == 1 || (a.q_batch_stride % 8 == 0 && a.k_batch_stride % 8 == 0 && a.v_batch_stride % 8 == 0 &&
+                                a.o_batch_stride % 8 == 0),
+               "attention: batch strides must be multiples of 8 elements");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int variant = a.variant == 0 ? 1 : a.variant;
+  if (a.head_dim == 128) {
+    if (variant == 1) return launch_attention<128, true>(a, s);
+    if (variant == 2) return launch_attention<128, false>(a, s);
+  } else if (a.head_dim == 64) {
+    if (variant == 1) return launch_attention<64, true>(a, s);
+    if (variant == 2) return launch_attention<64, false>(a, s);
+  } else {
+    set_error("attention: head_dim %d not supported (64 or 128)", a.head_dim);
+    return UG_ERR_UNSUPPORTED;
+  }
+  set_error("attention: unknown variant %d", a.variant);
+  return UG_ERR_INVALID;
+}
+
+extern "C" int ug_expand_segment_mask(int32_t seq, int32_t n_seg, const int32_t* bounds, const uint32_t* visible,
+                                      uint8_t* mask_dev, void* stream) {
+  UG_CHECK_ARG(seq >= 1 && mask_dev, "expand_segment_mask: bad arguments");
+  AttnParams p;
+  int st = fill_segments(p, seq, n_seg, bounds, visible);
+  if (st != UG_OK) return st;
+  const long long total = (long long)seq * seq;
+  expand_mask_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(seq, n_seg, p, mask_dev);
+  UG_CHECK_LAUNCH("expand_segment_mask");
+  return UG_OK;
+}
