@@ -131,10 +131,13 @@ int ug_ln_modulate(const void* x, int64_t x_row_stride, int64_t x_batch_stride, 
 
 /* In-place per-head RMSNorm (learned weight) followed by interleaved-pair RoPE on rows of a [batch, rows, heads, dh]
  * bf16 view: diffusers RMSNorm(dh, eps) + apply_rotary_emb (src/UniGenUtils.py:597-599).
+ * norm_weight: bf16 [heads / heads_per_weight, dh] — head h uses row h / heads_per_weight, so the Q and K halves of a
+ * fused QKV buffer (heads = 2H, heads_per_weight = H) are normalised with norm_q / norm_k in one launch
+ * (heads_per_weight <= 0: one weight row for all heads).
  * cos_sin: fp32 [rows, dh/2, 2] (cos, sin of pair i) shared by all batches/heads, or NULL for no rotation. */
 int ug_qk_rmsnorm_rope(void* x, int64_t row_stride, int64_t batch_stride, int32_t batch, int32_t rows,
-                       int32_t heads, int32_t head_dim, const void* norm_weight_bf16, float eps,
-                       const float* cos_sin, void* stream);
+                       int32_t heads, int32_t head_dim, const void* norm_weight_bf16, int32_t heads_per_weight,
+                       float eps, const float* cos_sin, void* stream);
 
 /* RoPE table from position ids: FluxPosEmbed(theta, axes_dim)(ids), float64 angles -> fp32.
  * ids: fp32 [rows, 3]; axes_dim: host int[3] (sum = head_dim); out: fp32 [rows, head_dim/2, 2]. */

@@ -315,7 +315,7 @@ def condition_ids(condition_type: str, height: int, width: int) -> Tuple[Tensor,
     h2, w2 = height // 16, width // 16
     ids = prepare_latent_image_ids(h2, w2)
     if condition_type == "subject":
-        ids[:, 2] += w2
+        ids[:, 2] += h2  # `cond_ids[:, 2] += cond_img.shape[2] // 2` — the latent HEIGHT // 2 (src/condition.py:109-110)
     type_id = torch.ones_like(ids[:, :1]) * CONDITION_DICT[condition_type]
     return ids, type_id
 
@@ -324,6 +324,106 @@ def weave_schedule(n_base: int, n_ctrl: int) -> List[int]:
     """cn_block_idx = int(index_block / (n_base / n_ctrl)) (src/UniGenTransformer.py:1126-1127,1159-1160)."""
     interval = n_base / n_ctrl
     return [int(i / interval) for i in range(n_base)]
+
+
+def weave(h, enc, temb, preprocess, base_double, base_single, ctrl_double, ctrl_single, add_double, add_single,
+          conditioning_scale: float, method: str = "overall_add", rec=None):
+    """UniGenFlux.base_forward + control_forward (src/UniGenTransformer.py:1070-1180) over pluggable blocks.
+    base_double[i](h, enc, temb) -> (enc, h); base_single[i](x, temb) -> x; ctrl_* take (.., condition_temb);
+    add_*[j](x) are the zero-linears; preprocess(h, enc) -> moe_output dict, run at the FIRST control call only."""
+    rec = rec or (lambda *_: None)
+    moe = None
+    sched_d = weave_schedule(len(base_double), len(ctrl_double))
+    for i, blk in enumerate(base_double):
+        enc, h = blk(h, enc, temb)
+        rec(f"double.{i}.base_hidden", h); rec(f"double.{i}.base_context", enc)
+        j = sched_d[i]
+        if moe is None:  # :1084-1089 — first call: control stream := expert_hidden + expert_cond
+            moe = preprocess(h, enc)
+            ctrl_in = moe["expert_hidden_states"] + moe["expert_condition_hidden_states"]
+            rec("moe.ctrl_in", ctrl_in)
+        else:            # later calls: the control block reads the BASE stream (1st positional arg, :1137)
+            ctrl_in = h
+        _, ch = ctrl_double[j](ctrl_in, moe["control_encoder_hidden_states"], moe["condition_temb"])
+        h = h + add_double[j](ch) * conditioning_scale
+        rec(f"double.{i}.ctrl_hidden", ch); rec(f"double.{i}.hidden", h)
+    T = enc.shape[1]
+    x = torch.cat([enc, h], dim=1)  # :1146 text first
+    sched_s = weave_schedule(len(base_single), len(ctrl_single)) if len(ctrl_single) else []
+    for i, blk in enumerate(base_single):
+        x = blk(x, temb)
+        rec(f"single.{i}.base_hidden", x)
+        if len(ctrl_single):
+            j = sched_s[i]
+            cx = ctrl_single[j](x, moe["condition_temb"])
+            zero = add_single[j](cx) * conditioning_scale
+            if method == "overall_add":  # :1166-1172
+                x = x + zero
+            else:
+                x = torch.cat([x[:, :T], x[:, T:] + zero[:, T:]], dim=1)
+        rec(f"single.{i}.hidden", x)
+    return x[:, T:], enc, moe
+
+
+# --- src/lora_switching_module.py:4-39 + peft 0.15 LoraLayer.set_scale (SURVEY.md §A.6, §8 A14) ---
+def module_active_adapters(module) -> List[str]:
+    if hasattr(module, "active_adapters"):
+        return [a for a in module.active_adapters if a in module.scaling.keys()]
+    return []
+
+
+class enable_lora:
+    """Context manager: zero the scale of every active adapter not in `enable_adapters`, restore on exit through
+    `set_scale(adapter, saved_scaling)` (which re-multiplies by lora_alpha/r — exact only when alpha == r; replicated)."""
+
+    def __init__(self, lora_modules, enable_adapters, tuner_type=None):
+        self.lora_modules = [m for m in lora_modules if (tuner_type is None and hasattr(m, "set_scale"))
+                             or (tuner_type is not None and isinstance(m, tuner_type))]
+        self.saved = [{a: m.scaling[a] for a in module_active_adapters(m)} for m in self.lora_modules]
+        self.enable_adapters = enable_adapters
+
+    def __enter__(self):
+        for m in self.lora_modules:
+            for a in module_active_adapters(m):
+                if a not in self.enable_adapters:
+                    m.set_scale(a, 0)
+
+    def __exit__(self, *exc):
+        for i, m in enumerate(self.lora_modules):
+            for a in module_active_adapters(m):
+                m.set_scale(a, self.saved[i][a])
+
+
+def lora_linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], adapters: Dict[str, Tuple[Tensor, Tensor, float]],
+                active: List[str]) -> Tensor:
+    """peft 0.15 lora.Linear.forward: base(x) + sum_a B_a(A_a(x)) * scaling_a over active adapters."""
+    y = F.linear(x, weight, bias)
+    for a in active:
+        A, Bm, scaling = adapters[a]
+        y = y + F.linear(F.linear(x, A), Bm) * scaling
+    return y
+
+
+def segment_mask(bounds: List[int], visible: List[int]) -> Tensor:
+    """Dense boolean (S,S) attention mask from the segment rule: query in segment i attends keys of
+    segment j iff bit j of visible[i]. P-variant rule: txt,img -> all; c_i -> {txt, img, c_i}."""
+    S = bounds[-1]
+    seg = torch.zeros(S, dtype=torch.long)
+    for i in range(len(bounds) - 1):
+        seg[bounds[i]:bounds[i + 1]] = i
+    n = len(visible)
+    vm = torch.tensor([[(visible[i] >> j) & 1 for j in range(n)] for i in range(n)], dtype=torch.bool)
+    return vm[seg][:, seg]
+
+
+def pvariant_visibility(n_cond: int, strict: bool = False) -> List[int]:
+    """Segments [txt, img, c_1..c_n]. Reference rule (UniCombineTransformerBlock.pyc L98-110): main queries see every
+    segment; c_i sees txt, img, c_i. strict=True is the north-star wording (condition tokens see only themselves)."""
+    n = 2 + n_cond
+    vis = [(1 << n) - 1, (1 << n) - 1]
+    for i in range(n_cond):
+        vis.append((1 << (2 + i)) | (0 if strict else 0b11))
+    return vis
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -431,41 +531,23 @@ class UniGenFluxOracle:
         rope_ctrl = rope  # control_pos_embed_input is a deepcopy of the parameter-free pos_embed (:727), same ids order
         self._rec("temb", temb); self._rec("x_embed", h); self._rec("context_embed", enc)
 
-        moe = None
-        T = enc.shape[1]
-        sched_d = weave_schedule(cfg.num_layers, cfg.cn_joint_layers)
-        for i in range(cfg.num_layers):
-            enc, h = flux_double_block(sd, f"transformer_blocks.{i}", H, h, enc, temb, rope)
-            self._rec(f"double.{i}.base_hidden", h); self._rec(f"double.{i}.base_context", enc)
-            j = sched_d[i]
-            if moe is None:  # first control_forward call (:1084-1089)
-                moe = self.preprocess_moe_forward(h, condition_hidden_states, enc, pooled_projections,
-                                                  condition_pooled_projections, timestep, guidance,
-                                                  (img_ids, txt_ids, condition_ids), rts_uniform)
-                ctrl_in = moe["expert_hidden_states"] + moe["expert_condition_hidden_states"]
-                self._rec("moe.ctrl_in", ctrl_in)
-            else:
-                ctrl_in = h
-            _, ch = flux_double_block(sd, f"control_joint_trans_blocks.{j}", H, ctrl_in,
-                                      moe["control_encoder_hidden_states"], moe["condition_temb"], rope_ctrl)
-            zero = linear(sd, f"controlnet_add_joint_blocks.{j}", ch) * conditioning_scale
-            h = h + zero
-            self._rec(f"double.{i}.ctrl_hidden", ch); self._rec(f"double.{i}.hidden", h)
+        def preprocess(h_, enc_):
+            return self.preprocess_moe_forward(h_, condition_hidden_states, enc_, pooled_projections,
+                                               condition_pooled_projections, timestep, guidance,
+                                               (img_ids, txt_ids, condition_ids), rts_uniform)
 
-        x = torch.cat([enc, h], dim=1)
-        sched_s = weave_schedule(cfg.num_single_layers, cfg.cn_single_layers)
-        for i in range(cfg.num_single_layers):
-            x = flux_single_block(sd, f"single_transformer_blocks.{i}", H, x, temb, rope)
-            self._rec(f"single.{i}.base_hidden", x)
-            j = sched_s[i]
-            cx = flux_single_block(sd, f"control_single_trans_blocks.{j}", H, x, moe["condition_temb"], rope_ctrl)
-            zero = linear(sd, f"controlnet_add_single_blocks.{j}", cx) * conditioning_scale
-            if cfg.single_block_control_method == "overall_add":
-                x = x + zero
-            else:
-                x = torch.cat([x[:, :T], x[:, T:] + zero[:, T:]], dim=1)
-            self._rec(f"single.{i}.hidden", x)
-        h = x[:, T:]
+        dbl = lambda p: (lambda h_, c_, t_: flux_double_block(sd, p, H, h_, c_, t_, rope))  # noqa: E731
+        sgl = lambda p: (lambda x_, t_: flux_single_block(sd, p, H, x_, t_, rope_ctrl))      # noqa: E731
+        lin = lambda p: (lambda x_: linear(sd, p, x_))                                        # noqa: E731
+        h, enc, moe = weave(
+            h, enc, temb, preprocess,
+            [dbl(f"transformer_blocks.{i}") for i in range(cfg.num_layers)],
+            [sgl(f"single_transformer_blocks.{i}") for i in range(cfg.num_single_layers)],
+            [dbl(f"control_joint_trans_blocks.{j}") for j in range(cfg.cn_joint_layers)],
+            [sgl(f"control_single_trans_blocks.{j}") for j in range(cfg.cn_single_layers)],
+            [lin(f"controlnet_add_joint_blocks.{j}") for j in range(cfg.cn_joint_layers)],
+            [lin(f"controlnet_add_single_blocks.{j}") for j in range(cfg.cn_single_layers)],
+            conditioning_scale, cfg.single_block_control_method, self._rec)
         out = linear(sd, "proj_out", ada_layer_norm_continuous(sd, "norm_out", h, temb))
         self._rec("velocity", out)
         return out, dict(moe_loss=moe["moe_loss"] * 0.1), dict(expert_counts=moe["exp_count"])

@@ -57,7 +57,7 @@ SIGNATURES = {
     "ug_attention_bf16": (C.c_int, [C.POINTER(AttnArgs), _VP]),
     "ug_expand_segment_mask": (C.c_int, [_I32, _I32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), _VP, _VP]),
     "ug_ln_modulate": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _I64, _VP, _VP, _I64, _I32, _I32, _I32, _F32, _VP]),
-    "ug_qk_rmsnorm_rope": (C.c_int, [_VP, _I64, _I64, _I32, _I32, _I32, _I32, _VP, _F32, _VP, _VP]),
+    "ug_qk_rmsnorm_rope": (C.c_int, [_VP, _I64, _I64, _I32, _I32, _I32, _I32, _VP, _I32, _F32, _VP, _VP]),
     "ug_rope_table": (C.c_int, [_VP, _I32, C.POINTER(C.c_int32), _F32, _VP, _VP]),
     "ug_gemv": (C.c_int, [_VP, _I64, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "ug_timestep_embedding": (C.c_int, [_VP, _I32, _I32, _VP, _VP]),

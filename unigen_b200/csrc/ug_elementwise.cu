@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const __nv_bfloat16* _
 template <int kDh>
 __global__ void __launch_bounds__(256) qk_rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long rs, long long bs,
                                                               int batch, int rows, int heads,
-                                                              const __nv_bfloat16* __restrict__ w, float eps,
-                                                              const float* __restrict__ cos_sin) {
+                                                              const __nv_bfloat16* __restrict__ w, int heads_per_weight,
+                                                              float eps, const float* __restrict__ cos_sin) {
   constexpr int EPL = kDh / 32;  // elements per lane: 4 (dh=128) or 2 (dh=64)
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -100,14 +100,17 @@ __global__ void __launch_bounds__(256) qk_rmsnorm_rope_kernel(__nv_bfloat16* __r
   const int b = warp_global / rows, r = warp_global % rows;
   __nv_bfloat16* row = x + (long long)b * bs + (long long)r * rs;
   float wv[EPL], cs[EPL], sn[EPL];
-#pragma unroll
-  for (int i = 0; i < EPL; ++i) wv[i] = __bfloat162float(w[lane * EPL + i]);
   if (cos_sin) {
     const float* t = cos_sin + (long long)r * kDh + lane * EPL;  // [rows, dh/2, 2]: (cos, sin) of pair
 #pragma unroll
     for (int i = 0; i < EPL; i += 2) { cs[i] = cs[i + 1] = t[i]; sn[i] = sn[i + 1] = t[i + 1]; }
   }
   for (int h = 0; h < heads; ++h) {
+    if (h % heads_per_weight == 0) {  // q heads then k heads: one weight vector per group
+      const __nv_bfloat16* wp = w + (h / heads_per_weight) * kDh + lane * EPL;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) wv[i] = __bfloat162float(wp[i]);
+    }
     __nv_bfloat16* p = row + h * kDh + lane * EPL;
     float f[EPL];
     if constexpr (EPL == 4) {
@@ -321,18 +324,20 @@ extern "C" int ug_ln_modulate(const void* x, int64_t x_rs, int64_t x_bs, void* o
 }
 
 extern "C" int ug_qk_rmsnorm_rope(void* x, int64_t rs, int64_t bs, int32_t batch, int32_t rows, int32_t heads,
-                                  int32_t head_dim, const void* w, float eps, const float* cos_sin, void* stream) {
+                                  int32_t head_dim, const void* w, int32_t heads_per_weight, float eps,
+                                  const float* cos_sin, void* stream) {
   UG_CHECK_ARG(x && w, "qk_rmsnorm_rope: null pointer");
   UG_CHECK_ARG(batch >= 1 && rows >= 1 && heads >= 1, "qk_rmsnorm_rope: bad shape");
+  if (heads_per_weight <= 0) heads_per_weight = heads;
   UG_CHECK_ARG(rs % 4 == 0 && bs % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0, "qk_rmsnorm_rope: alignment");
   const long long warps = (long long)batch * rows;
   const int block = 256;
   const int grid = (int)((warps * 32 + block - 1) / block);
   auto s = reinterpret_cast<cudaStream_t>(stream);
   if (head_dim == 128)
-    qk_rmsnorm_rope_kernel<128><<<grid, block, 0, s>>>((__nv_bfloat16*)x, rs, bs, batch, rows, heads, (const __nv_bfloat16*)w, eps, cos_sin);
+    qk_rmsnorm_rope_kernel<128><<<grid, block, 0, s>>>((__nv_bfloat16*)x, rs, bs, batch, rows, heads, (const __nv_bfloat16*)w, heads_per_weight, eps, cos_sin);
   else if (head_dim == 64)
-    qk_rmsnorm_rope_kernel<64><<<grid, block, 0, s>>>((__nv_bfloat16*)x, rs, bs, batch, rows, heads, (const __nv_bfloat16*)w, eps, cos_sin);
+    qk_rmsnorm_rope_kernel<64><<<grid, block, 0, s>>>((__nv_bfloat16*)x, rs, bs, batch, rows, heads, (const __nv_bfloat16*)w, heads_per_weight, eps, cos_sin);
   else {
     set_error("qk_rmsnorm_rope: head_dim %d not supported (64 or 128)", head_dim);
     return UG_ERR_UNSUPPORTED;

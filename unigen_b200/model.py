@@ -1,0 +1,534 @@
+"""Host-side mirror of the reference's denoiser interface for the B200-native path.
+
+`UniGenFlux` here keeps the reference's public surface — `init_condition_block(...)`, `forward(hidden_states,
+condition_hidden_states, conditioning_scale, encoder_hidden_states, pooled_projections, condition_pooled_projections,
+timestep, img_ids, txt_ids, guidance, condition_ids, joint_attention_kwargs, ...) -> (velocity, add_losses,
+add_outputs)` (reference src/UniGenTransformer.py:712-716,1182-1271), `state_dict()/load_state_dict()` under the
+reference's key names, `.config`, `.dtype`, `.trainable_control_modules` — while every arithmetic op of the step
+runs in libunigen_b200.so (unigen_b200.ops).  torch supplies device memory, the stream and (optionally) CUDA-graph
+capture; there is no eager/CPU fallback.
+
+Data layout in HBM (bf16 unless noted)
+  X    [B, T+N, D]   joint residual stream, TEXT ROWS FIRST — the `cat([text, image])` of base_forward (:1146) is free
+  NX   [B, Smax, D]  LN+modulated operand, QKV [B, Smax, 3D] fused q|k|v, AO attention out, FF [B, Smax, 4D]
+  CAT  [B, S, 5D]    single blocks: attention writes cols [0,D), GELU(proj_mlp) writes [D,5D) — `cat([attn, mlp])` is free
+  MOD  fp32          AdaLN shift/scale/gate vectors of ALL blocks, computed once per step (temb is step-constant)
+  weights            fused per block (to_q|to_k|to_v -> one [3D, D] matrix, experts stacked [E, D, D]); the reference's
+                     parameter names are VIEWS into the fused storage, so state dicts load in place without copies.
+"""
+from __future__ import annotations
+
+import math
+import types
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .ops import UG_ACT_GELU_TANH
+
+BF16 = torch.bfloat16
+
+
+class FluxArch:
+    """diffusers FluxTransformer2DModel config fields read on the path + UniGen control_params."""
+
+    def __init__(self, num_layers=19, num_single_layers=38, attention_head_dim=128, num_attention_heads=24, in_channels=64,
+                 joint_attention_dim=4096, pooled_projection_dim=768, guidance_embeds=False, axes_dims_rope=(16, 56, 56),
+                 theta=10000.0):
+        self.num_layers, self.num_single_layers = num_layers, num_single_layers
+        self.attention_head_dim, self.num_attention_heads = attention_head_dim, num_attention_heads
+        self.in_channels, self.joint_attention_dim = in_channels, joint_attention_dim
+        self.pooled_projection_dim, self.guidance_embeds = pooled_projection_dim, guidance_embeds
+        self.axes_dims_rope, self.theta = tuple(axes_dims_rope), theta
+        self.hidden_size = num_layers and num_attention_heads * attention_head_dim
+
+    @staticmethod
+    def tiny():
+        return FluxArch(num_layers=2, num_single_layers=4, attention_head_dim=64, num_attention_heads=6, axes_dims_rope=(8, 28, 28))
+
+
+class _Weights:
+    """Fused device storage + reference-name views."""
+
+    def __init__(self, device):
+        self.device = device
+        self.views: Dict[str, torch.Tensor] = {}
+
+    def alloc(self, *shape, dtype=BF16) -> torch.Tensor:
+        return torch.zeros(*shape, device=self.device, dtype=dtype)
+
+    def linear(self, name: str, out_f: int, in_f: int, w: Optional[torch.Tensor] = None, b: Optional[torch.Tensor] = None):
+        w = self.alloc(out_f, in_f) if w is None else w
+        b = self.alloc(out_f) if b is None else b
+        self.views[name + ".weight"], self.views[name + ".bias"] = w, b
+        return w, b
+
+    def fused(self, names: Sequence[str], out_each: int, in_f: int):
+        """One [len(names)*out_each, in_f] matrix (+ bias); names[i] is a row-slice view."""
+        W, Bv = self.alloc(len(names) * out_each, in_f), self.alloc(len(names) * out_each)
+        for i, n in enumerate(names):
+            self.views[n + ".weight"] = W[i * out_each:(i + 1) * out_each]
+            self.views[n + ".bias"] = Bv[i * out_each:(i + 1) * out_each]
+        return W, Bv
+
+
+class _DoubleBlockW:
+    def __init__(self, ws: _Weights, p: str, D: int, dh: int):
+        self.norm1 = ws.linear(p + ".norm1.linear", 6 * D, D)
+        self.norm1_ctx = ws.linear(p + ".norm1_context.linear", 6 * D, D)
+        self.qkv = ws.fused([f"{p}.attn.to_q", f"{p}.attn.to_k", f"{p}.attn.to_v"], D, D)
+        self.add_qkv = ws.fused([f"{p}.attn.add_q_proj", f"{p}.attn.add_k_proj", f"{p}.attn.add_v_proj"], D, D)
+        self.to_out = ws.linear(p + ".attn.to_out.0", D, D)
+        self.to_add_out = ws.linear(p + ".attn.to_add_out", D, D)
+        self.rms = ws.alloc(2, dh)       # [norm_q; norm_k]
+        self.rms_ctx = ws.alloc(2, dh)   # [norm_added_q; norm_added_k]
+        ws.views[p + ".attn.norm_q.weight"], ws.views[p + ".attn.norm_k.weight"] = self.rms[0], self.rms[1]
+        ws.views[p + ".attn.norm_added_q.weight"], ws.views[p + ".attn.norm_added_k.weight"] = self.rms_ctx[0], self.rms_ctx[1]
+        self.ff1 = ws.linear(p + ".ff.net.0.proj", 4 * D, D)
+        self.ff2 = ws.linear(p + ".ff.net.2", D, 4 * D)
+        self.ffc1 = ws.linear(p + ".ff_context.net.0.proj", 4 * D, D)
+        self.ffc2 = ws.linear(p + ".ff_context.net.2", D, 4 * D)
+
+
+class _SingleBlockW:
+    def __init__(self, ws: _Weights, p: str, D: int, dh: int):
+        self.norm = ws.linear(p + ".norm.linear", 3 * D, D)
+        self.qkv = ws.fused([f"{p}.attn.to_q", f"{p}.attn.to_k", f"{p}.attn.to_v"], D, D)
+        self.mlp = ws.linear(p + ".proj_mlp", 4 * D, D)
+        self.out = ws.linear(p + ".proj_out", D, 5 * D)
+        self.rms = ws.alloc(2, dh)
+        ws.views[p + ".attn.norm_q.weight"], ws.views[p + ".attn.norm_k.weight"] = self.rms[0], self.rms[1]
+
+
+class _TimeTextW:
+    def __init__(self, ws: _Weights, p: str, D: int, pooled: int, guidance: bool):
+        self.t1 = ws.linear(p + ".timestep_embedder.linear_1", D, 256)
+        self.t2 = ws.linear(p + ".timestep_embedder.linear_2", D, D)
+        self.g1 = ws.linear(p + ".guidance_embedder.linear_1", D, 256) if guidance else None
+        self.g2 = ws.linear(p + ".guidance_embedder.linear_2", D, D) if guidance else None
+        self.p1 = ws.linear(p + ".text_embedder.linear_1", D, pooled)
+        self.p2 = ws.linear(p + ".text_embedder.linear_2", D, D)
+
+
+class UniGenFlux(torch.nn.Module):
+    """B200-native drop-in for the reference `UniGenFlux` (Flux-arch denoiser + WeaveNet control branch + CoMoE)."""
+
+    def __init__(self, arch: Optional[FluxArch] = None, device: Any = "cuda", **config):
+        super().__init__()
+        self.arch = arch or FluxArch(**config)
+        self.device_ = torch.device(device)
+        if self.device_.type != "cuda":
+            raise ops.UgError("UniGenFlux (B200-native) needs a CUDA device: the hot path has no CPU fallback")
+        a = self.arch
+        self.config = types.SimpleNamespace(in_channels=a.in_channels, guidance_embeds=a.guidance_embeds,
+                                            num_attention_heads=a.num_attention_heads, attention_head_dim=a.attention_head_dim,
+                                            pooled_projection_dim=a.pooled_projection_dim, joint_attention_dim=a.joint_attention_dim,
+                                            axes_dims_rope=a.axes_dims_rope, num_layers=a.num_layers,
+                                            num_single_layers=a.num_single_layers)
+        self.inner_dim = a.num_attention_heads * a.attention_head_dim
+        D, dh = self.inner_dim, a.attention_head_dim
+        ws = self._ws = _Weights(self.device_)
+        self.x_embedder_w = ws.linear("x_embedder", D, a.in_channels)
+        self.context_embedder_w = ws.linear("context_embedder", D, a.joint_attention_dim)
+        self.time_text = _TimeTextW(ws, "time_text_embed", D, a.pooled_projection_dim, a.guidance_embeds)
+        self.double = [_DoubleBlockW(ws, f"transformer_blocks.{i}", D, dh) for i in range(a.num_layers)]
+        self.single = [_SingleBlockW(ws, f"single_transformer_blocks.{i}", D, dh) for i in range(a.num_single_layers)]
+        self.norm_out_w = ws.linear("norm_out.linear", 2 * D, D)
+        # proj_out has only in_channels (64) output features: keep it as is, the GEMM masks the partial N tile
+        self.proj_out_w = ws.linear("proj_out", a.in_channels, D)
+        self._control_ready = False
+        self._buf_key = None
+        self._graphs: Dict[Any, Any] = {}
+        self.use_cuda_graph = False
+        self.gemm_variant = 0
+        self.attn_variant = 0
+        self.trace: Optional[Dict[str, torch.Tensor]] = None  # set to {} to record per-block intermediates
+
+    # ---------------------------------------------------------------------------------------------------------
+    # reference API: construction
+    # ---------------------------------------------------------------------------------------------------------
+    def init_condition_block(self, condition_nums: int = 1, **kwargs):
+        """reference src/UniGenTransformer.py:713-715 -> init_control_block(kwargs['control_params'])."""
+        self.condition_nums = condition_nums
+        self.init_control_block(kwargs.get("control_params", None))
+
+    def init_control_block(self, control_params=None):
+        """reference :717-783 (+ init_moe_block :806-923) for the canonical configuration."""
+        assert control_params is not None, ValueError("Please provice control net model parameter")
+        get = control_params.get
+        a, ws, D, dh = self.arch, self._ws, self.inner_dim, self.arch.attention_head_dim
+        self.use_pooled_prompt_embeds = get("use_pooled_prompt_embeds", True)
+        self.use_rope = get("use_rope", False)
+        self.use_modulate = get("use_modulate", False)
+        if not (self.use_rope or self.use_modulate):
+            # the predecessor forbids it outright (MoeCombineTransformer.pyc L557-570) and the shipped transformer-block
+            # experts are shape-broken with a per-token temb
+            raise ValueError("Warning: please use rope or modulated")
+        if get("use_consis_module", False):
+            raise ops.UgError("use_consis_module is not supported by the B200-native path (SURVEY.md §A.1: left off)")
+        if not get("use_shared_expert", False):
+            raise ops.UgError("use_shared_expert=False is not covered by the B200-native path yet")
+        dev = get("single_control_dev", 2)
+        self.cn_joint_layers, self.cn_single_joint_layers = a.num_layers // dev, a.num_single_layers // dev
+        self.single_block_control_method = get("single_block_control_method", "overall_add")
+        self.use_single_trans_blocks = get("use_single_trans_blocks", True)
+        self.expert_nums = get("expert_num", None) or (self.condition_nums + 1) * get("expert_num_each_condition", 3)
+        self.top_k = get("top_num", 1)
+        assert self.top_k == 1, "only top-1 gating (the shipped configuration) is implemented"
+        self.num_local_experts = self.expert_nums
+        self.cn_method = get("cn2base_method", "add")
+
+        self.control_time_text = _TimeTextW(ws, "control_time_text_embed", D, a.pooled_projection_dim, a.guidance_embeds)
+        self.control_condition = _TimeTextW(ws, "control_condition_embed", D, a.pooled_projection_dim, a.guidance_embeds)
+        self.control_context_embedder_w = ws.linear("control_context_embedder", D, D)
+        self.control_x_embedder_w = ws.linear("control_x_embedder", D, a.in_channels)
+        self.ctrl_double = [_DoubleBlockW(ws, f"control_joint_trans_blocks.{j}", D, dh) for j in range(self.cn_joint_layers)]
+        self.add_double = [ws.linear(f"controlnet_add_joint_blocks.{j}", D, D) for j in range(self.cn_joint_layers)]
+        self.ctrl_single, self.add_single = [], []
+        if self.use_single_trans_blocks:
+            self.ctrl_single = [_SingleBlockW(ws, f"control_single_trans_blocks.{j}", D, dh)
+                                for j in range(self.cn_single_joint_layers)]
+            self.add_single = [ws.linear(f"controlnet_add_single_blocks.{j}", D, D) for j in range(self.cn_single_joint_layers)]
+        E, P = self.expert_nums, a.pooled_projection_dim
+        self.gate_wg = ws.alloc(E, D, dtype=torch.float32)  # evaluated in fp32
+        ws.views["moe.moe_layer.gate.wg.weight"] = self.gate_wg
+        # experts stacked: branch 0 = condition modulate, branch 1 = hidden modulate; [.0] = Linear(D,D), [.1] = Linear(P,D)
+        self.exp_w = [ws.alloc(E, D, D), ws.alloc(E, D, D)]
+        self.exp_b = [ws.alloc(E, D), ws.alloc(E, D)]
+        self.exp_mod_w = [ws.alloc(E * D, P), ws.alloc(E * D, P)]
+        self.exp_mod_b = [ws.alloc(E * D), ws.alloc(E * D)]
+        for e in range(E):
+            for br in (0, 1):
+                p = f"moe.moe_layer.experts.deepspeed_experts.{e}.{br}"
+                ws.views[p + ".0.weight"], ws.views[p + ".0.bias"] = self.exp_w[br][e], self.exp_b[br][e]
+                ws.views[p + ".1.weight"] = self.exp_mod_w[br][e * D:(e + 1) * D]
+                ws.views[p + ".1.bias"] = self.exp_mod_b[br][e * D:(e + 1) * D]
+        self.shared = [_DoubleBlockW(ws, f"shared_expert.{s}", D, dh) for s in (0, 1)]
+        self.trainable_control_modules = {k: None for k in (
+            "control_pos_embed_input", "control_time_text_embed", "control_condition_embed", "control_context_embedder",
+            "control_x_embedder", "control_joint_trans_blocks", "controlnet_add_joint_blocks", "control_single_trans_blocks",
+            "controlnet_add_single_blocks", "moe", "shared_expert")}
+        self._control_ready = True
+
+    # ---------------------------------------------------------------------------------------------------------
+    # weights
+    # ---------------------------------------------------------------------------------------------------------
+    @property
+    def dtype(self):
+        return BF16
+
+    @property
+    def device(self):
+        return self.device_
+
+    def state_dict(self, *args, **kwargs):  # reference key names, views into the fused storage
+        return dict(self._ws.views)
+
+    def parameters(self, recurse: bool = True):
+        return iter(self._ws.views.values())
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        missing = [k for k in self._ws.views if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in self._ws.views]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"load_state_dict: missing {missing[:5]}... unexpected {unexpected[:5]}...")
+        with torch.no_grad():
+            for k, v in state_dict.items():
+                if k in self._ws.views:
+                    dst = self._ws.views[k]
+                    if tuple(dst.shape) != tuple(v.shape):
+                        raise RuntimeError(f"size mismatch for {k}: {tuple(v.shape)} vs {tuple(dst.shape)}")
+                    dst.copy_(v.to(device=dst.device, dtype=dst.dtype))
+        return types.SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
+
+    @torch.no_grad()
+    def init_random_(self, seed: int = 0, zero_linear_std: Optional[float] = 0.02):
+        """nn.Linear default init directly on the device (bench: 18.7 B parameters never exist on the host)."""
+        gen = torch.Generator(device=self.device_).manual_seed(seed)
+        for k, v in self._ws.views.items():
+            if k.startswith("controlnet_add_"):
+                if zero_linear_std is None:
+                    v.zero_()
+                else:
+                    v.copy_(torch.randn(v.shape, device=v.device, generator=gen) * zero_linear_std)
+            elif ".norm_q." in k or ".norm_k." in k or ".norm_added_" in k:
+                v.fill_(1.0)
+            else:
+                fan_in = self._ws.views[k[:-4] + "weight"].shape[-1] if k.endswith(".bias") else v.shape[-1]
+                bound = 1.0 / math.sqrt(fan_in)
+                v.copy_((torch.rand(v.shape, device=v.device, generator=gen) * 2 - 1) * bound)
+        return self
+
+    # ---------------------------------------------------------------------------------------------------------
+    # workspaces
+    # ---------------------------------------------------------------------------------------------------------
+    def _workspace(self, B: int, N: int, T: int):
+        key = (B, N, T)
+        if self._buf_key == key:
+            return self._buf
+        D, dev = self.inner_dim, self.device_
+        S = T + N
+        Smax = T + 2 * N  # shared_expert[1] runs over [txt | img | cond]
+        E = self.expert_nums
+        C = ops.moe_capacity(B * N, E)
+        z = lambda *s, dt=BF16: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
+        n_mod = (6 * 2 * (self.arch.num_layers + self.cn_joint_layers + 2) + 3 * (self.arch.num_single_layers + self.cn_single_joint_layers) + 2)
+        b = types.SimpleNamespace(
+            X=z(B, S, D), NX=z(B, Smax, D), QKV=z(B, Smax, 3 * D), AO=z(B, Smax, D), FF=z(B, Smax, 4 * D),
+            CAT=z(B, S, 5 * D), CH=z(B, N, D), CS=z(B, S, D), CENC=z(B, T, D), COND=z(B, N, D), HC=z(B, 2 * N, D),
+            G=z(B * N, D), A=z(E * C, D), YC=z(E * C, D), YH=z(E * C, D), EH=z(B * N, D), EC=z(B * N, D), CIN=z(B, N, D),
+            MOD=z(B, n_mod * D, dt=torch.float32), temb=z(B, D, dt=torch.float32), tmp=z(B, D, dt=torch.float32),
+            ctemb=z(B, D, dt=torch.float32), cdtemb=z(B, D, dt=torch.float32),
+            MODC=z(B, E, D, dt=torch.float32), MODH=z(B, E, D, dt=torch.float32),
+            rope=z(S, self.arch.attention_head_dim, dt=torch.float32),
+            rope0=z(2 * N, self.arch.attention_head_dim, dt=torch.float32),
+            rope1=z(Smax, self.arch.attention_head_dim, dt=torch.float32),
+            NO=z(B, N, D), OUT=z(B, N, self.arch.in_channels), capacity=C)
+        self._buf, self._buf_key = b, key
+        return b
+
+    # ---------------------------------------------------------------------------------------------------------
+    # building blocks (each line = one kernel launch in libunigen_b200.so)
+    # ---------------------------------------------------------------------------------------------------------
+    def _time_text(self, w: _TimeTextW, t_emb: torch.Tensor, pooled: torch.Tensor, out: torch.Tensor, tmp: torch.Tensor,
+                   g_emb: Optional[torch.Tensor] = None):
+        """CombinedTimestep(Guidance)TextProjEmbeddings."""
+        ops.gemv(t_emb, w.t1[0], w.t1[1], out=tmp, silu_out=True)
+        ops.gemv(tmp, w.t2[0], w.t2[1], out=out)
+        if g_emb is not None and w.g1 is not None:
+            ops.gemv(g_emb, w.g1[0], w.g1[1], out=tmp, silu_out=True)
+            ops.gemv(tmp, w.g2[0], w.g2[1], out=out, accumulate=True)
+        ops.gemv(pooled, w.p1[0], w.p1[1], out=tmp, silu_out=True)
+        ops.gemv(tmp, w.p2[0], w.p2[1], out=out, accumulate=True)
+        return out
+
+    def _mods(self, buf, slot: int, n_chunks: int, w, temb: torch.Tensor) -> List[torch.Tensor]:
+        """AdaLN parameter vectors `linear(silu(temb)).chunk(n)`: fp32 [B, D] views into MOD."""
+        D = self.inner_dim
+        region = buf.MOD[:, slot * D:(slot + n_chunks) * D]
+        ops.gemv(temb, w[0], w[1], out=region, silu_in=True)
+        return [region[:, i * D:(i + 1) * D] for i in range(n_chunks)]
+
+    def _joint_attention(self, buf, B, n_ctx, n_smp, rms_ctx, rms_smp, rope, out_view=None):
+        """RMSNorm(q,k)+RoPE in place on QKV rows [0, n_ctx+n_smp), then joint attention -> AO (or out_view)."""
+        a = self.arch
+        H, dh, D = a.num_attention_heads, a.attention_head_dim, self.inner_dim
+        S = n_ctx + n_smp
+        qk = buf.QKV[:, :S, :2 * D]
+        if n_ctx:
+            ops.qk_rmsnorm_rope(qk[:, :n_ctx], 2 * H, dh, rms_ctx, rope[:n_ctx] if rope is not None else None, heads_per_weight=H)
+        ops.qk_rmsnorm_rope(qk[:, n_ctx:], 2 * H, dh, rms_smp, rope[n_ctx:S] if rope is not None else None, heads_per_weight=H)
+        out = buf.AO[:, :S] if out_view is None else out_view
+        ops.attention(buf.QKV[:, :S, 0:D], buf.QKV[:, :S, D:2 * D], buf.QKV[:, :S, 2 * D:3 * D], out, H, dh,
+                      variant=self.attn_variant)
+        return out
+
+    def _double_block(self, buf, w: _DoubleBlockW, mod_smp, mod_ctx, smp_in, ctx_in, smp_out, ctx_out, rope):
+        """diffusers FluxTransformerBlock. smp/ctx = image-role / text-role streams ([B, n, D] views);
+        outputs may alias inputs (in-place residual). ctx_out=None skips the context stream's post-attention half —
+        exact whenever the caller discards `encoder_hidden_states` (control blocks, shared_expert[1])."""
+        D = self.inner_dim
+        B, n_smp, n_ctx = smp_in.shape[0], smp_in.shape[1], ctx_in.shape[1]
+        S = n_ctx + n_smp
+        gv = self.gemm_variant
+        sh_a, sc_a, g_a, sh_m, sc_m, g_m = mod_smp
+        csh_a, csc_a, cg_a, csh_m, csc_m, cg_m = mod_ctx
+        nx_c, nx_s = buf.NX[:, :n_ctx], buf.NX[:, n_ctx:S]
+        ops.ln_modulate(ctx_in, nx_c, csh_a, csc_a)
+        ops.ln_modulate(smp_in, nx_s, sh_a, sc_a)
+        ops.gemm(nx_c, w.add_qkv[0], out=buf.QKV[:, :n_ctx], bias=w.add_qkv[1], variant=gv)
+        ops.gemm(nx_s, w.qkv[0], out=buf.QKV[:, n_ctx:S], bias=w.qkv[1], variant=gv)
+        ao = self._joint_attention(buf, B, n_ctx, n_smp, w.rms_ctx, w.rms, rope)
+        # h = h + gate_msa * to_out(attn)
+        ops.gemm(ao[:, n_ctx:S], w.to_out[0], out=smp_out, bias=w.to_out[1], gate=g_a, residual=smp_in, variant=gv)
+        # h = h + gate_mlp * ff(LN(h) * (1 + scale_mlp) + shift_mlp)
+        ops.ln_modulate(smp_out, nx_s, sh_m, sc_m)
+        ops.gemm(nx_s, w.ff1[0], out=buf.FF[:, n_ctx:S], bias=w.ff1[1], act=UG_ACT_GELU_TANH, variant=gv)
+        ops.gemm(buf.FF[:, n_ctx:S], w.ff2[0], out=smp_out, bias=w.ff2[1], gate=g_m, residual=smp_out, variant=gv)
+        if ctx_out is not None:
+            ops.gemm(ao[:, :n_ctx], w.to_add_out[0], out=ctx_out, bias=w.to_add_out[1], gate=cg_a, residual=ctx_in, variant=gv)
+            ops.ln_modulate(ctx_out, nx_c, csh_m, csc_m)
+            ops.gemm(nx_c, w.ffc1[0], out=buf.FF[:, :n_ctx], bias=w.ffc1[1], act=UG_ACT_GELU_TANH, variant=gv)
+            ops.gemm(buf.FF[:, :n_ctx], w.ffc2[0], out=ctx_out, bias=w.ffc2[1], gate=cg_m, residual=ctx_out, variant=gv)
+
+    def _single_block(self, buf, w: _SingleBlockW, mod, x_in, x_out, rope):
+        """diffusers FluxSingleTransformerBlock: x_out = x_in + gate * proj_out([attn | gelu(mlp)])."""
+        a = self.arch
+        H, dh, D = a.num_attention_heads, a.attention_head_dim, self.inner_dim
+        B, S = x_in.shape[0], x_in.shape[1]
+        gv = self.gemm_variant
+        shift, scale, gate = mod
+        nx = buf.NX[:, :S]
+        ops.ln_modulate(x_in, nx, shift, scale)
+        ops.gemm(nx, w.qkv[0], out=buf.QKV[:, :S], bias=w.qkv[1], variant=gv)
+        ops.gemm(nx, w.mlp[0], out=buf.CAT[:, :, D:], bias=w.mlp[1], act=UG_ACT_GELU_TANH, variant=gv)
+        ops.qk_rmsnorm_rope(buf.QKV[:, :S, :2 * D], 2 * H, dh, w.rms, rope[:S] if rope is not None else None, heads_per_weight=H)
+        ops.attention(buf.QKV[:, :S, 0:D], buf.QKV[:, :S, D:2 * D], buf.QKV[:, :S, 2 * D:3 * D], buf.CAT[:, :, :D], H, dh,
+                      variant=self.attn_variant)
+        ops.gemm(buf.CAT, w.out[0], out=x_out, bias=w.out[1], gate=gate, residual=x_in, variant=gv)
+
+    def _rec(self, name: str, t: torch.Tensor):
+        if self.trace is not None:
+            self.trace[name] = t.detach().float().clone()
+
+    # ---------------------------------------------------------------------------------------------------------
+    # CoMoE pre-stage (reference preprocess_moe_forward :1028-1068, moe_forward :969-1026, MOELayer.forward,
+    # expert_forward :925-967) — runs once per step at the first control call
+    # ---------------------------------------------------------------------------------------------------------
+    def _prestage(self, buf, B, N, T, h_img, enc_txt, cond_tokens, pooled, cond_pooled, rts_uniform, mods):
+        D, E, C = self.inner_dim, self.expert_nums, buf.capacity
+        gv = self.gemm_variant
+        ops.gemm(cond_tokens, self.control_x_embedder_w[0], out=buf.COND, bias=self.control_x_embedder_w[1], variant=gv)
+        ops.gemm(enc_txt, self.control_context_embedder_w[0], out=buf.CENC, bias=self.control_context_embedder_w[1], variant=gv)
+        # --- gate + Random-Token-Selection routing (DeepSpeed top1gating) ---
+        g = buf.G.view(B, N, D)
+        ops.add(h_img, buf.COND, g)
+        route = ops.moe_route(buf.G, self.gate_wg, rts_uniform, C)
+        # --- condition-modulated experts: cond' = Wc (s_c . cond) + bc ; hid' = Wh (s_h . (hid + cond')) + bh ---
+        ops.gemv(cond_pooled, self.exp_mod_w[0], self.exp_mod_b[0], out=buf.MODC.view(B, E * D))
+        ops.gemv(pooled, self.exp_mod_w[1], self.exp_mod_b[1], out=buf.MODH.view(B, E * D))
+        ops.moe_gather_modulate(buf.COND.view(B * N, D), route["slot_token"], buf.MODC, E, C, N, out=buf.A)
+        ops.gemm(buf.A.view(E, C, D), self.exp_w[0], out=buf.YC.view(E, C, D), bias=self.exp_b[0], variant=gv)
+        hid_flat = buf.EH  # contiguous copy of the image rows of X (they are strided inside the joint buffer)
+        ops.copy(h_img, hid_flat.view(B, N, D))
+        ops.moe_gather_modulate(hid_flat, route["slot_token"], buf.MODH, E, C, N, addend=buf.YC, out=buf.A)
+        ops.gemm(buf.A.view(E, C, D), self.exp_w[1], out=buf.YH.view(E, C, D), bias=self.exp_b[1], variant=gv)
+        # --- shared experts (V2, :1013-1022) ---
+        hc_h, hc_c = buf.HC[:, :N], buf.HC[:, N:]
+        self._double_block(buf, self.shared[0], mods["shared0_smp"], mods["shared0_ctx"], h_img, buf.COND, hc_h, hc_c, buf.rope0)
+        self._double_block(buf, self.shared[1], mods["shared1_smp"], mods["shared1_ctx"], buf.HC, buf.CENC, buf.HC, None, buf.rope1)
+        # --- combine (gate-probability weighted, dropped tokens -> 0) and sum: ctrl_in = (hid + EH) + (cond + EC) ---
+        ops.moe_combine(buf.YH, route, C, buf.EH)
+        ops.moe_combine(buf.YC, route, C, buf.EC)
+        self._rec("moe.expert_hidden", buf.EH.view(B, N, D)); self._rec("moe.expert_cond", buf.EC.view(B, N, D))
+        self._rec("moe.shared_hidden", hc_h); self._rec("moe.shared_cond", hc_c)
+        ops.add(hc_h, buf.EH.view(B, N, D), buf.CIN)
+        ops.add(buf.CIN, hc_c, buf.CIN)
+        ops.add(buf.CIN, buf.EC.view(B, N, D), buf.CIN)
+        self._rec("moe.ctrl_in", buf.CIN)
+        return route
+
+    # ---------------------------------------------------------------------------------------------------------
+    # forward (reference :1182-1271 + base_forward :1106-1180 + control_forward :1070-1104)
+    # ---------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, hidden_states, condition_hidden_states=None, conditioning_scale: float = 1.0,
+                encoder_hidden_states=None, pooled_projections=None, condition_pooled_projections=None, timestep=None,
+                img_ids=None, txt_ids=None, guidance=None, condition_ids=None, joint_attention_kwargs=None,
+                skip_layers=None, rts_uniform=None, **kwargs):
+        if not self._control_ready:
+            raise ops.UgError("call init_condition_block(condition_nums=..., control_params=...) before forward")
+        a = self.arch
+        D, H, dh = self.inner_dim, a.num_attention_heads, a.attention_head_dim
+        B, N, _ = hidden_states.shape
+        T = encoder_hidden_states.shape[1]
+        S = T + N
+        if condition_hidden_states.shape[1] != N:
+            raise ops.UgError("condition tokens must match the image token count (Nc == N) for the CoMoE pre-stage")
+        if T == N:
+            raise ops.UgError("T == N: the reference MOELayer would also dispatch the text tensor (SURVEY.md §8 A9); unsupported")
+        buf = self._workspace(B, N, T)
+        dev = self.device_
+        f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+        if txt_ids.dim() == 3:
+            txt_ids = txt_ids[0]
+        if img_ids.dim() == 3:
+            img_ids = img_ids[0]
+        if condition_ids.dim() == 3:
+            condition_ids = condition_ids[0]
+        txt_ids, img_ids, condition_ids = f32(txt_ids), f32(img_ids), f32(condition_ids)
+        if rts_uniform is None:
+            # DeepSpeed draws this uniform tensor in train AND eval; torch RNG is plumbing here
+            rts_uniform = torch.rand(B * N, self.expert_nums, device=dev, dtype=torch.float32)
+        rts_uniform = f32(rts_uniform)
+
+        hs = ops.to_bf16(hidden_states.to(dev).contiguous())
+        cs = ops.to_bf16(condition_hidden_states.to(dev).contiguous())
+        es = ops.to_bf16(encoder_hidden_states.to(dev).contiguous())
+        pooled, cond_pooled = f32(pooled_projections), f32(condition_pooled_projections)
+        gv = self.gemm_variant
+
+        # ---- embeddings (:1215-1239) ----
+        x_txt, x_img = buf.X[:, :T], buf.X[:, T:]
+        ops.gemm(hs, self.x_embedder_w[0], out=x_img, bias=self.x_embedder_w[1], variant=gv)
+        ops.gemm(es, self.context_embedder_w[0], out=x_txt, bias=self.context_embedder_w[1], variant=gv)
+        t_emb = ops.timestep_embedding(f32(timestep) * 1000.0)
+        g_emb = ops.timestep_embedding(f32(guidance) * 1000.0) if guidance is not None else None
+        self._time_text(self.time_text, t_emb, pooled, buf.temb, buf.tmp, g_emb)
+        ctrl_pooled = pooled if self.use_pooled_prompt_embeds else torch.zeros_like(pooled)
+        self._time_text(self.control_time_text, t_emb, ctrl_pooled, buf.ctemb, buf.tmp, g_emb)      # control_temb
+        self._time_text(self.control_condition, t_emb, cond_pooled, buf.cdtemb, buf.tmp, g_emb)     # condition_temb
+        ops.rope_table(torch.cat([txt_ids, img_ids], 0), a.axes_dims_rope, a.theta, out=buf.rope)
+        ops.rope_table(torch.cat([condition_ids, img_ids], 0), a.axes_dims_rope, a.theta, out=buf.rope0)
+        ops.rope_table(torch.cat([txt_ids, img_ids, condition_ids], 0), a.axes_dims_rope, a.theta, out=buf.rope1)
+        self._rec("temb", buf.temb); self._rec("x_embed", x_img); self._rec("context_embed", x_txt)
+
+        # ---- every block's AdaLN vectors, once per step (temb / condition_temb are step constants) ----
+        slot = 0
+        m_double, m_cdouble, m_single, m_csingle = [], [], [], []
+        for w in self.double:
+            m_double.append((self._mods(buf, slot, 6, w.norm1, buf.temb), self._mods(buf, slot + 6, 6, w.norm1_ctx, buf.temb)))
+            slot += 12
+        for w in self.ctrl_double:
+            m_cdouble.append((self._mods(buf, slot, 6, w.norm1, buf.cdtemb), self._mods(buf, slot + 6, 6, w.norm1_ctx, buf.cdtemb)))
+            slot += 12
+        for w in self.single:
+            m_single.append(self._mods(buf, slot, 3, w.norm, buf.temb)); slot += 3
+        for w in self.ctrl_single:
+            m_csingle.append(self._mods(buf, slot, 3, w.norm, buf.cdtemb)); slot += 3
+        mods = dict(shared0_smp=self._mods(buf, slot, 6, self.shared[0].norm1, buf.cdtemb),
+                    shared0_ctx=self._mods(buf, slot + 6, 6, self.shared[0].norm1_ctx, buf.cdtemb),
+                    shared1_smp=self._mods(buf, slot + 12, 6, self.shared[1].norm1, buf.ctemb),
+                    shared1_ctx=self._mods(buf, slot + 18, 6, self.shared[1].norm1_ctx, buf.ctemb))
+        slot += 24
+        m_out = self._mods(buf, slot, 2, self.norm_out_w, buf.temb)  # AdaLayerNormContinuous: (scale, shift)
+
+        # ---- 19 x [base double -> control double -> add] (:1124-1141) ----
+        route = None
+        n_cd = len(self.ctrl_double)
+        for i, w in enumerate(self.double):
+            self._double_block(buf, w, m_double[i][0], m_double[i][1], x_img, x_txt, x_img, x_txt, buf.rope)
+            self._rec(f"double.{i}.base_hidden", x_img); self._rec(f"double.{i}.base_context", x_txt)
+            j = int(i / (len(self.double) / n_cd))
+            if route is None:  # first control call: CoMoE pre-stage, control stream := expert_hidden + expert_cond
+                route = self._prestage(buf, B, N, T, x_img, x_txt, cs, pooled, cond_pooled, rts_uniform, mods)
+                ctrl_in = buf.CIN
+            else:               # later calls: the control block reads the base stream
+                ctrl_in = x_img
+            self._double_block(buf, self.ctrl_double[j], m_cdouble[j][0], m_cdouble[j][1], ctrl_in, buf.CENC, buf.CH, None, buf.rope)
+            wa = self.add_double[j]
+            ops.gemm(buf.CH, wa[0], out=x_img, bias=wa[1], alpha=float(conditioning_scale), residual=x_img, variant=gv)
+            self._rec(f"double.{i}.ctrl_hidden", buf.CH); self._rec(f"double.{i}.hidden", x_img)
+
+        # ---- 38 x [base single -> control single -> add] over the joint [text | image] stream (:1146-1172) ----
+        n_cs = len(self.ctrl_single)
+        for i, w in enumerate(self.single):
+            self._single_block(buf, w, m_single[i], buf.X, buf.X, buf.rope)
+            self._rec(f"single.{i}.base_hidden", buf.X)
+            if n_cs:
+                j = int(i / (len(self.single) / n_cs))
+                self._single_block(buf, self.ctrl_single[j], m_csingle[j], buf.X, buf.CS, buf.rope)
+                wa = self.add_single[j]
+                if self.single_block_control_method == "overall_add":
+                    ops.gemm(buf.CS, wa[0], out=buf.X, bias=wa[1], alpha=float(conditioning_scale), residual=buf.X, variant=gv)
+                else:  # single_add: only the image rows receive the control signal
+                    ops.gemm(buf.CS[:, T:], wa[0], out=x_img, bias=wa[1], alpha=float(conditioning_scale), residual=x_img, variant=gv)
+            self._rec(f"single.{i}.hidden", buf.X)
+
+        # ---- norm_out (AdaLayerNormContinuous: scale first, then shift) + proj_out (:1264-1265) ----
+        ops.ln_modulate(x_img, buf.NO, m_out[1], m_out[0])
+        ops.gemm(buf.NO, self.proj_out_w[0], out=buf.OUT, bias=self.proj_out_w[1], variant=gv)
+        self._rec("velocity", buf.OUT)
+        self._last_route = route
+        add_losses = dict(moe_loss=route["l_aux"][0] * 0.1)
+        add_outputs = dict(expert_counts=route["exp_counts"])
+        return buf.OUT, add_losses, add_outputs
+
+
+def canonical_control_params() -> Dict[str, Any]:
+    """config/unigen.yaml:3-11 + `use_rope: True`."""
+    return dict(use_transformer_params=False, use_pooled_prompt_embeds=True, use_encoder_hidden_states=True, use_rope=True,
+                expert_num_each_condition=3, top_num=1, use_modulate=False, use_shared_expert=True, use_consis_module=False,
+                use_single_trans_blocks=True, single_block_control_method="overall_add", single_control_dev=2,
+                cn2base_method="add")

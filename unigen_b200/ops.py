@@ -1,0 +1,284 @@
+"""Host-side operator layer: torch tensors in, C-ABI calls out (include/unigen_b200.h).  torch is used for device
+memory and streams only; every arithmetic op below runs in libunigen_b200.so on the current CUDA stream.
+There is no fallback: a CPU tensor or a missing library raises."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import UG_ACT_GELU_TANH, UG_ACT_NONE, AttnArgs, GemmArgs, UgError, check
+
+__all__ = ["gemm", "attention", "expand_segment_mask", "ln_modulate", "qk_rmsnorm_rope", "rope_table", "gemv",
+           "timestep_embedding", "add", "copy", "to_bf16", "to_f32", "moe_route", "moe_gather_modulate",
+           "moe_combine", "launch_count", "reset_launch_count", "UG_ACT_NONE", "UG_ACT_GELU_TANH", "UgError"]
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    if not t.is_cuda:
+        raise UgError(f"{name}: expected a CUDA tensor — the UniGen hot path has no CPU fallback")
+    if dtype is not None and t.dtype != dtype:
+        raise UgError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    return t
+
+
+def _view3(t: torch.Tensor, name: str) -> torch.Tensor:
+    """[R, C] -> [1, R, C]; requires a unit inner stride."""
+    if t.dim() == 2:
+        t = t.unsqueeze(0)
+    if t.dim() != 3 or t.stride(2) != 1:
+        raise UgError(f"{name}: expected a [batch, rows, cols] view with contiguous cols, got shape {tuple(t.shape)} "
+                      f"strides {t.stride()}")
+    return t
+
+
+def launch_count() -> int:
+    return int(_lib.load().ug_launch_count())
+
+
+def reset_launch_count() -> None:
+    _lib.load().ug_reset_launch_count()
+
+
+def device_check() -> None:
+    check(_lib.load().ug_device_check(), "ug_device_check")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+         gate: Optional[torch.Tensor] = None, alpha: float = 1.0, act: int = UG_ACT_NONE,
+         residual: Optional[torch.Tensor] = None, variant: int = 0) -> torch.Tensor:
+    """out[b,r,:] = residual + alpha * gate[b,:] * act(a[b,r,:] @ w^T + bias).  a: [B,R,K] view, w: [N,K] or [B,N,K]."""
+    a = _view3(_dev(a, "gemm.a", BF16), "gemm.a")
+    _dev(w, "gemm.w", BF16)
+    B, R, K = a.shape
+    N = w.shape[-2]
+    if w.shape[-1] != K:
+        raise UgError(f"gemm: K mismatch a {tuple(a.shape)} w {tuple(w.shape)}")
+    if out is None:
+        out = torch.empty(B, R, N, device=a.device, dtype=BF16)
+    o3 = _view3(_dev(out, "gemm.out", BF16), "gemm.out")
+    g = GemmArgs()
+    g.a, g.a_row_stride, g.a_batch_stride = a.data_ptr(), a.stride(1), a.stride(0)
+    g.w, g.w_row_stride = w.data_ptr(), w.stride(-2)
+    g.w_batch_stride = w.stride(0) if w.dim() == 3 else 0
+    g.c, g.c_row_stride, g.c_batch_stride = o3.data_ptr(), o3.stride(1), o3.stride(0)
+    g.batch, g.rows, g.n, g.k = B, R, N, K
+    if bias is not None:
+        _dev(bias, "gemm.bias", BF16)
+        g.bias = bias.data_ptr()
+        g.bias_batch_stride = bias.stride(0) if bias.dim() == 2 else 0
+    if gate is not None:
+        _dev(gate, "gemm.gate", torch.float32)
+        if gate.dim() == 1:
+            gate = gate.unsqueeze(0)
+        g.gate, g.gate_batch_stride = gate.data_ptr(), gate.stride(0)
+    g.alpha, g.act = float(alpha), int(act)
+    if residual is not None:
+        r3 = _view3(_dev(residual, "gemm.residual", BF16), "gemm.residual")
+        g.residual, g.res_row_stride, g.res_batch_stride = r3.data_ptr(), r3.stride(1), r3.stride(0)
+    g.variant = variant
+    check(_lib.load().ug_gemm_bf16(C.byref(g), _stream()), "ug_gemm_bf16")
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, heads: int, head_dim: int,
+              seg_bounds: Optional[Sequence[int]] = None, seg_visible: Optional[Sequence[int]] = None,
+              scale: Optional[float] = None, variant: int = 0) -> torch.Tensor:
+    """q/k/v/out: [B, S, heads*head_dim] views (any row / batch stride, contiguous inner dim)."""
+    q, k, v, o = (_view3(_dev(t, n, BF16), n) for t, n in ((q, "attn.q"), (k, "attn.k"), (v, "attn.v"), (out, "attn.out")))
+    B, S, HD = q.shape
+    if HD != heads * head_dim:
+        raise UgError(f"attention: inner dim {HD} != heads {heads} x head_dim {head_dim}")
+    a = AttnArgs()
+    a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
+    a.q_row_stride, a.q_batch_stride = q.stride(1), q.stride(0)
+    a.k_row_stride, a.k_batch_stride = k.stride(1), k.stride(0)
+    a.v_row_stride, a.v_batch_stride = v.stride(1), v.stride(0)
+    a.o_row_stride, a.o_batch_stride = o.stride(1), o.stride(0)
+    a.batch, a.heads, a.seq, a.head_dim = B, heads, S, head_dim
+    a.scale = float(scale if scale is not None else 1.0 / math.sqrt(head_dim))
+    keep = None
+    if seg_bounds is not None:
+        n = len(seg_bounds) - 1
+        sb = (C.c_int32 * (n + 1))(*seg_bounds)
+        sv = (C.c_uint32 * n)(*seg_visible)
+        keep = (sb, sv)
+        a.n_seg, a.seg_bounds, a.seg_visible = n, sb, sv
+    a.variant = variant
+    check(_lib.load().ug_attention_bf16(C.byref(a), _stream()), "ug_attention_bf16")
+    del keep
+    return out
+
+
+def expand_segment_mask(seq: int, seg_bounds: Sequence[int], seg_visible: Sequence[int], device) -> torch.Tensor:
+    n = len(seg_visible)
+    m = torch.empty(seq, seq, dtype=torch.uint8, device=device)
+    sb = (C.c_int32 * (n + 1))(*seg_bounds)
+    sv = (C.c_uint32 * n)(*seg_visible)
+    check(_lib.load().ug_expand_segment_mask(seq, n, sb, sv, m.data_ptr(), _stream()), "ug_expand_segment_mask")
+    return m.bool()
+
+
+def ln_modulate(x: torch.Tensor, out: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """out = LayerNorm(x) * (1 + scale[b]) + shift[b]; shift/scale: fp32 [B, D] views (same batch stride)."""
+    x3, o3 = _view3(_dev(x, "ln.x", BF16), "ln.x"), _view3(_dev(out, "ln.out", BF16), "ln.out")
+    _dev(shift, "ln.shift", torch.float32), _dev(scale, "ln.scale", torch.float32)
+    B, R, D = x3.shape
+    if shift.stride(0) != scale.stride(0) and B > 1:
+        raise UgError("ln_modulate: shift and scale need the same batch stride")
+    check(_lib.load().ug_ln_modulate(x3.data_ptr(), x3.stride(1), x3.stride(0), o3.data_ptr(), o3.stride(1), o3.stride(0),
+                                     shift.data_ptr(), scale.data_ptr(), shift.stride(0), B, R, D, float(eps), _stream()),
+          "ug_ln_modulate")
+    return out
+
+
+def qk_rmsnorm_rope(x: torch.Tensor, heads: int, head_dim: int, weight: torch.Tensor,
+                    cos_sin: Optional[torch.Tensor] = None, eps: float = 1e-6, heads_per_weight: int = 0) -> torch.Tensor:
+    """In-place RMSNorm(weight)+RoPE on a [B, rows, heads*head_dim] view. cos_sin: fp32 [rows, head_dim] table.
+    weight: bf16 [heads/heads_per_weight, head_dim] (e.g. [norm_q; norm_k] for the Q|K halves of a fused QKV row)."""
+    x3 = _view3(_dev(x, "rms.x", BF16), "rms.x")
+    _dev(weight, "rms.weight", BF16)
+    B, R, HD = x3.shape
+    if HD != heads * head_dim:
+        raise UgError("qk_rmsnorm_rope: inner dim mismatch")
+    cs = 0
+    if cos_sin is not None:
+        _dev(cos_sin, "rms.cos_sin", torch.float32)
+        if cos_sin.shape[0] < R or not cos_sin.is_contiguous():
+            raise UgError("qk_rmsnorm_rope: cos_sin table too short / not contiguous")
+        cs = cos_sin.data_ptr()
+    check(_lib.load().ug_qk_rmsnorm_rope(x3.data_ptr(), x3.stride(1), x3.stride(0), B, R, heads, head_dim,
+                                         weight.data_ptr(), int(heads_per_weight), float(eps), cs, _stream()), "ug_qk_rmsnorm_rope")
+    return x
+
+
+def rope_table(ids: torch.Tensor, axes_dim: Sequence[int], theta: float = 10000.0,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """FluxPosEmbed: ids fp32 [rows, 3] -> fp32 [rows, head_dim] table laid out (cos_i, sin_i) per rotation pair."""
+    ids = _dev(ids, "rope.ids").to(torch.float32).contiguous()
+    rows, hd = ids.shape[0], sum(axes_dim)
+    if out is None:
+        out = torch.empty(rows, hd, device=ids.device, dtype=torch.float32)
+    ax = (C.c_int32 * 3)(*axes_dim)
+    check(_lib.load().ug_rope_table(ids.data_ptr(), rows, ax, float(theta), out.data_ptr(), _stream()), "ug_rope_table")
+    return out
+
+
+def gemv(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+         silu_in: bool = False, silu_out: bool = False, accumulate: bool = False) -> torch.Tensor:
+    """out[b,:] (+)= w @ f(x[b,:]) + bias; x/out fp32 [B, K] / [B, N]; w bf16 [N, K]."""
+    _dev(x, "gemv.x", torch.float32), _dev(w, "gemv.w", BF16)
+    B, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(B, N, device=x.device, dtype=torch.float32)
+    if not w.is_contiguous() or x.stride(1) != 1 or out.stride(1) != 1:
+        raise UgError("gemv: w must be contiguous, x/out need unit inner stride")
+    check(_lib.load().ug_gemv(x.data_ptr(), x.stride(0), w.data_ptr(), bias.data_ptr() if bias is not None else 0,
+                              out.data_ptr(), out.stride(0), B, N, K, int(silu_in), int(silu_out), int(accumulate),
+                              _stream()), "ug_gemv")
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int = 256) -> torch.Tensor:
+    t = _dev(t, "timestep").to(torch.float32).contiguous()
+    out = torch.empty(t.shape[0], dim, device=t.device, dtype=torch.float32)
+    check(_lib.load().ug_timestep_embedding(t.data_ptr(), t.shape[0], dim, out.data_ptr(), _stream()), "ug_timestep_embedding")
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    a3, b3, o3 = (_view3(_dev(t, "add", BF16), "add") for t in (a, b, out))
+    B, R, D = a3.shape
+    check(_lib.load().ug_add_bf16(a3.data_ptr(), a3.stride(1), a3.stride(0), b3.data_ptr(), b3.stride(1), b3.stride(0),
+                                  o3.data_ptr(), o3.stride(1), o3.stride(0), B, R, D, _stream()), "ug_add_bf16")
+    return out
+
+
+def copy(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    s3, d3 = _view3(_dev(src, "copy", BF16), "copy"), _view3(_dev(dst, "copy", BF16), "copy")
+    B, R, D = s3.shape
+    check(_lib.load().ug_copy_bf16(s3.data_ptr(), s3.stride(1), s3.stride(0), d3.data_ptr(), d3.stride(1), d3.stride(0),
+                                   B, R, D, _stream()), "ug_copy_bf16")
+    return dst
+
+
+def to_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _dev(x, "to_bf16")
+    if x.dtype == BF16:
+        return x
+    x = x.to(torch.float32).contiguous() if x.dtype != torch.float32 or not x.is_contiguous() else x
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    check(_lib.load().ug_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "ug_cast_f32_to_bf16")
+    return out
+
+
+def to_f32(x: torch.Tensor) -> torch.Tensor:
+    _dev(x, "to_f32", BF16)
+    x = x.contiguous()
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    check(_lib.load().ug_cast_bf16_to_f32(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "ug_cast_bf16_to_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def moe_capacity(tokens: int, experts: int, capacity_factor: float = 1.0, min_capacity: int = 4) -> int:
+    """DeepSpeed `_capacity`: max(ceil(tokens/experts * factor), min_capacity)."""
+    return max(int(math.ceil(tokens / experts * capacity_factor)), min_capacity)
+
+
+def moe_route(x: torch.Tensor, wg: torch.Tensor, rts_uniform: torch.Tensor, capacity: int):
+    """x bf16 [tokens, D]; wg fp32 [E, D]; rts_uniform fp32 [tokens, E] ->
+    dict(expert_idx, slot, prob, slot_token, exp_counts, l_aux)."""
+    _dev(x, "route.x", BF16), _dev(wg, "route.wg", torch.float32), _dev(rts_uniform, "route.uniform", torch.float32)
+    tokens, D = x.shape
+    E = wg.shape[0]
+    if not (x.is_contiguous() and wg.is_contiguous() and rts_uniform.is_contiguous()) or rts_uniform.shape != (tokens, E):
+        raise UgError("moe_route: contiguous x [tokens,D], wg [E,D], uniform [tokens,E] required")
+    dev = x.device
+    r = dict(expert_idx=torch.empty(tokens, dtype=torch.int32, device=dev),
+             slot=torch.empty(tokens, dtype=torch.int32, device=dev),
+             prob=torch.empty(tokens, dtype=torch.float32, device=dev),
+             slot_token=torch.empty(E * capacity, dtype=torch.int32, device=dev),
+             exp_counts=torch.empty(E, dtype=torch.int64, device=dev),
+             l_aux=torch.empty(1, dtype=torch.float32, device=dev))
+    ws = torch.empty(tokens * E + E, dtype=torch.float32, device=dev)
+    check(_lib.load().ug_moe_route(x.data_ptr(), wg.data_ptr(), rts_uniform.data_ptr(), tokens, D, E, capacity,
+                                   r["expert_idx"].data_ptr(), r["slot"].data_ptr(), r["prob"].data_ptr(),
+                                   r["slot_token"].data_ptr(), r["exp_counts"].data_ptr(), r["l_aux"].data_ptr(),
+                                   ws.data_ptr(), _stream()), "ug_moe_route")
+    r["gates"] = ws[: tokens * E].view(tokens, E)
+    return r
+
+
+def moe_gather_modulate(x: torch.Tensor, slot_token: torch.Tensor, mod: torch.Tensor, experts: int, capacity: int,
+                        tokens_per_batch: int, addend: Optional[torch.Tensor] = None,
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[e*C+s] = mod[b(token), e] * (x[token] (+ addend[e*C+s])); mod: fp32 [B, E, D] (batch-major, as one stacked GEMV writes it)."""
+    _dev(x, "gather.x", BF16), _dev(mod, "gather.mod", torch.float32)
+    D = x.shape[-1]
+    if out is None:
+        out = torch.empty(experts * capacity, D, device=x.device, dtype=BF16)
+    check(_lib.load().ug_moe_gather_modulate(x.data_ptr(), slot_token.data_ptr(), mod.data_ptr(), mod.stride(1), mod.stride(0),
+                                             addend.data_ptr() if addend is not None else 0, out.data_ptr(), experts,
+                                             capacity, tokens_per_batch, D, _stream()), "ug_moe_gather_modulate")
+    return out
+
+
+def moe_combine(y: torch.Tensor, route: dict, capacity: int, out: torch.Tensor) -> torch.Tensor:
+    tokens = route["slot"].shape[0]
+    D = y.shape[-1]
+    check(_lib.load().ug_moe_combine(y.data_ptr(), route["expert_idx"].data_ptr(), route["slot"].data_ptr(),
+                                     route["prob"].data_ptr(), out.data_ptr(), tokens, capacity, D, _stream()), "ug_moe_combine")
+    return out
