@@ -159,7 +159,7 @@ def main() -> None:
     out_dir = ROOT / "gpurun_out"
     out_dir.mkdir(exist_ok=True)
     log = open(out_dir / "probe_attn.log", "w")
-    for v in [int(x) for x in os.environ.get("UG_PROBE_VARIANTS", "2,1").split(",")]:
+    for v in [int(x) for x in os.environ.get("UG_PROBE_VARIANTS", "3,1").split(",")]:
         t0 = time.time()
         try:
             r = subprocess.run([sys.executable, __file__, "--variant", str(v)], capture_output=True, text=True, timeout=300)

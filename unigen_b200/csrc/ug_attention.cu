@@ -16,6 +16,7 @@ namespace ug {
 constexpr int kBlockQ = 128;
 constexpr int kBlockKV = 128;
 constexpr int kMaxTiles = 512;  // seq <= 65536
+constexpr float kRescaleLog2 = 8.0f;  // lazy-rescale threshold in the exp2 domain
 
 struct AttnParams {
   __nv_bfloat16* o;
@@ -44,8 +45,8 @@ struct AttnCfg {
 
 // Is key tile `kt` needed by query tile `qt` (any visible (query segment, key segment) pair)?  flags bit0 = needed,
 // bit1 = per-element masking required (some pair invisible, or the tile holds the sequence tail).
-__device__ __forceinline__ int classify_tile(const AttnParams& p, int qt, int kt) {
-  const int q_lo = qt * kBlockQ, q_hi = min(q_lo + kBlockQ, p.seq);
+__device__ __forceinline__ int classify_tile(const AttnParams& p, int qt, int kt, int block_q = kBlockQ) {
+  const int q_lo = qt * block_q, q_hi = min(q_lo + block_q, p.seq);
   const int k_lo = kt * kBlockKV, k_hi_full = k_lo + kBlockKV, k_hi = min(k_hi_full, p.seq);
   int needed = 0, partial = (k_hi_full > p.seq) ? 1 : 0;
   if (p.n_seg == 0) return 1 | (partial << 1);
@@ -264,16 +265,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       float rmax = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 128; ++c) rmax = fmaxf(rmax, __uint_as_float(s[c]));
-      const float m_new = fmaxf(m, rmax);
+      // Lazy rescaling: the running reference max m only moves when some row of this warp would otherwise see
+      // exp2 arguments above kRescaleLog2 (P values up to 2^8 are harmless in bf16 / fp32); O and l stay consistent
+      // with the reference max, so the result is exact. Most tiles then skip the TMEM round trip of O.
+      const float m_cand = fmaxf(m, rmax);
+      const bool grow = (m_cand - m) * p.scale_log2 > kRescaleLog2;  // also true when m == -inf and rmax is finite
+      const bool rescale = __any_sync(0xffffffffu, grow);
+      const float m_new = rescale ? m_cand : m;
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f((m - m_use) * p.scale_log2);  // m = -inf -> 0
+      const float alpha = rescale ? ex2_ftz((m - m_use) * p.scale_log2) : 1.f;  // m = -inf -> 0
       const float neg_ms = -m_use * p.scale_log2;
       float rsum = 0.f;
       uint32_t pk[64];
 #pragma unroll
       for (int c = 0; c < 64; ++c) {
-        const float p0 = exp2f(fmaf(__uint_as_float(s[2 * c]), p.scale_log2, neg_ms));
-        const float p1 = exp2f(fmaf(__uint_as_float(s[2 * c + 1]), p.scale_log2, neg_ms));
+        const float p0 = ex2_ftz(fmaf(__uint_as_float(s[2 * c]), p.scale_log2, neg_ms));
+        const float p1 = ex2_ftz(fmaf(__uint_as_float(s[2 * c + 1]), p.scale_log2, neg_ms));
         rsum += p0 + p1;
         pk[c] = pack_bf16x2(p0, p1);
       }
@@ -294,7 +301,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         // O must be quiescent (PV of the previous tile retired) before it is rescaled
         mbar_wait(&pv_done[(i - 1) & 1], ((i - 1) >> 1) & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, m_new > m)) {
+        if (rescale) {
           const uint32_t o_addr = tmem_base + lane_off + Cfg::TMEM_O;
 #pragma unroll
           for (int c = 0; c < kDh / 32; ++c) {
@@ -325,6 +332,319 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     const float inv_l = l > 0.f ? 1.f / l : 0.f;
     __nv_bfloat16* orow = p.o + (long long)b * p.o_bs + (long long)q_row * p.o_rs + head * kDh;
     const uint32_t o_addr = tmem_base + lane_off + Cfg::TMEM_O;
+#pragma unroll
+    for (int c = 0; c < kDh / 32; ++c) {
+      uint32_t o[32];
+      if (n_tiles > 0) {
+        tmem_ld_32x32(o_addr + 32 * c, o);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = 0u;
+      }
+      if (q_row < p.seq) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[8 * j]) * inv_l, __uint_as_float(o[8 * j + 1]) * inv_l);
+          u.y = pack_bf16x2(__uint_as_float(o[8 * j + 2]) * inv_l, __uint_as_float(o[8 * j + 3]) * inv_l);
+          u.z = pack_bf16x2(__uint_as_float(o[8 * j + 4]) * inv_l, __uint_as_float(o[8 * j + 5]) * inv_l);
+          u.w = pack_bf16x2(__uint_as_float(o[8 * j + 6]) * inv_l, __uint_as_float(o[8 * j + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + 32 * c + 8 * j) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+
+// =====================================================================================================================
+// v2: 256 query rows per CTA = two 128-row tiles that share every K/V tile and ping-pong on the tensor pipe.
+// Warps: 0 TMA, 1 MMA, 2-3 idle (register donors), 4-7 softmax group 0 (rows 0..127), 8-11 softmax group 1 (rows 128..255).
+// Each group owns S_w (128 TMEM columns, P aliases its first 64) and O_w (head_dim columns). The MMA warp issues
+//   PV0(j), S0(j+1), PV1(j), S1(j+1)
+// so group 0's softmax overlaps group 1's MMAs and vice versa; K/V smem traffic per FLOP halves vs v1.
+// s_full[w](j) is committed after S_w(j), i.e. after PV_w(j-1) in issue order, so it also tells group w that O_w is
+// quiescent and may be rescaled.
+// =====================================================================================================================
+template <int kDh>
+struct Attn2Cfg {
+  static constexpr int SLABS = kDh / 64;
+  static constexpr int SLAB_BYTES = 128 * 128;
+  static constexpr int TILE_BYTES = SLABS * SLAB_BYTES;
+  static constexpr int KV_STAGES = 2;
+  static constexpr int SMEM_TILES = TILE_BYTES * (2 + 2 * KV_STAGES);
+  static constexpr int NUM_BARS = 1 + 4 * KV_STAGES + 6;
+  static constexpr int SMEM_BYTES = SMEM_TILES + NUM_BARS * 8 + 16 + kMaxTiles * 2 + 1024;
+  static constexpr int TMEM_COLS = 512;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <int kDh>
+__global__ void __launch_bounds__(384, 1)
+attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                  const __grid_constant__ CUtensorMap tma_v, const AttnParams p) {
+  using Cfg = Attn2Cfg<kDh>;
+  constexpr int KS = Cfg::KV_STAGES;
+  constexpr int kBlockQ2 = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_q = smem;                                // 2 query tiles
+  uint8_t* smem_k = smem_q + 2 * Cfg::TILE_BYTES;
+  uint8_t* smem_v = smem_k + KS * Cfg::TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::SMEM_TILES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = q_full + 1;
+  uint64_t* k_empty = k_full + KS;
+  uint64_t* v_full = k_empty + KS;
+  uint64_t* v_empty = v_full + KS;
+  uint64_t* s_full = v_empty + KS;   // [2] per softmax group
+  uint64_t* p_ready = s_full + 2;    // [2]
+  uint64_t* pv_done = p_ready + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  int* n_tiles_smem = reinterpret_cast<int*>(tmem_slot + 1);
+  uint16_t* tile_list = reinterpret_cast<uint16_t*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_k);
+    tma_prefetch_desc(&tma_v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KS; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_ready[s], 128);
+      mbar_init(&pv_done[s], 1);
+    }
+    fence_mbar_init();
+    const int total = (p.seq + kBlockKV - 1) / kBlockKV;
+    int n = 0;
+    for (int kt = 0; kt < total; ++kt) {
+      const int f = classify_tile(p, qt, kt, kBlockQ2);
+      if (f & 1) tile_list[n++] = (uint16_t)(kt | ((f >> 1) << 15));
+    }
+    *n_tiles_smem = n;
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_tiles = *n_tiles_smem;
+
+  if (warp < 4) {
+    setmaxnreg_dec<72>();  // 168*384 = 64512 registers per CTA: 72*128 + 208*256 = 62464 fits
+    if (warp == 0) {
+      // ------------------------------ TMA producer ------------------------------
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int s = 0; s < Cfg::SLABS; ++s)
+            tma_load_4d(smem_q + t * Cfg::TILE_BYTES + s * Cfg::SLAB_BYTES, &tma_q, q_full, s * 64, head,
+                        qt * kBlockQ2 + t * 128, b);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < n_tiles; ++i) {
+        const int kt = tile_list[i] & 0x7fff;
+        mbar_wait(&k_empty[stage], phase ^ 1);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&k_full[stage], Cfg::TILE_BYTES);
+#pragma unroll
+          for (int s = 0; s < Cfg::SLABS; ++s)
+            tma_load_4d(smem_k + stage * Cfg::TILE_BYTES + s * Cfg::SLAB_BYTES, &tma_k, &k_full[stage], s * 64, head,
+                        kt * kBlockKV, b);
+        }
+        mbar_wait(&v_empty[stage], phase ^ 1);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&v_full[stage], Cfg::TILE_BYTES);
+#pragma unroll
+          for (int s = 0; s < Cfg::SLABS; ++s)
+            tma_load_4d(smem_v + stage * Cfg::TILE_BYTES + s * Cfg::SLAB_BYTES, &tma_v, &v_full[stage], s * 64, head,
+                        kt * kBlockKV, b);
+        }
+        __syncwarp();
+        if (++stage == KS) { stage = 0; phase ^= 1; }
+      }
+    } else if (warp == 1) {
+      // ------------------------------ MMA issuer ------------------------------
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, kBlockKV, false, false);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, kDh, false, true);
+      auto issue_s = [&](int w, int stage) {
+        const uint32_t d = tmem_base + w * 128;
+#pragma unroll
+        for (int k = 0; k < kDh / 16; ++k) {
+          const uint32_t off = (k >> 2) * Cfg::SLAB_BYTES + (k & 3) * 32;
+          const uint64_t a_desc = make_sdesc_sw128(smem_u32(smem_q + w * Cfg::TILE_BYTES) + off, 16, 1024);
+          const uint64_t b_desc = make_sdesc_sw128(smem_u32(smem_k + stage * Cfg::TILE_BYTES) + off, 16, 1024);
+          umma_ss<1>(d, a_desc, b_desc, idesc_s, k != 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int w, int stage, bool accumulate) {
+        const uint32_t d = tmem_base + 256 + w * 128;
+#pragma unroll
+        for (int k = 0; k < kBlockKV / 16; ++k) {
+          const uint64_t b_desc =
+              make_sdesc_sw128(smem_u32(smem_v + stage * Cfg::TILE_BYTES) + k * 2048, Cfg::SLAB_BYTES, 1024);
+          umma_ts(d, tmem_base + w * 128 + k * 8, b_desc, idesc_o, (accumulate || k != 0) ? 1u : 0u);
+        }
+      };
+      if (n_tiles > 0) {
+        mbar_wait(q_full, 0);
+        mbar_wait(&k_full[0], 0);
+        tc_fence_after();
+        if (lane == 0) {
+          issue_s(0, 0);
+          umma_commit(&s_full[0]);
+          issue_s(1, 0);
+          umma_commit(&s_full[1]);
+          umma_commit(&k_empty[0]);
+        }
+        __syncwarp();
+        for (int i = 0; i < n_tiles; ++i) {
+          const int stage = i % KS;
+          const uint32_t phase = (i / KS) & 1;
+          const bool more = i + 1 < n_tiles;
+          const int nstage = (i + 1) % KS;
+          // ---- group 0 ----
+          mbar_wait(&p_ready[0], i & 1);
+          mbar_wait(&v_full[stage], phase);
+          if (more) mbar_wait(&k_full[nstage], ((i + 1) / KS) & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            issue_pv(0, stage, i > 0);
+            umma_commit(&pv_done[0]);
+            if (more) {
+              issue_s(0, nstage);
+              umma_commit(&s_full[0]);
+            }
+          }
+          __syncwarp();
+          // ---- group 1 ----
+          mbar_wait(&p_ready[1], i & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            issue_pv(1, stage, i > 0);
+            umma_commit(&pv_done[1]);
+            umma_commit(&v_empty[stage]);
+            if (more) {
+              issue_s(1, nstage);
+              umma_commit(&s_full[1]);
+              umma_commit(&k_empty[nstage]);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ------------------------------ softmax groups ------------------------------
+    setmaxnreg_inc<208>();
+    const int w = (warp - 4) >> 2;            // group
+    const int qd = warp & 3;                  // TMEM lane quarter
+    const int row_local = qd * 32 + lane;
+    const int q_row = qt * kBlockQ2 + w * 128 + row_local;
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_off + w * 128;
+    const uint32_t o_addr = tmem_base + lane_off + 256 + w * 128;
+    unsigned int vis = 0xffffffffu;
+    if (p.n_seg > 0) {
+      int sq = p.n_seg - 1;
+      for (int s = 0; s < p.n_seg; ++s)
+        if (q_row >= p.bounds[s] && q_row < p.bounds[s + 1]) sq = s;
+      vis = p.visible[sq];
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int i = 0; i < n_tiles; ++i) {
+      const int entry = tile_list[i];
+      const int kt = entry & 0x7fff;
+      mbar_wait(&s_full[w], i & 1);
+      tc_fence_after();
+      uint32_t s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(s_addr + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
+      tmem_ld_wait();
+      if (entry & 0x8000) {
+        unsigned int mw[4] = {0u, 0u, 0u, 0u};
+        const int k_lo = kt * kBlockKV;
+        auto mask_range = [&](int lo, int hi) {
+          lo = max(lo, 0); hi = min(hi, kBlockKV);
+          for (int ww = 0; ww < 4; ++ww) {
+            const int a = max(lo - 32 * ww, 0), e = min(hi - 32 * ww, 32);
+            if (a < e) mw[ww] |= (e - a == 32) ? 0xffffffffu : (((1u << (e - a)) - 1u) << a);
+          }
+        };
+        if (p.seq < k_lo + kBlockKV) mask_range(p.seq - k_lo, kBlockKV);
+        for (int sk = 0; sk < p.n_seg; ++sk)
+          if (!((vis >> sk) & 1u)) mask_range(p.bounds[sk] - k_lo, p.bounds[sk + 1] - k_lo);
+#pragma unroll
+        for (int c = 0; c < 128; ++c)
+          if ((mw[c >> 5] >> (c & 31)) & 1u) s[c] = 0xff800000u;
+      }
+      float rmax = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 128; ++c) rmax = fmaxf(rmax, __uint_as_float(s[c]));
+      const float m_cand = fmaxf(m, rmax);
+      const bool grow = (m_cand - m) * p.scale_log2 > kRescaleLog2;  // lazy rescaling, see attention_kernel
+      const bool rescale = __any_sync(0xffffffffu, grow);
+      const float m_new = rescale ? m_cand : m;
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = rescale ? ex2_ftz((m - m_use) * p.scale_log2) : 1.f;
+      const float neg_ms = -m_use * p.scale_log2;
+      // O_w is quiescent here (s_full(i) is committed after PV_w(i-1)): rescale it when the reference max moved
+      if (i > 0 && rescale) {
+#pragma unroll
+        for (int c = 0; c < kDh / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld_32x32(o_addr + 32 * c, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+          tmem_st_32x32(o_addr + 32 * c, o);
+        }
+      }
+      float rsum0 = 0.f, rsum1 = 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float p0 = ex2_ftz(fmaf(__uint_as_float(s[64 * half + 2 * c]), p.scale_log2, neg_ms));
+          const float p1 = ex2_ftz(fmaf(__uint_as_float(s[64 * half + 2 * c + 1]), p.scale_log2, neg_ms));
+          rsum0 += p0;
+          rsum1 += p1;
+          pk[c] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_32x32(s_addr + 32 * half, pk);
+      }
+      l = l * alpha + (rsum0 + rsum1);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_ready[w]);
+      m = m_new;
+    }
+    if (n_tiles > 0) {
+      mbar_wait(&pv_done[w], (n_tiles - 1) & 1);
+      tc_fence_after();
+    }
+    const float inv_l = l > 0.f ? 1.f / l : 0.f;
+    __nv_bfloat16* orow = p.o + (long long)b * p.o_bs + (long long)q_row * p.o_rs + head * kDh;
 #pragma unroll
     for (int c = 0; c < kDh / 32; ++c) {
       uint32_t o[32];
@@ -424,6 +744,44 @@ static int launch_attention(const ug_attn_args& a, cudaStream_t stream) {
   return UG_OK;
 }
 
+
+template <int kDh>
+static int launch_attention2(const ug_attn_args& a, cudaStream_t stream) {
+  using Cfg = Attn2Cfg<kDh>;
+  auto kern = attention2_kernel<kDh>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("attention2: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return UG_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  CUtensorMap maps[3];
+  const void* ptrs[3] = {a.q, a.k, a.v};
+  const int64_t rs[3] = {a.q_row_stride, a.k_row_stride, a.v_row_stride};
+  const int64_t bs[3] = {a.q_batch_stride, a.k_batch_stride, a.v_batch_stride};
+  for (int i = 0; i < 3; ++i) {
+    uint64_t dims[4] = {(uint64_t)kDh, (uint64_t)a.heads, (uint64_t)a.seq, (uint64_t)a.batch};
+    uint64_t bstride = a.batch > 1 ? (uint64_t)bs[i] : (uint64_t)a.seq * rs[i];
+    uint64_t strides[3] = {(uint64_t)kDh * 2, (uint64_t)rs[i] * 2, bstride * 2};
+    uint32_t box[4] = {64, 1, 128, 1};
+    int st = encode_tmap_bf16(&maps[i], ptrs[i], 4, dims, strides, box);
+    if (st != UG_OK) return st;
+  }
+  AttnParams p;
+  p.o = (__nv_bfloat16*)a.o; p.o_rs = a.o_row_stride; p.o_bs = a.o_batch_stride;
+  p.seq = a.seq; p.heads = a.heads; p.batch = a.batch;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  int st = fill_segments(p, a.seq, a.n_seg, a.seg_bounds, a.seg_visible);
+  if (st != UG_OK) return st;
+  dim3 grid((a.seq + 255) / 256, a.heads, a.batch);
+  kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], p);
+  UG_CHECK_LAUNCH("attention2");
+  return UG_OK;
+}
+
 }  // namespace ug
 
 using namespace ug;
@@ -441,13 +799,17 @@ extern "C" int ug_attention_bf16(const ug_attn_args* args, void* stream) {
                                 a.o_batch_stride % 8 == 0),
                "attention: batch strides must be multiples of 8 elements");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int variant = a.variant == 0 ? 1 : a.variant;
+  // auto: the two-tile ping-pong kernel once there are enough 256-row query tiles to fill the machine
+  int variant = a.variant;
+  if (variant == 0) variant = ((long long)((a.seq + 255) / 256) * a.heads * a.batch >= num_sms()) ? 3 : 1;
   if (a.head_dim == 128) {
     if (variant == 1) return launch_attention<128, true>(a, s);
     if (variant == 2) return launch_attention<128, false>(a, s);
+    if (variant == 3) return launch_attention2<128>(a, s);
   } else if (a.head_dim == 64) {
     if (variant == 1) return launch_attention<64, true>(a, s);
     if (variant == 2) return launch_attention<64, false>(a, s);
+    if (variant == 3) return launch_attention2<64>(a, s);
   } else {
     set_error("attention: head_dim %d not supported (64 or 128)", a.head_dim);
     return UG_ERR_UNSUPPORTED;

@@ -417,18 +417,18 @@ class UniGenFlux(torch.nn.Module):
                 encoder_hidden_states=None, pooled_projections=None, condition_pooled_projections=None, timestep=None,
                 img_ids=None, txt_ids=None, guidance=None, condition_ids=None, joint_attention_kwargs=None,
                 skip_layers=None, rts_uniform=None, **kwargs):
+        """Reference signature (src/UniGenTransformer.py:1182-1198). `joint_attention_kwargs['scale']` (PEFT LoRA scale)
+        is accepted and ignored: the S-variant forward never applies an adapter."""
         if not self._control_ready:
             raise ops.UgError("call init_condition_block(condition_nums=..., control_params=...) before forward")
-        a = self.arch
-        D, H, dh = self.inner_dim, a.num_attention_heads, a.attention_head_dim
+        if encoder_hidden_states is None or condition_hidden_states is None or timestep is None:
+            raise ops.UgError("forward needs hidden_states, condition_hidden_states, encoder_hidden_states and timestep")
         B, N, _ = hidden_states.shape
         T = encoder_hidden_states.shape[1]
-        S = T + N
         if condition_hidden_states.shape[1] != N:
             raise ops.UgError("condition tokens must match the image token count (Nc == N) for the CoMoE pre-stage")
         if T == N:
             raise ops.UgError("T == N: the reference MOELayer would also dispatch the text tensor (SURVEY.md §8 A9); unsupported")
-        buf = self._workspace(B, N, T)
         dev = self.device_
         f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
         if txt_ids.dim() == 3:
@@ -437,24 +437,54 @@ class UniGenFlux(torch.nn.Module):
             img_ids = img_ids[0]
         if condition_ids.dim() == 3:
             condition_ids = condition_ids[0]
-        txt_ids, img_ids, condition_ids = f32(txt_ids), f32(img_ids), f32(condition_ids)
         if rts_uniform is None:
             # DeepSpeed draws this uniform tensor in train AND eval; torch RNG is plumbing here
             rts_uniform = torch.rand(B * N, self.expert_nums, device=dev, dtype=torch.float32)
-        rts_uniform = f32(rts_uniform)
+        staged = dict(
+            hs=hidden_states.to(dev), cs=condition_hidden_states.to(dev), es=encoder_hidden_states.to(dev),
+            pooled=f32(pooled_projections), cond_pooled=f32(condition_pooled_projections), timestep=f32(timestep),
+            guidance=f32(guidance) if guidance is not None else None,
+            txt_ids=f32(txt_ids), img_ids=f32(img_ids), condition_ids=f32(condition_ids), rts_uniform=f32(rts_uniform))
+        if not self.use_cuda_graph or self.trace is not None:
+            return self._forward_impl(float(conditioning_scale), **staged)
+        # ---- CUDA-graph path: static input buffers, one captured graph per (shape, scale) ----
+        key = (B, N, T, float(conditioning_scale), guidance is not None,
+               tuple((k, v.dtype) for k, v in staged.items() if v is not None))
+        g = self._graphs.get(key)
+        if g is None:
+            static = {k: (v.clone() if v is not None else None) for k, v in staged.items()}
+            self._forward_impl(float(conditioning_scale), **static)  # warm-up: attribute setup, workspace allocation
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._forward_impl(float(conditioning_scale), **static)
+            g = self._graphs[key] = (graph, static, out, ops.launch_count_in_last_capture())
+        graph, static, out, n_launch = g
+        for k, v in staged.items():
+            if v is not None:
+                static[k].copy_(v)
+        graph.replay()
+        ops.add_launches(n_launch)
+        return out
 
-        hs = ops.to_bf16(hidden_states.to(dev).contiguous())
-        cs = ops.to_bf16(condition_hidden_states.to(dev).contiguous())
-        es = ops.to_bf16(encoder_hidden_states.to(dev).contiguous())
-        pooled, cond_pooled = f32(pooled_projections), f32(condition_pooled_projections)
+    def _forward_impl(self, conditioning_scale, hs, cs, es, pooled, cond_pooled, timestep, guidance, txt_ids, img_ids,
+                      condition_ids, rts_uniform):
+        a = self.arch
+        D, H, dh = self.inner_dim, a.num_attention_heads, a.attention_head_dim
+        B, N, _ = hs.shape
+        T = es.shape[1]
+        S = T + N
+        buf = self._workspace(B, N, T)
+        n0 = ops.launch_count()
+        hs, cs, es = ops.to_bf16(hs.contiguous()), ops.to_bf16(cs.contiguous()), ops.to_bf16(es.contiguous())
         gv = self.gemm_variant
 
         # ---- embeddings (:1215-1239) ----
         x_txt, x_img = buf.X[:, :T], buf.X[:, T:]
         ops.gemm(hs, self.x_embedder_w[0], out=x_img, bias=self.x_embedder_w[1], variant=gv)
         ops.gemm(es, self.context_embedder_w[0], out=x_txt, bias=self.context_embedder_w[1], variant=gv)
-        t_emb = ops.timestep_embedding(f32(timestep) * 1000.0)
-        g_emb = ops.timestep_embedding(f32(guidance) * 1000.0) if guidance is not None else None
+        t_emb = ops.timestep_embedding(timestep * 1000.0)
+        g_emb = ops.timestep_embedding(guidance * 1000.0) if guidance is not None else None
         self._time_text(self.time_text, t_emb, pooled, buf.temb, buf.tmp, g_emb)
         ctrl_pooled = pooled if self.use_pooled_prompt_embeds else torch.zeros_like(pooled)
         self._time_text(self.control_time_text, t_emb, ctrl_pooled, buf.ctemb, buf.tmp, g_emb)      # control_temb
@@ -521,6 +551,7 @@ class UniGenFlux(torch.nn.Module):
         ops.gemm(buf.NO, self.proj_out_w[0], out=buf.OUT, bias=self.proj_out_w[1], variant=gv)
         self._rec("velocity", buf.OUT)
         self._last_route = route
+        ops.note_capture_launches(ops.launch_count() - n0)
         add_losses = dict(moe_loss=route["l_aux"][0] * 0.1)
         add_outputs = dict(expert_counts=route["exp_counts"])
         return buf.OUT, add_losses, add_outputs

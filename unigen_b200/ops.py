@@ -42,11 +42,33 @@ def _view3(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 def launch_count() -> int:
-    return int(_lib.load().ug_launch_count())
+    return int(_lib.load().ug_launch_count()) + _extra_launches
 
 
 def reset_launch_count() -> None:
+    global _extra_launches
+    _extra_launches = 0
     _lib.load().ug_reset_launch_count()
+
+
+_extra_launches = 0
+_last_forward_launches = 0
+
+
+def note_capture_launches(n: int) -> None:
+    """Kernels issued by the last forward (so a CUDA-graph replay can account for the launches it re-issues)."""
+    global _last_forward_launches
+    _last_forward_launches = int(n)
+
+
+def launch_count_in_last_capture() -> int:
+    return _last_forward_launches
+
+
+def add_launches(n: int) -> None:
+    """Graph replays launch the captured kernels without passing through the C ABI: keep the counter truthful."""
+    global _extra_launches
+    _extra_launches += int(n)
 
 
 def device_check() -> None:
