@@ -195,6 +195,7 @@ def run_native(args):
     model.init_condition_block(condition_nums=1, control_params=canonical_control_params())
     model.init_random_(seed=0)
     model.gemm_variant, model.attn_variant = args.gemm_variant, args.attn_variant
+    model.use_cuda_graph = not args.no_graph
     E = model.expert_nums
 
     # synthetic inputs of the named shape, one distinct set per rank, resident in pinned host memory
@@ -290,6 +291,7 @@ def run_native(args):
             return r
 
         ops.gemm, ops.attention = gemm_timed, attn_timed
+        model.use_cuda_graph = False  # per-launch events need the eager launch path
         try:
             step_resident()
             torch.cuda.synchronize()
@@ -341,7 +343,8 @@ def run_native(args):
                    "tflop_per_step_per_sample_executed": (g_ex + a_ex) / 1e12,
                    "tflop_per_step_per_sample_reference_algorithmic": (g_alg + a_alg) / 1e12,
                    "model_tflops_per_gpu": (g_ex + a_ex) * B / (ms_step / 1e3) / 1e12,
-                   "gemm_variant": args.gemm_variant, "attn_variant": args.attn_variant},
+                   "gemm_variant": args.gemm_variant, "attn_variant": args.attn_variant,
+                   "cuda_graph": not args.no_graph},
         "e2e": {"value": value_e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_step_e2e},
         "gpu_launches": launches,
@@ -364,6 +367,7 @@ def main():
     ap.add_argument("--gemm-variant", type=int, default=0)
     ap.add_argument("--attn-variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -262,9 +262,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         for (int c = 0; c < 128; ++c)
           if ((mw[c >> 5] >> (c & 31)) & 1u) s[c] = 0xff800000u;  // -inf
       }
-      float rmax = -INFINITY;
+      // 8 independent max chains (3-input FMNMX3), then a short tree: the row reduction is latency-, not issue-bound
+      float rm[8];
 #pragma unroll
-      for (int c = 0; c < 128; ++c) rmax = fmaxf(rmax, __uint_as_float(s[c]));
+      for (int c = 0; c < 8; ++c) rm[c] = fmaxf(__uint_as_float(s[c]), __uint_as_float(s[c + 8]));
+#pragma unroll
+      for (int c = 16; c < 128; c += 16) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rm[j] = fmaxf(rm[j], fmaxf(__uint_as_float(s[c + j]), __uint_as_float(s[c + j + 8])));
+      }
+      const float rmax = fmaxf(fmaxf(fmaxf(rm[0], rm[1]), fmaxf(rm[2], rm[3])), fmaxf(fmaxf(rm[4], rm[5]), fmaxf(rm[6], rm[7])));
       // Lazy rescaling: the running reference max m only moves when some row of this warp would otherwise see
       // exp2 arguments above kRescaleLog2 (P values up to 2^8 are harmless in bf16 / fp32); O and l stay consistent
       // with the reference max, so the result is exact. Most tiles then skip the TMEM round trip of O.
@@ -275,16 +282,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = rescale ? ex2_ftz((m - m_use) * p.scale_log2) : 1.f;  // m = -inf -> 0
       const float neg_ms = -m_use * p.scale_log2;
-      float rsum = 0.f;
+      float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       uint32_t pk[64];
 #pragma unroll
       for (int c = 0; c < 64; ++c) {
         const float p0 = ex2_ftz(fmaf(__uint_as_float(s[2 * c]), p.scale_log2, neg_ms));
         const float p1 = ex2_ftz(fmaf(__uint_as_float(s[2 * c + 1]), p.scale_log2, neg_ms));
-        rsum += p0 + p1;
+        rs[(2 * c) & 7] += p0;
+        rs[(2 * c + 1) & 7] += p1;
         pk[c] = pack_bf16x2(p0, p1);
       }
-      l = l * alpha + rsum;
+      l = l * alpha + (((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7])));
       if constexpr (kPInTmem) {
         tmem_st_32x32(s_addr, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
         tmem_st_32x32(s_addr + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
@@ -597,9 +605,16 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         for (int c = 0; c < 128; ++c)
           if ((mw[c >> 5] >> (c & 31)) & 1u) s[c] = 0xff800000u;
       }
-      float rmax = -INFINITY;
+      // 8 independent max chains (3-input FMNMX3), then a short tree: the row reduction is latency-, not issue-bound
+      float rm[8];
 #pragma unroll
-      for (int c = 0; c < 128; ++c) rmax = fmaxf(rmax, __uint_as_float(s[c]));
+      for (int c = 0; c < 8; ++c) rm[c] = fmaxf(__uint_as_float(s[c]), __uint_as_float(s[c + 8]));
+#pragma unroll
+      for (int c = 16; c < 128; c += 16) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rm[j] = fmaxf(rm[j], fmaxf(__uint_as_float(s[c + j]), __uint_as_float(s[c + j + 8])));
+      }
+      const float rmax = fmaxf(fmaxf(fmaxf(rm[0], rm[1]), fmaxf(rm[2], rm[3])), fmaxf(fmaxf(rm[4], rm[5]), fmaxf(rm[6], rm[7])));
       const float m_cand = fmaxf(m, rmax);
       const bool grow = (m_cand - m) * p.scale_log2 > kRescaleLog2;  // lazy rescaling, see attention_kernel
       const bool rescale = __any_sync(0xffffffffu, grow);
@@ -619,7 +634,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
           tmem_st_32x32(o_addr + 32 * c, o);
         }
       }
-      float rsum0 = 0.f, rsum1 = 0.f;
+      float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t pk[32];
@@ -627,13 +642,13 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         for (int c = 0; c < 32; ++c) {
           const float p0 = ex2_ftz(fmaf(__uint_as_float(s[64 * half + 2 * c]), p.scale_log2, neg_ms));
           const float p1 = ex2_ftz(fmaf(__uint_as_float(s[64 * half + 2 * c + 1]), p.scale_log2, neg_ms));
-          rsum0 += p0;
-          rsum1 += p1;
+          rs[(2 * c) & 7] += p0;
+          rs[(2 * c + 1) & 7] += p1;
           pk[c] = pack_bf16x2(p0, p1);
         }
         tmem_st_32x32(s_addr + 32 * half, pk);
       }
-      l = l * alpha + (rsum0 + rsum1);
+      l = l * alpha + (((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7])));
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_ready[w]);
