@@ -532,6 +532,24 @@ class UniGenFluxOracle:
         self._rec("temb", temb); self._rec("x_embed", h); self._rec("context_embed", enc)
 
         def preprocess(h_, enc_):
+            if isinstance(condition_hidden_states, (list, tuple)):
+                # MultiCondtionUniGenFlux.preprocess_moe_forward (src/UniGenTransformer.py:1275-1322): one full CoMoE
+                # pass per condition; control stream := sum_c (expert_hidden + expert_cond); condition_temb := sum_c;
+                # moe_loss / exp_count are those of the LAST condition (:1320-1321).
+                merged, merged_temb, last = 0, 0, None
+                for c, (cid, chs, cp) in enumerate(zip(condition_ids, condition_hidden_states,
+                                                       condition_pooled_projections)):
+                    cid = cid[0] if cid.dim() == 3 else cid
+                    last = self.preprocess_moe_forward(h_, chs, enc_, pooled_projections, cp, timestep, guidance,
+                                                       (img_ids, txt_ids, cid), rts_uniform[c])
+                    merged = merged + (last["expert_hidden_states"] + last["expert_condition_hidden_states"])
+                    merged_temb = merged_temb + last["condition_temb"]
+                    self._rec(f"moe.cond{c}.ctrl_in", last["expert_hidden_states"] + last["expert_condition_hidden_states"])
+                z = torch.zeros_like(merged)
+                return dict(expert_hidden_states=merged, expert_condition_hidden_states=z,
+                            control_encoder_hidden_states=last["control_encoder_hidden_states"],
+                            control_temb=last["control_temb"], condition_temb=merged_temb,
+                            exp_count=last["exp_count"], moe_loss=last["moe_loss"])
             return self.preprocess_moe_forward(h_, condition_hidden_states, enc_, pooled_projections,
                                                condition_pooled_projections, timestep, guidance,
                                                (img_ids, txt_ids, condition_ids), rts_uniform)
@@ -665,3 +683,18 @@ def make_inputs(cfg: FluxConfig, height: int, width: int, text_len: int = 512, b
         img_ids=img_ids, txt_ids=torch.zeros(text_len, 3), condition_ids=cond_ids,
         rts_uniform=torch.rand(batch * N, cfg.expert_nums, generator=gen),
     )
+
+
+def make_multi_inputs(cfg: FluxConfig, height: int, width: int, condition_types=("depth", "canny", "subject"),
+                      text_len: int = 512, batch: int = 1, seed: int = 1234, step: int = 0, steps: int = 4):
+    """Inputs for MultiCondtionUniGenFlux (src/UniGenTransformer.py:1360-1450): LISTS of condition tokens / pooled
+    embeddings / ids, one RTS uniform draw per condition (every MoE call draws its own)."""
+    base = make_inputs(cfg, height, width, text_len, batch, seed, step, steps, condition_types[0])
+    gen = torch.Generator().manual_seed(seed + 1)
+    N = base["hidden_states"].shape[1]
+    base["condition_hidden_states"] = [torch.randn(batch, N, cfg.in_channels, generator=gen) for _ in condition_types]
+    base["condition_pooled_projections"] = [torch.randn(batch, cfg.pooled_projection_dim, generator=gen)
+                                            for _ in condition_types]
+    base["condition_ids"] = [condition_ids(t, height, width)[0] for t in condition_types]
+    base["rts_uniform"] = [torch.rand(batch * N, cfg.expert_nums, generator=gen) for _ in condition_types]
+    return base

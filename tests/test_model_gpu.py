@@ -101,6 +101,41 @@ def test_batch2_equals_two_independent_samples_in_attention_and_gemm_paths():
         assert torch.equal(model.trace["double.0.base_hidden"][0], t2[b])
 
 
+def test_multi_condition_forward_matches_oracle():
+    """MultiCondtionUniGenFlux (reference :1274-1450): 3 conditions (depth + canny + subject), E = 12, one CoMoE pass per
+    condition, summed control stream / condition_temb, last condition's loss and counts."""
+    from oracle import unigen_oracle as O
+    from unigen_b200.model import FluxArch, MultiCondtionUniGenFlux, canonical_control_params
+    cfg = O.FluxConfig.tiny()
+    cfg.condition_nums = 3
+    sd = O.init_state_dict(cfg, seed=3)
+    sd = {k: (v if k.endswith("gate.wg.weight") else v.to(torch.bfloat16).float()) for k, v in sd.items()}
+    inp = O.make_multi_inputs(cfg, 256, 256)
+    for k in ("hidden_states", "encoder_hidden_states"):
+        inp[k] = inp[k].to(torch.bfloat16).float()
+    inp["condition_hidden_states"] = [c.to(torch.bfloat16).float() for c in inp["condition_hidden_states"]]
+    oracle = O.UniGenFluxOracle(cfg, sd)
+    oracle.record = True
+    want, want_l, want_o = oracle.forward(**inp)
+    model = MultiCondtionUniGenFlux(FluxArch.tiny(), device="cuda")
+    model.init_condition_block(condition_nums=3, control_params=canonical_control_params())
+    assert model.expert_nums == 12
+    model.load_state_dict(sd, strict=True)
+    model.trace = {}
+    to_dev = lambda v: [t.cuda() for t in v] if isinstance(v, list) else (v.cuda() if torch.is_tensor(v) else v)  # noqa: E731
+    got, losses, outs = model(**{k: to_dev(v) for k, v in inp.items()})
+    for name in ("moe.cond0.ctrl_in", "moe.cond2.ctrl_in", "moe.ctrl_in", "double.0.hidden", "single.3.hidden", "velocity"):
+        g = model.trace.get(name)
+        if g is None and name.endswith("ctrl_in") and "cond" in name:
+            continue
+        assert rel_l2(g, oracle.trace[name]) < 1e-2, name
+    cos = torch.nn.functional.cosine_similarity(got.float().cpu().flatten(), want.flatten(), dim=0).item()
+    assert cos >= 0.999
+    assert (outs["expert_counts"].cpu() - want_o["expert_counts"]).abs().sum() <= 4
+    with pytest.raises(Exception):
+        model(**{k: to_dev(v) for k, v in dict(inp, condition_hidden_states=inp["condition_hidden_states"][:2]).items()})
+
+
 def test_forward_rejects_missing_control_init_and_cpu_device():
     from unigen_b200.model import FluxArch, UniGenFlux
     from unigen_b200.ops import UgError

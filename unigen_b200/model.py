@@ -273,13 +273,14 @@ class UniGenFlux(torch.nn.Module):
         E = self.expert_nums
         C = ops.moe_capacity(B * N, E)
         z = lambda *s, dt=BF16: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
-        n_mod = (6 * 2 * (self.arch.num_layers + self.cn_joint_layers + 2) + 3 * (self.arch.num_single_layers + self.cn_single_joint_layers) + 2)
+        n_mod = (6 * 2 * (self.arch.num_layers + self.cn_joint_layers + 1 + self.condition_nums) + 3 * (self.arch.num_single_layers + self.cn_single_joint_layers) + 2)
         b = types.SimpleNamespace(
             X=z(B, S, D), NX=z(B, Smax, D), QKV=z(B, Smax, 3 * D), AO=z(B, Smax, D), FF=z(B, Smax, 4 * D),
             CAT=z(B, S, 5 * D), CH=z(B, N, D), CS=z(B, S, D), CENC=z(B, T, D), COND=z(B, N, D), HC=z(B, 2 * N, D),
             G=z(B * N, D), A=z(E * C, D), YC=z(E * C, D), YH=z(E * C, D), EH=z(B * N, D), EC=z(B * N, D), CIN=z(B, N, D),
             MOD=z(B, n_mod * D, dt=torch.float32), temb=z(B, D, dt=torch.float32), tmp=z(B, D, dt=torch.float32),
             ctemb=z(B, D, dt=torch.float32), cdtemb=z(B, D, dt=torch.float32),
+            cdtemb_c=[z(B, D, dt=torch.float32) for _ in range(self.condition_nums)],
             MODC=z(B, E, D, dt=torch.float32), MODH=z(B, E, D, dt=torch.float32),
             rope=z(S, self.arch.attention_head_dim, dt=torch.float32),
             rope0=z(2 * N, self.arch.attention_head_dim, dt=torch.float32),
@@ -292,10 +293,11 @@ class UniGenFlux(torch.nn.Module):
     # building blocks (each line = one kernel launch in libunigen_b200.so)
     # ---------------------------------------------------------------------------------------------------------
     def _time_text(self, w: _TimeTextW, t_emb: torch.Tensor, pooled: torch.Tensor, out: torch.Tensor, tmp: torch.Tensor,
-                   g_emb: Optional[torch.Tensor] = None):
-        """CombinedTimestep(Guidance)TextProjEmbeddings."""
+                   g_emb: Optional[torch.Tensor] = None, accumulate: bool = False):
+        """CombinedTimestep(Guidance)TextProjEmbeddings; accumulate=True adds into `out`
+        (merged_condition_temb = sum over conditions, reference :1314,1319)."""
         ops.gemv(t_emb, w.t1[0], w.t1[1], out=tmp, silu_out=True)
-        ops.gemv(tmp, w.t2[0], w.t2[1], out=out)
+        ops.gemv(tmp, w.t2[0], w.t2[1], out=out, accumulate=accumulate)
         if g_emb is not None and w.g1 is not None:
             ops.gemv(g_emb, w.g1[0], w.g1[1], out=tmp, silu_out=True)
             ops.gemv(tmp, w.g2[0], w.g2[1], out=out, accumulate=True)
@@ -376,11 +378,16 @@ class UniGenFlux(torch.nn.Module):
     # CoMoE pre-stage (reference preprocess_moe_forward :1028-1068, moe_forward :969-1026, MOELayer.forward,
     # expert_forward :925-967) — runs once per step at the first control call
     # ---------------------------------------------------------------------------------------------------------
-    def _prestage(self, buf, B, N, T, h_img, enc_txt, cond_tokens, pooled, cond_pooled, rts_uniform, mods):
+    def _prestage(self, buf, B, N, T, h_img, cond_tokens, pooled, cond_pooled, rts_uniform, mods_s0, mods_s1, cond_index,
+                  txt_ids, img_ids, cond_ids):
+        """One CoMoE pass for one condition; the control stream `CIN` accumulates over conditions
+        (MultiCondtionUniGenFlux: merged_hidden_states = sum_c (expert_hidden + expert_cond), :1313-1316)."""
+        a = self.arch
         D, E, C = self.inner_dim, self.expert_nums, buf.capacity
         gv = self.gemm_variant
         ops.gemm(cond_tokens, self.control_x_embedder_w[0], out=buf.COND, bias=self.control_x_embedder_w[1], variant=gv)
-        ops.gemm(enc_txt, self.control_context_embedder_w[0], out=buf.CENC, bias=self.control_context_embedder_w[1], variant=gv)
+        ops.rope_table(torch.cat([cond_ids, img_ids], 0), a.axes_dims_rope, a.theta, out=buf.rope0)
+        ops.rope_table(torch.cat([txt_ids, img_ids, cond_ids], 0), a.axes_dims_rope, a.theta, out=buf.rope1)
         # --- gate + Random-Token-Selection routing (DeepSpeed top1gating, SURVEY.md §A.5) ---
         g = buf.G.view(B, N, D)
         ops.add(h_img, buf.COND, g)
@@ -396,17 +403,21 @@ class UniGenFlux(torch.nn.Module):
         ops.gemm(buf.A.view(E, C, D), self.exp_w[1], out=buf.YH.view(E, C, D), bias=self.exp_b[1], variant=gv)
         # --- shared experts (V2, :1013-1022) ---
         hc_h, hc_c = buf.HC[:, :N], buf.HC[:, N:]
-        self._double_block(buf, self.shared[0], mods["shared0_smp"], mods["shared0_ctx"], h_img, buf.COND, hc_h, hc_c, buf.rope0)
-        self._double_block(buf, self.shared[1], mods["shared1_smp"], mods["shared1_ctx"], buf.HC, buf.CENC, buf.HC, None, buf.rope1)
-        # --- combine (gate-probability weighted, dropped tokens -> 0) and sum: ctrl_in = (hid + EH) + (cond + EC) ---
+        self._double_block(buf, self.shared[0], mods_s0[0], mods_s0[1], h_img, buf.COND, hc_h, hc_c, buf.rope0)
+        self._double_block(buf, self.shared[1], mods_s1[0], mods_s1[1], buf.HC, buf.CENC, buf.HC, None, buf.rope1)
+        # --- combine (gate-probability weighted, dropped tokens -> 0) and sum: ctrl_in (+)= (hid + EH) + (cond + EC) ---
         ops.moe_combine(buf.YH, route, C, buf.EH)
         ops.moe_combine(buf.YC, route, C, buf.EC)
-        self._rec("moe.expert_hidden", buf.EH.view(B, N, D)); self._rec("moe.expert_cond", buf.EC.view(B, N, D))
-        self._rec("moe.shared_hidden", hc_h); self._rec("moe.shared_cond", hc_c)
-        ops.add(hc_h, buf.EH.view(B, N, D), buf.CIN)
+        tag = "moe" if cond_index == 0 and self.condition_nums == 1 else f"moe.cond{cond_index}"
+        self._rec(tag + ".expert_hidden", buf.EH.view(B, N, D)); self._rec(tag + ".expert_cond", buf.EC.view(B, N, D))
+        self._rec(tag + ".shared_hidden", hc_h); self._rec(tag + ".shared_cond", hc_c)
+        if cond_index == 0:
+            ops.add(hc_h, buf.EH.view(B, N, D), buf.CIN)
+        else:
+            ops.add(buf.CIN, hc_h, buf.CIN)
+            ops.add(buf.CIN, buf.EH.view(B, N, D), buf.CIN)
         ops.add(buf.CIN, hc_c, buf.CIN)
         ops.add(buf.CIN, buf.EC.view(B, N, D), buf.CIN)
-        self._rec("moe.ctrl_in", buf.CIN)
         return route
 
     # ---------------------------------------------------------------------------------------------------------
@@ -425,26 +436,36 @@ class UniGenFlux(torch.nn.Module):
             raise ops.UgError("forward needs hidden_states, condition_hidden_states, encoder_hidden_states and timestep")
         B, N, _ = hidden_states.shape
         T = encoder_hidden_states.shape[1]
-        if condition_hidden_states.shape[1] != N:
+        # MultiCondtionUniGenFlux passes LISTS (condition tokens / pooled embeddings / ids), reference :1297
+        multi = isinstance(condition_hidden_states, (list, tuple))
+        cond_list = list(condition_hidden_states) if multi else [condition_hidden_states]
+        cpool_list = list(condition_pooled_projections) if multi else [condition_pooled_projections]
+        cid_list = list(condition_ids) if multi else [condition_ids]
+        if len(cond_list) != self.condition_nums or len(cpool_list) != len(cond_list) or len(cid_list) != len(cond_list):
+            raise ops.UgError(f"expected {self.condition_nums} condition(s) (init_condition_block), got {len(cond_list)}")
+        if any(c.shape[-2] != N for c in cond_list):
             raise ops.UgError("condition tokens must match the image token count (Nc == N) for the CoMoE pre-stage")
         if T == N:
             raise ops.UgError("T == N: the reference MOELayer would also dispatch the text tensor (SURVEY.md §8 A9); unsupported")
         dev = self.device_
         f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
-        if txt_ids.dim() == 3:
-            txt_ids = txt_ids[0]
-        if img_ids.dim() == 3:
-            img_ids = img_ids[0]
-        if condition_ids.dim() == 3:
-            condition_ids = condition_ids[0]
+        sq = lambda t: t[0] if t.dim() == 3 else t  # noqa: E731  (3-D ids are accepted and squeezed, reference :1225-1236)
         if rts_uniform is None:
             # DeepSpeed draws this uniform tensor in train AND eval; torch RNG is plumbing here
-            rts_uniform = torch.rand(B * N, self.expert_nums, device=dev, dtype=torch.float32)
+            u_list = [torch.rand(B * N, self.expert_nums, device=dev, dtype=torch.float32) for _ in cond_list]
+        else:
+            u_list = list(rts_uniform) if isinstance(rts_uniform, (list, tuple)) else [rts_uniform]
         staged = dict(
-            hs=hidden_states.to(dev), cs=condition_hidden_states.to(dev), es=encoder_hidden_states.to(dev),
-            pooled=f32(pooled_projections), cond_pooled=f32(condition_pooled_projections), timestep=f32(timestep),
-            guidance=f32(guidance) if guidance is not None else None,
-            txt_ids=f32(txt_ids), img_ids=f32(img_ids), condition_ids=f32(condition_ids), rts_uniform=f32(rts_uniform))
+            hs=hidden_states.to(dev), es=encoder_hidden_states.to(dev), pooled=f32(pooled_projections),
+            timestep=f32(timestep), guidance=f32(guidance) if guidance is not None else None,
+            txt_ids=f32(sq(txt_ids)), img_ids=f32(sq(img_ids)))
+        for c in range(len(cond_list)):
+            x = cond_list[c].to(dev)
+            staged[f"cs{c}"] = x if x.dim() == 3 else x.unsqueeze(0)
+            cp = f32(cpool_list[c])
+            staged[f"cp{c}"] = cp if cp.dim() == 2 else cp.unsqueeze(0)
+            staged[f"cid{c}"] = f32(sq(cid_list[c]))
+            staged[f"u{c}"] = f32(u_list[c])
         if not self.use_cuda_graph or self.trace is not None:
             return self._forward_impl(float(conditioning_scale), **staged)
         # ---- CUDA-graph path: static input buffers, one captured graph per (shape, scale) ----
@@ -467,16 +488,21 @@ class UniGenFlux(torch.nn.Module):
         ops.add_launches(n_launch)
         return out
 
-    def _forward_impl(self, conditioning_scale, hs, cs, es, pooled, cond_pooled, timestep, guidance, txt_ids, img_ids,
-                      condition_ids, rts_uniform):
+    def _forward_impl(self, conditioning_scale, hs, es, pooled, timestep, guidance, txt_ids, img_ids, **cond):
         a = self.arch
+        n_cond = self.condition_nums
+        cs = [cond[f"cs{c}"] for c in range(n_cond)]
+        cond_pooled = [cond[f"cp{c}"] for c in range(n_cond)]
+        condition_ids = [cond[f"cid{c}"] for c in range(n_cond)]
+        rts_uniform = [cond[f"u{c}"] for c in range(n_cond)]
         D, H, dh = self.inner_dim, a.num_attention_heads, a.attention_head_dim
         B, N, _ = hs.shape
         T = es.shape[1]
         S = T + N
         buf = self._workspace(B, N, T)
         n0 = ops.launch_count()
-        hs, cs, es = ops.to_bf16(hs.contiguous()), ops.to_bf16(cs.contiguous()), ops.to_bf16(es.contiguous())
+        hs, es = ops.to_bf16(hs.contiguous()), ops.to_bf16(es.contiguous())
+        cs = [ops.to_bf16(c.contiguous()) for c in cs]
         gv = self.gemm_variant
 
         # ---- embeddings (:1215-1239) ----
@@ -488,10 +514,10 @@ class UniGenFlux(torch.nn.Module):
         self._time_text(self.time_text, t_emb, pooled, buf.temb, buf.tmp, g_emb)
         ctrl_pooled = pooled if self.use_pooled_prompt_embeds else torch.zeros_like(pooled)
         self._time_text(self.control_time_text, t_emb, ctrl_pooled, buf.ctemb, buf.tmp, g_emb)      # control_temb
-        self._time_text(self.control_condition, t_emb, cond_pooled, buf.cdtemb, buf.tmp, g_emb)     # condition_temb
+        for c in range(n_cond):  # condition_temb per condition and their sum (what the control blocks are modulated by)
+            self._time_text(self.control_condition, t_emb, cond_pooled[c], buf.cdtemb_c[c], buf.tmp, g_emb)
+            self._time_text(self.control_condition, t_emb, cond_pooled[c], buf.cdtemb, buf.tmp, g_emb, accumulate=c > 0)
         ops.rope_table(torch.cat([txt_ids, img_ids], 0), a.axes_dims_rope, a.theta, out=buf.rope)
-        ops.rope_table(torch.cat([condition_ids, img_ids], 0), a.axes_dims_rope, a.theta, out=buf.rope0)
-        ops.rope_table(torch.cat([txt_ids, img_ids, condition_ids], 0), a.axes_dims_rope, a.theta, out=buf.rope1)
         self._rec("temb", buf.temb); self._rec("x_embed", x_img); self._rec("context_embed", x_txt)
 
         # ---- every block's AdaLN vectors, once per step (temb / condition_temb are step constants) ----
@@ -507,11 +533,14 @@ class UniGenFlux(torch.nn.Module):
             m_single.append(self._mods(buf, slot, 3, w.norm, buf.temb)); slot += 3
         for w in self.ctrl_single:
             m_csingle.append(self._mods(buf, slot, 3, w.norm, buf.cdtemb)); slot += 3
-        mods = dict(shared0_smp=self._mods(buf, slot, 6, self.shared[0].norm1, buf.cdtemb),
-                    shared0_ctx=self._mods(buf, slot + 6, 6, self.shared[0].norm1_ctx, buf.cdtemb),
-                    shared1_smp=self._mods(buf, slot + 12, 6, self.shared[1].norm1, buf.ctemb),
-                    shared1_ctx=self._mods(buf, slot + 18, 6, self.shared[1].norm1_ctx, buf.ctemb))
-        slot += 24
+        mods_s0 = []
+        for c in range(n_cond):  # shared_expert[0] is modulated by THIS condition's temb, shared_expert[1] by control_temb
+            mods_s0.append((self._mods(buf, slot, 6, self.shared[0].norm1, buf.cdtemb_c[c]),
+                            self._mods(buf, slot + 6, 6, self.shared[0].norm1_ctx, buf.cdtemb_c[c])))
+            slot += 12
+        mods_s1 = (self._mods(buf, slot, 6, self.shared[1].norm1, buf.ctemb),
+                   self._mods(buf, slot + 6, 6, self.shared[1].norm1_ctx, buf.ctemb))
+        slot += 12
         m_out = self._mods(buf, slot, 2, self.norm_out_w, buf.temb)  # AdaLayerNormContinuous: (scale, shift)
 
         # ---- 19 x [base double -> control double -> add] (:1124-1141) ----
@@ -521,8 +550,12 @@ class UniGenFlux(torch.nn.Module):
             self._double_block(buf, w, m_double[i][0], m_double[i][1], x_img, x_txt, x_img, x_txt, buf.rope)
             self._rec(f"double.{i}.base_hidden", x_img); self._rec(f"double.{i}.base_context", x_txt)
             j = int(i / (len(self.double) / n_cd))
-            if route is None:  # first control call: CoMoE pre-stage, control stream := expert_hidden + expert_cond
-                route = self._prestage(buf, B, N, T, x_img, x_txt, cs, pooled, cond_pooled, rts_uniform, mods)
+            if route is None:  # first control call: CoMoE pre-stage, control stream := sum_c (expert_hidden + expert_cond)
+                ops.gemm(x_txt, self.control_context_embedder_w[0], out=buf.CENC, bias=self.control_context_embedder_w[1], variant=gv)
+                for c in range(n_cond):
+                    route = self._prestage(buf, B, N, T, x_img, cs[c], pooled, cond_pooled[c], rts_uniform[c], mods_s0[c],
+                                           mods_s1, c, txt_ids, img_ids, condition_ids[c])
+                self._rec("moe.ctrl_in", buf.CIN)
                 ctrl_in = buf.CIN
             else:               # later calls: the control block reads the base stream
                 ctrl_in = x_img
@@ -555,6 +588,13 @@ class UniGenFlux(torch.nn.Module):
         add_losses = dict(moe_loss=route["l_aux"][0] * 0.1)
         add_outputs = dict(expert_counts=route["exp_counts"])
         return buf.OUT, add_losses, add_outputs
+
+
+class MultiCondtionUniGenFlux(UniGenFlux):
+    """Reference `MultiCondtionUniGenFlux` (src/UniGenTransformer.py:1274-1450, spelling kept): `condition_hidden_states`,
+    `condition_pooled_projections`, `condition_ids` (and the optional `rts_uniform`) are LISTS with one entry per condition;
+    the CoMoE pre-stage runs once per condition, the control stream and condition_temb are summed, and moe_loss /
+    expert_counts are those of the last condition. The base class already implements the list form."""
 
 
 def canonical_control_params() -> Dict[str, Any]:
