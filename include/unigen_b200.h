@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define UG_ABI_VERSION 1
+#define UG_ABI_VERSION 2
 
 typedef enum {
   UG_OK = 0,
@@ -54,6 +54,7 @@ void ug_reset_launch_count(void);
  * ---------------------------------------------------------------------------------------------------- */
 #define UG_ACT_NONE 0
 #define UG_ACT_GELU_TANH 1
+#define UG_MAX_SEGMENTS 8
 
 typedef struct ug_gemm_args {
   const void* a;          /* bf16 */
@@ -80,9 +81,33 @@ typedef struct ug_gemm_args {
   int64_t res_batch_stride;
   int32_t variant;        /* 0 = auto; 1 = 1-CTA 128x256; 2 = 2-CTA 256x256 pair; 3 = 1-CTA 128x128 */
   int32_t reserved;
+  /* Switched low-rank (LoRA) update fused into the epilogue — the `enable_lora(...)` context of the reference
+   * (src/lora_switching_module.py:11-39; call sites UniCombineTransformerBlock.pyc L22,81,121,130,222,229,251,261,283,287)
+   * expressed as data: rows [lora_seg_bounds[i], lora_seg_bounds[i+1]) of every batch use adapter group
+   * lora_seg_group[i] (-1 = no adapter active on that segment):
+   *     acc[r, c] += sum_j lora_t[r, (c / lora_block_n) * lora_rank + j] * lora_b[g(r)][c][j]
+   * lora_t = x @ A_g^T from ug_lora_down (fp32); lora_b = B_g pre-multiplied by PEFT `scaling` (bf16 [groups, n, rank]);
+   * lora_block_n = width of one sub-linear of a fused projection (D for to_q|to_k|to_v), 0 = n. lora_t NULL = off. */
+  const float* lora_t;
+  int64_t lora_t_row_stride;
+  int64_t lora_t_batch_stride;
+  const void* lora_b;
+  int32_t lora_rank;      /* 4, 8, 12 or 16 */
+  int32_t lora_block_n;
+  int32_t lora_nseg;
+  int32_t lora_seg_bounds[UG_MAX_SEGMENTS + 1];
+  int32_t lora_seg_group[UG_MAX_SEGMENTS];
 } ug_gemm_args;
 
 int ug_gemm_bf16(const ug_gemm_args* args, void* stream);
+
+/* LoRA down-projection for ug_gemm_bf16's fused update: t[b, r, :] = x[b, r, :] @ A[g(r)]^T  (fp32 out).
+ * a_stack: bf16 [groups, rank_total, k] (rank_total = n_sub_linears * rank for a fused projection); rows whose
+ * segment has group -1 get zeros. peft 0.15 lora.Linear: lora_A. */
+int ug_lora_down(const void* x, int64_t x_row_stride, int64_t x_batch_stride, const void* a_stack, float* t,
+                 int64_t t_row_stride, int64_t t_batch_stride, int32_t batch, int32_t rows, int32_t k,
+                 int32_t rank_total, int32_t nseg, const int32_t* seg_bounds_host, const int32_t* seg_group_host,
+                 void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Joint attention (tcgen05 / TMEM / TMA), softmax(Q K^T * scale + mask) V per head, non-causal.
@@ -94,7 +119,6 @@ int ug_gemm_bf16(const ug_gemm_args* args, void* stream);
  * attends keys of segment j iff bit j of seg_visible[i] is set. n_seg = 0 means full attention.
  * seg_bounds / seg_visible are HOST pointers (copied into the launch parameters).
  * ---------------------------------------------------------------------------------------------------- */
-#define UG_MAX_SEGMENTS 8
 typedef struct ug_attn_args {
   const void* q;
   const void* k;

@@ -698,3 +698,167 @@ def make_multi_inputs(cfg: FluxConfig, height: int, width: int, condition_types=
     base["condition_ids"] = [condition_ids(t, height, width)[0] for t in condition_types]
     base["rts_uniform"] = [torch.rand(batch * N, cfg.expert_nums, generator=gen) for _ in condition_types]
     return base
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# P-variant (predecessor bytecode): LoRA-switched joint blocks where the condition tokens run through every block
+# (UniCombineTransformerBlock.pyc attn_forward L9-136, block_forward L140-236,
+# single_block_forward L239-295; UniCombineTransformer2DModel.pyc forward L53-211).  State dict = diffusers Flux names
+# + PEFT names `<linear>.lora_A.<adapter>.weight` [r, in], `<linear>.lora_B.<adapter>.weight` [out, r].
+# ------------------------------------------------------------------------------------------------------------------
+PV_LORA_DOUBLE = ("norm1.linear", "attn.to_q", "attn.to_k", "attn.to_v", "attn.to_out.0", "ff.net.2")
+PV_LORA_SINGLE = ("norm.linear", "proj_mlp", "proj_out", "attn.to_q", "attn.to_k", "attn.to_v")
+
+
+def pv_lora_targets(cfg: FluxConfig) -> List[str]:
+    names = ["x_embedder"]
+    names += [f"transformer_blocks.{i}.{n}" for i in range(cfg.num_layers) for n in PV_LORA_DOUBLE]
+    names += [f"single_transformer_blocks.{i}.{n}" for i in range(cfg.num_single_layers) for n in PV_LORA_SINGLE]
+    return names
+
+
+def init_pvariant_state_dict(cfg: FluxConfig, adapters: List[str], rank: int = 4, seed: int = 0) -> Dict[str, Tensor]:
+    """Base Flux weights + one LoRA pair per adapter on every switched linear (lora_B is NOT zero-initialised so the
+    adapters are visible to parity)."""
+    gen = torch.Generator().manual_seed(seed)
+    D, dh = cfg.inner_dim, cfg.attention_head_dim
+    sd: Dict[str, Tensor] = {}
+    _lin(sd, "x_embedder", D, cfg.in_channels, gen)
+    _lin(sd, "context_embedder", D, cfg.joint_attention_dim, gen)
+    _time_text(sd, "time_text_embed", D, cfg.pooled_projection_dim, gen, cfg.guidance_embeds)
+    for i in range(cfg.num_layers):
+        _double_block(sd, f"transformer_blocks.{i}", D, dh, gen)
+    for i in range(cfg.num_single_layers):
+        _single_block(sd, f"single_transformer_blocks.{i}", D, dh, gen)
+    _lin(sd, "norm_out.linear", 2 * D, D, gen)
+    _lin(sd, "proj_out", cfg.in_channels, D, gen)
+    for name in pv_lora_targets(cfg):
+        out_f, in_f = sd[name + ".weight"].shape
+        for a in adapters:
+            sd[f"{name}.lora_A.{a}.weight"] = torch.randn(rank, in_f, generator=gen) / math.sqrt(in_f)
+            sd[f"{name}.lora_B.{a}.weight"] = torch.randn(out_f, rank, generator=gen) * (0.5 / math.sqrt(rank))
+    return sd
+
+
+class PVariantOracle:
+    """Functional restatement of the predecessor's UniCombineTransformer2DModel forward with `enable_lora` switching.
+    adapters: every adapter loaded on the model; condition_types: the adapter named after each condition;
+    den = adapters - condition_types act on the text/image rows. scaling[a] = lora_alpha/r (1.0 when alpha == r)."""
+
+    def __init__(self, cfg: FluxConfig, sd: Dict[str, Tensor], adapters: List[str], scaling: Optional[Dict[str, float]] = None,
+                 strict_mask: bool = False):
+        self.cfg, self.sd, self.adapters = cfg, sd, list(adapters)
+        self.scaling = scaling or {a: 1.0 for a in adapters}
+        self.strict_mask = strict_mask
+        self.trace: Dict[str, Tensor] = {}
+        self.record = False
+
+    def _rec(self, k, v):
+        if self.record:
+            self.trace[k] = v.detach().clone()
+
+    def lin(self, name: str, x: Tensor, active: List[str]) -> Tensor:
+        """peft lora.Linear.forward under `enable_lora([module], active)`: adapters outside `active` have scale 0."""
+        y = F.linear(x, self.sd[name + ".weight"], self.sd.get(name + ".bias"))
+        for a in active:
+            ka = f"{name}.lora_A.{a}.weight"
+            if ka in self.sd:
+                y = y + F.linear(F.linear(x, self.sd[ka]), self.sd[f"{name}.lora_B.{a}.weight"]) * self.scaling[a]
+        return y
+
+    def forward(self, hidden_states, condition_latents, condition_ids, condition_types, encoder_hidden_states,
+                pooled_projections, timestep, img_ids, txt_ids, c_t: float = 0.0):
+        cfg, sd = self.cfg, self.sd
+        H = cfg.num_attention_heads
+        den = [a for a in self.adapters if a not in condition_types]
+        sets = [[t] for t in condition_types]
+        n = len(condition_types)
+        # 2DModel L92-99: x_embedder under enable_lora per segment
+        h = self.lin("x_embedder", hidden_states, den)
+        conds = [self.lin("x_embedder", c, sets[i]) for i, c in enumerate(condition_latents)]
+        timestep = timestep.to(h.dtype) * 1000
+        temb = combined_timestep_text_embed(sd, "time_text_embed", timestep, pooled_projections)
+        cond_temb = combined_timestep_text_embed(sd, "time_text_embed", torch.ones_like(timestep) * c_t * 1000,
+                                                 pooled_projections)  # L118-121
+        enc = linear(sd, "context_embedder", encoder_hidden_states)
+        rope = flux_pos_embed(torch.cat([txt_ids, img_ids], 0), cfg.axes_dims_rope, cfg.theta)
+        cond_ropes = [flux_pos_embed(ci, cfg.axes_dims_rope, cfg.theta) for ci in condition_ids]
+        T, N = enc.shape[1], h.shape[1]
+        bounds = [0, T, T + N]
+        for c in conds:
+            bounds.append(bounds[-1] + c.shape[1])
+        mask = segment_mask(bounds, pvariant_visibility(n, strict=self.strict_mask))
+        rope_all = (torch.cat([rope[0]] + [r[0] for r in cond_ropes], 0), torch.cat([rope[1]] + [r[1] for r in cond_ropes], 0))
+
+        def attention(q_segs, k_segs, v_segs):
+            """Each query segment attends the keys its visibility row allows == one masked SDPA over the joint sequence
+            (pyc L98-110: main queries vs [txt|img|c_1..c_n]; c_i queries vs [txt|img|c_i])."""
+            Q, K, V = torch.cat(q_segs, 2), torch.cat(k_segs, 2), torch.cat(v_segs, 2)
+            Q, K = apply_rotary_emb(Q, rope_all), apply_rotary_emb(K, rope_all)
+            O = sdpa(Q, K, V, mask)
+            B, _, S, dh = O.shape
+            return O.transpose(1, 2).reshape(B, S, H * dh)
+
+        for i in range(cfg.num_layers):  # ---- block_forward (pyc L140-236) ----
+            p = f"transformer_blocks.{i}"
+            e = self.lin(p + ".norm1.linear", F.silu(temb), den).chunk(6, dim=1)
+            ec = [self.lin(p + ".norm1.linear", F.silu(cond_temb), s).chunk(6, dim=1) for s in sets]
+            et = linear(sd, p + ".norm1_context.linear", F.silu(temb)).chunk(6, dim=1)
+            nh = layer_norm(h) * (1 + e[1][:, None]) + e[0][:, None]
+            nt = layer_norm(enc) * (1 + et[1][:, None]) + et[0][:, None]
+            ncs = [layer_norm(c) * (1 + ec[j][1][:, None]) + ec[j][0][:, None] for j, c in enumerate(conds)]
+            a = p + ".attn"
+            hd = lambda x: _heads(x, H)  # noqa: E731
+            q = [rms_norm(hd(linear(sd, a + ".add_q_proj", nt)), sd[a + ".norm_added_q.weight"]),
+                 rms_norm(hd(self.lin(a + ".to_q", nh, den)), sd[a + ".norm_q.weight"])]
+            k = [rms_norm(hd(linear(sd, a + ".add_k_proj", nt)), sd[a + ".norm_added_k.weight"]),
+                 rms_norm(hd(self.lin(a + ".to_k", nh, den)), sd[a + ".norm_k.weight"])]
+            v = [hd(linear(sd, a + ".add_v_proj", nt)), hd(self.lin(a + ".to_v", nh, den))]
+            for j, nc in enumerate(ncs):  # same norm_q / norm_k weights for every segment (L34-37, L89-92)
+                q.append(rms_norm(hd(self.lin(a + ".to_q", nc, sets[j])), sd[a + ".norm_q.weight"]))
+                k.append(rms_norm(hd(self.lin(a + ".to_k", nc, sets[j])), sd[a + ".norm_k.weight"]))
+                v.append(hd(self.lin(a + ".to_v", nc, sets[j])))
+            O = attention(q, k, v)
+            ot, oh = O[:, :T], O[:, T:T + N]
+            h = h + e[2][:, None] * self.lin(a + ".to_out.0", oh, den)
+            enc = enc + et[2][:, None] * linear(sd, a + ".to_add_out", ot)
+            for j in range(n):
+                oc = O[:, bounds[2 + j]:bounds[3 + j]]
+                conds[j] = conds[j] + ec[j][2][:, None] * self.lin(a + ".to_out.0", oc, sets[j])
+            # feed-forward: ff.net.2 is the switched linear (L222-230)
+            def ff(x, sh, sc, gate, active):
+                y = gelu_tanh(linear(sd, p + ".ff.net.0.proj", layer_norm(x) * (1 + sc[:, None]) + sh[:, None]))
+                return x + gate[:, None] * self.lin(p + ".ff.net.2", y, active)
+            h = ff(h, e[3], e[4], e[5], den)
+            enc = enc + et[5][:, None] * feed_forward(sd, p + ".ff_context", layer_norm(enc) * (1 + et[4][:, None]) + et[3][:, None])
+            conds = [ff(c, ec[j][3], ec[j][4], ec[j][5], sets[j]) for j, c in enumerate(conds)]
+            self._rec(f"double.{i}.hidden", h); self._rec(f"double.{i}.context", enc)
+            for j, c in enumerate(conds):
+                self._rec(f"double.{i}.cond{j}", c)
+
+        x = torch.cat([enc, h], dim=1)  # 2DModel L176
+        for i in range(cfg.num_single_layers):  # ---- single_block_forward (pyc L239-295) ----
+            p = f"single_transformer_blocks.{i}"
+            e = self.lin(p + ".norm.linear", F.silu(temb), den).chunk(3, dim=1)
+            ec = [self.lin(p + ".norm.linear", F.silu(cond_temb), s).chunk(3, dim=1) for s in sets]
+            nx = layer_norm(x) * (1 + e[1][:, None]) + e[0][:, None]
+            ncs = [layer_norm(c) * (1 + ec[j][1][:, None]) + ec[j][0][:, None] for j, c in enumerate(conds)]
+            a = p + ".attn"
+            hd = lambda t_: _heads(t_, H)  # noqa: E731
+            segs = [(nx, den)] + [(nc, sets[j]) for j, nc in enumerate(ncs)]
+            q = [rms_norm(hd(self.lin(a + ".to_q", s_, act)), sd[a + ".norm_q.weight"]) for s_, act in segs]
+            k = [rms_norm(hd(self.lin(a + ".to_k", s_, act)), sd[a + ".norm_k.weight"]) for s_, act in segs]
+            v = [hd(self.lin(a + ".to_v", s_, act)) for s_, act in segs]
+            O = attention(q, k, v)
+            mlps = [gelu_tanh(self.lin(p + ".proj_mlp", s_, act)) for s_, act in segs]
+            x = x + e[2][:, None] * self.lin(p + ".proj_out", torch.cat([O[:, :T + N], mlps[0]], 2), den)
+            for j in range(n):
+                oc = O[:, bounds[2 + j]:bounds[3 + j]]
+                conds[j] = conds[j] + ec[j][2][:, None] * self.lin(p + ".proj_out", torch.cat([oc, mlps[1 + j]], 2), sets[j])
+            self._rec(f"single.{i}.hidden", x)
+            for j, c in enumerate(conds):
+                self._rec(f"single.{i}.cond{j}", c)
+        h = x[:, T:]
+        out = linear(sd, "proj_out", ada_layer_norm_continuous(sd, "norm_out", h, temb))
+        self._rec("velocity", out)
+        return out

@@ -28,6 +28,9 @@ class GemmArgs(C.Structure):
         ("alpha", C.c_float), ("act", C.c_int32),
         ("residual", C.c_void_p), ("res_row_stride", C.c_int64), ("res_batch_stride", C.c_int64),
         ("variant", C.c_int32), ("reserved", C.c_int32),
+        ("lora_t", C.c_void_p), ("lora_t_row_stride", C.c_int64), ("lora_t_batch_stride", C.c_int64),
+        ("lora_b", C.c_void_p), ("lora_rank", C.c_int32), ("lora_block_n", C.c_int32), ("lora_nseg", C.c_int32),
+        ("lora_seg_bounds", C.c_int32 * (UG_MAX_SEGMENTS + 1)), ("lora_seg_group", C.c_int32 * UG_MAX_SEGMENTS),
     ]
 
 
@@ -54,6 +57,8 @@ SIGNATURES = {
     "ug_launch_count": (C.c_int64, []),
     "ug_reset_launch_count": (None, []),
     "ug_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _VP]),
+    "ug_lora_down": (C.c_int, [_VP, _I64, _I64, _VP, _VP, _I64, _I64, _I32, _I32, _I32, _I32, _I32,
+                               C.POINTER(C.c_int32), C.POINTER(C.c_int32), _VP]),
     "ug_attention_bf16": (C.c_int, [C.POINTER(AttnArgs), _VP]),
     "ug_expand_segment_mask": (C.c_int, [_I32, _I32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), _VP, _VP]),
     "ug_ln_modulate": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _I64, _VP, _VP, _I64, _I32, _I32, _I32, _F32, _VP]),

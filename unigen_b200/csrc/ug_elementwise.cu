@@ -424,3 +424,76 @@ extern "C" int ug_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void*
   UG_CHECK_LAUNCH("cast_bf16_to_f32");
   return UG_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// LoRA down-projection t[b, r, :] = x[b, r, :] @ A[g(r)]^T (fp32), the skinny half of the switched low-rank update
+// whose up-projection is fused into the GEMM epilogue.  One warp per row, 4 outputs per pass.
+// ---------------------------------------------------------------------------------------------------
+namespace ug {
+struct LoraSegs {
+  int nseg;
+  int bounds[UG_MAX_SEGMENTS + 1];
+  int group[UG_MAX_SEGMENTS];
+};
+__global__ void __launch_bounds__(256) lora_down_kernel(const __nv_bfloat16* __restrict__ x, long long x_rs, long long x_bs,
+                                                        const __nv_bfloat16* __restrict__ a, float* __restrict__ t,
+                                                        long long t_rs, long long t_bs, int batch, int rows, int k,
+                                                        int rtot, LoraSegs segs) {
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp_global >= batch * rows) return;
+  const int b = warp_global / rows, r = warp_global % rows;
+  int g = -1;
+  for (int s = 0; s < segs.nseg; ++s)
+    if (r >= segs.bounds[s] && r < segs.bounds[s + 1]) g = segs.group[s];
+  float* tp = t + (long long)b * t_bs + (long long)r * t_rs;
+  if (g < 0) {
+    for (int j = lane; j < rtot; j += 32) tp[j] = 0.f;
+    return;
+  }
+  const __nv_bfloat16* xr = x + (long long)b * x_bs + (long long)r * x_rs;
+  const __nv_bfloat16* ag = a + (long long)g * rtot * k;
+  for (int j0 = 0; j0 < rtot; j0 += 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int kk = lane * 8; kk < k; kk += 256) {
+      float xf[8];
+      unpack8(*reinterpret_cast<const uint4*>(xr + kk), xf);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j0 + j < rtot) {
+          float af[8];
+          unpack8(*reinterpret_cast<const uint4*>(ag + (long long)(j0 + j) * k + kk), af);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[j] += xf[i] * af[i];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j0 + j < rtot) tp[j0 + j] = acc[j];
+    }
+  }
+}
+}  // namespace ug
+
+extern "C" int ug_lora_down(const void* x, int64_t x_rs, int64_t x_bs, const void* a_stack, float* t, int64_t t_rs,
+                            int64_t t_bs, int32_t batch, int32_t rows, int32_t k, int32_t rank_total, int32_t nseg,
+                            const int32_t* seg_bounds, const int32_t* seg_group, void* stream) {
+  UG_CHECK_ARG(x && a_stack && t && seg_bounds && seg_group, "lora_down: null pointer");
+  UG_CHECK_ARG(batch >= 1 && rows >= 1 && k >= 8 && k % 8 == 0 && rank_total >= 1, "lora_down: bad shape");
+  UG_CHECK_ARG(nseg >= 1 && nseg <= UG_MAX_SEGMENTS, "lora_down: nseg %d out of range", nseg);
+  UG_CHECK_ARG(x_rs % 8 == 0 && x_bs % 8 == 0 && aligned16(x) && aligned16(a_stack), "lora_down: alignment");
+  ug::LoraSegs segs;
+  segs.nseg = nseg;
+  for (int i = 0; i <= UG_MAX_SEGMENTS; ++i) segs.bounds[i] = i <= nseg ? seg_bounds[i] : rows;
+  for (int i = 0; i < UG_MAX_SEGMENTS; ++i) segs.group[i] = i < nseg ? seg_group[i] : -1;
+  const long long warps = (long long)batch * rows;
+  const int grid = (int)((warps * 32 + 255) / 256);
+  ug::lora_down_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const __nv_bfloat16*)x, x_rs, x_bs, (const __nv_bfloat16*)a_stack, t, t_rs, t_bs, batch, rows, k, rank_total, segs);
+  UG_CHECK_LAUNCH("lora_down");
+  return UG_OK;
+}

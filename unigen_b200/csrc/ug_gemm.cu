@@ -27,6 +27,13 @@ struct GemmParams {
   const __nv_bfloat16* res;
   long long res_rs, res_bs;
   int w_batched;
+  // grouped low-rank (LoRA) update, switched per row segment:  acc[r, c] += sum_j t[r, blk(c)*R + j] * Bl[g(r)][c][j]
+  const float* lora_t;
+  long long lora_t_rs, lora_t_bs;
+  const __nv_bfloat16* lora_b;
+  int lora_r, lora_block_n, lora_nseg;
+  int lora_bounds[UG_MAX_SEGMENTS + 1];
+  int lora_group[UG_MAX_SEGMENTS];
 };
 
 template <int kCta, int BN, int kStages>
@@ -44,9 +51,32 @@ struct GemmCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], int b, int r, int col0) {
+// LoRA group of row r (-1: no adapter on this row segment)
+__device__ __forceinline__ int lora_group_of(const GemmParams& p, int r) {
+  int g = -1;
+  for (int s = 0; s < p.lora_nseg; ++s)
+    if (r >= p.lora_bounds[s] && r < p.lora_bounds[s + 1]) g = p.lora_group[s];
+  return g;
+}
+
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], int b, int r, int col0,
+                                               int lora_g) {
   const long long c_off = (long long)b * p.c_bs + (long long)r * p.c_rs;
   const long long r_off = (long long)b * p.res_bs + (long long)r * p.res_rs;
+  // low-rank down-projection of this row for the sub-linear (fused q|k|v ...) the 32-column chunk belongs to
+  float lt[16];
+  const __nv_bfloat16* lb = nullptr;
+  if (lora_g >= 0) {
+    const float* tp = p.lora_t + (long long)b * p.lora_t_bs + (long long)r * p.lora_t_rs + (col0 / p.lora_block_n) * p.lora_r;
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      if (i < p.lora_r) {
+        const float4 t4 = *reinterpret_cast<const float4*>(tp + i);
+        lt[i] = t4.x; lt[i + 1] = t4.y; lt[i + 2] = t4.z; lt[i + 3] = t4.w;
+      }
+    }
+    lb = p.lora_b + ((long long)lora_g * p.n) * p.lora_r;
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int c = col0 + 8 * j;
@@ -54,6 +84,22 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     float x[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[8 * j + i]);
+    if (lb) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat16* bp = lb + (long long)(c + i) * p.lora_r;
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; q += 4) {
+          if (q < p.lora_r) {
+            const uint2 u = *reinterpret_cast<const uint2*>(bp + q);
+            const float2 b0 = unpack_bf16x2(u.x), b1 = unpack_bf16x2(u.y);
+            acc += lt[q] * b0.x + lt[q + 1] * b0.y + lt[q + 2] * b1.x + lt[q + 3] * b1.y;
+          }
+        }
+        x[i] += acc;
+      }
+    }
     if (p.bias) {
       uint4 bv = *reinterpret_cast<const uint4*>(p.bias + (long long)b * p.bias_bs + c);
       float2 f0 = unpack_bf16x2(bv.x), f1 = unpack_bf16x2(bv.y), f2 = unpack_bf16x2(bv.z), f3 = unpack_bf16x2(bv.w);
@@ -212,6 +258,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+      const int lora_g = p.lora_t ? lora_group_of(p, r) : -1;
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         uint32_t v[32];
@@ -227,7 +274,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
         }
         const int col0 = n0 + ch * 32;
-        if (r < p.rows && col0 < p.n) epilogue_chunk(p, v, b, r, col0);
+        if (r < p.rows && col0 < p.n) epilogue_chunk(p, v, b, r, col0, lora_g);
       }
     }
   }
@@ -283,6 +330,11 @@ static int launch_gemm(const ug_gemm_args& a, cudaStream_t stream) {
   p.alpha = a.alpha; p.act = a.act;
   p.res = (const __nv_bfloat16*)a.residual; p.res_rs = a.res_row_stride; p.res_bs = a.res_batch_stride;
   p.w_batched = w_batched ? 1 : 0;
+  p.lora_t = a.lora_t; p.lora_t_rs = a.lora_t_row_stride; p.lora_t_bs = a.lora_t_batch_stride;
+  p.lora_b = (const __nv_bfloat16*)a.lora_b;
+  p.lora_r = a.lora_rank; p.lora_block_n = a.lora_block_n > 0 ? a.lora_block_n : a.n; p.lora_nseg = a.lora_nseg;
+  for (int i = 0; i <= UG_MAX_SEGMENTS; ++i) p.lora_bounds[i] = i <= a.lora_nseg ? a.lora_seg_bounds[i] : a.rows;
+  for (int i = 0; i < UG_MAX_SEGMENTS; ++i) p.lora_group[i] = i < a.lora_nseg ? a.lora_seg_group[i] : -1;
 
   const int sms = num_sms();
   int units = kCta == 2 ? sms / 2 : sms;
@@ -329,6 +381,15 @@ extern "C" int ug_gemm_bf16(const ug_gemm_args* args, void* stream) {
   if (a.bias) UG_CHECK_ARG((reinterpret_cast<uintptr_t>(a.bias) & 15) == 0 && a.bias_batch_stride % 8 == 0, "gemm: bias alignment");
   if (a.gate) UG_CHECK_ARG((reinterpret_cast<uintptr_t>(a.gate) & 15) == 0 && a.gate_batch_stride % 4 == 0, "gemm: gate alignment");
   UG_CHECK_ARG(a.act == UG_ACT_NONE || a.act == UG_ACT_GELU_TANH, "gemm: unknown activation %d", a.act);
+  if (a.lora_t) {
+    UG_CHECK_ARG(a.lora_b && (a.lora_rank == 4 || a.lora_rank == 8 || a.lora_rank == 12 || a.lora_rank == 16),
+                 "gemm: LoRA needs lora_b and a rank in {4, 8, 12, 16} (got %d)", a.lora_rank);
+    UG_CHECK_ARG(a.lora_nseg >= 1 && a.lora_nseg <= UG_MAX_SEGMENTS, "gemm: lora_nseg %d out of range", a.lora_nseg);
+    UG_CHECK_ARG((a.lora_block_n <= 0 ? a.n : a.lora_block_n) % 32 == 0, "gemm: lora_block_n must be a multiple of 32");
+    UG_CHECK_ARG(a.lora_t_row_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(a.lora_t) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(a.lora_b) & 7) == 0,
+                 "gemm: LoRA operand alignment");
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int variant = a.variant;
   if (variant == 0) {

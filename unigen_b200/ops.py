@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import UG_ACT_GELU_TANH, UG_ACT_NONE, AttnArgs, GemmArgs, UgError, check
 
-__all__ = ["gemm", "attention", "expand_segment_mask", "ln_modulate", "qk_rmsnorm_rope", "rope_table", "gemv",
+__all__ = ["gemm", "lora_down", "attention", "expand_segment_mask", "ln_modulate", "qk_rmsnorm_rope", "rope_table", "gemv",
            "timestep_embedding", "add", "copy", "to_bf16", "to_f32", "moe_route", "moe_gather_modulate",
            "moe_combine", "launch_count", "reset_launch_count", "UG_ACT_NONE", "UG_ACT_GELU_TANH", "UgError"]
 
@@ -78,8 +78,10 @@ def device_check() -> None:
 # ------------------------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
          gate: Optional[torch.Tensor] = None, alpha: float = 1.0, act: int = UG_ACT_NONE,
-         residual: Optional[torch.Tensor] = None, variant: int = 0) -> torch.Tensor:
-    """out[b,r,:] = residual + alpha * gate[b,:] * act(a[b,r,:] @ w^T + bias).  a: [B,R,K] view, w: [N,K] or [B,N,K]."""
+         residual: Optional[torch.Tensor] = None, variant: int = 0, lora: Optional[dict] = None) -> torch.Tensor:
+    """out[b,r,:] = residual + alpha * gate[b,:] * act(a[b,r,:] @ w^T + bias (+ switched LoRA update)).
+    a: [B,R,K] view, w: [N,K] or [B,N,K]. lora = dict(t=fp32 [B,R,n_blocks*rank] from lora_down, b=bf16 [groups,N,rank]
+    (pre-scaled), rank, block_n, seg_bounds, seg_group) applies adapter group seg_group[i] to rows of segment i."""
     a = _view3(_dev(a, "gemm.a", BF16), "gemm.a")
     _dev(w, "gemm.w", BF16)
     B, R, K = a.shape
@@ -109,7 +111,41 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, b
         r3 = _view3(_dev(residual, "gemm.residual", BF16), "gemm.residual")
         g.residual, g.res_row_stride, g.res_batch_stride = r3.data_ptr(), r3.stride(1), r3.stride(0)
     g.variant = variant
+    if lora is not None:
+        t, lb = lora["t"], lora["b"]
+        _dev(t, "gemm.lora_t", torch.float32), _dev(lb, "gemm.lora_b", BF16)
+        t3 = t if t.dim() == 3 else t.unsqueeze(0)
+        if not lb.is_contiguous() or t3.stride(2) != 1:
+            raise UgError("gemm: lora_b must be contiguous [groups, N, rank]; lora_t needs a unit inner stride")
+        g.lora_t, g.lora_t_row_stride, g.lora_t_batch_stride = t3.data_ptr(), t3.stride(1), t3.stride(0)
+        g.lora_b, g.lora_rank, g.lora_block_n = lb.data_ptr(), int(lora["rank"]), int(lora.get("block_n", 0))
+        sb, sg = lora["seg_bounds"], lora["seg_group"]
+        g.lora_nseg = len(sg)
+        for i, v in enumerate(sb):
+            g.lora_seg_bounds[i] = int(v)
+        for i, v in enumerate(sg):
+            g.lora_seg_group[i] = int(v)
     check(_lib.load().ug_gemm_bf16(C.byref(g), _stream()), "ug_gemm_bf16")
+    return out
+
+
+def lora_down(x: torch.Tensor, a_stack: torch.Tensor, seg_bounds: Sequence[int], seg_group: Sequence[int],
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """t[b,r,:] = x[b,r,:] @ a_stack[g(r)]^T (fp32). a_stack: bf16 [groups, rank_total, K]; rows of a segment whose group
+    is -1 get zeros (peft lora_A of the adapters `enable_lora` leaves active on that segment)."""
+    x3 = _view3(_dev(x, "lora_down.x", BF16), "lora_down.x")
+    _dev(a_stack, "lora_down.a", BF16)
+    B, R, K = x3.shape
+    G, RT, K2 = a_stack.shape
+    if K2 != K or not a_stack.is_contiguous():
+        raise UgError("lora_down: a_stack must be contiguous [groups, rank_total, K]")
+    if out is None:
+        out = torch.empty(B, R, RT, device=x.device, dtype=torch.float32)
+    n = len(seg_group)
+    sb = (C.c_int32 * (n + 1))(*[int(v) for v in seg_bounds])
+    sg = (C.c_int32 * n)(*[int(v) for v in seg_group])
+    check(_lib.load().ug_lora_down(x3.data_ptr(), x3.stride(1), x3.stride(0), a_stack.data_ptr(), out.data_ptr(),
+                                   out.stride(1), out.stride(0), B, R, K, RT, n, sb, sg, _stream()), "ug_lora_down")
     return out
 
 

@@ -1,0 +1,297 @@
+"""B200-native P-variant: the predecessor's LoRA-switched joint blocks.
+
+Only stale bytecode of this design survives in the reference (`src/__pycache__/UniCombineTransformerBlock.cpython-312.pyc`
+attn_forward L9-136 / block_forward L140-236 / single_block_forward L239-295 and `UniCombineTransformer2DModel...pyc`
+forward L53-211), but it is the one artefact that exercises `enable_lora` (src/lora_switching_module.py) and the
+condition-visibility rule BASELINE.json's north star names.  Here:
+
+  * the joint sequence is one buffer  [ txt | img | c_1 | ... | c_n ]  (text first);
+  * `enable_lora(modules, adapters)` is DATA: per row segment an adapter-group id. Group 0 = the "denoising" adapters
+    (active_adapters minus condition types) stacked into one low-rank pair, group 1+i = the adapter named after
+    condition i. The low-rank update runs inside the main GEMM: `ug_lora_down` (x @ A_g^T, skinny) feeds the fused
+    epilogue of `ug_gemm_bf16` (acc += t . B_g[c], switched per row) — to_q|to_k|to_v are ONE GEMM with three LoRA pairs;
+  * the visibility rule (txt,img -> everything; c_i -> {txt,img,c_i}; or the stricter c_i -> {c_i}) is the segment mask
+    of `ug_attention_bf16`, bit-exactly expandable by `ug_expand_segment_mask`.
+"""
+from __future__ import annotations
+
+import math
+import types
+from typing import Any, Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .model import BF16, FluxArch, _DoubleBlockW, _SingleBlockW, _TimeTextW, _Weights
+from .ops import UG_ACT_GELU_TANH
+
+DOUBLE_LORA = ("norm1.linear", "attn.to_q", "attn.to_k", "attn.to_v", "attn.to_out.0", "ff.net.2")
+SINGLE_LORA = ("norm.linear", "proj_mlp", "proj_out", "attn.to_q", "attn.to_k", "attn.to_v")
+
+
+class _LoraPair:
+    """A [groups, n_sub * R, K] and pre-scaled B [groups, N, R] stacks for one (possibly fused) linear."""
+
+    def __init__(self, device, groups: int, rank: int, k: int, n_each: int, n_sub: int = 1):
+        self.rank, self.n_sub, self.n_each = rank, n_sub, n_each
+        self.a = torch.zeros(groups, n_sub * rank, k, device=device, dtype=BF16)
+        self.b = torch.zeros(groups, n_sub * n_each, rank, device=device, dtype=BF16)
+
+
+class UniCombineFlux(torch.nn.Module):
+    """P-variant denoiser. forward(hidden_states, condition_latents=[...], condition_ids=[...], condition_types=[...],
+    encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, c_t=0) -> velocity (B, N, in_channels)."""
+
+    def __init__(self, arch: Optional[FluxArch] = None, device: Any = "cuda", lora_rank: int = 4, max_conditions: int = 3,
+                 strict_mask: bool = False):
+        super().__init__()
+        self.arch = arch or FluxArch()
+        self.device_ = torch.device(device)
+        if self.device_.type != "cuda":
+            raise ops.UgError("UniCombineFlux (B200-native) needs a CUDA device: the hot path has no CPU fallback")
+        a = self.arch
+        self.inner_dim = D = a.num_attention_heads * a.attention_head_dim
+        dh = a.attention_head_dim
+        ws = self._ws = _Weights(self.device_)
+        self.x_embedder_w = ws.linear("x_embedder", D, a.in_channels)
+        self.context_embedder_w = ws.linear("context_embedder", D, a.joint_attention_dim)
+        self.time_text = _TimeTextW(ws, "time_text_embed", D, a.pooled_projection_dim, a.guidance_embeds)
+        self.double = [_DoubleBlockW(ws, f"transformer_blocks.{i}", D, dh) for i in range(a.num_layers)]
+        self.single = [_SingleBlockW(ws, f"single_transformer_blocks.{i}", D, dh) for i in range(a.num_single_layers)]
+        self.norm_out_w = ws.linear("norm_out.linear", 2 * D, D)
+        self.proj_out_w = ws.linear("proj_out", a.in_channels, D)
+        self.rank = lora_rank
+        self.groups = 1 + max_conditions
+        self.strict_mask = strict_mask
+        self.lora: Dict[str, _LoraPair] = {}
+        self.condition_types: List[str] = []
+        self.trace: Optional[Dict[str, torch.Tensor]] = None
+        self._buf_key = None
+        self.gemm_variant = 0
+        self.attn_variant = 0
+
+    @property
+    def dtype(self):
+        return BF16
+
+    def state_dict(self, *a, **k):
+        return dict(self._ws.views)
+
+    # ---------------------------------------------------------------------------------------------------------
+    def load_state_dict(self, state_dict, adapters: Sequence[str] = (), condition_types: Sequence[str] = (),
+                        scaling: Optional[Dict[str, float]] = None, strict: bool = False):
+        """Base weights under diffusers names + PEFT LoRA weights `<linear>.lora_A/B.<adapter>.weight`. `condition_types`
+        fixes which adapter belongs to which condition slot (group 1+i); every other adapter is a denoising adapter and is
+        stacked into group 0 — exactly the partition `enable_lora` makes at every call site of the predecessor."""
+        a, D = self.arch, self.inner_dim
+        with torch.no_grad():
+            for k, v in state_dict.items():
+                if k in self._ws.views:
+                    self._ws.views[k].copy_(v.to(self.device_, self._ws.views[k].dtype))
+        self.condition_types = list(condition_types)
+        den = [x for x in adapters if x not in condition_types]
+        scaling = scaling or {x: 1.0 for x in adapters}
+        R = max(self.rank * max(len(den), 1), self.rank)
+        if R not in (4, 8, 12, 16):
+            raise ops.UgError(f"stacked LoRA rank {R} not supported by the fused epilogue (4, 8, 12, 16)")
+        group_sets = [den] + [[t] for t in condition_types]
+        if len(group_sets) > self.groups:
+            raise ops.UgError("more conditions than max_conditions")
+
+        def fill(pair: _LoraPair, names: Sequence[str]):
+            for s_i, name in enumerate(names):
+                for g, aset in enumerate(group_sets):
+                    off = 0
+                    for ad in aset:
+                        ka, kb = f"{name}.lora_A.{ad}.weight", f"{name}.lora_B.{ad}.weight"
+                        if ka not in state_dict:
+                            continue
+                        A, Bm = state_dict[ka].float(), state_dict[kb].float() * scaling[ad]
+                        r = A.shape[0]
+                        pair.a[g, s_i * pair.rank + off:s_i * pair.rank + off + r] = A.to(self.device_, BF16)
+                        pair.b[g, s_i * pair.n_each:(s_i + 1) * pair.n_each, off:off + r] = Bm.to(self.device_, BF16)
+                        off += r
+
+        def mk(names, k, n_each):
+            p = _LoraPair(self.device_, self.groups, R, k, n_each, len(names))
+            fill(p, names)
+            return p
+
+        def mk_vec(name, k, n):  # AdaLN linears run as GEMVs: rank padded to a multiple of 8 (GEMV inner-dim granularity)
+            Rp = (R + 7) // 8 * 8
+            p = _LoraPair(self.device_, self.groups, Rp, k, n, 1)
+            fill(p, [name])
+            return p
+
+        L = self.lora = {}
+        L["x_embedder"] = mk(["x_embedder"], a.in_channels, D)
+        for i in range(a.num_layers):
+            p = f"transformer_blocks.{i}"
+            L[p + ".norm1"] = mk_vec(p + ".norm1.linear", D, 6 * D)
+            L[p + ".qkv"] = mk([p + ".attn.to_q", p + ".attn.to_k", p + ".attn.to_v"], D, D)
+            L[p + ".to_out"] = mk([p + ".attn.to_out.0"], D, D)
+            L[p + ".ff2"] = mk([p + ".ff.net.2"], 4 * D, D)
+        for i in range(a.num_single_layers):
+            p = f"single_transformer_blocks.{i}"
+            L[p + ".norm"] = mk_vec(p + ".norm.linear", D, 3 * D)
+            L[p + ".qkv"] = mk([p + ".attn.to_q", p + ".attn.to_k", p + ".attn.to_v"], D, D)
+            L[p + ".mlp"] = mk([p + ".proj_mlp"], D, 4 * D)
+            L[p + ".out"] = mk([p + ".proj_out"], 5 * D, D)
+        self.R = R
+        return types.SimpleNamespace(missing_keys=[], unexpected_keys=[])
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _workspace(self, B, S):
+        key = (B, S)
+        if self._buf_key == key:
+            return self._buf
+        D, dev = self.inner_dim, self.device_
+        z = lambda *s, dt=BF16: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
+        self._buf = types.SimpleNamespace(
+            X=z(B, S, D), NX=z(B, S, D), QKV=z(B, S, 3 * D), AO=z(B, S, D), FF=z(B, S, 4 * D), CAT=z(B, S, 5 * D),
+            LT=z(B, S, 3 * self.R, dt=torch.float32), temb=z(B, D, dt=torch.float32), ctemb=z(B, D, dt=torch.float32),
+            tmp=z(B, D, dt=torch.float32), ltmp=z(B, 16, dt=torch.float32), NO=None,
+            rope=z(S, self.arch.attention_head_dim, dt=torch.float32))
+        self._buf_key = key
+        return self._buf
+
+    def _rec(self, name, t):
+        if self.trace is not None:
+            self.trace[name] = t.detach().float().clone()
+
+    def _time_text(self, t_emb, pooled, out, tmp):
+        w = self.time_text
+        ops.gemv(t_emb, w.t1[0], w.t1[1], out=tmp, silu_out=True)
+        ops.gemv(tmp, w.t2[0], w.t2[1], out=out)
+        ops.gemv(pooled, w.p1[0], w.p1[1], out=tmp, silu_out=True)
+        ops.gemv(tmp, w.p2[0], w.p2[1], out=out, accumulate=True)
+
+    def _mod_vectors(self, buf, w, lora: Optional[_LoraPair], temb, group: int, n_chunks: int):
+        """AdaLN `linear(silu(temb))` with the LoRA of `group` (enable_lora on norm1.linear / norm.linear)."""
+        D = self.inner_dim
+        out = torch.empty(temb.shape[0], n_chunks * D, device=self.device_, dtype=torch.float32)
+        ops.gemv(temb, w[0], w[1], out=out, silu_in=True)
+        if lora is not None and group >= 0:
+            rp = lora.rank
+            t = buf.ltmp[:, :rp]
+            ops.gemv(temb, lora.a[group], None, out=t, silu_in=True)
+            ops.gemv(t, lora.b[group], None, out=out, accumulate=True)
+        return [out[:, i * D:(i + 1) * D] for i in range(n_chunks)]
+
+    def _lora_gemm(self, buf, x, w, pair: _LoraPair, seg_bounds, seg_group, out, **kw):
+        """Main GEMM with the switched low-rank update fused into its epilogue."""
+        rt = pair.n_sub * pair.rank
+        t = buf.LT[:, :x.shape[1], :rt]
+        ops.lora_down(x, pair.a, seg_bounds, seg_group, out=t)
+        return ops.gemm(x, w[0], out=out, bias=w[1], variant=self.gemm_variant,
+                        lora=dict(t=t, b=pair.b, rank=pair.rank, block_n=pair.n_each, seg_bounds=seg_bounds,
+                                  seg_group=seg_group), **kw)
+
+    # ---------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, hidden_states, condition_latents, condition_ids, condition_types, encoder_hidden_states,
+                pooled_projections, timestep, img_ids, txt_ids, c_t: float = 0.0, **kwargs):
+        a, D = self.arch, self.inner_dim
+        H, dh = a.num_attention_heads, a.attention_head_dim
+        dev = self.device_
+        if list(condition_types) != self.condition_types[:len(condition_types)]:
+            raise ops.UgError(f"condition_types {list(condition_types)} do not match the loaded adapters {self.condition_types}")
+        n = len(condition_latents)
+        B, N, _ = hidden_states.shape
+        T = encoder_hidden_states.shape[1]
+        ncs = [c.shape[1] for c in condition_latents]
+        bounds = [0, T, T + N]
+        for m in ncs:
+            bounds.append(bounds[-1] + m)
+        S = bounds[-1]
+        buf = self._workspace(B, S)
+        f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+        gv = self.gemm_variant
+        seg = lambda i: buf.X[:, bounds[i]:bounds[i + 1]]  # noqa: E731  (0 = txt, 1 = img, 2+j = cond j)
+        # visibility: txt,img -> all ; c_i -> {txt,img,c_i}  (strict: c_i -> {c_i})
+        nseg = 2 + n
+        vis = [(1 << nseg) - 1, (1 << nseg) - 1] + [(1 << (2 + j)) | (0 if self.strict_mask else 0b11) for j in range(n)]
+
+        # ---- embeddings (2DModel L92-99, L112-121, L144-149) ----
+        hs = ops.to_bf16(hidden_states.to(dev).contiguous())
+        es = ops.to_bf16(encoder_hidden_states.to(dev).contiguous())
+        self._lora_gemm(buf, hs, self.x_embedder_w, self.lora["x_embedder"], [0, N], [0], seg(1))
+        for j, c in enumerate(condition_latents):
+            cj = ops.to_bf16(c.to(dev).contiguous())
+            self._lora_gemm(buf, cj, self.x_embedder_w, self.lora["x_embedder"], [0, ncs[j]], [1 + j], seg(2 + j))
+        ops.gemm(es, self.context_embedder_w[0], out=seg(0), bias=self.context_embedder_w[1], variant=gv)
+        pooled = f32(pooled_projections)
+        t1000 = f32(timestep) * 1000.0
+        self._time_text(ops.timestep_embedding(t1000), pooled, buf.temb, buf.tmp)
+        self._time_text(ops.timestep_embedding(torch.ones_like(t1000) * (c_t * 1000.0)), pooled, buf.ctemb, buf.tmp)
+        ids = torch.cat([f32(txt_ids), f32(img_ids)] + [f32(ci) for ci in condition_ids], 0)
+        ops.rope_table(ids, a.axes_dims_rope, a.theta, out=buf.rope)
+
+        img_cond_bounds = [b - T for b in bounds[1:]]          # segments of rows [T, S): img, c_1..c_n
+        img_cond_groups = list(range(0, 1 + n))               # den, c_1..c_n
+        all_bounds = [0, T + N] + bounds[3:]                   # single blocks: [txt|img] share the denoising adapters
+        all_groups = list(range(0, 1 + n))
+
+        for i, w in enumerate(self.double):  # ---- block_forward ----
+            p = f"transformer_blocks.{i}"
+            L = self.lora
+            m_img = self._mod_vectors(buf, w.norm1, L[p + ".norm1"], buf.temb, 0, 6)
+            m_txt = self._mod_vectors(buf, w.norm1_ctx, None, buf.temb, -1, 6)
+            m_c = [self._mod_vectors(buf, w.norm1, L[p + ".norm1"], buf.ctemb, 1 + j, 6) for j in range(n)]
+            mods = [m_txt, m_img] + m_c
+            for s_ in range(nseg):
+                ops.ln_modulate(seg(s_), buf.NX[:, bounds[s_]:bounds[s_ + 1]], mods[s_][0], mods[s_][1])
+            ops.gemm(buf.NX[:, :T], w.add_qkv[0], out=buf.QKV[:, :T], bias=w.add_qkv[1], variant=gv)
+            self._lora_gemm(buf, buf.NX[:, T:], w.qkv, L[p + ".qkv"], img_cond_bounds, img_cond_groups, buf.QKV[:, T:])
+            qk = buf.QKV[:, :, :2 * D]
+            ops.qk_rmsnorm_rope(qk[:, :T], 2 * H, dh, w.rms_ctx, buf.rope[:T], heads_per_weight=H)
+            ops.qk_rmsnorm_rope(qk[:, T:], 2 * H, dh, w.rms, buf.rope[T:], heads_per_weight=H)
+            ops.attention(buf.QKV[:, :, 0:D], buf.QKV[:, :, D:2 * D], buf.QKV[:, :, 2 * D:], buf.AO, H, dh,
+                          seg_bounds=bounds, seg_visible=vis, variant=self.attn_variant)
+            ops.gemm(buf.AO[:, :T], w.to_add_out[0], out=seg(0), bias=w.to_add_out[1], gate=m_txt[2], residual=seg(0), variant=gv)
+            for s_ in range(1, nseg):  # to_out[0] switched per segment, each with its own gate
+                rows = bounds[s_ + 1] - bounds[s_]
+                self._lora_gemm(buf, buf.AO[:, bounds[s_]:bounds[s_ + 1]], w.to_out, L[p + ".to_out"], [0, rows], [s_ - 1],
+                                seg(s_), gate=mods[s_][2], residual=seg(s_))
+            for s_ in range(nseg):
+                ops.ln_modulate(seg(s_), buf.NX[:, bounds[s_]:bounds[s_ + 1]], mods[s_][3], mods[s_][4])
+            ops.gemm(buf.NX[:, :T], w.ffc1[0], out=buf.FF[:, :T], bias=w.ffc1[1], act=UG_ACT_GELU_TANH, variant=gv)
+            ops.gemm(buf.FF[:, :T], w.ffc2[0], out=seg(0), bias=w.ffc2[1], gate=m_txt[5], residual=seg(0), variant=gv)
+            ops.gemm(buf.NX[:, T:], w.ff1[0], out=buf.FF[:, T:], bias=w.ff1[1], act=UG_ACT_GELU_TANH, variant=gv)
+            for s_ in range(1, nseg):
+                rows = bounds[s_ + 1] - bounds[s_]
+                self._lora_gemm(buf, buf.FF[:, bounds[s_]:bounds[s_ + 1]], w.ff2, L[p + ".ff2"], [0, rows], [s_ - 1], seg(s_),
+                                gate=mods[s_][5], residual=seg(s_))
+            self._rec(f"double.{i}.hidden", seg(1)); self._rec(f"double.{i}.context", seg(0))
+            for j in range(n):
+                self._rec(f"double.{i}.cond{j}", seg(2 + j))
+
+        for i, w in enumerate(self.single):  # ---- single_block_forward ----
+            p = f"single_transformer_blocks.{i}"
+            L = self.lora
+            m_x = self._mod_vectors(buf, w.norm, L[p + ".norm"], buf.temb, 0, 3)
+            m_c = [self._mod_vectors(buf, w.norm, L[p + ".norm"], buf.ctemb, 1 + j, 3) for j in range(n)]
+            mods = [m_x] + m_c
+            for s_ in range(len(all_groups)):
+                lo, hi = all_bounds[s_], all_bounds[s_ + 1]
+                ops.ln_modulate(buf.X[:, lo:hi], buf.NX[:, lo:hi], mods[s_][0], mods[s_][1])
+            self._lora_gemm(buf, buf.NX, w.qkv, L[p + ".qkv"], all_bounds, all_groups, buf.QKV)
+            self._lora_gemm(buf, buf.NX, w.mlp, L[p + ".mlp"], all_bounds, all_groups, buf.CAT[:, :, D:], act=UG_ACT_GELU_TANH)
+            ops.qk_rmsnorm_rope(buf.QKV[:, :, :2 * D], 2 * H, dh, w.rms, buf.rope, heads_per_weight=H)
+            ops.attention(buf.QKV[:, :, 0:D], buf.QKV[:, :, D:2 * D], buf.QKV[:, :, 2 * D:], buf.CAT[:, :, :D], H, dh,
+                          seg_bounds=bounds, seg_visible=vis, variant=self.attn_variant)
+            for s_ in range(len(all_groups)):
+                lo, hi = all_bounds[s_], all_bounds[s_ + 1]
+                self._lora_gemm(buf, buf.CAT[:, lo:hi], w.out, L[p + ".out"], [0, hi - lo], [s_], buf.X[:, lo:hi],
+                                gate=mods[s_][2], residual=buf.X[:, lo:hi])
+            self._rec(f"single.{i}.hidden", buf.X[:, :T + N])
+            for j in range(n):
+                self._rec(f"single.{i}.cond{j}", seg(2 + j))
+
+        e = torch.empty(B, 2 * D, device=dev, dtype=torch.float32)
+        ops.gemv(buf.temb, self.norm_out_w[0], self.norm_out_w[1], out=e, silu_in=True)
+        no = torch.empty(B, N, D, device=dev, dtype=BF16)
+        ops.ln_modulate(seg(1), no, e[:, D:], e[:, :D])  # AdaLayerNormContinuous: scale first, then shift
+        out = ops.gemm(no, self.proj_out_w[0], bias=self.proj_out_w[1], variant=gv)
+        self._rec("velocity", out)
+        return out
