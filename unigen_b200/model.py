@@ -312,24 +312,31 @@ class UniGenFlux(torch.nn.Module):
         ops.gemv(temb, w[0], w[1], out=region, silu_in=True)
         return [region[:, i * D:(i + 1) * D] for i in range(n_chunks)]
 
-    def _joint_attention(self, buf, B, n_ctx, n_smp, rms_ctx, rms_smp, rope, out_view=None):
-        """RMSNorm(q,k)+RoPE in place on QKV rows [0, n_ctx+n_smp), then joint attention -> AO (or out_view)."""
+    def _attend(self, buf, S: int, out: torch.Tensor):
+        """Joint attention over rows [0, S) of the fused QKV buffer (q/k already normalised + rotated) -> out [B, S, D].
+        The sequence-parallel subclass replaces this with the Ulysses exchange (parallel.py)."""
+        a, D = self.arch, self.inner_dim
+        ops.attention(buf.QKV[:, :S, 0:D], buf.QKV[:, :S, D:2 * D], buf.QKV[:, :S, 2 * D:3 * D], out, a.num_attention_heads,
+                      a.attention_head_dim, variant=self.attn_variant)
+        return out
+
+    def _joint_attention(self, buf, B, n_ctx, n_smp, rms_ctx, rms_smp, rope):
+        """RMSNorm(q,k)+RoPE in place on QKV rows [0, n_ctx+n_smp), then joint attention -> AO."""
         a = self.arch
         H, dh, D = a.num_attention_heads, a.attention_head_dim, self.inner_dim
         S = n_ctx + n_smp
         qk = buf.QKV[:, :S, :2 * D]
         if n_ctx:
             ops.qk_rmsnorm_rope(qk[:, :n_ctx], 2 * H, dh, rms_ctx, rope[:n_ctx] if rope is not None else None, heads_per_weight=H)
-        ops.qk_rmsnorm_rope(qk[:, n_ctx:], 2 * H, dh, rms_smp, rope[n_ctx:S] if rope is not None else None, heads_per_weight=H)
-        out = buf.AO[:, :S] if out_view is None else out_view
-        ops.attention(buf.QKV[:, :S, 0:D], buf.QKV[:, :S, D:2 * D], buf.QKV[:, :S, 2 * D:3 * D], out, H, dh,
-                      variant=self.attn_variant)
-        return out
+        if n_smp:
+            ops.qk_rmsnorm_rope(qk[:, n_ctx:], 2 * H, dh, rms_smp, rope[n_ctx:S] if rope is not None else None, heads_per_weight=H)
+        return self._attend(buf, S, buf.AO[:, :S])
 
     def _double_block(self, buf, w: _DoubleBlockW, mod_smp, mod_ctx, smp_in, ctx_in, smp_out, ctx_out, rope):
         """diffusers FluxTransformerBlock (SURVEY.md §A.2). smp/ctx = image-role / text-role streams ([B, n, D] views);
         outputs may alias inputs (in-place residual). ctx_out=None skips the context stream's post-attention half —
-        exact whenever the caller discards `encoder_hidden_states` (control blocks, shared_expert[1])."""
+        exact whenever the caller discards `encoder_hidden_states` (control blocks, shared_expert[1]). Either stream may
+        be empty on a sequence-parallel rank."""
         D = self.inner_dim
         B, n_smp, n_ctx = smp_in.shape[0], smp_in.shape[1], ctx_in.shape[1]
         S = n_ctx + n_smp
@@ -337,18 +344,21 @@ class UniGenFlux(torch.nn.Module):
         sh_a, sc_a, g_a, sh_m, sc_m, g_m = mod_smp
         csh_a, csc_a, cg_a, csh_m, csc_m, cg_m = mod_ctx
         nx_c, nx_s = buf.NX[:, :n_ctx], buf.NX[:, n_ctx:S]
-        ops.ln_modulate(ctx_in, nx_c, csh_a, csc_a)
-        ops.ln_modulate(smp_in, nx_s, sh_a, sc_a)
-        ops.gemm(nx_c, w.add_qkv[0], out=buf.QKV[:, :n_ctx], bias=w.add_qkv[1], variant=gv)
-        ops.gemm(nx_s, w.qkv[0], out=buf.QKV[:, n_ctx:S], bias=w.qkv[1], variant=gv)
+        if n_ctx:
+            ops.ln_modulate(ctx_in, nx_c, csh_a, csc_a)
+            ops.gemm(nx_c, w.add_qkv[0], out=buf.QKV[:, :n_ctx], bias=w.add_qkv[1], variant=gv)
+        if n_smp:
+            ops.ln_modulate(smp_in, nx_s, sh_a, sc_a)
+            ops.gemm(nx_s, w.qkv[0], out=buf.QKV[:, n_ctx:S], bias=w.qkv[1], variant=gv)
         ao = self._joint_attention(buf, B, n_ctx, n_smp, w.rms_ctx, w.rms, rope)
-        # h = h + gate_msa * to_out(attn)
-        ops.gemm(ao[:, n_ctx:S], w.to_out[0], out=smp_out, bias=w.to_out[1], gate=g_a, residual=smp_in, variant=gv)
-        # h = h + gate_mlp * ff(LN(h) * (1 + scale_mlp) + shift_mlp)
-        ops.ln_modulate(smp_out, nx_s, sh_m, sc_m)
-        ops.gemm(nx_s, w.ff1[0], out=buf.FF[:, n_ctx:S], bias=w.ff1[1], act=UG_ACT_GELU_TANH, variant=gv)
-        ops.gemm(buf.FF[:, n_ctx:S], w.ff2[0], out=smp_out, bias=w.ff2[1], gate=g_m, residual=smp_out, variant=gv)
-        if ctx_out is not None:
+        if n_smp:
+            # h = h + gate_msa * to_out(attn)
+            ops.gemm(ao[:, n_ctx:S], w.to_out[0], out=smp_out, bias=w.to_out[1], gate=g_a, residual=smp_in, variant=gv)
+            # h = h + gate_mlp * ff(LN(h) * (1 + scale_mlp) + shift_mlp)
+            ops.ln_modulate(smp_out, nx_s, sh_m, sc_m)
+            ops.gemm(nx_s, w.ff1[0], out=buf.FF[:, n_ctx:S], bias=w.ff1[1], act=UG_ACT_GELU_TANH, variant=gv)
+            ops.gemm(buf.FF[:, n_ctx:S], w.ff2[0], out=smp_out, bias=w.ff2[1], gate=g_m, residual=smp_out, variant=gv)
+        if ctx_out is not None and n_ctx:
             ops.gemm(ao[:, :n_ctx], w.to_add_out[0], out=ctx_out, bias=w.to_add_out[1], gate=cg_a, residual=ctx_in, variant=gv)
             ops.ln_modulate(ctx_out, nx_c, csh_m, csc_m)
             ops.gemm(nx_c, w.ffc1[0], out=buf.FF[:, :n_ctx], bias=w.ffc1[1], act=UG_ACT_GELU_TANH, variant=gv)
@@ -361,14 +371,13 @@ class UniGenFlux(torch.nn.Module):
         B, S = x_in.shape[0], x_in.shape[1]
         gv = self.gemm_variant
         shift, scale, gate = mod
-        nx = buf.NX[:, :S]
+        nx, cat = buf.NX[:, :S], buf.CAT[:, :S]
         ops.ln_modulate(x_in, nx, shift, scale)
         ops.gemm(nx, w.qkv[0], out=buf.QKV[:, :S], bias=w.qkv[1], variant=gv)
-        ops.gemm(nx, w.mlp[0], out=buf.CAT[:, :, D:], bias=w.mlp[1], act=UG_ACT_GELU_TANH, variant=gv)
+        ops.gemm(nx, w.mlp[0], out=cat[:, :, D:], bias=w.mlp[1], act=UG_ACT_GELU_TANH, variant=gv)
         ops.qk_rmsnorm_rope(buf.QKV[:, :S, :2 * D], 2 * H, dh, w.rms, rope[:S] if rope is not None else None, heads_per_weight=H)
-        ops.attention(buf.QKV[:, :S, 0:D], buf.QKV[:, :S, D:2 * D], buf.QKV[:, :S, 2 * D:3 * D], buf.CAT[:, :, :D], H, dh,
-                      variant=self.attn_variant)
-        ops.gemm(buf.CAT, w.out[0], out=x_out, bias=w.out[1], gate=gate, residual=x_in, variant=gv)
+        self._attend(buf, S, cat[:, :, :D])
+        ops.gemm(cat, w.out[0], out=x_out, bias=w.out[1], gate=gate, residual=x_in, variant=gv)
 
     def _rec(self, name: str, t: torch.Tensor):
         if self.trace is not None:
