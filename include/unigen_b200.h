@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define UG_ABI_VERSION 2
+#define UG_ABI_VERSION 3
 
 typedef enum {
   UG_OK = 0,
@@ -97,6 +97,16 @@ typedef struct ug_gemm_args {
   int32_t lora_nseg;
   int32_t lora_seg_bounds[UG_MAX_SEGMENTS + 1];
   int32_t lora_seg_group[UG_MAX_SEGMENTS];
+  /* Fused QK-RMSNorm + RoPE for the q|k|v projection GEMM (n = 3 * qk_d): every q / k head (qk_head_dim columns) is
+   * RMS-normalised in fp32 straight from the TMEM accumulator, scaled by norm_q / norm_k, rotated with the (cos, sin)
+   * table row of its token, and only then rounded to bf16 — diffusers RMSNorm + apply_rotary_emb after to_q/to_k
+   * (src/UniGenUtils.py:597-599) without a second pass over HBM. qk_norm_weight NULL = off. */
+  const void* qk_norm_weight; /* bf16 [2, qk_head_dim]: norm_q.weight, norm_k.weight */
+  const float* qk_cos_sin;    /* fp32 [rows, qk_head_dim] as written by ug_rope_table, row = row of the C view; NULL = no RoPE */
+  int32_t qk_head_dim;        /* 64 or 128 */
+  int32_t qk_d;               /* heads * head_dim */
+  float qk_eps;
+  int32_t reserved2;
 } ug_gemm_args;
 
 int ug_gemm_bf16(const ug_gemm_args* args, void* stream);

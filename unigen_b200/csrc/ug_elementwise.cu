@@ -93,56 +93,59 @@ __global__ void __launch_bounds__(256) qk_rmsnorm_rope_kernel(__nv_bfloat16* __r
                                                               int batch, int rows, int heads,
                                                               const __nv_bfloat16* __restrict__ w, int heads_per_weight,
                                                               float eps, const float* __restrict__ cos_sin) {
-  constexpr int EPL = kDh / 32;  // elements per lane: 4 (dh=128) or 2 (dh=64)
+  // 16 bytes (8 elements) per lane: a head spans LPH lanes, a warp covers HPW heads per pass; kUnroll passes are
+  // loaded before any is reduced so that enough bytes are in flight to approach HBM bandwidth.
+  constexpr int LPH = kDh / 8, HPW = 32 / LPH, kUnroll = 4;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp_global >= batch * rows) return;
   const int b = warp_global / rows, r = warp_global % rows;
   __nv_bfloat16* row = x + (long long)b * bs + (long long)r * rs;
-  float wv[EPL], cs[EPL], sn[EPL];
+  const int sub = lane / LPH, e0 = (lane % LPH) * 8;  // head slot inside the pass, first element inside the head
+  float cs[4], sn[4];
   if (cos_sin) {
-    const float* t = cos_sin + (long long)r * kDh + lane * EPL;  // [rows, dh/2, 2]: (cos, sin) of pair
-#pragma unroll
-    for (int i = 0; i < EPL; i += 2) { cs[i] = cs[i + 1] = t[i]; sn[i] = sn[i + 1] = t[i + 1]; }
+    const float* t = cos_sin + (long long)r * kDh + e0;  // [rows, dh/2, 2]: (cos, sin) of pair
+    const float4 t0 = *reinterpret_cast<const float4*>(t), t1 = *reinterpret_cast<const float4*>(t + 4);
+    cs[0] = t0.x; sn[0] = t0.y; cs[1] = t0.z; sn[1] = t0.w; cs[2] = t1.x; sn[2] = t1.y; cs[3] = t1.z; sn[3] = t1.w;
   }
-  for (int h = 0; h < heads; ++h) {
-    if (h % heads_per_weight == 0) {  // q heads then k heads: one weight vector per group
-      const __nv_bfloat16* wp = w + (h / heads_per_weight) * kDh + lane * EPL;
+  for (int h0 = 0; h0 < heads; h0 += HPW * kUnroll) {
+    uint4 u[kUnroll];
 #pragma unroll
-      for (int i = 0; i < EPL; ++i) wv[i] = __bfloat162float(wp[i]);
+    for (int k = 0; k < kUnroll; ++k) {
+      const int h = h0 + k * HPW + sub;
+      if (h < heads) u[k] = *reinterpret_cast<const uint4*>(row + h * kDh + e0);
     }
-    __nv_bfloat16* p = row + h * kDh + lane * EPL;
-    float f[EPL];
-    if constexpr (EPL == 4) {
-      uint2 u = *reinterpret_cast<const uint2*>(p);
-      float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y);
-      f[0] = a.x; f[1] = a.y; f[2] = c.x; f[3] = c.y;
-    } else {
-      uint32_t u = *reinterpret_cast<const uint32_t*>(p);
-      float2 a = unpack_bf16x2(u);
-      f[0] = a.x; f[1] = a.y;
-    }
-    float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) ss += f[i] * f[i];
-    const float rstd = rsqrtf(warp_sum(ss) / (float)kDh + eps);
+    for (int k = 0; k < kUnroll; ++k) {
+      const int h = h0 + k * HPW + sub;
+      const bool on = h < heads;
+      float f[8];
+      if (on) unpack8(u[k], f);
+      else {
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) f[i] = f[i] * rstd * wv[i];
-    if (cos_sin) {
-#pragma unroll
-      for (int i = 0; i < EPL; i += 2) {
-        const float x0 = f[i], x1 = f[i + 1];
-        f[i] = x0 * cs[i] - x1 * sn[i];
-        f[i + 1] = x1 * cs[i + 1] + x0 * sn[i + 1];
+        for (int i = 0; i < 8; ++i) f[i] = 0.f;
       }
-    }
-    if constexpr (EPL == 4) {
-      uint2 u;
-      u.x = pack_bf16x2(f[0], f[1]);
-      u.y = pack_bf16x2(f[2], f[3]);
-      *reinterpret_cast<uint2*>(p) = u;
-    } else {
-      *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(f[0], f[1]);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+#pragma unroll
+      for (int o = LPH / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      if (on) {
+        const float rstd = rsqrtf(ss / (float)kDh + eps);
+        float wf[8];
+        unpack8(*reinterpret_cast<const uint4*>(w + (h / heads_per_weight) * kDh + e0), wf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = f[i] * rstd * wf[i];
+        if (cos_sin) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float x0 = f[2 * q], x1 = f[2 * q + 1];
+            f[2 * q] = x0 * cs[q] - x1 * sn[q];
+            f[2 * q + 1] = x1 * cs[q] + x0 * sn[q];
+          }
+        }
+        *reinterpret_cast<uint4*>(row + h * kDh + e0) = pack8(f);
+      }
     }
   }
 }
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, 
                                                    const __nv_bfloat16* __restrict__ bias, float* __restrict__ out,
                                                    long long out_stride, int batch0, int batch, int n, int k,
                                                    int silu_in, int silu_out, int accumulate) {
-  constexpr int kRows = 2;
+  constexpr int kRows = 4;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int n0 = warp_global * kRows;
@@ -329,7 +332,7 @@ extern "C" int ug_qk_rmsnorm_rope(void* x, int64_t rs, int64_t bs, int32_t batch
   UG_CHECK_ARG(x && w, "qk_rmsnorm_rope: null pointer");
   UG_CHECK_ARG(batch >= 1 && rows >= 1 && heads >= 1, "qk_rmsnorm_rope: bad shape");
   if (heads_per_weight <= 0) heads_per_weight = heads;
-  UG_CHECK_ARG(rs % 4 == 0 && bs % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0, "qk_rmsnorm_rope: alignment");
+  UG_CHECK_ARG(rs % 8 == 0 && bs % 8 == 0 && aligned16(x) && aligned16(w) && (!cos_sin || aligned16(cos_sin)), "qk_rmsnorm_rope: alignment");
   const long long warps = (long long)batch * rows;
   const int block = 256;
   const int grid = (int)((warps * 32 + block - 1) / block);
@@ -363,7 +366,7 @@ extern "C" int ug_gemv(const float* x, int64_t x_stride, const void* w, const vo
   UG_CHECK_ARG(batch >= 1 && n >= 1 && k >= 8 && k % 8 == 0, "gemv: bad shape batch %d n %d k %d", batch, n, k);
   UG_CHECK_ARG(x_stride % 4 == 0 && aligned16(x) && aligned16(w), "gemv: x / w must be 16-byte aligned");
   auto s = reinterpret_cast<cudaStream_t>(stream);
-  const int warps = (n + 1) / 2;
+  const int warps = (n + 3) / 4;
   const int block = 256;
   const int grid = (warps * 32 + block - 1) / block;
   auto wp = (const __nv_bfloat16*)w;

@@ -34,6 +34,11 @@ struct GemmParams {
   int lora_r, lora_block_n, lora_nseg;
   int lora_bounds[UG_MAX_SEGMENTS + 1];
   int lora_group[UG_MAX_SEGMENTS];
+  // fused QK-RMSNorm + RoPE (QKV projections): columns [0, qk_d) = q heads, [qk_d, 2 qk_d) = k heads, rest = v
+  const __nv_bfloat16* qk_w;  // [2, qk_dh]: norm_q, norm_k weights (NULL = plain epilogue)
+  const float* qk_cos_sin;    // fp32 [rows, qk_dh]: (cos, sin) per rotation pair, row = row of the C view (NULL = no RoPE)
+  int qk_dh, qk_d;
+  float qk_eps;
 };
 
 template <int kCta, int BN, int kStages>
@@ -132,6 +137,70 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     o.w = pack_bf16x2(x[6], x[7]);
     *reinterpret_cast<uint4*>(p.c + c_off + c) = o;
   }
+}
+
+// bias (+ per-head RMSNorm weight * rstd + interleaved-pair RoPE for q / k columns) -> bf16.  c_in_head = column of the
+// first element of this 32-column chunk inside its head; `which` 0/1 = q/k head (normalised), 2 = v head (plain).
+__device__ __forceinline__ void epilogue_qkv_chunk(const GemmParams& p, const uint32_t (&v)[32], int b, int r, int col0,
+                                                   int c_in_head, int which, float rstd) {
+  const long long c_off = (long long)b * p.c_bs + (long long)r * p.c_rs;
+  const float* cs = (which < 2 && p.qk_cos_sin) ? p.qk_cos_sin + (long long)r * p.qk_dh + c_in_head : nullptr;
+  const __nv_bfloat16* wq = p.qk_w + which * p.qk_dh + c_in_head;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = col0 + 8 * j;
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[8 * j + i]);
+    if (p.bias) {
+      uint4 bv = *reinterpret_cast<const uint4*>(p.bias + (long long)b * p.bias_bs + c);
+      float2 f0 = unpack_bf16x2(bv.x), f1 = unpack_bf16x2(bv.y), f2 = unpack_bf16x2(bv.z), f3 = unpack_bf16x2(bv.w);
+      x[0] += f0.x; x[1] += f0.y; x[2] += f1.x; x[3] += f1.y;
+      x[4] += f2.x; x[5] += f2.y; x[6] += f3.x; x[7] += f3.y;
+    }
+    if (which < 2) {
+      uint4 wv = *reinterpret_cast<const uint4*>(wq + 8 * j);
+      float2 w0 = unpack_bf16x2(wv.x), w1 = unpack_bf16x2(wv.y), w2 = unpack_bf16x2(wv.z), w3 = unpack_bf16x2(wv.w);
+      x[0] *= rstd * w0.x; x[1] *= rstd * w0.y; x[2] *= rstd * w1.x; x[3] *= rstd * w1.y;
+      x[4] *= rstd * w2.x; x[5] *= rstd * w2.y; x[6] *= rstd * w3.x; x[7] *= rstd * w3.y;
+      if (cs) {
+        const float4 t0 = *reinterpret_cast<const float4*>(cs + 8 * j), t1 = *reinterpret_cast<const float4*>(cs + 8 * j + 4);
+        const float co[4] = {t0.x, t0.z, t1.x, t1.z}, si[4] = {t0.y, t0.w, t1.y, t1.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float a0 = x[2 * q], a1 = x[2 * q + 1];
+          x[2 * q] = a0 * co[q] - a1 * si[q];
+          x[2 * q + 1] = a1 * co[q] + a0 * si[q];
+        }
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(x[0], x[1]);
+    o.y = pack_bf16x2(x[2], x[3]);
+    o.z = pack_bf16x2(x[4], x[5]);
+    o.w = pack_bf16x2(x[6], x[7]);
+    *reinterpret_cast<uint4*>(p.c + c_off + c) = o;
+  }
+}
+
+// sum over the chunk of (acc + bias)^2 — first pass of the fused per-head RMSNorm
+__device__ __forceinline__ float chunk_sumsq(const GemmParams& p, const uint32_t (&v)[32], int b, int col0) {
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[8 * j + i]);
+    if (p.bias) {
+      uint4 bv = *reinterpret_cast<const uint4*>(p.bias + (long long)b * p.bias_bs + col0 + 8 * j);
+      float2 f0 = unpack_bf16x2(bv.x), f1 = unpack_bf16x2(bv.y), f2 = unpack_bf16x2(bv.z), f3 = unpack_bf16x2(bv.w);
+      x[0] += f0.x; x[1] += f0.y; x[2] += f1.x; x[3] += f1.y;
+      x[4] += f2.x; x[5] += f2.y; x[6] += f3.x; x[7] += f3.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ss += x[i] * x[i];
+  }
+  return ss;
 }
 
 template <int kCta, int BN, int kStages>
@@ -259,22 +328,54 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
       const int lora_g = p.lora_t ? lora_group_of(p, r) : -1;
+      auto release_acc = [&]() {
+        // accumulator stage fully read: hand it back to the MMA warp before doing the last stores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kCta == 1 || cta_rank == 0) mbar_arrive(&tmem_empty[as]);
+          else mbar_arrive_cluster(&tmem_empty[as], 0);
+        }
+      };
+      if (p.qk_w) {
+        // ---- QKV projection: per-head RMSNorm (two passes over the TMEM columns of a head) + RoPE, fused ----
+        const int cph = p.qk_dh >> 5;  // 32-column chunks per head
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + ch * 32, v);
-        tmem_ld_wait();
-        if (ch == BN / 32 - 1) {
-          // accumulator stage fully read: hand it back to the MMA warp before doing the last stores
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (kCta == 1 || cta_rank == 0) mbar_arrive(&tmem_empty[as]);
-            else mbar_arrive_cluster(&tmem_empty[as], 0);
+        for (int c_h = 0; c_h < BN; c_h += p.qk_dh) {
+          const int col_h = n0 + c_h;
+          const bool active = col_h < p.n;             // warp-uniform
+          const int which = active ? col_h / p.qk_d : 2;  // 0 = q head, 1 = k head, 2 = v head
+          float rstd = 1.f;
+          if (which < 2) {
+            float ss = 0.f;
+#pragma unroll 1
+            for (int ch = 0; ch < cph; ++ch) {
+              uint32_t v[32];
+              tmem_ld_32x32(taddr + c_h + ch * 32, v);
+              tmem_ld_wait();
+              ss += chunk_sumsq(p, v, b, col_h + ch * 32);
+            }
+            rstd = rsqrtf(ss / (float)p.qk_dh + p.qk_eps);
+          }
+#pragma unroll 1
+          for (int ch = 0; ch < cph; ++ch) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + c_h + ch * 32, v);
+            tmem_ld_wait();
+            if (c_h + p.qk_dh >= BN && ch == cph - 1) release_acc();
+            if (r < p.rows && active) epilogue_qkv_chunk(p, v, b, r, col_h + ch * 32, ch * 32, which, rstd);
           }
         }
-        const int col0 = n0 + ch * 32;
-        if (r < p.rows && col0 < p.n) epilogue_chunk(p, v, b, r, col0, lora_g);
+      } else {
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + ch * 32, v);
+          tmem_ld_wait();
+          if (ch == BN / 32 - 1) release_acc();
+          const int col0 = n0 + ch * 32;
+          if (r < p.rows && col0 < p.n) epilogue_chunk(p, v, b, r, col0, lora_g);
+        }
       }
     }
   }
@@ -330,6 +431,8 @@ static int launch_gemm(const ug_gemm_args& a, cudaStream_t stream) {
   p.alpha = a.alpha; p.act = a.act;
   p.res = (const __nv_bfloat16*)a.residual; p.res_rs = a.res_row_stride; p.res_bs = a.res_batch_stride;
   p.w_batched = w_batched ? 1 : 0;
+  p.qk_w = (const __nv_bfloat16*)a.qk_norm_weight; p.qk_cos_sin = a.qk_cos_sin; p.qk_dh = a.qk_head_dim;
+  p.qk_d = a.qk_d; p.qk_eps = a.qk_eps;
   p.lora_t = a.lora_t; p.lora_t_rs = a.lora_t_row_stride; p.lora_t_bs = a.lora_t_batch_stride;
   p.lora_b = (const __nv_bfloat16*)a.lora_b;
   p.lora_r = a.lora_rank; p.lora_block_n = a.lora_block_n > 0 ? a.lora_block_n : a.n; p.lora_nseg = a.lora_nseg;
@@ -381,6 +484,15 @@ extern "C" int ug_gemm_bf16(const ug_gemm_args* args, void* stream) {
   if (a.bias) UG_CHECK_ARG((reinterpret_cast<uintptr_t>(a.bias) & 15) == 0 && a.bias_batch_stride % 8 == 0, "gemm: bias alignment");
   if (a.gate) UG_CHECK_ARG((reinterpret_cast<uintptr_t>(a.gate) & 15) == 0 && a.gate_batch_stride % 4 == 0, "gemm: gate alignment");
   UG_CHECK_ARG(a.act == UG_ACT_NONE || a.act == UG_ACT_GELU_TANH, "gemm: unknown activation %d", a.act);
+  if (a.qk_norm_weight) {
+    UG_CHECK_ARG(a.qk_head_dim == 64 || a.qk_head_dim == 128, "gemm: fused QK-norm needs head_dim 64 or 128 (got %d)", a.qk_head_dim);
+    UG_CHECK_ARG(a.qk_d > 0 && a.qk_d % a.qk_head_dim == 0 && a.n % a.qk_head_dim == 0 && a.n == 3 * a.qk_d,
+                 "gemm: fused QK-norm expects n = 3 * qk_d with qk_d a multiple of head_dim (n %d, qk_d %d)", a.n, a.qk_d);
+    UG_CHECK_ARG(!a.lora_t && !a.gate && !a.residual && a.act == UG_ACT_NONE && a.alpha == 1.0f,
+                 "gemm: the fused QK-norm epilogue composes with bias only");
+    UG_CHECK_ARG((reinterpret_cast<uintptr_t>(a.qk_norm_weight) & 15) == 0 &&
+                     (!a.qk_cos_sin || (reinterpret_cast<uintptr_t>(a.qk_cos_sin) & 15) == 0), "gemm: QK-norm operand alignment");
+  }
   if (a.lora_t) {
     UG_CHECK_ARG(a.lora_b && (a.lora_rank == 4 || a.lora_rank == 8 || a.lora_rank == 12 || a.lora_rank == 16),
                  "gemm: LoRA needs lora_b and a rank in {4, 8, 12, 16} (got %d)", a.lora_rank);

@@ -143,6 +143,7 @@ class UniGenFlux(torch.nn.Module):
         self.use_cuda_graph = False
         self.gemm_variant = 0
         self.attn_variant = 0
+        self.fuse_qk_norm = False  # QK-RMSNorm + RoPE inside the q|k|v projection GEMM epilogue (False: separate in-place pass)
         self.trace: Optional[Dict[str, torch.Tensor]] = None  # set to {} to record per-block intermediates
 
     # ---------------------------------------------------------------------------------------------------------
@@ -320,16 +321,23 @@ class UniGenFlux(torch.nn.Module):
                       a.attention_head_dim, variant=self.attn_variant)
         return out
 
+    def _qk_norm(self, rms_w: torch.Tensor, rope_rows: Optional[torch.Tensor]):
+        """Arguments of the fused QK-RMSNorm + RoPE epilogue of a q|k|v projection GEMM (ops.gemm qk_norm=...)."""
+        if not self.fuse_qk_norm:
+            return None
+        return dict(weight=rms_w, head_dim=self.arch.attention_head_dim, d=self.inner_dim, cos_sin=rope_rows, eps=1e-6)
+
     def _joint_attention(self, buf, B, n_ctx, n_smp, rms_ctx, rms_smp, rope):
-        """RMSNorm(q,k)+RoPE in place on QKV rows [0, n_ctx+n_smp), then joint attention -> AO."""
+        """(RMSNorm(q,k)+RoPE in place on QKV rows unless it was fused into the projection GEMMs) + joint attention -> AO."""
         a = self.arch
         H, dh, D = a.num_attention_heads, a.attention_head_dim, self.inner_dim
         S = n_ctx + n_smp
-        qk = buf.QKV[:, :S, :2 * D]
-        if n_ctx:
-            ops.qk_rmsnorm_rope(qk[:, :n_ctx], 2 * H, dh, rms_ctx, rope[:n_ctx] if rope is not None else None, heads_per_weight=H)
-        if n_smp:
-            ops.qk_rmsnorm_rope(qk[:, n_ctx:], 2 * H, dh, rms_smp, rope[n_ctx:S] if rope is not None else None, heads_per_weight=H)
+        if not self.fuse_qk_norm:
+            qk = buf.QKV[:, :S, :2 * D]
+            if n_ctx:
+                ops.qk_rmsnorm_rope(qk[:, :n_ctx], 2 * H, dh, rms_ctx, rope[:n_ctx] if rope is not None else None, heads_per_weight=H)
+            if n_smp:
+                ops.qk_rmsnorm_rope(qk[:, n_ctx:], 2 * H, dh, rms_smp, rope[n_ctx:S] if rope is not None else None, heads_per_weight=H)
         return self._attend(buf, S, buf.AO[:, :S])
 
     def _double_block(self, buf, w: _DoubleBlockW, mod_smp, mod_ctx, smp_in, ctx_in, smp_out, ctx_out, rope):
@@ -346,10 +354,12 @@ class UniGenFlux(torch.nn.Module):
         nx_c, nx_s = buf.NX[:, :n_ctx], buf.NX[:, n_ctx:S]
         if n_ctx:
             ops.ln_modulate(ctx_in, nx_c, csh_a, csc_a)
-            ops.gemm(nx_c, w.add_qkv[0], out=buf.QKV[:, :n_ctx], bias=w.add_qkv[1], variant=gv)
+            ops.gemm(nx_c, w.add_qkv[0], out=buf.QKV[:, :n_ctx], bias=w.add_qkv[1], variant=gv,
+                     qk_norm=self._qk_norm(w.rms_ctx, rope[:n_ctx] if rope is not None else None))
         if n_smp:
             ops.ln_modulate(smp_in, nx_s, sh_a, sc_a)
-            ops.gemm(nx_s, w.qkv[0], out=buf.QKV[:, n_ctx:S], bias=w.qkv[1], variant=gv)
+            ops.gemm(nx_s, w.qkv[0], out=buf.QKV[:, n_ctx:S], bias=w.qkv[1], variant=gv,
+                     qk_norm=self._qk_norm(w.rms, rope[n_ctx:S] if rope is not None else None))
         ao = self._joint_attention(buf, B, n_ctx, n_smp, w.rms_ctx, w.rms, rope)
         if n_smp:
             # h = h + gate_msa * to_out(attn)
@@ -373,9 +383,11 @@ class UniGenFlux(torch.nn.Module):
         shift, scale, gate = mod
         nx, cat = buf.NX[:, :S], buf.CAT[:, :S]
         ops.ln_modulate(x_in, nx, shift, scale)
-        ops.gemm(nx, w.qkv[0], out=buf.QKV[:, :S], bias=w.qkv[1], variant=gv)
+        ops.gemm(nx, w.qkv[0], out=buf.QKV[:, :S], bias=w.qkv[1], variant=gv,
+                 qk_norm=self._qk_norm(w.rms, rope[:S] if rope is not None else None))
         ops.gemm(nx, w.mlp[0], out=cat[:, :, D:], bias=w.mlp[1], act=UG_ACT_GELU_TANH, variant=gv)
-        ops.qk_rmsnorm_rope(buf.QKV[:, :S, :2 * D], 2 * H, dh, w.rms, rope[:S] if rope is not None else None, heads_per_weight=H)
+        if not self.fuse_qk_norm:
+            ops.qk_rmsnorm_rope(buf.QKV[:, :S, :2 * D], 2 * H, dh, w.rms, rope[:S] if rope is not None else None, heads_per_weight=H)
         self._attend(buf, S, cat[:, :, :D])
         ops.gemm(cat, w.out[0], out=x_out, bias=w.out[1], gate=gate, residual=x_in, variant=gv)
 

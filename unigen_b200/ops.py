@@ -78,7 +78,8 @@ def device_check() -> None:
 # ------------------------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
          gate: Optional[torch.Tensor] = None, alpha: float = 1.0, act: int = UG_ACT_NONE,
-         residual: Optional[torch.Tensor] = None, variant: int = 0, lora: Optional[dict] = None) -> torch.Tensor:
+         residual: Optional[torch.Tensor] = None, variant: int = 0, lora: Optional[dict] = None,
+         qk_norm: Optional[dict] = None) -> torch.Tensor:
     """out[b,r,:] = residual + alpha * gate[b,:] * act(a[b,r,:] @ w^T + bias (+ switched LoRA update)).
     a: [B,R,K] view, w: [N,K] or [B,N,K]. lora = dict(t=fp32 [B,R,n_blocks*rank] from lora_down, b=bf16 [groups,N,rank]
     (pre-scaled), rank, block_n, seg_bounds, seg_group) applies adapter group seg_group[i] to rows of segment i."""
@@ -125,6 +126,17 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, b
             g.lora_seg_bounds[i] = int(v)
         for i, v in enumerate(sg):
             g.lora_seg_group[i] = int(v)
+    if qk_norm is not None:
+        # fused per-head RMSNorm + RoPE epilogue of a q|k|v projection: dict(weight=[2,dh] bf16, head_dim, d, cos_sin, eps)
+        wq = _dev(qk_norm["weight"], "gemm.qk_norm.weight", BF16)
+        g.qk_norm_weight, g.qk_head_dim, g.qk_d = wq.data_ptr(), int(qk_norm["head_dim"]), int(qk_norm["d"])
+        g.qk_eps = float(qk_norm.get("eps", 1e-6))
+        cs = qk_norm.get("cos_sin")
+        if cs is not None:
+            _dev(cs, "gemm.qk_norm.cos_sin", torch.float32)
+            if cs.shape[0] < R or not cs.is_contiguous():
+                raise UgError("gemm: qk_norm cos_sin table too short / not contiguous")
+            g.qk_cos_sin = cs.data_ptr()
     check(_lib.load().ug_gemm_bf16(C.byref(g), _stream()), "ug_gemm_bf16")
     return out
 
