@@ -395,7 +395,7 @@ struct Attn2Cfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <int kDh>
+template <int kDh, int kPolyMod>
 __global__ void __launch_bounds__(384, 1)
 attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                   const __grid_constant__ CUtensorMap tma_v, const AttnParams p) {
@@ -640,8 +640,11 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         uint32_t pk[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const float p0 = ex2_ftz(fmaf(__uint_as_float(s[64 * half + 2 * c]), p.scale_log2, neg_ms));
-          const float p1 = ex2_ftz(fmaf(__uint_as_float(s[64 * half + 2 * c + 1]), p.scale_log2, neg_ms));
+          // every kPolyMod-th element takes the polynomial path (FMA pipe) instead of MUFU.EX2
+          const float a0 = fmaf(__uint_as_float(s[64 * half + 2 * c]), p.scale_log2, neg_ms);
+          const float a1 = fmaf(__uint_as_float(s[64 * half + 2 * c + 1]), p.scale_log2, neg_ms);
+          const float p0 = (kPolyMod > 0 && ((2 * c) % kPolyMod) == 0) ? ex2_poly(a0) : ex2_ftz(a0);
+          const float p1 = (kPolyMod > 0 && ((2 * c + 1) % kPolyMod) == 0) ? ex2_poly(a1) : ex2_ftz(a1);
           rs[(2 * c) & 7] += p0;
           rs[(2 * c + 1) & 7] += p1;
           pk[c] = pack_bf16x2(p0, p1);
@@ -691,6 +694,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     tmem_dealloc<1>(tmem_base, Cfg::TMEM_COLS);
   }
 }
+
 
 __global__ void expand_mask_kernel(int seq, int n_seg, AttnParams p, uint8_t* __restrict__ mask) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -760,10 +764,10 @@ static int launch_attention(const ug_attn_args& a, cudaStream_t stream) {
 }
 
 
-template <int kDh>
+template <int kDh, int kPolyMod>
 static int launch_attention2(const ug_attn_args& a, cudaStream_t stream) {
   using Cfg = Attn2Cfg<kDh>;
-  auto kern = attention2_kernel<kDh>;
+  auto kern = attention2_kernel<kDh, kPolyMod>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -820,11 +824,13 @@ extern "C" int ug_attention_bf16(const ug_attn_args* args, void* stream) {
   if (a.head_dim == 128) {
     if (variant == 1) return launch_attention<128, true>(a, s);
     if (variant == 2) return launch_attention<128, false>(a, s);
-    if (variant == 3) return launch_attention2<128>(a, s);
+    if (variant == 3) return launch_attention2<128, 0>(a, s);
+    if (variant == 4) return launch_attention2<128, 4>(a, s);
   } else if (a.head_dim == 64) {
     if (variant == 1) return launch_attention<64, true>(a, s);
     if (variant == 2) return launch_attention<64, false>(a, s);
-    if (variant == 3) return launch_attention2<64>(a, s);
+    if (variant == 3) return launch_attention2<64, 0>(a, s);
+    if (variant == 4) return launch_attention2<64, 4>(a, s);
   } else {
     set_error("attention: head_dim %d not supported (64 or 128)", a.head_dim);
     return UG_ERR_UNSUPPORTED;

@@ -240,6 +240,15 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v
       "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
+// registers -> TMEM (32 lanes x 16 columns)
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
@@ -265,6 +274,19 @@ __device__ __forceinline__ float ex2_ftz(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// exp2 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = i + f, f in [-0.5, 0.5], degree-3 minimax
+// polynomial for 2^f (max rel. error 1.0e-4, below bf16 resolution), exponent patched in with integer adds.
+// Used for a fraction of the softmax elements so that the 16/clk/SM MUFU unit stops being the attention bottleneck.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float magic = 12582912.0f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float xr = x + magic;
+  const float f = x - (xr - magic);
+  float p = fmaf(f, 0.05500893f, 0.24221096f);
+  p = fmaf(p, f, 0.69328293f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
 }
 // register budget hand-off between warp roles (whole warpgroups of 4 warps, values multiple of 8)
 template <int kRegs>
