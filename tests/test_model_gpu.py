@@ -101,6 +101,48 @@ def test_batch2_equals_two_independent_samples_in_attention_and_gemm_paths():
         assert torch.equal(model.trace["double.0.base_hidden"][0], t2[b])
 
 
+def test_ragged_shapes_guidance_batch2_single_add_scale():
+    """Edge configuration: non-tile-multiple token counts (N = 240, T = 77), batch 2 (one pooled MoE routing pool of B*N
+    tokens, as the reference does), guidance-embedding architecture, `single_add` control method, conditioning_scale 0.6."""
+    from oracle import unigen_oracle as O
+    from unigen_b200.model import FluxArch, UniGenFlux, canonical_control_params
+    cfg = O.FluxConfig.tiny()
+    cfg.guidance_embeds = True
+    cfg.single_block_control_method = "single_add"
+    sd = O.init_state_dict(cfg, seed=5)
+    sd = {k: (v if k.endswith("gate.wg.weight") else v.to(torch.bfloat16).float()) for k, v in sd.items()}
+    inp = O.make_inputs(cfg, 320, 192, text_len=77, batch=2)
+    for k in ("hidden_states", "condition_hidden_states", "encoder_hidden_states"):
+        inp[k] = inp[k].to(torch.bfloat16).float()
+    inp["guidance"] = torch.tensor([3.5, 1.0])  # the pipeline passes guidance un-scaled; forward multiplies by 1000 (:1217-1218)
+    inp["conditioning_scale"] = 0.6
+    oracle = O.UniGenFluxOracle(cfg, sd)
+    oracle.record = True
+    want, _, want_o = oracle.forward(**inp)
+    arch = FluxArch(num_layers=2, num_single_layers=4, attention_head_dim=64, num_attention_heads=6, axes_dims_rope=(8, 28, 28),
+                    guidance_embeds=True)
+    model = UniGenFlux(arch, device="cuda")
+    params = canonical_control_params()
+    params["single_block_control_method"] = "single_add"
+    model.init_condition_block(condition_nums=1, control_params=params)
+    model.load_state_dict(sd, strict=True)
+    model.trace = {}
+    got, _, outs = model(**{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()})
+    bad = {k: rel_l2(model.trace[k], v) for k, v in oracle.trace.items()
+           if k in model.trace and not k.startswith("moe.") and rel_l2(model.trace[k], v) > 1e-2}
+    assert not bad, bad
+    cos = torch.nn.functional.cosine_similarity(got.float().cpu().flatten(), want.flatten(), dim=0).item()
+    assert cos >= 0.999
+    assert (outs["expert_counts"].cpu() - want_o["expert_counts"]).abs().sum() <= 4
+    # CUDA-graph replay == eager launch path, bit for bit
+    model.trace = None
+    eager = model(**{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()})[0].clone()
+    model.use_cuda_graph = True
+    for _ in range(2):
+        graphed = model(**{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()})[0]
+    assert torch.equal(eager, graphed)
+
+
 def test_multi_condition_forward_matches_oracle():
     """MultiCondtionUniGenFlux (reference :1274-1450): 3 conditions (depth + canny + subject), E = 12, one CoMoE pass per
     condition, summed control stream / condition_temb, last condition's loss and counts."""
