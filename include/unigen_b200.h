@@ -231,6 +231,17 @@ int ug_moe_gather_modulate(const void* x, const int32_t* slot_token, const float
 int ug_moe_combine(const void* y, const int32_t* expert_idx, const int32_t* slot, const float* prob, void* out,
                    int32_t tokens, int32_t capacity, int32_t d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Denoise-loop glue (callers of the path: src/UniGenPipeline.py:1050-1116), kept on the device between steps.
+ * ---------------------------------------------------------------------------------------------------- */
+/* FlowMatchEulerDiscreteScheduler.step: latents <- bf16(float(latents) + (sigma_next - sigma) * float(velocity)), n elements. */
+int ug_euler_step(void* latents_bf16, const void* velocity_bf16, float sigma, float sigma_next, int64_t n, void* stream);
+/* classifier-free guidance (src/UniGenPipeline.py:405-412): out = uncond + guidance_scale * (text - uncond). */
+int ug_cfg_combine(const void* uncond_bf16, const void* text_bf16, float guidance_scale, void* out_bf16, int64_t n, void* stream);
+/* FluxPipeline._pack_latents (unpack = 0): (B, C, H, W) -> (B, (H/2)(W/2), 4C); _unpack_latents (unpack = 1): inverse. */
+int ug_pack_latents(const void* src_bf16, void* dst_bf16, int32_t batch, int32_t channels, int32_t height, int32_t width,
+                    int32_t unpack, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -862,3 +862,44 @@ class PVariantOracle:
         out = linear(sd, "proj_out", ada_layer_norm_continuous(sd, "norm_out", h, temb))
         self._rec("velocity", out)
         return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# denoise-loop glue (callers of the path)
+# ------------------------------------------------------------------------------------------------------------------
+def calculate_shift(image_seq_len, base_seq_len=256, max_seq_len=4096, base_shift=0.5, max_shift=1.16):
+    """diffusers pipeline_flux.calculate_shift (src/UniGenPipeline.py:991-997)."""
+    m = (max_shift - base_shift) / (max_seq_len - base_seq_len)
+    return image_seq_len * m + (base_shift - m * base_seq_len)
+
+
+def flow_match_sigmas(n: int, image_seq_len: int, use_dynamic_shifting: bool = True) -> Tensor:
+    """np.linspace(1, 1/n, n) (src/UniGenPipeline.py:989) + FlowMatchEulerDiscreteScheduler exponential time shift + [0]."""
+    s = torch.linspace(1.0, 1.0 / n, n, dtype=torch.float64)
+    if use_dynamic_shifting:
+        mu = calculate_shift(image_seq_len)
+        s = math.exp(mu) / (math.exp(mu) + (1.0 / s - 1.0))
+    return torch.cat([s, torch.zeros(1, dtype=torch.float64)]).float()
+
+
+def pack_latents(x: Tensor) -> Tensor:
+    """FluxPipeline._pack_latents."""
+    B, C, H, W = x.shape
+    return x.view(B, C, H // 2, 2, W // 2, 2).permute(0, 2, 4, 1, 3, 5).reshape(B, (H // 2) * (W // 2), C * 4)
+
+
+def unpack_latents(x: Tensor, H: int, W: int) -> Tensor:
+    """FluxPipeline._unpack_latents with H, W the latent height / width."""
+    B, _, C4 = x.shape
+    return x.view(B, H // 2, W // 2, C4 // 4, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(B, C4 // 4, H, W)
+
+
+def denoise_loop(model: "UniGenFluxOracle", inp: Dict[str, Tensor], steps: int, rts: List[Tensor]) -> Tensor:
+    """Loop body of UniGenFLUXPipeline.__call__ (src/UniGenPipeline.py:1050-1116) with the Euler flow-match step."""
+    x = inp["hidden_states"].clone()
+    sig = flow_match_sigmas(steps, x.shape[1])
+    for i in range(steps):
+        args = dict(inp, hidden_states=x, timestep=sig[i].expand(x.shape[0]).clone(), rts_uniform=rts[i])
+        v = model.forward(**args)[0]
+        x = x + (sig[i + 1] - sig[i]) * v
+    return x

@@ -75,6 +75,9 @@ SIGNATURES = {
     "ug_moe_route": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "ug_moe_gather_modulate": (C.c_int, [_VP, _VP, _VP, _I64, _I64, _VP, _VP, _I32, _I32, _I32, _I32, _VP]),
     "ug_moe_combine": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP]),
+    "ug_euler_step": (C.c_int, [_VP, _VP, _F32, _F32, _I64, _VP]),
+    "ug_cfg_combine": (C.c_int, [_VP, _VP, _F32, _VP, _I64, _VP]),
+    "ug_pack_latents": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
 }
 
 _lib = None

@@ -14,7 +14,7 @@ from ._lib import UG_ACT_GELU_TANH, UG_ACT_NONE, AttnArgs, GemmArgs, UgError, ch
 
 __all__ = ["gemm", "lora_down", "attention", "expand_segment_mask", "ln_modulate", "qk_rmsnorm_rope", "rope_table", "gemv",
            "timestep_embedding", "add", "copy", "to_bf16", "to_f32", "moe_route", "moe_gather_modulate",
-           "moe_combine", "launch_count", "reset_launch_count", "UG_ACT_NONE", "UG_ACT_GELU_TANH", "UgError"]
+           "moe_combine", "euler_step", "cfg_combine", "pack_latents", "unpack_latents", "launch_count", "reset_launch_count", "UG_ACT_NONE", "UG_ACT_GELU_TANH", "UgError"]
 
 BF16 = torch.bfloat16
 
@@ -351,4 +351,42 @@ def moe_combine(y: torch.Tensor, route: dict, capacity: int, out: torch.Tensor) 
     D = y.shape[-1]
     check(_lib.load().ug_moe_combine(y.data_ptr(), route["expert_idx"].data_ptr(), route["slot"].data_ptr(),
                                      route["prob"].data_ptr(), out.data_ptr(), tokens, capacity, D, _stream()), "ug_moe_combine")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def euler_step(latents: torch.Tensor, velocity: torch.Tensor, sigma: float, sigma_next: float) -> torch.Tensor:
+    """In place: latents <- latents + (sigma_next - sigma) * velocity (bf16 storage, fp32 math)."""
+    _dev(latents, "euler.latents", BF16), _dev(velocity, "euler.velocity", BF16)
+    if not (latents.is_contiguous() and velocity.is_contiguous()) or latents.numel() != velocity.numel():
+        raise UgError("euler_step: contiguous tensors of equal size required")
+    check(_lib.load().ug_euler_step(latents.data_ptr(), velocity.data_ptr(), float(sigma), float(sigma_next), latents.numel(),
+                                    _stream()), "ug_euler_step")
+    return latents
+
+
+def cfg_combine(uncond: torch.Tensor, text: torch.Tensor, guidance_scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _dev(uncond, "cfg.uncond", BF16), _dev(text, "cfg.text", BF16)
+    if out is None:
+        out = torch.empty_like(text)
+    check(_lib.load().ug_cfg_combine(uncond.contiguous().data_ptr(), text.contiguous().data_ptr(), float(guidance_scale),
+                                     out.data_ptr(), text.numel(), _stream()), "ug_cfg_combine")
+    return out
+
+
+def pack_latents(x: torch.Tensor) -> torch.Tensor:
+    """(B, C, H, W) bf16 -> (B, (H/2)(W/2), 4C)."""
+    _dev(x, "pack.x", BF16)
+    B, Cc, H, W = x.shape
+    out = torch.empty(B, (H // 2) * (W // 2), Cc * 4, device=x.device, dtype=BF16)
+    check(_lib.load().ug_pack_latents(x.contiguous().data_ptr(), out.data_ptr(), B, Cc, H, W, 0, _stream()), "ug_pack_latents")
+    return out
+
+
+def unpack_latents(x: torch.Tensor, height: int, width: int) -> torch.Tensor:
+    """(B, (H/2)(W/2), 4C) bf16 -> (B, C, H, W) with H, W the latent height / width."""
+    _dev(x, "unpack.x", BF16)
+    B, _, C4 = x.shape
+    out = torch.empty(B, C4 // 4, height, width, device=x.device, dtype=BF16)
+    check(_lib.load().ug_pack_latents(x.contiguous().data_ptr(), out.data_ptr(), B, C4 // 4, height, width, 1, _stream()), "ug_pack_latents")
     return out
