@@ -507,7 +507,9 @@ extern "C" int ug_gemm_bf16(const ug_gemm_args* args, void* stream) {
   if (variant == 0) {
     // auto: narrow tiles when a 128x256 grid would leave most SMs idle
     const long long tiles256 = (long long)a.batch * ((a.rows + 127) / 128) * ((a.n + 255) / 256);
-    variant = (a.n <= 128 || tiles256 < num_sms()) ? 3 : 1;
+    // big problems: the 2-CTA pair tile halves the per-SM W traffic (measured 2 % faster per cfg3 step than 1-CTA
+    // 128x256 at equal tensor throughput: less smem / L2 energy under the 1 kW power cap)
+    variant = (a.n <= 128 || tiles256 < num_sms()) ? 3 : 2;
   }
   switch (variant) {
     case 1: return launch_gemm<1, 256, 4>(a, s);

@@ -143,6 +143,8 @@ class UniGenFlux(torch.nn.Module):
         self.use_cuda_graph = False
         self.gemm_variant = 0
         self.attn_variant = 0
+        self.overlap_mod_gemv = True  # AdaLN GEMVs (HBM-bound) on a side stream under the tensor-core-bound blocks
+        self._side_stream = torch.cuda.Stream(device=self.device_)
         self.fuse_qk_norm = False  # QK-RMSNorm + RoPE inside the q|k|v projection GEMM epilogue (False: separate in-place pass)
         self.trace: Optional[Dict[str, torch.Tensor]] = None  # set to {} to record per-block intermediates
 
@@ -542,32 +544,56 @@ class UniGenFlux(torch.nn.Module):
         self._rec("temb", buf.temb); self._rec("x_embed", x_img); self._rec("context_embed", x_txt)
 
         # ---- every block's AdaLN vectors, once per step (temb / condition_temb are step constants) ----
-        slot = 0
-        m_double, m_cdouble, m_single, m_csingle = [], [], [], []
-        for w in self.double:
-            m_double.append((self._mods(buf, slot, 6, w.norm1, buf.temb), self._mods(buf, slot + 6, 6, w.norm1_ctx, buf.temb)))
-            slot += 12
-        for w in self.ctrl_double:
-            m_cdouble.append((self._mods(buf, slot, 6, w.norm1, buf.cdtemb), self._mods(buf, slot + 6, 6, w.norm1_ctx, buf.cdtemb)))
-            slot += 12
-        for w in self.single:
-            m_single.append(self._mods(buf, slot, 3, w.norm, buf.temb)); slot += 3
-        for w in self.ctrl_single:
-            m_csingle.append(self._mods(buf, slot, 3, w.norm, buf.cdtemb)); slot += 3
+        # 13 GB of bf16 weights are streamed by HBM-bound GEMVs: only what the first double block and the pre-stage need
+        # is computed on the main stream; the rest runs on a side stream UNDER the tensor-core-bound block kernels.
+        nd, ncd, ns, ncs_ = len(self.double), len(self.ctrl_double), len(self.single), len(self.ctrl_single)
+        s_d, s_cd = 0, 12 * nd
+        s_s, s_cs = s_cd + 12 * ncd, s_cd + 12 * ncd + 3 * ns
+        s_sh = s_cs + 3 * ncs_
+        s_out = s_sh + 12 * n_cond + 12
+        m_double, m_cdouble = [None] * nd, [None] * ncd
+        m_single, m_csingle = [None] * ns, [None] * ncs_
+
+        def mod_double(i):
+            w = self.double[i]
+            m_double[i] = (self._mods(buf, s_d + 12 * i, 6, w.norm1, buf.temb), self._mods(buf, s_d + 12 * i + 6, 6, w.norm1_ctx, buf.temb))
+
+        def mod_cdouble(j):
+            w = self.ctrl_double[j]
+            m_cdouble[j] = (self._mods(buf, s_cd + 12 * j, 6, w.norm1, buf.cdtemb),
+                            self._mods(buf, s_cd + 12 * j + 6, 6, w.norm1_ctx, buf.cdtemb))
+
+        mod_double(0)
+        mod_cdouble(0)
         mods_s0 = []
         for c in range(n_cond):  # shared_expert[0] is modulated by THIS condition's temb, shared_expert[1] by control_temb
-            mods_s0.append((self._mods(buf, slot, 6, self.shared[0].norm1, buf.cdtemb_c[c]),
-                            self._mods(buf, slot + 6, 6, self.shared[0].norm1_ctx, buf.cdtemb_c[c])))
-            slot += 12
-        mods_s1 = (self._mods(buf, slot, 6, self.shared[1].norm1, buf.ctemb),
-                   self._mods(buf, slot + 6, 6, self.shared[1].norm1_ctx, buf.ctemb))
-        slot += 12
-        m_out = self._mods(buf, slot, 2, self.norm_out_w, buf.temb)  # AdaLayerNormContinuous: (scale, shift)
+            mods_s0.append((self._mods(buf, s_sh + 12 * c, 6, self.shared[0].norm1, buf.cdtemb_c[c]),
+                            self._mods(buf, s_sh + 12 * c + 6, 6, self.shared[0].norm1_ctx, buf.cdtemb_c[c])))
+        mods_s1 = (self._mods(buf, s_sh + 12 * n_cond, 6, self.shared[1].norm1, buf.ctemb),
+                   self._mods(buf, s_sh + 12 * n_cond + 6, 6, self.shared[1].norm1_ctx, buf.ctemb))
+        main_stream = torch.cuda.current_stream()
+        side = self._side_stream if self.overlap_mod_gemv else None
+        if side is not None:
+            side.wait_stream(main_stream)
+        with torch.cuda.stream(side if side is not None else main_stream):
+            for i in range(1, nd):
+                mod_double(i)
+            for j in range(1, ncd):
+                mod_cdouble(j)
+            for i, w in enumerate(self.single):
+                m_single[i] = self._mods(buf, s_s + 3 * i, 3, w.norm, buf.temb)
+            for j, w in enumerate(self.ctrl_single):
+                m_csingle[j] = self._mods(buf, s_cs + 3 * j, 3, w.norm, buf.cdtemb)
+            m_out = self._mods(buf, s_out, 2, self.norm_out_w, buf.temb)  # AdaLayerNormContinuous: (scale, shift)
+        mods_joined = side is None
 
         # ---- 19 x [base double -> control double -> add] (:1124-1141) ----
         route = None
         n_cd = len(self.ctrl_double)
         for i, w in enumerate(self.double):
+            if i == 1 and not mods_joined:  # everything after the first block pair needs the side-stream vectors
+                main_stream.wait_stream(side)
+                mods_joined = True
             self._double_block(buf, w, m_double[i][0], m_double[i][1], x_img, x_txt, x_img, x_txt, buf.rope)
             self._rec(f"double.{i}.base_hidden", x_img); self._rec(f"double.{i}.base_context", x_txt)
             j = int(i / (len(self.double) / n_cd))
@@ -585,6 +611,8 @@ class UniGenFlux(torch.nn.Module):
             ops.gemm(buf.CH, wa[0], out=x_img, bias=wa[1], alpha=float(conditioning_scale), residual=x_img, variant=gv)
             self._rec(f"double.{i}.ctrl_hidden", buf.CH); self._rec(f"double.{i}.hidden", x_img)
 
+        if not mods_joined:
+            main_stream.wait_stream(side)
         # ---- 38 x [base single -> control single -> add] over the joint [text | image] stream (:1146-1172) ----
         n_cs = len(self.ctrl_single)
         for i, w in enumerate(self.single):
