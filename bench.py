@@ -26,12 +26,15 @@ WORKLOADS = {
     # name: (arch, height, width, text_len, description)
     "cfg3": ("flux", 1024, 1024, 512, "cfg3: Flux-arch UniGen (19 double + 38 single base blocks, 9 + 19 control blocks, E=6 CoMoE, "
                                        "hidden 3072) 1024x1024 + 1 depth condition: 4096 image + 4096 condition + 512 text tokens"),
+    "cfg4": ("flux3", 1024, 1024, 512, "cfg4 (S-variant): Flux-arch MultiCondtionUniGenFlux 1024x1024 + depth + canny + openpose conditions "
+                                        "(E=12 CoMoE, one pre-stage pass per condition; 4608 tokens in the main blocks)"),
     "cfg2": ("flux", 512, 512, 512, "cfg2: FLUX.1-schnell-arch UniGen 512x512 + 1 canny condition: 1024 image + 1024 condition + 512 text tokens"),
     "tiny": ("tiny", 256, 256, 512, "cfg1: tiny UniGenFlux (2 double + 4 single, hidden 384, 6 heads) 256x256 + 1 canny condition"),
 }
 
 
-def step_flops(D, H, N, T, n_double, n_single, n_cd_calls, n_cs_calls, E, in_ch=64, joint=4096, pooled=768, executed=True):
+def step_flops(D, H, N, T, n_double, n_single, n_cd_calls, n_cs_calls, E, in_ch=64, joint=4096, pooled=768, executed=True,
+               n_cond=1):
     """FLOPs (2 x MAC) of one forward per sample, SURVEY.md §8(d) formulas. executed=True leaves out the work the native
     path never does because its result is discarded by the reference (text-stream post-attention half of the control
     double blocks and of shared_expert[1]); executed=False is the reference-algorithmic count (159.3 TFLOP for cfg3)."""
@@ -52,10 +55,19 @@ def step_flops(D, H, N, T, n_double, n_single, n_cd_calls, n_cs_calls, E, in_ch=
     g += n_cs_calls * (x + 2 * S * D * D); a += n_cs_calls * y
     # embeddings, norm_out/proj_out, pre-stage
     g += 2 * (N * in_ch * D + T * joint * D + 2 * D * D + N * D * in_ch)
-    g += 2 * (N * in_ch * D + T * D * D + N * D * E + N * (2 * D * D) + 2 * E * pooled * D)
-    x, y = dbl(N, N); g += x; a += y
-    x, y = dbl(2 * N, T, ctx_post=not executed); g += x; a += y
+    g += 2 * T * D * D
+    for _ in range(n_cond):  # one CoMoE pass per condition (MultiCondtionUniGenFlux)
+        g += 2 * (N * in_ch * D + N * D * E + N * (2 * D * D) + 2 * E * pooled * D)
+        x, y = dbl(N, N); g += x; a += y
+        x, y = dbl(2 * N, T, ctx_post=not executed); g += x; a += y
     return g, a
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the committed `ncu --set full`
+# capture (profiles/prof_gemm2cta_r01.ncu-rep, summary profiles/r01_ncu_gemm_2cta_summary.txt)
+NCU_GEMM_TRAFFIC = {"bytes": 104.824064e6 + 84.813312e6,
+                    "note": "gemm_bf16_kernel<2,256,6> M=4608 N=12288 K=3072: algorithmic 28.3 MB (A) + 75.5 MB (W) + 113.2 MB (C) "
+                            "= 217 MB per launch; measured 189.6 MB (A partly served from L2)"}
 
 
 def sample_clocks(stop, out):
@@ -105,6 +117,8 @@ def cpu_reference_sample(workload: str, steps: int, warmup: int):
     from oracle import unigen_oracle as O
     arch, height, width, T, _ = WORKLOADS[workload]
     cfg = O.FluxConfig.tiny() if arch == "tiny" else O.FluxConfig.flux()
+    if arch == "flux3":
+        cfg.condition_nums = 3
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     N = (height // 16) * (width // 16)
@@ -138,7 +152,8 @@ def cpu_reference_sample(workload: str, steps: int, warmup: int):
         times.append(time.perf_counter() - t0)
     t_sample = statistics.median(times)
     n_cd, n_cs = cfg.num_layers, cfg.num_single_layers
-    g_full, a_full = step_flops(D, H, N, T, cfg.num_layers, cfg.num_single_layers, n_cd, n_cs, cfg.expert_nums, executed=False)
+    g_full, a_full = step_flops(D, H, N, T, cfg.num_layers, cfg.num_single_layers, n_cd, n_cs, cfg.expert_nums, executed=False,
+                                n_cond=cfg.condition_nums)
     g_s, a_s = step_flops(D, H, N, T, 1, 1, 1, 1, cfg.expert_nums, executed=False)
     # remove the embedding / pre-stage terms from the sample's count (the slice has none of them)
     g0, a0 = step_flops(D, H, N, T, 0, 0, 0, 0, cfg.expert_nums, executed=False)
@@ -189,10 +204,11 @@ def run_native(args):
 
     arch_name, height, width, T, desc = WORKLOADS[args.workload]
     arch = FluxArch.tiny() if arch_name == "tiny" else FluxArch()
+    n_cond = 3 if arch_name == "flux3" else 1
     B = args.batch
     N = (height // 16) * (width // 16)
     model = UniGenFlux(arch, device=dev)
-    model.init_condition_block(condition_nums=1, control_params=canonical_control_params())
+    model.init_condition_block(condition_nums=n_cond, control_params=canonical_control_params())
     model.init_random_(seed=0)
     model.gemm_variant, model.attn_variant = args.gemm_variant, args.attn_variant
     model.use_cuda_graph = not args.no_graph
@@ -214,16 +230,23 @@ def run_native(args):
         condition_pooled_projections=pin(torch.randn(B, arch.pooled_projection_dim, generator=g)),
         timestep=pin(torch.full((B,), 0.75)), img_ids=pin(ids.clone()), txt_ids=pin(torch.zeros(T, 3)),
         condition_ids=pin(ids.clone()), rts_uniform=pin(torch.rand(B * N, E, generator=g)))
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    if n_cond > 1:  # MultiCondtionUniGenFlux takes LISTS, one entry per condition
+        host["condition_hidden_states"] = [pin(torch.randn(B, N, arch.in_channels, generator=g).to(torch.bfloat16)) for _ in range(n_cond)]
+        host["condition_pooled_projections"] = [pin(torch.randn(B, arch.pooled_projection_dim, generator=g)) for _ in range(n_cond)]
+        host["condition_ids"] = [pin(ids.clone()) for _ in range(n_cond)]
+        host["rts_uniform"] = [pin(torch.rand(B * N, E, generator=g)) for _ in range(n_cond)]
+    flat = [t for v in host.values() for t in (v if isinstance(v, list) else [v])]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in flat)
     out_host = pin(torch.empty(B, N, arch.in_channels, dtype=torch.bfloat16))
     d2h_bytes = out_host.numel() * out_host.element_size()
-    resident = {k: v.to(dev) for k, v in host.items()}
+    to_dev = lambda v, **k: [t.to(dev, **k) for t in v] if isinstance(v, list) else v.to(dev, **k)  # noqa: E731
+    resident = {k: to_dev(v) for k, v in host.items()}
 
     def step_resident():
         return model(**resident)[0]
 
     def step_e2e():
-        devin = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        devin = {k: to_dev(v, non_blocking=True) for k, v in host.items()}
         out = model(**devin)[0]
         out_host.copy_(out, non_blocking=True)
         return out
@@ -312,7 +335,8 @@ def run_native(args):
             tot[kname] = dict(ms=ms, flops=fl, launches=len(lst), tflops=fl / ms / 1e9 if ms > 0 else 0.0)
         gm = tot["gemm"]
         roof = {"bound": "tensor", "kernel": "ug::gemm_bf16_kernel (tcgen05)", "achieved": gm["tflops"], "peak": peak,
-                "unit": "TFLOP/s", "frac": gm["tflops"] / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "TFLOP/s", "frac": gm["tflops"] / peak, "traffic": NCU_GEMM_TRAFFIC["bytes"],
+                "traffic_note": NCU_GEMM_TRAFFIC["note"], "peak_source": peak_src,
                 "flops_per_step": gm["flops"], "launches_per_step": gm["launches"], "ms_per_step_in_kernel": gm["ms"],
                 "attention": {"achieved": tot["attn"]["tflops"], "frac": tot["attn"]["tflops"] / peak,
                               "launches_per_step": tot["attn"]["launches"], "ms_per_step_in_kernel": tot["attn"]["ms"]}}
@@ -324,8 +348,10 @@ def run_native(args):
         return
 
     D, H = model.inner_dim, arch.num_attention_heads
-    g_ex, a_ex = step_flops(D, H, N, T, arch.num_layers, arch.num_single_layers, arch.num_layers, arch.num_single_layers, E)
-    g_alg, a_alg = step_flops(D, H, N, T, arch.num_layers, arch.num_single_layers, arch.num_layers, arch.num_single_layers, E, executed=False)
+    g_ex, a_ex = step_flops(D, H, N, T, arch.num_layers, arch.num_single_layers, arch.num_layers, arch.num_single_layers, E,
+                            n_cond=n_cond)
+    g_alg, a_alg = step_flops(D, H, N, T, arch.num_layers, arch.num_single_layers, arch.num_layers, arch.num_single_layers, E,
+                              executed=False, n_cond=n_cond)
     cpu = None
     if not args.no_cpu_baseline:
         try:
