@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define UG_ABI_VERSION 3
+#define UG_ABI_VERSION 4
 
 typedef enum {
   UG_OK = 0,
@@ -164,6 +164,23 @@ int ug_ln_modulate(const void* x, int64_t x_row_stride, int64_t x_batch_stride, 
                    int64_t o_batch_stride, const float* shift, const float* scale, int64_t mod_batch_stride,
                    int32_t batch, int32_t rows, int32_t d, float eps, void* stream);
 
+/* Per-token AdaLN on capacity-slot buffers — the SD3.5 transformer-block experts run `SD3SingleTransformerBlock` on the
+ * dispatched (1, C, D) chunks with a PER-TOKEN (1, C, D) temb (src/UniGenUtils.py:354-363,386-414 with a 3-D `emb`;
+ * src/UniGenTransformer.py:256-258). A dispatched temb row is the temb of the sample the slot's token came from, or 0 for
+ * an empty slot, so its AdaLN vector is one of (samples + 1) distinct rows:
+ *   idx(r) = slot_token[r] < 0 ? empty_index : slot_token[r] / tokens_per_batch,   e(r) = r / capacity
+ *   out[r,:] = LayerNorm(x[r,:]) * (1 + scale[e, idx, :]) + shift[e, idx, :]         r in [0, experts*capacity)
+ * shift/scale: fp32, element (e, idx, c) at ptr[e*mod_expert_stride + idx*mod_index_stride + c]. */
+int ug_ln_modulate_slots(const void* x, int64_t x_row_stride, void* out, int64_t o_row_stride, const float* shift,
+                         const float* scale, int64_t mod_expert_stride, int64_t mod_index_stride,
+                         const int32_t* slot_token, int32_t experts, int32_t capacity, int32_t tokens_per_batch,
+                         int32_t empty_index, int32_t d, float eps, void* stream);
+/* x[r,:] += gate[e(r), idx(r), :] * y[r,:] — `gate_msa * attn_output` / `gate_mlp * ff_output` + residual of the same
+ * per-token AdaLN (src/UniGenUtils.py:399-400,410-412). x, y bf16; gate fp32 with the strides above. */
+int ug_gated_add_slots(void* x, int64_t x_row_stride, const void* y, int64_t y_row_stride, const float* gate,
+                       int64_t mod_expert_stride, int64_t mod_index_stride, const int32_t* slot_token, int32_t experts,
+                       int32_t capacity, int32_t tokens_per_batch, int32_t empty_index, int32_t d, void* stream);
+
 /* In-place per-head RMSNorm (learned weight) followed by interleaved-pair RoPE on rows of a [batch, rows, heads, dh]
  * bf16 view: diffusers RMSNorm(dh, eps) + apply_rotary_emb (src/UniGenUtils.py:597-599).
  * norm_weight: bf16 [heads / heads_per_weight, dh] — head h uses row h / heads_per_weight, so the Q and K halves of a
@@ -222,6 +239,7 @@ int ug_moe_route(const void* x, const float* wg, const float* rts_uniform, int32
 
 /* Gather + modulate: out[e*capacity + s, :] = mod[e, b(token), :] * (x[token, :] (+ addend[e*capacity+s, :]))
  * with token = slot_token[e*capacity+s]; empty slots give zero rows. tokens_per_batch maps token -> b.
+ * mod == NULL: plain dispatch (einsum sec,sm->ecm of src/UniGenUtils.py:140) without modulation.
  * `s ⊙ x` prologue of modulated_flatten (src/UniGenUtils.py:204-228) on the dispatched rows. */
 int ug_moe_gather_modulate(const void* x, const int32_t* slot_token, const float* mod, int64_t mod_expert_stride,
                            int64_t mod_batch_stride, const void* addend, void* out, int32_t experts,
@@ -241,6 +259,12 @@ int ug_cfg_combine(const void* uncond_bf16, const void* text_bf16, float guidanc
 /* FluxPipeline._pack_latents (unpack = 0): (B, C, H, W) -> (B, (H/2)(W/2), 4C); _unpack_latents (unpack = 1): inverse. */
 int ug_pack_latents(const void* src_bf16, void* dst_bf16, int32_t batch, int32_t channels, int32_t height, int32_t width,
                     int32_t unpack, void* stream);
+
+/* SD3 un-patchify (src/UniGenTransformer.py:693-704, `nhwpqc->nchpwq`): tokens bf16 (B, h*w, p*p*C) whose channel index is
+ * (py*p + px)*C + c  ->  image bf16 (B, C, h*p, w*p). (The patchify side of diffusers PatchEmbed's Conv2d(k=2, s=2) is
+ * ug_pack_latents: channel = c*4 + py*2 + px is exactly the flattened conv-weight layout, so the conv is one ug_gemm_bf16.) */
+int ug_unpatchify(const void* tokens_bf16, void* image_bf16, int32_t batch, int32_t h, int32_t w, int32_t p, int32_t channels,
+                  void* stream);
 
 #ifdef __cplusplus
 }

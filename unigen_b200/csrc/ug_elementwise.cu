@@ -32,11 +32,20 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const __nv_bfloat16* _
                                                           long long o_rs, long long o_bs,
                                                           const float* __restrict__ shift,
                                                           const float* __restrict__ scale, long long mod_bs, int batch,
-                                                          int rows, int d, float eps) {
+                                                          int rows, int d, float eps,
+                                                          const int* __restrict__ slot_token = nullptr, int capacity = 1,
+                                                          int tokens_per_batch = 1, int empty_index = 0,
+                                                          long long mod_es = 0) {
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp_global >= batch * rows) return;
   const int b = warp_global / rows, r = warp_global % rows;
+  // modulation row: the sample index b, or (slot mode) expert e = r / capacity and the sample the slot's token came from
+  long long mod_off = (long long)b * mod_bs;
+  if (slot_token) {
+    const int token = slot_token[r];
+    mod_off = (long long)(r / capacity) * mod_es + (long long)(token < 0 ? empty_index : token / tokens_per_batch) * mod_bs;
+  }
   const uint4* xp = reinterpret_cast<const uint4*>(x + (long long)b * x_bs + (long long)r * x_rs);
   const int nvec = d >> 3;
   uint4 buf[kMaxV];
@@ -66,8 +75,8 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const __nv_bfloat16* _
   }
   const float rstd = rsqrtf(warp_sum(var) / (float)d + eps);
   uint4* op = reinterpret_cast<uint4*>(out + (long long)b * o_bs + (long long)r * o_rs);
-  const float* sh = shift + (long long)b * mod_bs;
-  const float* sc = scale + (long long)b * mod_bs;
+  const float* sh = shift + mod_off;
+  const float* sc = scale + mod_off;
 #pragma unroll
   for (int i = 0; i < kMaxV; ++i) {
     const int v = lane + 32 * i;
@@ -289,6 +298,31 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, float*
     d[i] = __bfloat162float(s[i]);
 }
 
+// x[r,:] += gate[e(r), idx(r), :] * y[r,:] on capacity-slot buffers (per-token AdaLN gates of the SD3 experts)
+__global__ void __launch_bounds__(256) gated_add_slots_kernel(__nv_bfloat16* __restrict__ x, long long x_rs,
+                                                              const __nv_bfloat16* __restrict__ y, long long y_rs,
+                                                              const float* __restrict__ gate, long long mod_es, long long mod_bs,
+                                                              const int* __restrict__ slot_token, int rows, int capacity,
+                                                              int tokens_per_batch, int empty_index, int d) {
+  const int nvec = d >> 3;
+  const long long total = (long long)rows * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    const int r = (int)(i / nvec);
+    const int token = slot_token[r];
+    const float* g = gate + (long long)(r / capacity) * mod_es +
+                     (long long)(token < 0 ? empty_index : token / tokens_per_batch) * mod_bs + 8 * v;
+    const float4 g0 = *reinterpret_cast<const float4*>(g), g1 = *reinterpret_cast<const float4*>(g + 4);
+    const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    float xf[8], yf[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + (long long)r * x_rs + 8 * v), xf);
+    unpack8(*reinterpret_cast<const uint4*>(y + (long long)r * y_rs + 8 * v), yf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xf[j] += gv[j] * yf[j];
+    *reinterpret_cast<uint4*>(x + (long long)r * x_rs + 8 * v) = pack8(xf);
+  }
+}
+
 static inline int grid_for(long long threads, int block) {
   long long g = (threads + block - 1) / block;
   const long long cap = (long long)num_sms() * 16;
@@ -300,16 +334,17 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 using namespace ug;
 
-extern "C" int ug_ln_modulate(const void* x, int64_t x_rs, int64_t x_bs, void* out, int64_t o_rs, int64_t o_bs,
-                              const float* shift, const float* scale, int64_t mod_bs, int32_t batch, int32_t rows,
-                              int32_t d, float eps, void* stream) {
-  UG_CHECK_ARG(x && out && shift && scale, "ln_modulate: null pointer");
-  UG_CHECK_ARG(batch >= 1 && rows >= 1 && d >= 8 && d % 8 == 0, "ln_modulate: bad shape batch %d rows %d d %d", batch, rows, d);
-  UG_CHECK_ARG(x_rs % 8 == 0 && o_rs % 8 == 0 && x_bs % 8 == 0 && o_bs % 8 == 0 && mod_bs % 4 == 0 && aligned16(x) &&
-                   aligned16(out) && aligned16(shift) && aligned16(scale),
-               "ln_modulate: operands must be 16-byte aligned");
+static int launch_ln_modulate(const void* x, int64_t x_rs, int64_t x_bs, void* out, int64_t o_rs, int64_t o_bs,
+                              const float* shift, const float* scale, int64_t mod_bs, int32_t batch, int32_t rows, int32_t d,
+                              float eps, const int32_t* slot_token, int32_t capacity, int32_t tokens_per_batch,
+                              int32_t empty_index, int64_t mod_es, void* stream, const char* name) {
+  UG_CHECK_ARG(x && out && shift && scale, "%s: null pointer", name);
+  UG_CHECK_ARG(batch >= 1 && rows >= 1 && d >= 8 && d % 8 == 0, "%s: bad shape batch %d rows %d d %d", name, batch, rows, d);
+  UG_CHECK_ARG(x_rs % 8 == 0 && o_rs % 8 == 0 && x_bs % 8 == 0 && o_bs % 8 == 0 && mod_bs % 4 == 0 && mod_es % 4 == 0 &&
+                   aligned16(x) && aligned16(out) && aligned16(shift) && aligned16(scale),
+               "%s: operands must be 16-byte aligned", name);
   if (d > 8 * 32 * 16) {
-    set_error("ln_modulate: d = %d exceeds the register-resident row limit (4096)", d);
+    set_error("%s: d = %d exceeds the register-resident row limit (4096)", name, d);
     return UG_ERR_UNSUPPORTED;
   }
   const long long warps = (long long)batch * rows;
@@ -318,11 +353,47 @@ extern "C" int ug_ln_modulate(const void* x, int64_t x_rs, int64_t x_bs, void* o
   auto s = reinterpret_cast<cudaStream_t>(stream);
   auto xp = (const __nv_bfloat16*)x;
   auto op = (__nv_bfloat16*)out;
-  if (d <= 8 * 32 * 2) ln_modulate_kernel<2><<<grid, block, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, batch, rows, d, eps);
-  else if (d <= 8 * 32 * 6) ln_modulate_kernel<6><<<grid, block, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, batch, rows, d, eps);
-  else if (d <= 8 * 32 * 12) ln_modulate_kernel<12><<<grid, block, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, batch, rows, d, eps);
-  else ln_modulate_kernel<16><<<grid, block, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, batch, rows, d, eps);
-  UG_CHECK_LAUNCH("ln_modulate");
+#define UG_LN_LAUNCH(V) ln_modulate_kernel<V><<<grid, block, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, batch, rows, d, eps, slot_token, capacity, tokens_per_batch, empty_index, mod_es)
+  if (d <= 8 * 32 * 2) UG_LN_LAUNCH(2);
+  else if (d <= 8 * 32 * 6) UG_LN_LAUNCH(6);
+  else if (d <= 8 * 32 * 12) UG_LN_LAUNCH(12);
+  else UG_LN_LAUNCH(16);
+#undef UG_LN_LAUNCH
+  UG_CHECK_LAUNCH(name);
+  return UG_OK;
+}
+
+extern "C" int ug_ln_modulate(const void* x, int64_t x_rs, int64_t x_bs, void* out, int64_t o_rs, int64_t o_bs,
+                              const float* shift, const float* scale, int64_t mod_bs, int32_t batch, int32_t rows,
+                              int32_t d, float eps, void* stream) {
+  return launch_ln_modulate(x, x_rs, x_bs, out, o_rs, o_bs, shift, scale, mod_bs, batch, rows, d, eps, nullptr, 1, 1, 0, 0, stream,
+                            "ln_modulate");
+}
+
+extern "C" int ug_ln_modulate_slots(const void* x, int64_t x_rs, void* out, int64_t o_rs, const float* shift, const float* scale,
+                                    int64_t mod_expert_stride, int64_t mod_index_stride, const int32_t* slot_token,
+                                    int32_t experts, int32_t capacity, int32_t tokens_per_batch, int32_t empty_index, int32_t d,
+                                    float eps, void* stream) {
+  UG_CHECK_ARG(slot_token && experts >= 1 && capacity >= 1 && tokens_per_batch >= 1 && empty_index >= 0,
+               "ln_modulate_slots: bad slot arguments");
+  return launch_ln_modulate(x, x_rs, 0, out, o_rs, 0, shift, scale, mod_index_stride, 1, experts * capacity, d, eps, slot_token,
+                            capacity, tokens_per_batch, empty_index, mod_expert_stride, stream, "ln_modulate_slots");
+}
+
+extern "C" int ug_gated_add_slots(void* x, int64_t x_rs, const void* y, int64_t y_rs, const float* gate, int64_t mod_expert_stride,
+                                  int64_t mod_index_stride, const int32_t* slot_token, int32_t experts, int32_t capacity,
+                                  int32_t tokens_per_batch, int32_t empty_index, int32_t d, void* stream) {
+  UG_CHECK_ARG(x && y && gate && slot_token, "gated_add_slots: null pointer");
+  UG_CHECK_ARG(experts >= 1 && capacity >= 1 && tokens_per_batch >= 1 && empty_index >= 0 && d >= 8 && d % 8 == 0,
+               "gated_add_slots: bad shape");
+  UG_CHECK_ARG(x_rs % 8 == 0 && y_rs % 8 == 0 && mod_expert_stride % 4 == 0 && mod_index_stride % 4 == 0 && aligned16(x) &&
+                   aligned16(y) && aligned16(gate), "gated_add_slots: operands must be 16-byte aligned");
+  const int rows = experts * capacity;
+  const long long total = (long long)rows * (d >> 3);
+  gated_add_slots_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (__nv_bfloat16*)x, x_rs, (const __nv_bfloat16*)y, y_rs, gate, mod_expert_stride, mod_index_stride, slot_token, rows, capacity,
+      tokens_per_batch, empty_index, d);
+  UG_CHECK_LAUNCH("gated_add_slots");
   return UG_OK;
 }
 

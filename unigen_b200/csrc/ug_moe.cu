@@ -244,9 +244,11 @@ __global__ void __launch_bounds__(256) gather_modulate_kernel(const __nv_bfloat1
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = __bfloat162float(__float2bfloat16(f[j]));
       }
-      const float* m = mod + (long long)e * mod_es + (long long)b * mod_bs + 8 * v;
-      const float4 m0 = *reinterpret_cast<const float4*>(m), m1 = *reinterpret_cast<const float4*>(m + 4);
-      f[0] *= m0.x; f[1] *= m0.y; f[2] *= m0.z; f[3] *= m0.w; f[4] *= m1.x; f[5] *= m1.y; f[6] *= m1.z; f[7] *= m1.w;
+      if (mod) {
+        const float* m = mod + (long long)e * mod_es + (long long)b * mod_bs + 8 * v;
+        const float4 m0 = *reinterpret_cast<const float4*>(m), m1 = *reinterpret_cast<const float4*>(m + 4);
+        f[0] *= m0.x; f[1] *= m0.y; f[2] *= m0.z; f[3] *= m0.w; f[4] *= m1.x; f[5] *= m1.y; f[6] *= m1.z; f[7] *= m1.w;
+      }
       o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
       o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
     }
@@ -313,7 +315,7 @@ extern "C" int ug_moe_route(const void* x, const float* wg, const float* rts_uni
 extern "C" int ug_moe_gather_modulate(const void* x, const int32_t* slot_token, const float* mod, int64_t mod_es,
                                       int64_t mod_bs, const void* addend, void* out, int32_t experts, int32_t capacity,
                                       int32_t tokens_per_batch, int32_t d, void* stream) {
-  UG_CHECK_ARG(x && slot_token && mod && out, "moe_gather_modulate: null pointer");
+  UG_CHECK_ARG(x && slot_token && out, "moe_gather_modulate: null pointer");
   UG_CHECK_ARG(experts >= 1 && capacity >= 1 && tokens_per_batch >= 1 && d >= 8 && d % 8 == 0, "moe_gather_modulate: bad shape");
   UG_CHECK_ARG(mod_es % 4 == 0 && mod_bs % 4 == 0, "moe_gather_modulate: modulation strides must be multiples of 4");
   const long long total = (long long)experts * capacity * (d >> 3);

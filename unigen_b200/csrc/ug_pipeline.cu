@@ -40,6 +40,23 @@ __global__ void __launch_bounds__(256) pack_latents_kernel(const __nv_bfloat16* 
   }
 }
 
+// SD3 un-patchify (src/UniGenTransformer.py:693-704): tokens (B, h*w, p*p*C) with channel = (py*p + px)*C + c
+// -> image (B, C, h*p, w*p).  i indexes the IMAGE layout so that the stores are coalesced.
+__global__ void __launch_bounds__(256) unpatchify_kernel(const __nv_bfloat16* __restrict__ tok, __nv_bfloat16* __restrict__ img,
+                                                         int B, int h, int w, int p, int C) {
+  const int H = h * p, W = w * p;
+  const long long total = (long long)B * C * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    long long t = i / W;
+    const int y = (int)(t % H);
+    t /= H;
+    const int c = (int)(t % C), b = (int)(t / C);
+    const long long token = ((long long)b * h + y / p) * w + x / p;
+    img[i] = tok[token * (p * p * C) + ((y % p) * p + (x % p)) * C + c];
+  }
+}
+
 static inline int grid1d(long long n) {
   long long g = (n + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
@@ -72,5 +89,14 @@ extern "C" int ug_pack_latents(const void* src, void* dst, int32_t batch, int32_
   if (unpack) pack_latents_kernel<false><<<grid1d(n), 256, 0, s>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, batch, channels, height, width);
   else pack_latents_kernel<true><<<grid1d(n), 256, 0, s>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, batch, channels, height, width);
   UG_CHECK_LAUNCH("pack_latents");
+  return UG_OK;
+}
+extern "C" int ug_unpatchify(const void* tokens, void* image, int32_t batch, int32_t h, int32_t w, int32_t p, int32_t channels,
+                             void* stream) {
+  UG_CHECK_ARG(tokens && image && batch >= 1 && h >= 1 && w >= 1 && p >= 1 && channels >= 1, "unpatchify: bad arguments");
+  const long long n = (long long)batch * channels * h * p * w * p;
+  unpatchify_kernel<<<grid1d(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const __nv_bfloat16*)tokens, (__nv_bfloat16*)image,
+                                                                                 batch, h, w, p, channels);
+  UG_CHECK_LAUNCH("unpatchify");
   return UG_OK;
 }

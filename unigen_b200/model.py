@@ -111,32 +111,15 @@ class _TimeTextW:
         self.p2 = ws.linear(p + ".text_embedder.linear_2", D, D)
 
 
-class UniGenFlux(torch.nn.Module):
-    """B200-native drop-in for the reference `UniGenFlux` (Flux-arch denoiser + WeaveNet control branch + CoMoE)."""
+class _DenoiserBase(torch.nn.Module):
+    """What the Flux (`UniGenFlux`) and SD3.5 (`UniGenSD3`, sd3.py) mirrors share: fused weight storage under the
+    reference's state-dict names, the per-step AdaLN / time-text GEMV helpers, tracing and CUDA-graph replay."""
 
-    def __init__(self, arch: Optional[FluxArch] = None, device: Any = "cuda", **config):
-        super().__init__()
-        self.arch = arch or FluxArch(**config)
+    def _init_base(self, device):
         self.device_ = torch.device(device)
         if self.device_.type != "cuda":
-            raise ops.UgError("UniGenFlux (B200-native) needs a CUDA device: the hot path has no CPU fallback")
-        a = self.arch
-        self.config = types.SimpleNamespace(in_channels=a.in_channels, guidance_embeds=a.guidance_embeds,
-                                            num_attention_heads=a.num_attention_heads, attention_head_dim=a.attention_head_dim,
-                                            pooled_projection_dim=a.pooled_projection_dim, joint_attention_dim=a.joint_attention_dim,
-                                            axes_dims_rope=a.axes_dims_rope, num_layers=a.num_layers,
-                                            num_single_layers=a.num_single_layers)
-        self.inner_dim = a.num_attention_heads * a.attention_head_dim
-        D, dh = self.inner_dim, a.attention_head_dim
-        ws = self._ws = _Weights(self.device_)
-        self.x_embedder_w = ws.linear("x_embedder", D, a.in_channels)
-        self.context_embedder_w = ws.linear("context_embedder", D, a.joint_attention_dim)
-        self.time_text = _TimeTextW(ws, "time_text_embed", D, a.pooled_projection_dim, a.guidance_embeds)
-        self.double = [_DoubleBlockW(ws, f"transformer_blocks.{i}", D, dh) for i in range(a.num_layers)]
-        self.single = [_SingleBlockW(ws, f"single_transformer_blocks.{i}", D, dh) for i in range(a.num_single_layers)]
-        self.norm_out_w = ws.linear("norm_out.linear", 2 * D, D)
-        # proj_out has only in_channels (64) output features: keep it as is, the GEMM masks the partial N tile
-        self.proj_out_w = ws.linear("proj_out", a.in_channels, D)
+            raise ops.UgError(f"{type(self).__name__} (B200-native) needs a CUDA device: the hot path has no CPU fallback")
+        self._ws = _Weights(self.device_)
         self._control_ready = False
         self._buf_key = None
         self._graphs: Dict[Any, Any] = {}
@@ -145,8 +128,134 @@ class UniGenFlux(torch.nn.Module):
         self.attn_variant = 0
         self.overlap_mod_gemv = True  # AdaLN GEMVs (HBM-bound) on a side stream under the tensor-core-bound blocks
         self._side_stream = torch.cuda.Stream(device=self.device_)
-        self.fuse_qk_norm = False  # QK-RMSNorm + RoPE inside the q|k|v projection GEMM epilogue (False: separate in-place pass)
         self.trace: Optional[Dict[str, torch.Tensor]] = None  # set to {} to record per-block intermediates
+
+    @property
+    def dtype(self):
+        return BF16
+
+    @property
+    def device(self):
+        return self.device_
+
+    def state_dict(self, *args, **kwargs):  # reference key names, views into the fused storage
+        return dict(self._ws.views)
+
+    def parameters(self, recurse: bool = True):
+        return iter(self._ws.views.values())
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        missing = [k for k in self._ws.views if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in self._ws.views]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"load_state_dict: missing {missing[:5]}... unexpected {unexpected[:5]}...")
+        with torch.no_grad():
+            for k, v in state_dict.items():
+                if k in self._ws.views:
+                    dst = self._ws.views[k]
+                    if tuple(dst.shape) != tuple(v.shape):
+                        raise RuntimeError(f"size mismatch for {k}: {tuple(v.shape)} vs {tuple(dst.shape)}")
+                    dst.copy_(v.to(device=dst.device, dtype=dst.dtype))
+        self._weights_loaded()
+        return types.SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
+
+    def _weights_loaded(self):
+        """Hook: derived (non-state-dict) device tensors are rebuilt after a load / random init."""
+
+    @torch.no_grad()
+    def init_random_(self, seed: int = 0, zero_linear_std: Optional[float] = 0.02):
+        """nn.Linear / nn.Conv2d default init directly on the device (bench: the 18.7 B Flux parameters never exist on
+        the host). Zero-linears (`controlnet_add_*`) get N(0, zero_linear_std), or true zeros for None."""
+        gen = torch.Generator(device=self.device_).manual_seed(seed)
+        for k, v in self._ws.views.items():
+            if k.endswith(".pos_embed"):
+                continue  # PatchEmbed's sincos buffer: a constant of the architecture, filled at construction
+            if k.startswith("controlnet_add_"):
+                if zero_linear_std is None:
+                    v.zero_()
+                else:
+                    v.copy_(torch.randn(v.shape, device=v.device, generator=gen) * zero_linear_std)
+            elif ".norm_q." in k or ".norm_k." in k or ".norm_added_" in k:
+                v.fill_(1.0)
+            else:
+                w = self._ws.views[k[:-4] + "weight"] if k.endswith(".bias") else v
+                bound = 1.0 / math.sqrt(w[0].numel())  # fan_in (Linear: in_features; Conv2d: C * kh * kw)
+                v.copy_((torch.rand(v.shape, device=v.device, generator=gen) * 2 - 1) * bound)
+        self._weights_loaded()
+        return self
+
+    def _time_text(self, w: "_TimeTextW", t_emb: torch.Tensor, pooled: torch.Tensor, out: torch.Tensor, tmp: torch.Tensor,
+                   g_emb: Optional[torch.Tensor] = None, accumulate: bool = False):
+        """CombinedTimestep(Guidance)TextProjEmbeddings (SURVEY.md §A.4); accumulate=True adds into `out`
+        (merged_condition_temb = sum over conditions, reference :1314,1319)."""
+        ops.gemv(t_emb, w.t1[0], w.t1[1], out=tmp, silu_out=True)
+        ops.gemv(tmp, w.t2[0], w.t2[1], out=out, accumulate=accumulate)
+        if g_emb is not None and w.g1 is not None:
+            ops.gemv(g_emb, w.g1[0], w.g1[1], out=tmp, silu_out=True)
+            ops.gemv(tmp, w.g2[0], w.g2[1], out=out, accumulate=True)
+        ops.gemv(pooled, w.p1[0], w.p1[1], out=tmp, silu_out=True)
+        ops.gemv(tmp, w.p2[0], w.p2[1], out=out, accumulate=True)
+        return out
+
+    def _mods(self, buf, slot: int, n_chunks: int, w, temb: torch.Tensor) -> List[torch.Tensor]:
+        """AdaLN parameter vectors `linear(silu(temb)).chunk(n)`: fp32 [B, D] views into MOD."""
+        D = self.inner_dim
+        region = buf.MOD[:, slot * D:(slot + n_chunks) * D]
+        ops.gemv(temb, w[0], w[1], out=region, silu_in=True)
+        return [region[:, i * D:(i + 1) * D] for i in range(n_chunks)]
+
+    def _rec(self, name: str, t: torch.Tensor):
+        if self.trace is not None:
+            self.trace[name] = t.detach().float().clone()
+
+    def _run_staged(self, key, staged: Dict[str, Optional[torch.Tensor]], *args):
+        """`self._forward_impl(*args, **staged)`, eagerly or as a replay of a CUDA graph captured over static copies of
+        the staged inputs (one graph per `key`)."""
+        if not self.use_cuda_graph or self.trace is not None:
+            return self._forward_impl(*args, **staged)
+        g = self._graphs.get(key)
+        if g is None:
+            static = {k: (v.clone() if v is not None else None) for k, v in staged.items()}
+            self._forward_impl(*args, **static)  # warm-up: attribute setup, workspace allocation
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._forward_impl(*args, **static)
+            g = self._graphs[key] = (graph, static, out, ops.launch_count_in_last_capture())
+        graph, static, out, n_launch = g
+        for k, v in staged.items():
+            if v is not None:
+                static[k].copy_(v)
+        graph.replay()
+        ops.add_launches(n_launch)
+        return out
+
+
+class UniGenFlux(_DenoiserBase):
+    """B200-native drop-in for the reference `UniGenFlux` (Flux-arch denoiser + WeaveNet control branch + CoMoE)."""
+
+    def __init__(self, arch: Optional[FluxArch] = None, device: Any = "cuda", **config):
+        super().__init__()
+        self.arch = arch or FluxArch(**config)
+        self._init_base(device)
+        a = self.arch
+        self.config = types.SimpleNamespace(in_channels=a.in_channels, guidance_embeds=a.guidance_embeds,
+                                            num_attention_heads=a.num_attention_heads, attention_head_dim=a.attention_head_dim,
+                                            pooled_projection_dim=a.pooled_projection_dim, joint_attention_dim=a.joint_attention_dim,
+                                            axes_dims_rope=a.axes_dims_rope, num_layers=a.num_layers,
+                                            num_single_layers=a.num_single_layers)
+        self.inner_dim = a.num_attention_heads * a.attention_head_dim
+        D, dh = self.inner_dim, a.attention_head_dim
+        ws = self._ws
+        self.x_embedder_w = ws.linear("x_embedder", D, a.in_channels)
+        self.context_embedder_w = ws.linear("context_embedder", D, a.joint_attention_dim)
+        self.time_text = _TimeTextW(ws, "time_text_embed", D, a.pooled_projection_dim, a.guidance_embeds)
+        self.double = [_DoubleBlockW(ws, f"transformer_blocks.{i}", D, dh) for i in range(a.num_layers)]
+        self.single = [_SingleBlockW(ws, f"single_transformer_blocks.{i}", D, dh) for i in range(a.num_single_layers)]
+        self.norm_out_w = ws.linear("norm_out.linear", 2 * D, D)
+        # proj_out has only in_channels (64) output features: keep it as is, the GEMM masks the partial N tile
+        self.proj_out_w = ws.linear("proj_out", a.in_channels, D)
+        self.fuse_qk_norm = False  # QK-RMSNorm + RoPE inside the q|k|v projection GEMM epilogue (False: separate in-place pass)
 
     # ---------------------------------------------------------------------------------------------------------
     # reference API: construction
@@ -215,55 +324,6 @@ class UniGenFlux(torch.nn.Module):
         self._control_ready = True
 
     # ---------------------------------------------------------------------------------------------------------
-    # weights
-    # ---------------------------------------------------------------------------------------------------------
-    @property
-    def dtype(self):
-        return BF16
-
-    @property
-    def device(self):
-        return self.device_
-
-    def state_dict(self, *args, **kwargs):  # reference key names, views into the fused storage
-        return dict(self._ws.views)
-
-    def parameters(self, recurse: bool = True):
-        return iter(self._ws.views.values())
-
-    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
-        missing = [k for k in self._ws.views if k not in state_dict]
-        unexpected = [k for k in state_dict if k not in self._ws.views]
-        if strict and (missing or unexpected):
-            raise RuntimeError(f"load_state_dict: missing {missing[:5]}... unexpected {unexpected[:5]}...")
-        with torch.no_grad():
-            for k, v in state_dict.items():
-                if k in self._ws.views:
-                    dst = self._ws.views[k]
-                    if tuple(dst.shape) != tuple(v.shape):
-                        raise RuntimeError(f"size mismatch for {k}: {tuple(v.shape)} vs {tuple(dst.shape)}")
-                    dst.copy_(v.to(device=dst.device, dtype=dst.dtype))
-        return types.SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
-
-    @torch.no_grad()
-    def init_random_(self, seed: int = 0, zero_linear_std: Optional[float] = 0.02):
-        """nn.Linear default init directly on the device (bench: 18.7 B parameters never exist on the host)."""
-        gen = torch.Generator(device=self.device_).manual_seed(seed)
-        for k, v in self._ws.views.items():
-            if k.startswith("controlnet_add_"):
-                if zero_linear_std is None:
-                    v.zero_()
-                else:
-                    v.copy_(torch.randn(v.shape, device=v.device, generator=gen) * zero_linear_std)
-            elif ".norm_q." in k or ".norm_k." in k or ".norm_added_" in k:
-                v.fill_(1.0)
-            else:
-                fan_in = self._ws.views[k[:-4] + "weight"].shape[-1] if k.endswith(".bias") else v.shape[-1]
-                bound = 1.0 / math.sqrt(fan_in)
-                v.copy_((torch.rand(v.shape, device=v.device, generator=gen) * 2 - 1) * bound)
-        return self
-
-    # ---------------------------------------------------------------------------------------------------------
     # workspaces
     # ---------------------------------------------------------------------------------------------------------
     def _workspace(self, B: int, N: int, T: int):
@@ -295,26 +355,6 @@ class UniGenFlux(torch.nn.Module):
     # ---------------------------------------------------------------------------------------------------------
     # building blocks (each line = one kernel launch in libunigen_b200.so)
     # ---------------------------------------------------------------------------------------------------------
-    def _time_text(self, w: _TimeTextW, t_emb: torch.Tensor, pooled: torch.Tensor, out: torch.Tensor, tmp: torch.Tensor,
-                   g_emb: Optional[torch.Tensor] = None, accumulate: bool = False):
-        """CombinedTimestep(Guidance)TextProjEmbeddings (SURVEY.md §A.4); accumulate=True adds into `out`
-        (merged_condition_temb = sum over conditions, reference :1314,1319)."""
-        ops.gemv(t_emb, w.t1[0], w.t1[1], out=tmp, silu_out=True)
-        ops.gemv(tmp, w.t2[0], w.t2[1], out=out, accumulate=accumulate)
-        if g_emb is not None and w.g1 is not None:
-            ops.gemv(g_emb, w.g1[0], w.g1[1], out=tmp, silu_out=True)
-            ops.gemv(tmp, w.g2[0], w.g2[1], out=out, accumulate=True)
-        ops.gemv(pooled, w.p1[0], w.p1[1], out=tmp, silu_out=True)
-        ops.gemv(tmp, w.p2[0], w.p2[1], out=out, accumulate=True)
-        return out
-
-    def _mods(self, buf, slot: int, n_chunks: int, w, temb: torch.Tensor) -> List[torch.Tensor]:
-        """AdaLN parameter vectors `linear(silu(temb)).chunk(n)`: fp32 [B, D] views into MOD."""
-        D = self.inner_dim
-        region = buf.MOD[:, slot * D:(slot + n_chunks) * D]
-        ops.gemv(temb, w[0], w[1], out=region, silu_in=True)
-        return [region[:, i * D:(i + 1) * D] for i in range(n_chunks)]
-
     def _attend(self, buf, S: int, out: torch.Tensor):
         """Joint attention over rows [0, S) of the fused QKV buffer (q/k already normalised + rotated) -> out [B, S, D].
         The sequence-parallel subclass replaces this with the Ulysses exchange (parallel.py)."""
@@ -392,10 +432,6 @@ class UniGenFlux(torch.nn.Module):
             ops.qk_rmsnorm_rope(buf.QKV[:, :S, :2 * D], 2 * H, dh, w.rms, rope[:S] if rope is not None else None, heads_per_weight=H)
         self._attend(buf, S, cat[:, :, :D])
         ops.gemm(cat, w.out[0], out=x_out, bias=w.out[1], gate=gate, residual=x_in, variant=gv)
-
-    def _rec(self, name: str, t: torch.Tensor):
-        if self.trace is not None:
-            self.trace[name] = t.detach().float().clone()
 
     # ---------------------------------------------------------------------------------------------------------
     # CoMoE pre-stage (reference preprocess_moe_forward :1028-1068, moe_forward :969-1026, MOELayer.forward,
@@ -489,27 +525,9 @@ class UniGenFlux(torch.nn.Module):
             staged[f"cp{c}"] = cp if cp.dim() == 2 else cp.unsqueeze(0)
             staged[f"cid{c}"] = f32(sq(cid_list[c]))
             staged[f"u{c}"] = f32(u_list[c])
-        if not self.use_cuda_graph or self.trace is not None:
-            return self._forward_impl(float(conditioning_scale), **staged)
-        # ---- CUDA-graph path: static input buffers, one captured graph per (shape, scale) ----
         key = (B, N, T, float(conditioning_scale), guidance is not None,
                tuple((k, v.dtype) for k, v in staged.items() if v is not None))
-        g = self._graphs.get(key)
-        if g is None:
-            static = {k: (v.clone() if v is not None else None) for k, v in staged.items()}
-            self._forward_impl(float(conditioning_scale), **static)  # warm-up: attribute setup, workspace allocation
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                out = self._forward_impl(float(conditioning_scale), **static)
-            g = self._graphs[key] = (graph, static, out, ops.launch_count_in_last_capture())
-        graph, static, out, n_launch = g
-        for k, v in staged.items():
-            if v is not None:
-                static[k].copy_(v)
-        graph.replay()
-        ops.add_launches(n_launch)
-        return out
+        return self._run_staged(key, staged, float(conditioning_scale))
 
     def _forward_impl(self, conditioning_scale, hs, es, pooled, timestep, guidance, txt_ids, img_ids, **cond):
         a = self.arch

@@ -14,7 +14,7 @@ from ._lib import UG_ACT_GELU_TANH, UG_ACT_NONE, AttnArgs, GemmArgs, UgError, ch
 
 __all__ = ["gemm", "lora_down", "attention", "expand_segment_mask", "ln_modulate", "qk_rmsnorm_rope", "rope_table", "gemv",
            "timestep_embedding", "add", "copy", "to_bf16", "to_f32", "moe_route", "moe_gather_modulate",
-           "moe_combine", "euler_step", "cfg_combine", "pack_latents", "unpack_latents", "launch_count", "reset_launch_count", "UG_ACT_NONE", "UG_ACT_GELU_TANH", "UgError"]
+           "moe_combine", "ln_modulate_slots", "gated_add_slots", "unpatchify", "euler_step", "cfg_combine", "pack_latents", "unpack_latents", "launch_count", "reset_launch_count", "UG_ACT_NONE", "UG_ACT_GELU_TANH", "UgError"]
 
 BF16 = torch.bfloat16
 
@@ -212,6 +212,43 @@ def ln_modulate(x: torch.Tensor, out: torch.Tensor, shift: torch.Tensor, scale: 
     return out
 
 
+def _slot_mod(t: torch.Tensor, name: str):
+    """fp32 [E, n_index, D] view of per-expert AdaLN rows -> (ptr, expert stride, index stride)."""
+    _dev(t, name, torch.float32)
+    if t.dim() != 3 or t.stride(2) != 1:
+        raise UgError(f"{name}: expected an fp32 [experts, index, d] view with contiguous d")
+    return t.data_ptr(), t.stride(0), t.stride(1)
+
+
+def ln_modulate_slots(x: torch.Tensor, out: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, slot_token: torch.Tensor,
+                      experts: int, capacity: int, tokens_per_batch: int, empty_index: int, eps: float = 1e-6) -> torch.Tensor:
+    """Per-token AdaLN on [experts*capacity, D] slot buffers; shift/scale: fp32 [experts, samples+1, D] views
+    (row `empty_index` = the AdaLN vector of an all-zero temb, used by empty slots)."""
+    _dev(x, "ln_slots.x", BF16), _dev(out, "ln_slots.out", BF16), _dev(slot_token, "ln_slots.slot_token", torch.int32)
+    D = x.shape[-1]
+    sp, ses, sis = _slot_mod(shift, "ln_slots.shift")
+    cp, ces, cis = _slot_mod(scale, "ln_slots.scale")
+    if (ses, sis) != (ces, cis) or x.shape[0] != experts * capacity or slot_token.numel() != experts * capacity:
+        raise UgError("ln_modulate_slots: shift / scale strides differ or the slot buffer has the wrong row count")
+    check(_lib.load().ug_ln_modulate_slots(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), sp, cp, ses, sis,
+                                           slot_token.data_ptr(), experts, capacity, tokens_per_batch, empty_index, D,
+                                           float(eps), _stream()), "ug_ln_modulate_slots")
+    return out
+
+
+def gated_add_slots(x: torch.Tensor, y: torch.Tensor, gate: torch.Tensor, slot_token: torch.Tensor, experts: int,
+                    capacity: int, tokens_per_batch: int, empty_index: int) -> torch.Tensor:
+    """In place: x[r] += gate[e(r), idx(r)] * y[r] on [experts*capacity, D] slot buffers."""
+    _dev(x, "gated_add.x", BF16), _dev(y, "gated_add.y", BF16), _dev(slot_token, "gated_add.slot_token", torch.int32)
+    gp, ges, gis = _slot_mod(gate, "gated_add.gate")
+    if x.shape != y.shape or x.shape[0] != experts * capacity:
+        raise UgError("gated_add_slots: x / y shape mismatch")
+    check(_lib.load().ug_gated_add_slots(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), gp, ges, gis,
+                                         slot_token.data_ptr(), experts, capacity, tokens_per_batch, empty_index,
+                                         x.shape[-1], _stream()), "ug_gated_add_slots")
+    return x
+
+
 def qk_rmsnorm_rope(x: torch.Tensor, heads: int, head_dim: int, weight: torch.Tensor,
                     cos_sin: Optional[torch.Tensor] = None, eps: float = 1e-6, heads_per_weight: int = 0) -> torch.Tensor:
     """In-place RMSNorm(weight)+RoPE on a [B, rows, heads*head_dim] view. cos_sin: fp32 [rows, head_dim] table.
@@ -332,15 +369,19 @@ def moe_route(x: torch.Tensor, wg: torch.Tensor, rts_uniform: torch.Tensor, capa
     return r
 
 
-def moe_gather_modulate(x: torch.Tensor, slot_token: torch.Tensor, mod: torch.Tensor, experts: int, capacity: int,
+def moe_gather_modulate(x: torch.Tensor, slot_token: torch.Tensor, mod: Optional[torch.Tensor], experts: int, capacity: int,
                         tokens_per_batch: int, addend: Optional[torch.Tensor] = None,
                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[e*C+s] = mod[b(token), e] * (x[token] (+ addend[e*C+s])); mod: fp32 [B, E, D] (batch-major, as one stacked GEMV writes it)."""
-    _dev(x, "gather.x", BF16), _dev(mod, "gather.mod", torch.float32)
+    """out[e*C+s] = mod[b(token), e] * (x[token] (+ addend[e*C+s])); mod: fp32 [B, E, D] (batch-major, as one stacked GEMV
+    writes it) or None for a plain dispatch gather."""
+    _dev(x, "gather.x", BF16)
+    if mod is not None:
+        _dev(mod, "gather.mod", torch.float32)
     D = x.shape[-1]
     if out is None:
         out = torch.empty(experts * capacity, D, device=x.device, dtype=BF16)
-    check(_lib.load().ug_moe_gather_modulate(x.data_ptr(), slot_token.data_ptr(), mod.data_ptr(), mod.stride(1), mod.stride(0),
+    check(_lib.load().ug_moe_gather_modulate(x.data_ptr(), slot_token.data_ptr(), mod.data_ptr() if mod is not None else 0,
+                                             mod.stride(1) if mod is not None else 0, mod.stride(0) if mod is not None else 0,
                                              addend.data_ptr() if addend is not None else 0, out.data_ptr(), experts,
                                              capacity, tokens_per_batch, D, _stream()), "ug_moe_gather_modulate")
     return out
@@ -374,11 +415,14 @@ def cfg_combine(uncond: torch.Tensor, text: torch.Tensor, guidance_scale: float,
     return out
 
 
-def pack_latents(x: torch.Tensor) -> torch.Tensor:
+def pack_latents(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(B, C, H, W) bf16 -> (B, (H/2)(W/2), 4C)."""
     _dev(x, "pack.x", BF16)
     B, Cc, H, W = x.shape
-    out = torch.empty(B, (H // 2) * (W // 2), Cc * 4, device=x.device, dtype=BF16)
+    if out is None:
+        out = torch.empty(B, (H // 2) * (W // 2), Cc * 4, device=x.device, dtype=BF16)
+    elif not out.is_contiguous() or out.numel() != x.numel():
+        raise UgError("pack_latents: out must be a contiguous (B, (H/2)(W/2), 4C) buffer")
     check(_lib.load().ug_pack_latents(x.contiguous().data_ptr(), out.data_ptr(), B, Cc, H, W, 0, _stream()), "ug_pack_latents")
     return out
 
@@ -389,4 +433,16 @@ def unpack_latents(x: torch.Tensor, height: int, width: int) -> torch.Tensor:
     B, _, C4 = x.shape
     out = torch.empty(B, C4 // 4, height, width, device=x.device, dtype=BF16)
     check(_lib.load().ug_pack_latents(x.contiguous().data_ptr(), out.data_ptr(), B, C4 // 4, height, width, 1, _stream()), "ug_pack_latents")
+    return out
+
+
+def unpatchify(tokens: torch.Tensor, h: int, w: int, p: int, channels: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B, h*w, p*p*C) bf16 tokens with channel order (py, px, c) -> (B, C, h*p, w*p)."""
+    _dev(tokens, "unpatchify.tokens", BF16)
+    B = tokens.shape[0]
+    if not tokens.is_contiguous() or tokens.shape[1] != h * w or tokens.shape[2] != p * p * channels:
+        raise UgError(f"unpatchify: expected contiguous (B, {h * w}, {p * p * channels}) tokens, got {tuple(tokens.shape)}")
+    if out is None:
+        out = torch.empty(B, channels, h * p, w * p, device=tokens.device, dtype=BF16)
+    check(_lib.load().ug_unpatchify(tokens.data_ptr(), out.data_ptr(), B, h, w, p, channels, _stream()), "ug_unpatchify")
     return out
