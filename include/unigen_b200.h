@@ -9,7 +9,7 @@
  *   - plain C types only; all pointers are DEVICE pointers unless a parameter says "host".
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
  *   - every function returns UG_OK (0) or a negative ug_status; the message is in ug_last_error().
- *   - no function allocates device memory, synchronises the stream, or falls back to the CPU.
+ *   - no function allocates device memory (except ug_peer_alloc), synchronises the stream, or falls back to the CPU.
  *   - strides are in ELEMENTS of the tensor's dtype; bf16 rows must be 16-byte aligned.
  *   - "batch" views: a logical [batch, rows, cols] tensor is (ptr, row_stride, batch_stride), which lets the
  *     text / image / condition streams live inside one joint buffer without concat copies.
@@ -55,6 +55,9 @@ void ug_reset_launch_count(void);
 #define UG_ACT_NONE 0
 #define UG_ACT_GELU_TANH 1
 #define UG_MAX_SEGMENTS 8
+#define UG_MAX_PEERS 8
+#define UG_PEER_HEADER_BYTES 4096
+#define UG_PEER_HANDLE_BYTES 64
 
 typedef struct ug_gemm_args {
   const void* a;          /* bf16 */
@@ -259,6 +262,59 @@ int ug_cfg_combine(const void* uncond_bf16, const void* text_bf16, float guidanc
 /* FluxPipeline._pack_latents (unpack = 0): (B, C, H, W) -> (B, (H/2)(W/2), 4C); _unpack_latents (unpack = 1): inverse. */
 int ug_pack_latents(const void* src_bf16, void* dst_bf16, int32_t batch, int32_t channels, int32_t height, int32_t width,
                     int32_t unpack, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Ulysses sequence parallelism over peer memory (NVLink 5 / NVSwitch), one process per GPU — north_star subsystem (4).
+ * The reference has no sequence parallelism; these entry points are the exchange step of the
+ * sharded forward, fused into the kernels that produce the data instead of staging copies + NCCL all-to-all.
+ * Every rank allocates a pool of the same size; bytes [0, UG_PEER_HEADER_BYTES) are the control block (barrier flags,
+ * epoch, error word), payload buffers live at offsets the host chooses identically on all ranks.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct ug_peer_table {
+  int32_t world, rank;
+  void* base[UG_MAX_PEERS]; /* this process's mapping of rank r's pool; base[rank] = the local pool */
+} ug_peer_table;
+
+/* cudaMalloc'd, zero-filled pool / cudaFree. (The only allocating calls of the ABI: IPC export needs a cudaMalloc base.) */
+int ug_peer_alloc(size_t bytes, void** dev_ptr);
+int ug_peer_free(void* dev_ptr);
+/* CUDA IPC handle of a pool (exchange the 64 bytes through any host channel, e.g. torch.distributed.all_gather_object). */
+int ug_peer_export(const void* dev_ptr, uint8_t handle[UG_PEER_HANDLE_BYTES]);
+int ug_peer_open(const uint8_t handle[UG_PEER_HANDLE_BYTES], void** peer_ptr);
+int ug_peer_close(void* peer_ptr);
+/* Device-side barrier of all ranks on `stream` (release/acquire flags in the control blocks; no host sync; graph-capturable).
+ * Every rank must issue the same sequence of barriers. A rank that waits ~2 s sets the error word instead of hanging. */
+int ug_peer_barrier(const ug_peer_table* table, void* stream);
+/* Reads the local error word (synchronous cudaMemcpy): 0 = every barrier so far completed. */
+int ug_peer_error(const ug_peer_table* table, int32_t* error_host);
+
+/* seq-shard x all heads -> all tokens x head-shard, fused with the per-token QK-RMSNorm + RoPE pass:
+ * reads `rows` local rows of the fused q|k|v projection ([rows, 3*heads*head_dim] bf16), normalises / rotates the q and k
+ * heads exactly like ug_qk_rmsnorm_rope, and stores head h of block `which` (q, k, v) into rank h / (heads/world)'s
+ * receive buffer  recv[which][dst_row0 + r][(h % (heads/world)) * head_dim ...],  recv = bf16 [3, seq_total,
+ * heads/world*head_dim] at byte `dst_offset` of that rank's pool. */
+typedef struct ug_qkv_scatter_args {
+  const void* qkv;
+  int64_t row_stride;
+  int32_t rows, heads, head_dim;
+  float eps;
+  const void* norm_weight; /* bf16 [2, head_dim] (norm_q, norm_k) or NULL */
+  const float* cos_sin;    /* fp32 [rows, head_dim] rows of the LOCAL tokens, or NULL */
+  int64_t dst_offset;
+  int32_t seq_total, dst_row0;
+} ug_qkv_scatter_args;
+int ug_qkv_scatter(const ug_peer_table* table, const ug_qkv_scatter_args* args, void* stream);
+
+/* ug_attention_bf16 over this rank's head shard of ALL tokens with the heads -> sequence exchange fused into the epilogue:
+ * output row q is stored into rank q / rows_per_rank's buffer (bf16 rows of args->o_row_stride elements at byte `o_offset`
+ * of its pool) at row q % rows_per_rank, columns [rank*heads*head_dim, (rank+1)*heads*head_dim). args->o is ignored. */
+int ug_attention_bf16_peer(const ug_attn_args* args, const ug_peer_table* table, int64_t o_offset, int32_t rows_per_rank,
+                           void* stream);
+
+/* All-gather by peer stores: rows [dst_row0, dst_row0 + rows) of the bf16 buffer at byte `dst_offset` of EVERY rank's pool
+ * <- src rows (the residual stream for the replicated CoMoE pre-stage; the final velocity). */
+int ug_peer_bcast_rows(const ug_peer_table* table, const void* src, int64_t src_row_stride, int32_t rows, int32_t d,
+                       int64_t dst_offset, int64_t dst_row_stride, int32_t dst_row0, void* stream);
 
 /* SD3 un-patchify (src/UniGenTransformer.py:693-704, `nhwpqc->nchpwq`): tokens bf16 (B, h*w, p*p*C) whose channel index is
  * (py*p + px)*C + c  ->  image bf16 (B, C, h*p, w*p). (The patchify side of diffusers PatchEmbed's Conv2d(k=2, s=2) is

@@ -1,4 +1,6 @@
-"""2-GPU check of Ulysses sequence parallelism against the single-GPU forward (skipped on a 1-GPU box)."""
+"""Ulysses sequence parallelism against the single-GPU forward: the fused peer-memory exchange (ug_qkv_scatter,
+ug_attention_bf16_peer, ug_peer_barrier, ug_peer_bcast_rows over CUDA IPC pools) runs with world size 1 on any box — every
+kernel of the exchange executes, all peer pointers map to the local pool — and with 2 ranks when the box has 2 GPUs."""
 import json
 import subprocess
 import sys
@@ -11,12 +13,22 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def test_ulysses_sp_equals_single_gpu_forward():
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-                        "127.0.0.1", "--master-port", "29541", str(ROOT / "tools" / "sp_check.py"), "--workload", "tiny"],
+def _run(world, port, *extra):
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), str(ROOT / "tools" / "sp_check.py"), "--workload", "tiny", *extra],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
-    rec = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+
+
+def test_peer_exchange_world1_equals_single_gpu_forward_and_graph_replay():
+    rec = _run(1, 29540, "--exchange", "peer", "--graph")
+    assert rec["ok"] and rec["rel_l2"] == 0.0 and rec["graph_equals_eager"] and rec["peer_barrier_timeouts"] == 0, rec
+
+
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_ulysses_sp_equals_single_gpu_forward(exchange):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rec = _run(2, 29541, "--exchange", exchange, *(["--graph"] if exchange == "peer" else []))
     assert rec["ok"], rec

@@ -17,6 +17,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="tiny")
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--graph", action="store_true", help="replay the sequence-parallel step as one CUDA graph per rank (peer exchange)")
     args = ap.parse_args()
     from unigen_b200.model import FluxArch, UniGenFlux, canonical_control_params
     from unigen_b200.parallel import SequenceParallelUniGenFlux
@@ -40,7 +42,7 @@ def main():
                condition_pooled_projections=torch.randn(1, 768, generator=g), timestep=torch.tensor([0.5]), img_ids=ids,
                txt_ids=torch.zeros(T, 3), condition_ids=ids.clone(), rts_uniform=torch.rand(N, E, generator=g))
     inp = {k: v.to(dev) for k, v in inp.items()}
-    sp = SequenceParallelUniGenFlux(arch, device=dev)
+    sp = SequenceParallelUniGenFlux(arch, device=dev, exchange=args.exchange)
     sp.init_condition_block(condition_nums=1, control_params=canonical_control_params())
     sp.init_random_(seed=0)
     out_sp = sp(**inp)[0].float().clone()
@@ -70,12 +72,27 @@ def main():
         t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
+    sp.use_cuda_graph = ref.use_cuda_graph = bool(args.graph)
+    if args.graph:  # the graph replay must reproduce the eager sequence-parallel result bit for bit
+        for _ in range(2):
+            out_g = sp(**inp)[0].float()
+        graph_equal = bool(torch.equal(out_g, out_sp))
+    else:
+        graph_equal = None
     ms_sp = timed(lambda: sp(**inp))
     ms_ref = timed(lambda: ref(**inp))
+    peer_err = sp._pool.error() if sp._pool is not None else 0
+    errs = torch.tensor([peer_err], device=dev)
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(json.dumps({"check": "ulysses_sp_vs_single_gpu", "workload": args.workload, "world": world, "rel_l2": rel,
-                          "routing_identical": same_route, "ok": bool(rel < 5e-3 and same_route), "ms_per_step_sp": ms_sp,
+                          "exchange": args.exchange,
+                          "cuda_graph": bool(args.graph), "graph_equals_eager": graph_equal, "peer_barrier_timeouts": int(errs.item()),
+                          "routing_identical": same_route,
+                          "ok": bool(rel < 5e-3 and same_route and errs.item() == 0 and graph_equal is not False), "ms_per_step_sp": ms_sp,
                           "ms_per_step_single_gpu": ms_ref, "latency_speedup": ms_ref / ms_sp}), flush=True)
+    if sp._pool is not None:
+        sp._pool.close()
     dist.destroy_process_group()
 
 

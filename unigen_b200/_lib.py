@@ -36,6 +36,21 @@ class GemmArgs(C.Structure):
     ]
 
 
+UG_MAX_PEERS = 8
+UG_PEER_HEADER_BYTES = 4096
+UG_PEER_HANDLE_BYTES = 64
+
+
+class PeerTable(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("base", C.c_void_p * UG_MAX_PEERS)]
+
+
+class QkvScatterArgs(C.Structure):
+    _fields_ = [("qkv", C.c_void_p), ("row_stride", C.c_int64), ("rows", C.c_int32), ("heads", C.c_int32),
+                ("head_dim", C.c_int32), ("eps", C.c_float), ("norm_weight", C.c_void_p), ("cos_sin", C.c_void_p),
+                ("dst_offset", C.c_int64), ("seq_total", C.c_int32), ("dst_row0", C.c_int32)]
+
+
 class AttnArgs(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p),
@@ -80,6 +95,16 @@ SIGNATURES = {
     "ug_euler_step": (C.c_int, [_VP, _VP, _F32, _F32, _I64, _VP]),
     "ug_cfg_combine": (C.c_int, [_VP, _VP, _F32, _VP, _I64, _VP]),
     "ug_pack_latents": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "ug_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "ug_peer_free": (C.c_int, [_VP]),
+    "ug_peer_export": (C.c_int, [_VP, C.POINTER(C.c_uint8)]),
+    "ug_peer_open": (C.c_int, [C.POINTER(C.c_uint8), C.POINTER(C.c_void_p)]),
+    "ug_peer_close": (C.c_int, [_VP]),
+    "ug_peer_barrier": (C.c_int, [C.POINTER(PeerTable), _VP]),
+    "ug_peer_error": (C.c_int, [C.POINTER(PeerTable), C.POINTER(C.c_int32)]),
+    "ug_qkv_scatter": (C.c_int, [C.POINTER(PeerTable), C.POINTER(QkvScatterArgs), _VP]),
+    "ug_attention_bf16_peer": (C.c_int, [C.POINTER(AttnArgs), C.POINTER(PeerTable), _I64, _I32, _VP]),
+    "ug_peer_bcast_rows": (C.c_int, [C.POINTER(PeerTable), _VP, _I64, _I32, _I32, _I64, _I64, _I32, _VP]),
     "ug_unpatchify": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
 }
 

@@ -26,7 +26,20 @@ struct AttnParams {
   int n_seg;
   int bounds[UG_MAX_SEGMENTS + 1];
   unsigned int visible[UG_MAX_SEGMENTS];
+  // Ulysses heads->sequence exchange fused into the epilogue (ug_attention_bf16_peer): query row q belongs to rank
+  // q / o_rows_per_rank and is stored at o_peer[rank] (that rank's peer-mapped output buffer, already offset to this
+  // rank's head columns) + (q % o_rows_per_rank) * o_rs.  o_rows_per_rank == 0: plain local output `o`.
+  int o_rows_per_rank;
+  __nv_bfloat16* o_peer[UG_MAX_PEERS];
 };
+
+__device__ __forceinline__ __nv_bfloat16* o_row_ptr(const AttnParams& p, int b, int q_row, int head, int dh) {
+  if (p.o_rows_per_rank > 0) {
+    const int r = q_row / p.o_rows_per_rank;
+    return p.o_peer[r] + (long long)(q_row - r * p.o_rows_per_rank) * p.o_rs + head * dh;
+  }
+  return p.o + (long long)b * p.o_bs + (long long)q_row * p.o_rs + head * dh;
+}
 
 template <int kDh, bool kPInTmem>
 struct AttnCfg {
@@ -338,7 +351,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       tc_fence_after();
     }
     const float inv_l = l > 0.f ? 1.f / l : 0.f;
-    __nv_bfloat16* orow = p.o + (long long)b * p.o_bs + (long long)q_row * p.o_rs + head * kDh;
+    __nv_bfloat16* orow = q_row < p.seq ? o_row_ptr(p, b, q_row, head, kDh) : p.o;
     const uint32_t o_addr = tmem_base + lane_off + Cfg::TMEM_O;
 #pragma unroll
     for (int c = 0; c < kDh / 32; ++c) {
@@ -362,6 +375,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         }
       }
     }
+    if (p.o_rows_per_rank > 0) __threadfence_system();  // peer stores: visible before the following flag barrier
   }
 
   tc_fence_before();
@@ -662,7 +676,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       tc_fence_after();
     }
     const float inv_l = l > 0.f ? 1.f / l : 0.f;
-    __nv_bfloat16* orow = p.o + (long long)b * p.o_bs + (long long)q_row * p.o_rs + head * kDh;
+    __nv_bfloat16* orow = q_row < p.seq ? o_row_ptr(p, b, q_row, head, kDh) : p.o;
 #pragma unroll
     for (int c = 0; c < kDh / 32; ++c) {
       uint32_t o[32];
@@ -685,6 +699,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         }
       }
     }
+    if (p.o_rows_per_rank > 0) __threadfence_system();  // peer stores: visible before the following flag barrier
   }
 
   tc_fence_before();
@@ -726,8 +741,17 @@ static int fill_segments(AttnParams& p, int seq, int n_seg, const int32_t* bound
   return UG_OK;
 }
 
+struct PeerO {
+  int rows_per_rank;
+  __nv_bfloat16* base[UG_MAX_PEERS];
+};
+static void set_peer(AttnParams& p, const PeerO* peer) {
+  p.o_rows_per_rank = peer ? peer->rows_per_rank : 0;
+  for (int i = 0; i < UG_MAX_PEERS; ++i) p.o_peer[i] = peer ? peer->base[i] : nullptr;
+}
+
 template <int kDh, bool kPInTmem>
-static int launch_attention(const ug_attn_args& a, cudaStream_t stream) {
+static int launch_attention(const ug_attn_args& a, const PeerO* peer, cudaStream_t stream) {
   using Cfg = AttnCfg<kDh, kPInTmem>;
   auto kern = attention_kernel<kDh, kPInTmem>;
   static bool attr_done = false;
@@ -754,6 +778,7 @@ static int launch_attention(const ug_attn_args& a, cudaStream_t stream) {
   AttnParams p;
   p.o = (__nv_bfloat16*)a.o; p.o_rs = a.o_row_stride; p.o_bs = a.o_batch_stride;
   p.seq = a.seq; p.heads = a.heads; p.batch = a.batch;
+  set_peer(p, peer);
   p.scale_log2 = a.scale * 1.4426950408889634f;
   int st = fill_segments(p, a.seq, a.n_seg, a.seg_bounds, a.seg_visible);
   if (st != UG_OK) return st;
@@ -765,7 +790,7 @@ static int launch_attention(const ug_attn_args& a, cudaStream_t stream) {
 
 
 template <int kDh, int kPolyMod>
-static int launch_attention2(const ug_attn_args& a, cudaStream_t stream) {
+static int launch_attention2(const ug_attn_args& a, const PeerO* peer, cudaStream_t stream) {
   using Cfg = Attn2Cfg<kDh>;
   auto kern = attention2_kernel<kDh, kPolyMod>;
   static bool attr_done = false;
@@ -792,6 +817,7 @@ static int launch_attention2(const ug_attn_args& a, cudaStream_t stream) {
   AttnParams p;
   p.o = (__nv_bfloat16*)a.o; p.o_rs = a.o_row_stride; p.o_bs = a.o_batch_stride;
   p.seq = a.seq; p.heads = a.heads; p.batch = a.batch;
+  set_peer(p, peer);
   p.scale_log2 = a.scale * 1.4426950408889634f;
   int st = fill_segments(p, a.seq, a.n_seg, a.seg_bounds, a.seg_visible);
   if (st != UG_OK) return st;
@@ -805,10 +831,10 @@ static int launch_attention2(const ug_attn_args& a, cudaStream_t stream) {
 
 using namespace ug;
 
-extern "C" int ug_attention_bf16(const ug_attn_args* args, void* stream) {
+static int attention_dispatch(const ug_attn_args* args, const PeerO* peer, void* stream) {
   UG_CHECK_ARG(args != nullptr, "attention: null args");
   const ug_attn_args& a = *args;
-  UG_CHECK_ARG(a.q && a.k && a.v && a.o, "attention: null operand pointer");
+  UG_CHECK_ARG(a.q && a.k && a.v && (a.o || peer), "attention: null operand pointer");
   UG_CHECK_ARG(a.batch >= 1 && a.heads >= 1 && a.seq >= 1, "attention: empty problem");
   UG_CHECK_ARG(a.seq <= kMaxTiles * kBlockKV, "attention: seq %d exceeds %d", a.seq, kMaxTiles * kBlockKV);
   UG_CHECK_ARG(a.q_row_stride % 8 == 0 && a.k_row_stride % 8 == 0 && a.v_row_stride % 8 == 0 && a.o_row_stride % 8 == 0,
@@ -822,21 +848,46 @@ extern "C" int ug_attention_bf16(const ug_attn_args* args, void* stream) {
   int variant = a.variant;
   if (variant == 0) variant = ((long long)((a.seq + 255) / 256) * a.heads * a.batch >= num_sms()) ? 3 : 1;
   if (a.head_dim == 128) {
-    if (variant == 1) return launch_attention<128, true>(a, s);
-    if (variant == 2) return launch_attention<128, false>(a, s);
-    if (variant == 3) return launch_attention2<128, 0>(a, s);
-    if (variant == 4) return launch_attention2<128, 4>(a, s);
+    if (variant == 1) return launch_attention<128, true>(a, peer, s);
+    if (variant == 2) return launch_attention<128, false>(a, peer, s);
+    if (variant == 3) return launch_attention2<128, 0>(a, peer, s);
+    if (variant == 4) return launch_attention2<128, 4>(a, peer, s);
   } else if (a.head_dim == 64) {
-    if (variant == 1) return launch_attention<64, true>(a, s);
-    if (variant == 2) return launch_attention<64, false>(a, s);
-    if (variant == 3) return launch_attention2<64, 0>(a, s);
-    if (variant == 4) return launch_attention2<64, 4>(a, s);
+    if (variant == 1) return launch_attention<64, true>(a, peer, s);
+    if (variant == 2) return launch_attention<64, false>(a, peer, s);
+    if (variant == 3) return launch_attention2<64, 0>(a, peer, s);
+    if (variant == 4) return launch_attention2<64, 4>(a, peer, s);
   } else {
     set_error("attention: head_dim %d not supported (64 or 128)", a.head_dim);
     return UG_ERR_UNSUPPORTED;
   }
   set_error("attention: unknown variant %d", a.variant);
   return UG_ERR_INVALID;
+}
+
+extern "C" int ug_attention_bf16(const ug_attn_args* args, void* stream) { return attention_dispatch(args, nullptr, stream); }
+
+extern "C" int ug_attention_bf16_peer(const ug_attn_args* args, const ug_peer_table* table, int64_t o_offset, int32_t rows_per_rank,
+                                      void* stream) {
+  UG_CHECK_ARG(args && table, "attention_peer: null args");
+  UG_CHECK_ARG(table->world >= 1 && table->world <= UG_MAX_PEERS && table->rank >= 0 && table->rank < table->world,
+               "attention_peer: bad world %d / rank %d", table->world, table->rank);
+  UG_CHECK_ARG(args->batch == 1, "attention_peer: one sample is sharded across the ranks (batch must be 1)");
+  UG_CHECK_ARG(rows_per_rank >= 1 && (long long)rows_per_rank * table->world >= args->seq,
+               "attention_peer: %d rows per rank x %d ranks do not cover seq %d", rows_per_rank, table->world, args->seq);
+  UG_CHECK_ARG(o_offset >= UG_PEER_HEADER_BYTES && o_offset % 16 == 0, "attention_peer: bad output offset");
+  PeerO peer;
+  peer.rows_per_rank = rows_per_rank;
+  // this rank's heads occupy columns [rank * heads * head_dim, (rank + 1) * heads * head_dim) of every rank's output rows
+  const long long col0 = (long long)table->rank * args->heads * args->head_dim;
+  for (int i = 0; i < UG_MAX_PEERS; ++i) {
+    peer.base[i] = nullptr;
+    if (i < table->world) {
+      UG_CHECK_ARG(table->base[i], "attention_peer: null peer base %d", i);
+      peer.base[i] = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(table->base[i]) + o_offset) + col0;
+    }
+  }
+  return attention_dispatch(args, &peer, stream);
 }
 
 extern "C" int ug_expand_segment_mask(int32_t seq, int32_t n_seg, const int32_t* bounds, const uint32_t* visible,

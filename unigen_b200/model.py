@@ -416,6 +416,15 @@ class UniGenFlux(_DenoiserBase):
             ops.gemm(nx_c, w.ffc1[0], out=buf.FF[:, :n_ctx], bias=w.ffc1[1], act=UG_ACT_GELU_TANH, variant=gv)
             ops.gemm(buf.FF[:, :n_ctx], w.ffc2[0], out=ctx_out, bias=w.ffc2[1], gate=cg_m, residual=ctx_out, variant=gv)
 
+    def _single_attention(self, buf, S: int, rms: torch.Tensor, rope, out: torch.Tensor):
+        """(RMSNorm(q,k)+RoPE in place on the QKV rows unless fused into the projection GEMM) + attention over rows [0, S) ->
+        `out` (the first D columns of CAT). The sequence-parallel subclass fuses both with the Ulysses exchange."""
+        a, D = self.arch, self.inner_dim
+        H, dh = a.num_attention_heads, a.attention_head_dim
+        if not self.fuse_qk_norm:
+            ops.qk_rmsnorm_rope(buf.QKV[:, :S, :2 * D], 2 * H, dh, rms, rope[:S] if rope is not None else None, heads_per_weight=H)
+        return self._attend(buf, S, out)
+
     def _single_block(self, buf, w: _SingleBlockW, mod, x_in, x_out, rope):
         """diffusers FluxSingleTransformerBlock: x_out = x_in + gate * proj_out([attn | gelu(mlp)])."""
         a = self.arch
@@ -428,9 +437,7 @@ class UniGenFlux(_DenoiserBase):
         ops.gemm(nx, w.qkv[0], out=buf.QKV[:, :S], bias=w.qkv[1], variant=gv,
                  qk_norm=self._qk_norm(w.rms, rope[:S] if rope is not None else None))
         ops.gemm(nx, w.mlp[0], out=cat[:, :, D:], bias=w.mlp[1], act=UG_ACT_GELU_TANH, variant=gv)
-        if not self.fuse_qk_norm:
-            ops.qk_rmsnorm_rope(buf.QKV[:, :S, :2 * D], 2 * H, dh, w.rms, rope[:S] if rope is not None else None, heads_per_weight=H)
-        self._attend(buf, S, cat[:, :, :D])
+        self._single_attention(buf, S, w.rms, rope, cat[:, :, :D])
         ops.gemm(cat, w.out[0], out=x_out, bias=w.out[1], gate=gate, residual=x_in, variant=gv)
 
     # ---------------------------------------------------------------------------------------------------------

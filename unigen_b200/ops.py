@@ -10,9 +10,9 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import UG_ACT_GELU_TANH, UG_ACT_NONE, AttnArgs, GemmArgs, UgError, check
+from ._lib import UG_ACT_GELU_TANH, UG_ACT_NONE, AttnArgs, GemmArgs, QkvScatterArgs, UgError, check
 
-__all__ = ["gemm", "lora_down", "attention", "expand_segment_mask", "ln_modulate", "qk_rmsnorm_rope", "rope_table", "gemv",
+__all__ = ["gemm", "lora_down", "attention", "attention_peer", "qkv_scatter", "peer_bcast_rows", "peer_barrier", "expand_segment_mask", "ln_modulate", "qk_rmsnorm_rope", "rope_table", "gemv",
            "timestep_embedding", "add", "copy", "to_bf16", "to_f32", "moe_route", "moe_gather_modulate",
            "moe_combine", "ln_modulate_slots", "gated_add_slots", "unpatchify", "euler_step", "cfg_combine", "pack_latents", "unpack_latents", "launch_count", "reset_launch_count", "UG_ACT_NONE", "UG_ACT_GELU_TANH", "UgError"]
 
@@ -161,20 +161,16 @@ def lora_down(x: torch.Tensor, a_stack: torch.Tensor, seg_bounds: Sequence[int],
     return out
 
 
-def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, heads: int, head_dim: int,
-              seg_bounds: Optional[Sequence[int]] = None, seg_visible: Optional[Sequence[int]] = None,
-              scale: Optional[float] = None, variant: int = 0) -> torch.Tensor:
-    """q/k/v/out: [B, S, heads*head_dim] views (any row / batch stride, contiguous inner dim)."""
-    q, k, v, o = (_view3(_dev(t, n, BF16), n) for t, n in ((q, "attn.q"), (k, "attn.k"), (v, "attn.v"), (out, "attn.out")))
+def _attn_args(q, k, v, heads, head_dim, seg_bounds, seg_visible, scale, variant):
+    q, k, v = (_view3(_dev(t, n, BF16), n) for t, n in ((q, "attn.q"), (k, "attn.k"), (v, "attn.v")))
     B, S, HD = q.shape
     if HD != heads * head_dim:
         raise UgError(f"attention: inner dim {HD} != heads {heads} x head_dim {head_dim}")
     a = AttnArgs()
-    a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
+    a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
     a.q_row_stride, a.q_batch_stride = q.stride(1), q.stride(0)
     a.k_row_stride, a.k_batch_stride = k.stride(1), k.stride(0)
     a.v_row_stride, a.v_batch_stride = v.stride(1), v.stride(0)
-    a.o_row_stride, a.o_batch_stride = o.stride(1), o.stride(0)
     a.batch, a.heads, a.seq, a.head_dim = B, heads, S, head_dim
     a.scale = float(scale if scale is not None else 1.0 / math.sqrt(head_dim))
     keep = None
@@ -185,9 +181,62 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
         keep = (sb, sv)
         a.n_seg, a.seg_bounds, a.seg_visible = n, sb, sv
     a.variant = variant
+    return a, keep
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, heads: int, head_dim: int,
+              seg_bounds: Optional[Sequence[int]] = None, seg_visible: Optional[Sequence[int]] = None,
+              scale: Optional[float] = None, variant: int = 0) -> torch.Tensor:
+    """q/k/v/out: [B, S, heads*head_dim] views (any row / batch stride, contiguous inner dim)."""
+    a, keep = _attn_args(q, k, v, heads, head_dim, seg_bounds, seg_visible, scale, variant)
+    o = _view3(_dev(out, "attn.out", BF16), "attn.out")
+    a.o, a.o_row_stride, a.o_batch_stride = o.data_ptr(), o.stride(1), o.stride(0)
     check(_lib.load().ug_attention_bf16(C.byref(a), _stream()), "ug_attention_bf16")
     del keep
     return out
+
+
+def attention_peer(table, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, head_dim: int, o_offset: int,
+                   o_row_stride: int, rows_per_rank: int, scale: Optional[float] = None, variant: int = 0) -> None:
+    """Attention over this rank's head shard of ALL tokens ([1, S, heads*head_dim] views); output row q lands in rank
+    q // rows_per_rank's pool at byte o_offset, row q % rows_per_rank (row stride o_row_stride elements), this rank's columns."""
+    a, keep = _attn_args(q, k, v, heads, head_dim, None, None, scale, variant)
+    a.o, a.o_row_stride, a.o_batch_stride = 0, int(o_row_stride), 0
+    check(_lib.load().ug_attention_bf16_peer(C.byref(a), C.byref(table), int(o_offset), int(rows_per_rank), _stream()),
+          "ug_attention_bf16_peer")
+    del keep
+
+
+def qkv_scatter(table, qkv_rows: torch.Tensor, heads: int, head_dim: int, norm_weight: Optional[torch.Tensor],
+                cos_sin: Optional[torch.Tensor], dst_offset: int, seq_total: int, dst_row0: int, eps: float = 1e-6) -> None:
+    """qkv_rows: local [rows, 3*heads*head_dim] bf16 view of the fused projection -> every head's owner rank (see header)."""
+    _dev(qkv_rows, "qkv_scatter.qkv", BF16)
+    if qkv_rows.dim() != 2 or qkv_rows.stride(1) != 1 or qkv_rows.shape[1] != 3 * heads * head_dim:
+        raise UgError(f"qkv_scatter: expected a [rows, {3 * heads * head_dim}] view, got {tuple(qkv_rows.shape)}")
+    a = QkvScatterArgs()
+    a.qkv, a.row_stride, a.rows, a.heads, a.head_dim, a.eps = qkv_rows.data_ptr(), qkv_rows.stride(0), qkv_rows.shape[0], heads, head_dim, eps
+    if norm_weight is not None:
+        a.norm_weight = _dev(norm_weight, "qkv_scatter.norm_weight", BF16).data_ptr()
+    if cos_sin is not None:
+        _dev(cos_sin, "qkv_scatter.cos_sin", torch.float32)
+        if cos_sin.shape[0] < qkv_rows.shape[0] or not cos_sin.is_contiguous():
+            raise UgError("qkv_scatter: cos_sin table too short / not contiguous")
+        a.cos_sin = cos_sin.data_ptr()
+    a.dst_offset, a.seq_total, a.dst_row0 = int(dst_offset), int(seq_total), int(dst_row0)
+    check(_lib.load().ug_qkv_scatter(C.byref(table), C.byref(a), _stream()), "ug_qkv_scatter")
+
+
+def peer_bcast_rows(table, src: torch.Tensor, dst_offset: int, dst_row_stride: int, dst_row0: int) -> None:
+    """src: [rows, d] bf16 view -> rows [dst_row0, dst_row0 + rows) of the buffer at byte dst_offset of EVERY rank's pool."""
+    _dev(src, "peer_bcast.src", BF16)
+    if src.dim() != 2 or src.stride(1) != 1:
+        raise UgError("peer_bcast_rows: expected a [rows, d] view with contiguous columns")
+    check(_lib.load().ug_peer_bcast_rows(C.byref(table), src.data_ptr(), src.stride(0), src.shape[0], src.shape[1], int(dst_offset),
+                                         int(dst_row_stride), int(dst_row0), _stream()), "ug_peer_bcast_rows")
+
+
+def peer_barrier(table) -> None:
+    check(_lib.load().ug_peer_barrier(C.byref(table), _stream()), "ug_peer_barrier")
 
 
 def expand_segment_mask(seq: int, seg_bounds: Sequence[int], seg_visible: Sequence[int], device) -> torch.Tensor:

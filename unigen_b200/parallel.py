@@ -8,18 +8,28 @@
   are per token and per head, so they run BEFORE the exchange on the local rows.
   The reference has no sequence parallelism at all — this is new design; its contract is numerical
   equality with the single-GPU forward (tests/test_parallel_gpu.py, tests/test_parallel_cpu.py).
+  Two implementations of the exchange (`exchange=`):
+    "peer" (default) — FUSED into the producing kernels over NVLink peer memory (CUDA IPC pools, `PeerPool`): the QK-RMSNorm +
+      RoPE pass stores every head straight into its owner rank's receive buffer (ug_qkv_scatter), the attention epilogue
+      stores every output row straight into its owner rank's buffer (ug_attention_bf16_peer), a device-side flag barrier
+      separates the phases (2 per attention); all-gathers are peer stores too, so the whole step has no NCCL call, no staging
+      copy and replays as ONE CUDA graph per rank.
+    "nccl" — staging copy + dist.all_to_all_single x4 per attention (the baseline the fused path is measured against).
   The CoMoE pre-stage (3.6 % of the step, once per step) needs a global top-C token selection per expert; it is computed
   REPLICATED on every rank from an all-gather of the residual stream (28 MB), which keeps routing bit-identical to
   the single-GPU run.
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Tuple
+import ctypes as C
+import math
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import _lib, ops
+from ._lib import UG_MAX_PEERS, UG_PEER_HANDLE_BYTES, UG_PEER_HEADER_BYTES
 from .model import UniGenFlux
 
 
@@ -39,6 +49,83 @@ def sp_row_split(T: int, N: int, world: int, rank: int) -> Tuple[int, int, int, 
     row0 = rank * rows
     t_loc = min(max(T - row0, 0), rows)
     return row0, rows, t_loc, max(row0 - T, 0)
+
+
+class _CudaBuf:
+    """`__cuda_array_interface__` carrier so torch can view memory this package allocated (ug_peer_alloc)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = dict(shape=(nbytes,), typestr="|u1", data=(ptr, False), version=2)
+
+
+def pool_layout(sizes: Sequence[Tuple[str, int]], header: int = UG_PEER_HEADER_BYTES, align: int = 256):
+    """Byte offsets of named payload buffers behind the control block: identical on every rank by construction."""
+    off, out = header, {}
+    for name, nbytes in sizes:
+        off = (off + align - 1) // align * align
+        out[name] = off
+        off += nbytes
+    return out, (off + align - 1) // align * align
+
+
+class PeerPool:
+    """A symmetric, peer-mapped device pool: every rank cudaMallocs the same number of bytes, the CUDA IPC handles are
+    exchanged once through the process group, and `table` holds this process's mapping of every rank's pool."""
+
+    def __init__(self, group, nbytes: int, device):
+        lib = _lib.load()
+        self.group, self.world, self.rank = group, dist.get_world_size(group), dist.get_rank(group)
+        if self.world > UG_MAX_PEERS:
+            raise ops.UgError(f"peer pools support up to {UG_MAX_PEERS} ranks")
+        self.nbytes, self.device = int(nbytes), torch.device(device)
+        ptr = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.ug_peer_alloc(self.nbytes, C.byref(ptr)), "ug_peer_alloc")
+            handle = (C.c_uint8 * UG_PEER_HANDLE_BYTES)()
+            _lib.check(lib.ug_peer_export(ptr, handle), "ug_peer_export")
+            handles: List[Optional[bytes]] = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            self.table = _lib.PeerTable()
+            self.table.world, self.table.rank = self.world, self.rank
+            self._opened = []
+            for r in range(self.world):
+                if r == self.rank:
+                    self.table.base[r] = ptr.value
+                    continue
+                peer = C.c_void_p()
+                h = (C.c_uint8 * UG_PEER_HANDLE_BYTES).from_buffer_copy(handles[r])
+                _lib.check(lib.ug_peer_open(h, C.byref(peer)), f"ug_peer_open(rank {r})")
+                self.table.base[r] = peer.value
+                self._opened.append(peer.value)
+        self._ptr = ptr.value
+        self.local = torch.as_tensor(_CudaBuf(self._ptr, self.nbytes), device=self.device)
+        dist.barrier(group=group)  # nobody stores into a pool before every rank has mapped it
+
+    def view(self, offset: int, shape, dtype=torch.bfloat16) -> torch.Tensor:
+        n = math.prod(shape) * torch.empty((), dtype=dtype).element_size()
+        if offset < UG_PEER_HEADER_BYTES or offset + n > self.nbytes:
+            raise ops.UgError("PeerPool.view outside the payload area")
+        return self.local[offset:offset + n].view(dtype).view(*shape)
+
+    def barrier(self):
+        ops.peer_barrier(self.table)
+
+    def error(self) -> int:
+        e = C.c_int32()
+        _lib.check(_lib.load().ug_peer_error(C.byref(self.table), C.byref(e)), "ug_peer_error")
+        return int(e.value)
+
+    def close(self):
+        lib = _lib.load()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        for p in self._opened:
+            lib.ug_peer_close(C.c_void_p(p))
+        self._opened = []
+        if self._ptr:
+            self.local = None
+            lib.ug_peer_free(C.c_void_p(self._ptr))
+            self._ptr = 0
 
 
 class UlyssesExchange:
@@ -82,18 +169,31 @@ class SequenceParallelUniGenFlux(UniGenFlux):
     """UniGenFlux whose main blocks run on S/P rows per rank with Ulysses attention (module docstring). Same public API;
     every rank passes the FULL inputs and receives the FULL velocity (all-gathered)."""
 
-    def __init__(self, arch=None, device="cuda", group=None, **config):
+    def __init__(self, arch=None, device="cuda", group=None, exchange: str = "peer", **config):
         super().__init__(arch, device, **config)
         if not dist.is_initialized():
             raise ops.UgError("SequenceParallelUniGenFlux needs an initialised torch.distributed process group")
+        if exchange not in ("peer", "nccl"):
+            raise ops.UgError("exchange must be 'peer' (fused NVLink peer-memory exchange) or 'nccl' (staged all-to-all)")
         self.sp_group = group
         self.sp_world = dist.get_world_size(group)
         self.sp_rank = dist.get_rank(group)
         if self.arch.num_attention_heads % self.sp_world:
             raise ops.UgError(f"{self.arch.num_attention_heads} heads are not divisible by {self.sp_world} ranks")
+        self.exchange = exchange
         self._sp_active = False
         self._xchg = None
+        self._pool: Optional[PeerPool] = None
+        self._pool_key = None
 
+    def _run_staged(self, key, staged, *args):
+        if self.exchange != "peer":  # NCCL collectives stay out of graph capture: the staged-exchange baseline runs eagerly
+            return self._forward_impl(*args, **staged)
+        return super()._run_staged(key, staged, *args)
+
+    # ---------------------------------------------------------------------------------------------------------
+    # exchange = "nccl": staging copy + all_to_all_single around a local attention call
+    # ---------------------------------------------------------------------------------------------------------
     def _attend(self, buf, S: int, out: torch.Tensor):
         if not self._sp_active:
             return super()._attend(buf, S, out)
@@ -104,6 +204,74 @@ class SequenceParallelUniGenFlux(UniGenFlux):
                       a.attention_head_dim, variant=self.attn_variant)
         x.heads_to_seq(out[0])
         return out
+
+    # ---------------------------------------------------------------------------------------------------------
+    # exchange = "peer": the exchange is fused into the QK-norm/RoPE pass and the attention epilogue
+    # ---------------------------------------------------------------------------------------------------------
+    def _peer_setup(self, buf, N: int, T: int, s_loc: int):
+        """Pool = [control | RECV [3, S, D/P] | AO [Smax, D] | CAT [S, 5D] | X [S, D] | OUTF [S, in_ch]]; the workspace's AO /
+        CAT / X become views of the pool so peers can store attention outputs / gathered rows straight into them."""
+        a, D, P = self.arch, self.inner_dim, self.sp_world
+        S, Smax = T + N, T + 2 * N
+        key = (N, T)
+        if self._pool_key != key:
+            if self._pool is not None:
+                self._pool.close()
+            sizes = [("RECV", 3 * S * (D // P) * 2), ("AO", Smax * D * 2), ("CAT", S * 5 * D * 2), ("X", S * D * 2),
+                     ("OUTF", S * a.in_channels * 2)]
+            self._off, total = pool_layout(sizes)
+            self._pool = PeerPool(self.sp_group, total, self.device_)
+            self._pool_key = key
+            self._recv = self._pool.view(self._off["RECV"], (3, 1, S, D // P))
+            self._outf = self._pool.view(self._off["OUTF"], (1, S, a.in_channels))
+        pool = self._pool
+        buf.AO, buf.CAT, buf.X = (pool.view(self._off["AO"], (1, Smax, D)), pool.view(self._off["CAT"], (1, S, 5 * D)),
+                                  pool.view(self._off["X"], (1, S, D)))
+        self._sp_rows = (self.sp_rank * s_loc, s_loc, S)
+
+    def _peer_attention(self, o_name: str, o_row_stride: int):
+        """barrier -> attention over this rank's heads of all tokens, output rows stored into their owners' `o_name` buffer ->
+        barrier. (barrier 1: every rank's q/k/v stores have landed in RECV; barrier 2: every rank's O stores have landed.)"""
+        a, pool = self.arch, self._pool
+        _, s_loc, _ = self._sp_rows
+        pool.barrier()
+        ops.attention_peer(pool.table, self._recv[0], self._recv[1], self._recv[2], a.num_attention_heads // self.sp_world,
+                           a.attention_head_dim, self._off[o_name], o_row_stride, s_loc, variant=self.attn_variant)
+        pool.barrier()
+
+    def _scatter(self, qkv_rows: torch.Tensor, rms, rope_rows, local_row0: int):
+        a = self.arch
+        row0, _, S = self._sp_rows
+        ops.qkv_scatter(self._pool.table, qkv_rows, a.num_attention_heads, a.attention_head_dim, rms, rope_rows, self._off["RECV"], S,
+                        row0 + local_row0)
+
+    def _joint_attention(self, buf, B, n_ctx, n_smp, rms_ctx, rms_smp, rope):
+        if not (self._sp_active and self.exchange == "peer"):
+            return super()._joint_attention(buf, B, n_ctx, n_smp, rms_ctx, rms_smp, rope)
+        s = n_ctx + n_smp
+        qkv = buf.QKV[0, :s]
+        if n_ctx:
+            self._scatter(qkv[:n_ctx], rms_ctx, rope[:n_ctx] if rope is not None else None, 0)
+        if n_smp:
+            self._scatter(qkv[n_ctx:], rms_smp, rope[n_ctx:s] if rope is not None else None, n_ctx)
+        self._peer_attention("AO", self.inner_dim)
+        return buf.AO[:, :s]
+
+    def _single_attention(self, buf, S: int, rms, rope, out: torch.Tensor):
+        if not (self._sp_active and self.exchange == "peer"):
+            return super()._single_attention(buf, S, rms, rope, out)
+        self._scatter(buf.QKV[0, :S], rms, rope[:S] if rope is not None else None, 0)
+        self._peer_attention("CAT", 5 * self.inner_dim)  # `out` is the first D columns of the (peer-mapped) CAT rows
+        return out
+
+    def _gather_rows(self, local: torch.Tensor, name: str, full: torch.Tensor):
+        """all-gather of [s_loc, d] row shards into the [S, d] buffer `name` of every rank."""
+        row0, s_loc, _ = self._sp_rows if self.exchange == "peer" else (0, 0, 0)
+        if self.exchange == "peer":
+            ops.peer_bcast_rows(self._pool.table, local[0], self._off[name], full.shape[-1], row0)
+            self._pool.barrier()
+        else:
+            dist.all_gather_into_tensor(full.view(-1), local.reshape(-1), group=self.sp_group)
 
     def _forward_impl(self, conditioning_scale, hs, es, pooled, timestep, guidance, txt_ids, img_ids, **cond):
         a = self.arch
@@ -123,12 +291,19 @@ class SequenceParallelUniGenFlux(UniGenFlux):
         n_img = s_loc - t_loc
         buf = self._workspace(B, N, T)
         dev = self.device_
-        if self._xchg is None or self._xchg.s_loc != s_loc:
-            self._xchg = UlyssesExchange(self.sp_group, P, s_loc, D, dev, torch.bfloat16)
+        n0 = ops.launch_count()
+        if getattr(self, "_sp_key", None) != (N, T):
+            if self.exchange == "nccl":
+                self._xchg = UlyssesExchange(self.sp_group, P, s_loc, D, dev, torch.bfloat16)
             self._sp_buf = dict(XL=torch.empty(1, s_loc, D, device=dev, dtype=torch.bfloat16),
                                 NOL=torch.empty(1, s_loc, D, device=dev, dtype=torch.bfloat16),
-                                OUTL=torch.empty(1, s_loc, a.in_channels, device=dev, dtype=torch.bfloat16),
-                                OUTF=torch.empty(1, S, a.in_channels, device=dev, dtype=torch.bfloat16))
+                                OUTL=torch.empty(1, s_loc, a.in_channels, device=dev, dtype=torch.bfloat16))
+            if self.exchange == "nccl":
+                self._sp_buf["OUTF"] = torch.empty(1, S, a.in_channels, device=dev, dtype=torch.bfloat16)
+            self._sp_key = (N, T)
+        if self.exchange == "peer":
+            self._peer_setup(buf, N, T, s_loc)
+            self._sp_buf["OUTF"] = self._outf
         XL = self._sp_buf["XL"]
         xl_txt, xl_img = XL[:, :t_loc], XL[:, t_loc:]
         hs, es = ops.to_bf16(hs.contiguous()), ops.to_bf16(es.contiguous())
@@ -150,27 +325,45 @@ class SequenceParallelUniGenFlux(UniGenFlux):
         ops.rope_table(torch.cat([txt_ids, img_ids], 0), a.axes_dims_rope, a.theta, out=buf.rope)
         rope_loc = buf.rope[row0:row0 + s_loc]
 
-        # ---- AdaLN vectors of every block (replicated: step constants) ----
-        slot = 0
-        m_double, m_cdouble, m_single, m_csingle, mods_s0 = [], [], [], [], []
-        for w in self.double:
-            m_double.append((self._mods(buf, slot, 6, w.norm1, buf.temb), self._mods(buf, slot + 6, 6, w.norm1_ctx, buf.temb)))
-            slot += 12
-        for w in self.ctrl_double:
-            m_cdouble.append((self._mods(buf, slot, 6, w.norm1, buf.cdtemb), self._mods(buf, slot + 6, 6, w.norm1_ctx, buf.cdtemb)))
-            slot += 12
-        for w in self.single:
-            m_single.append(self._mods(buf, slot, 3, w.norm, buf.temb)); slot += 3
-        for w in self.ctrl_single:
-            m_csingle.append(self._mods(buf, slot, 3, w.norm, buf.cdtemb)); slot += 3
+        # ---- AdaLN vectors of every block (replicated: step constants). Only what the first block pair and the pre-stage
+        # need is computed on the main stream; the other 13 GB of weight streaming runs on a side stream under the blocks ----
+        nd, ncd, ns, ncs_ = len(self.double), len(self.ctrl_double), len(self.single), len(self.ctrl_single)
+        s_cd, s_s = 12 * nd, 12 * nd + 12 * ncd
+        s_cs = s_s + 3 * ns
+        s_sh = s_cs + 3 * ncs_
+        s_out = s_sh + 12 * n_cond + 12
+        m_double, m_cdouble, m_single, m_csingle, mods_s0 = [None] * nd, [None] * ncd, [None] * ns, [None] * ncs_, []
+
+        def mod_double(i):
+            w = self.double[i]
+            m_double[i] = (self._mods(buf, 12 * i, 6, w.norm1, buf.temb), self._mods(buf, 12 * i + 6, 6, w.norm1_ctx, buf.temb))
+
+        def mod_cdouble(j):
+            w = self.ctrl_double[j]
+            m_cdouble[j] = (self._mods(buf, s_cd + 12 * j, 6, w.norm1, buf.cdtemb), self._mods(buf, s_cd + 12 * j + 6, 6, w.norm1_ctx, buf.cdtemb))
+
+        mod_double(0)
+        mod_cdouble(0)
         for c in range(n_cond):
-            mods_s0.append((self._mods(buf, slot, 6, self.shared[0].norm1, buf.cdtemb_c[c]),
-                            self._mods(buf, slot + 6, 6, self.shared[0].norm1_ctx, buf.cdtemb_c[c])))
-            slot += 12
-        mods_s1 = (self._mods(buf, slot, 6, self.shared[1].norm1, buf.ctemb),
-                   self._mods(buf, slot + 6, 6, self.shared[1].norm1_ctx, buf.ctemb))
-        slot += 12
-        m_out = self._mods(buf, slot, 2, self.norm_out_w, buf.temb)
+            mods_s0.append((self._mods(buf, s_sh + 12 * c, 6, self.shared[0].norm1, buf.cdtemb_c[c]),
+                            self._mods(buf, s_sh + 12 * c + 6, 6, self.shared[0].norm1_ctx, buf.cdtemb_c[c])))
+        mods_s1 = (self._mods(buf, s_sh + 12 * n_cond, 6, self.shared[1].norm1, buf.ctemb),
+                   self._mods(buf, s_sh + 12 * n_cond + 6, 6, self.shared[1].norm1_ctx, buf.ctemb))
+        main_stream = torch.cuda.current_stream()
+        side = self._side_stream if self.overlap_mod_gemv else None
+        if side is not None:
+            side.wait_stream(main_stream)
+        with torch.cuda.stream(side if side is not None else main_stream):
+            for i in range(1, nd):
+                mod_double(i)
+            for j in range(1, ncd):
+                mod_cdouble(j)
+            for i, w in enumerate(self.single):
+                m_single[i] = self._mods(buf, s_s + 3 * i, 3, w.norm, buf.temb)
+            for j, w in enumerate(self.ctrl_single):
+                m_csingle[j] = self._mods(buf, s_cs + 3 * j, 3, w.norm, buf.cdtemb)
+            m_out = self._mods(buf, s_out, 2, self.norm_out_w, buf.temb)
+        mods_joined = side is None
 
         # ---- double blocks on token shards ----
         route = None
@@ -179,12 +372,15 @@ class SequenceParallelUniGenFlux(UniGenFlux):
         self._sp_active = True
         try:
             for i, w in enumerate(self.double):
+                if i == 1 and not mods_joined:
+                    main_stream.wait_stream(side)
+                    mods_joined = True
                 self._double_block(buf, w, m_double[i][0], m_double[i][1], xl_img, xl_txt, xl_img, xl_txt, rope_loc)
                 j = int(i / (len(self.double) / n_cd))
                 if route is None:
                     # CoMoE pre-stage, replicated: gather the residual stream once, route / run experts on every rank
                     self._sp_active = False
-                    dist.all_gather_into_tensor(buf.X.view(-1), XL.view(-1), group=self.sp_group)
+                    self._gather_rows(XL, "X", buf.X)
                     x_txt, x_img = buf.X[:, :T], buf.X[:, T:]
                     ops.gemm(x_txt, self.control_context_embedder_w[0], out=buf.CENC, bias=self.control_context_embedder_w[1], variant=gv)
                     for c in range(n_cond):
@@ -200,6 +396,9 @@ class SequenceParallelUniGenFlux(UniGenFlux):
                 if n_img:
                     wa = self.add_double[j]
                     ops.gemm(ch, wa[0], out=xl_img, bias=wa[1], alpha=float(conditioning_scale), residual=xl_img, variant=gv)
+            if not mods_joined:
+                main_stream.wait_stream(side)
+                mods_joined = True
             # ---- single blocks ----
             n_cs = len(self.ctrl_single)
             csl = buf.CS[:, :s_loc]
@@ -219,6 +418,7 @@ class SequenceParallelUniGenFlux(UniGenFlux):
         sb = self._sp_buf
         ops.ln_modulate(XL, sb["NOL"], m_out[1], m_out[0])
         ops.gemm(sb["NOL"], self.proj_out_w[0], out=sb["OUTL"], bias=self.proj_out_w[1], variant=gv)
-        dist.all_gather_into_tensor(sb["OUTF"].view(-1), sb["OUTL"].view(-1), group=self.sp_group)
+        self._gather_rows(sb["OUTL"], "OUTF", sb["OUTF"])
         self._last_route = route
+        ops.note_capture_launches(ops.launch_count() - n0)
         return sb["OUTF"][:, T:], dict(moe_loss=route["l_aux"][0] * 0.1), dict(expert_counts=route["exp_counts"])
