@@ -307,7 +307,11 @@ int ug_qkv_scatter(const ug_peer_table* table, const ug_qkv_scatter_args* args, 
 
 /* ug_attention_bf16 over this rank's head shard of ALL tokens with the heads -> sequence exchange fused into the epilogue:
  * output row q is stored into rank q / rows_per_rank's buffer (bf16 rows of args->o_row_stride elements at byte `o_offset`
- * of its pool) at row q % rows_per_rank, columns [rank*heads*head_dim, (rank+1)*heads*head_dim). args->o is ignored. */
+ * of its pool) at row q % rows_per_rank, columns [rank*heads*head_dim, (rank+1)*heads*head_dim). args->o is ignored.
+ * rows_per_rank == 0 selects SEGMENT-SHARDED rows (needs args->n_seg >= 1, every bound a multiple of world): each segment
+ * [b_s, b_{s+1}) is split evenly over the ranks and a rank keeps its shards in segment order, so row q of segment s goes to
+ * rank (q - b_s) / ((b_{s+1} - b_s) / world), local row b_s / world + (q - b_s) % ((b_{s+1} - b_s) / world) — the layout of the
+ * sequence-parallel P-variant, where every rank holds 1/world of the text, image and each condition stream. */
 int ug_attention_bf16_peer(const ug_attn_args* args, const ug_peer_table* table, int64_t o_offset, int32_t rows_per_rank,
                            void* stream);
 

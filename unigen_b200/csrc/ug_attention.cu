@@ -38,6 +38,17 @@ __device__ __forceinline__ __nv_bfloat16* o_row_ptr(const AttnParams& p, int b, 
     const int r = q_row / p.o_rows_per_rank;
     return p.o_peer[r] + (long long)(q_row - r * p.o_rows_per_rank) * p.o_rs + head * dh;
   }
+  if (p.o_rows_per_rank < 0) {
+    // segment-sharded rows (world = -o_rows_per_rank): every segment [b_s, b_{s+1}) is split evenly over the ranks and a
+    // rank keeps its shards in segment order, so its local segment s starts at b_s / world
+    const int world = -p.o_rows_per_rank;
+    int sq = p.n_seg - 1;
+    for (int s = 0; s < p.n_seg; ++s)
+      if (q_row >= p.bounds[s] && q_row < p.bounds[s + 1]) sq = s;
+    const int per = (p.bounds[sq + 1] - p.bounds[sq]) / world, off = q_row - p.bounds[sq];
+    const int r = off / per;
+    return p.o_peer[r] + (long long)(p.bounds[sq] / world + off - r * per) * p.o_rs + head * dh;
+  }
   return p.o + (long long)b * p.o_bs + (long long)q_row * p.o_rs + head * dh;
 }
 
@@ -375,7 +386,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         }
       }
     }
-    if (p.o_rows_per_rank > 0) __threadfence_system();  // peer stores: visible before the following flag barrier
+    if (p.o_rows_per_rank != 0) __threadfence_system();  // peer stores: visible before the following flag barrier
   }
 
   tc_fence_before();
@@ -699,7 +710,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         }
       }
     }
-    if (p.o_rows_per_rank > 0) __threadfence_system();  // peer stores: visible before the following flag barrier
+    if (p.o_rows_per_rank != 0) __threadfence_system();  // peer stores: visible before the following flag barrier
   }
 
   tc_fence_before();
@@ -873,11 +884,18 @@ extern "C" int ug_attention_bf16_peer(const ug_attn_args* args, const ug_peer_ta
   UG_CHECK_ARG(table->world >= 1 && table->world <= UG_MAX_PEERS && table->rank >= 0 && table->rank < table->world,
                "attention_peer: bad world %d / rank %d", table->world, table->rank);
   UG_CHECK_ARG(args->batch == 1, "attention_peer: one sample is sharded across the ranks (batch must be 1)");
-  UG_CHECK_ARG(rows_per_rank >= 1 && (long long)rows_per_rank * table->world >= args->seq,
-               "attention_peer: %d rows per rank x %d ranks do not cover seq %d", rows_per_rank, table->world, args->seq);
+  if (rows_per_rank == 0) {  // segment-sharded rows
+    UG_CHECK_ARG(args->n_seg >= 1 && args->seg_bounds, "attention_peer: rows_per_rank = 0 selects segment-sharded rows and needs segments");
+    for (int i = 0; i <= args->n_seg; ++i)
+      UG_CHECK_ARG(args->seg_bounds[i] % table->world == 0, "attention_peer: segment bound %d is not a multiple of the world size %d",
+                   args->seg_bounds[i], table->world);
+  } else {
+    UG_CHECK_ARG(rows_per_rank >= 1 && (long long)rows_per_rank * table->world >= args->seq,
+                 "attention_peer: %d rows per rank x %d ranks do not cover seq %d", rows_per_rank, table->world, args->seq);
+  }
   UG_CHECK_ARG(o_offset >= UG_PEER_HEADER_BYTES && o_offset % 16 == 0, "attention_peer: bad output offset");
   PeerO peer;
-  peer.rows_per_rank = rows_per_rank;
+  peer.rows_per_rank = rows_per_rank > 0 ? rows_per_rank : -table->world;
   // this rank's heads occupy columns [rank * heads * head_dim, (rank + 1) * heads * head_dim) of every rank's output rows
   const long long col0 = (long long)table->rank * args->heads * args->head_dim;
   for (int i = 0; i < UG_MAX_PEERS; ++i) {

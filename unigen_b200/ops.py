@@ -197,10 +197,12 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
 
 
 def attention_peer(table, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, head_dim: int, o_offset: int,
-                   o_row_stride: int, rows_per_rank: int, scale: Optional[float] = None, variant: int = 0) -> None:
+                   o_row_stride: int, rows_per_rank: int, seg_bounds: Optional[Sequence[int]] = None,
+                   seg_visible: Optional[Sequence[int]] = None, scale: Optional[float] = None, variant: int = 0) -> None:
     """Attention over this rank's head shard of ALL tokens ([1, S, heads*head_dim] views); output row q lands in rank
-    q // rows_per_rank's pool at byte o_offset, row q % rows_per_rank (row stride o_row_stride elements), this rank's columns."""
-    a, keep = _attn_args(q, k, v, heads, head_dim, None, None, scale, variant)
+    q // rows_per_rank's pool at byte o_offset, row q % rows_per_rank (row stride o_row_stride elements), this rank's columns.
+    rows_per_rank = 0: segment-sharded rows (every segment of seg_bounds split evenly over the ranks)."""
+    a, keep = _attn_args(q, k, v, heads, head_dim, seg_bounds, seg_visible, scale, variant)
     a.o, a.o_row_stride, a.o_batch_stride = 0, int(o_row_stride), 0
     check(_lib.load().ug_attention_bf16_peer(C.byref(a), C.byref(table), int(o_offset), int(rows_per_rank), _stream()),
           "ug_attention_bf16_peer")

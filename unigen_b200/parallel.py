@@ -31,6 +31,7 @@ import torch.distributed as dist
 from . import _lib, ops
 from ._lib import UG_MAX_PEERS, UG_PEER_HANDLE_BYTES, UG_PEER_HEADER_BYTES
 from .model import UniGenFlux
+from .pvariant import UniCombineFlux
 
 
 def dp_shard(n_samples: int, world: int, rank: int) -> range:
@@ -422,3 +423,113 @@ class SequenceParallelUniGenFlux(UniGenFlux):
         self._last_route = route
         ops.note_capture_launches(ops.launch_count() - n0)
         return sb["OUTF"][:, T:], dict(moe_loss=route["l_aux"][0] * 0.1), dict(expert_counts=route["exp_counts"])
+
+
+class SequenceParallelUniCombineFlux(UniCombineFlux):
+    """P-variant (LoRA-switched joint blocks, all condition tokens in every block — BASELINE cfg4's "~17 k tokens") with
+    SEGMENT-SHARDED Ulysses attention: every rank holds 1/P of the text, image and each condition stream, so the local
+    sequence keeps the [txt | img | c_1 .. c_n] segment structure (all per-segment switches — LoRA group, AdaLN vectors,
+    gates — work unchanged on local bounds = global bounds / P). Around attention the exchange is fused into the kernels over
+    NVLink peer memory exactly as in `SequenceParallelUniGenFlux` (exchange="peer"): per segment, ug_qkv_scatter normalises /
+    rotates q,k and stores heads into their owner rank's receive buffer at the segment's GLOBAL rows; ug_attention_bf16_peer
+    runs the segment-visibility mask on global bounds and stores each output row into its owner's AO / CAT rows.
+    Every rank passes the FULL inputs and receives the FULL velocity. Numerical contract: bit-identical to the single-GPU
+    `UniCombineFlux.forward` (tools/sp_check_pvariant.py)."""
+
+    def __init__(self, arch=None, device="cuda", group=None, **kw):
+        super().__init__(arch, device, **kw)
+        if not dist.is_initialized():
+            raise ops.UgError("SequenceParallelUniCombineFlux needs an initialised torch.distributed process group")
+        self.sp_group, self.sp_world, self.sp_rank = group, dist.get_world_size(group), dist.get_rank(group)
+        if self.arch.num_attention_heads % self.sp_world:
+            raise ops.UgError(f"{self.arch.num_attention_heads} heads are not divisible by {self.sp_world} ranks")
+        self._pool: Optional[PeerPool] = None
+        self._pool_key = None
+        self.use_cuda_graph = False
+        self._graphs = {}
+
+    def _workspace(self, B, S_loc):
+        buf = super()._workspace(B, S_loc)
+        if B != 1:
+            raise ops.UgError("sequence parallelism shards ONE sample across ranks (use batch data-parallelism for B > 1)")
+        a, D, P = self.arch, self.inner_dim, self.sp_world
+        S = S_loc * P
+        if self._pool_key != S_loc:
+            if self._pool is not None:
+                self._pool.close()
+            n_max = S  # velocity rows <= S
+            sizes = [("RECV", 3 * S * (D // P) * 2), ("AO", S_loc * D * 2), ("CAT", S_loc * 5 * D * 2), ("OUTF", n_max * a.in_channels * 2)]
+            self._off, total = pool_layout(sizes)
+            self._pool = PeerPool(self.sp_group, total, self.device_)
+            self._pool_key = S_loc
+            self._recv = self._pool.view(self._off["RECV"], (3, 1, S, D // P))
+        buf.AO, buf.CAT = self._pool.view(self._off["AO"], (1, S_loc, D)), self._pool.view(self._off["CAT"], (1, S_loc, 5 * D))
+        return buf
+
+    def _attention(self, buf, parts, out_name: str, bounds, vis):
+        a, D, P, pool = self.arch, self.inner_dim, self.sp_world, self._pool
+        H, dh = a.num_attention_heads, a.attention_head_dim
+        gbounds = [b * P for b in bounds]
+        S = gbounds[-1]
+        qkv = buf.QKV[0]
+        for s in range(len(bounds) - 1):  # one scatter per local segment shard -> its global rows
+            lo, hi = bounds[s], bounds[s + 1]
+            if hi == lo:
+                continue
+            rms = next(w for plo, phi, w in parts if plo <= lo and hi <= phi)
+            ops.qkv_scatter(pool.table, qkv[lo:hi], H, dh, rms, buf.rope[lo:hi], self._off["RECV"], S,
+                            gbounds[s] + self.sp_rank * (hi - lo))
+        pool.barrier()
+        ops.attention_peer(pool.table, self._recv[0], self._recv[1], self._recv[2], H // P, dh, self._off[out_name],
+                           D if out_name == "AO" else 5 * D, 0, seg_bounds=gbounds, seg_visible=vis, variant=self.attn_variant)
+        pool.barrier()
+
+    def _forward_local(self, hs, cl, cids, es, pooled, timestep, img_ids, txt_ids, condition_types, c_t, N):
+        out_loc = super().forward(hs, cl, cids, condition_types, es, pooled, timestep, img_ids, txt_ids, c_t=c_t)
+        n_loc = out_loc.shape[1]
+        ops.peer_bcast_rows(self._pool.table, out_loc[0], self._off["OUTF"], self.arch.in_channels, self.sp_rank * n_loc)
+        self._pool.barrier()
+        return self._pool.view(self._off["OUTF"], (1, N, self.arch.in_channels))
+
+    @torch.no_grad()
+    def forward(self, hidden_states, condition_latents, condition_ids, condition_types, encoder_hidden_states,
+                pooled_projections, timestep, img_ids, txt_ids, c_t: float = 0.0, **kwargs):
+        P, r = self.sp_world, self.sp_rank
+        dev = self.device_
+
+        def shard(t, dim):
+            n = t.shape[dim]
+            if n % P:
+                raise ops.UgError(f"segment of {n} tokens is not divisible by the sequence-parallel world size {P}")
+            return t.narrow(dim, r * (n // P), n // P).to(dev).contiguous()
+
+        N = hidden_states.shape[1]
+        local = dict(hs=shard(hidden_states, 1), es=shard(encoder_hidden_states, 1), pooled=pooled_projections.to(dev),
+                     timestep=timestep.to(dev), img_ids=shard(img_ids, 0), txt_ids=shard(txt_ids, 0))
+        for j, (c, ci) in enumerate(zip(condition_latents, condition_ids)):
+            local[f"cl{j}"], local[f"cid{j}"] = shard(c, 1), shard(ci, 0)
+        n = len(condition_latents)
+
+        def run(t):
+            return self._forward_local(t["hs"], [t[f"cl{j}"] for j in range(n)], [t[f"cid{j}"] for j in range(n)], t["es"], t["pooled"],
+                                       t["timestep"], t["img_ids"], t["txt_ids"], list(condition_types), c_t, N)
+
+        if not self.use_cuda_graph or self.trace is not None:
+            return run(local)
+        key = (tuple((k, tuple(v.shape), v.dtype) for k, v in local.items()), tuple(condition_types), float(c_t))
+        g = self._graphs.get(key)
+        if g is None:
+            static = {k: v.clone() for k, v in local.items()}
+            run(static)  # warm-up: pool creation (IPC handle exchange), workspace allocation
+            torch.cuda.synchronize()
+            n0 = ops.launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = run(static)
+            g = self._graphs[key] = (graph, static, out, ops.launch_count() - n0)
+        graph, static, out, n_launch = g
+        for k, v in local.items():
+            static[k].copy_(v)
+        graph.replay()
+        ops.add_launches(n_launch)
+        return out

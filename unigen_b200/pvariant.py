@@ -187,6 +187,18 @@ class UniCombineFlux(torch.nn.Module):
                         lora=dict(t=t, b=pair.b, rank=pair.rank, block_n=pair.n_each, seg_bounds=seg_bounds,
                                   seg_group=seg_group), **kw)
 
+    def _attention(self, buf, parts, out_name: str, bounds, vis):
+        """QK-RMSNorm + RoPE in place on the q|k columns of row ranges `parts` = [(lo, hi, rms_weight)], then the joint
+        attention with the segment-visibility rule -> buf.AO, or the first D columns of buf.CAT (single blocks).
+        The sequence-parallel subclass (parallel.py) fuses both steps with the Ulysses exchange over peer memory."""
+        a, D = self.arch, self.inner_dim
+        H, dh = a.num_attention_heads, a.attention_head_dim
+        for lo, hi, rms in parts:
+            ops.qk_rmsnorm_rope(buf.QKV[:, lo:hi, :2 * D], 2 * H, dh, rms, buf.rope[lo:hi], heads_per_weight=H)
+        out = buf.AO if out_name == "AO" else buf.CAT[:, :, :D]
+        ops.attention(buf.QKV[:, :, 0:D], buf.QKV[:, :, D:2 * D], buf.QKV[:, :, 2 * D:], out, H, dh,
+                      seg_bounds=bounds, seg_visible=vis, variant=self.attn_variant)
+
     # ---------------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, hidden_states, condition_latents, condition_ids, condition_types, encoder_hidden_states,
@@ -243,11 +255,7 @@ class UniCombineFlux(torch.nn.Module):
                 ops.ln_modulate(seg(s_), buf.NX[:, bounds[s_]:bounds[s_ + 1]], mods[s_][0], mods[s_][1])
             ops.gemm(buf.NX[:, :T], w.add_qkv[0], out=buf.QKV[:, :T], bias=w.add_qkv[1], variant=gv)
             self._lora_gemm(buf, buf.NX[:, T:], w.qkv, L[p + ".qkv"], img_cond_bounds, img_cond_groups, buf.QKV[:, T:])
-            qk = buf.QKV[:, :, :2 * D]
-            ops.qk_rmsnorm_rope(qk[:, :T], 2 * H, dh, w.rms_ctx, buf.rope[:T], heads_per_weight=H)
-            ops.qk_rmsnorm_rope(qk[:, T:], 2 * H, dh, w.rms, buf.rope[T:], heads_per_weight=H)
-            ops.attention(buf.QKV[:, :, 0:D], buf.QKV[:, :, D:2 * D], buf.QKV[:, :, 2 * D:], buf.AO, H, dh,
-                          seg_bounds=bounds, seg_visible=vis, variant=self.attn_variant)
+            self._attention(buf, [(0, T, w.rms_ctx), (T, S, w.rms)], "AO", bounds, vis)
             ops.gemm(buf.AO[:, :T], w.to_add_out[0], out=seg(0), bias=w.to_add_out[1], gate=m_txt[2], residual=seg(0), variant=gv)
             for s_ in range(1, nseg):  # to_out[0] switched per segment, each with its own gate
                 rows = bounds[s_ + 1] - bounds[s_]
@@ -277,9 +285,7 @@ class UniCombineFlux(torch.nn.Module):
                 ops.ln_modulate(buf.X[:, lo:hi], buf.NX[:, lo:hi], mods[s_][0], mods[s_][1])
             self._lora_gemm(buf, buf.NX, w.qkv, L[p + ".qkv"], all_bounds, all_groups, buf.QKV)
             self._lora_gemm(buf, buf.NX, w.mlp, L[p + ".mlp"], all_bounds, all_groups, buf.CAT[:, :, D:], act=UG_ACT_GELU_TANH)
-            ops.qk_rmsnorm_rope(buf.QKV[:, :, :2 * D], 2 * H, dh, w.rms, buf.rope, heads_per_weight=H)
-            ops.attention(buf.QKV[:, :, 0:D], buf.QKV[:, :, D:2 * D], buf.QKV[:, :, 2 * D:], buf.CAT[:, :, :D], H, dh,
-                          seg_bounds=bounds, seg_visible=vis, variant=self.attn_variant)
+            self._attention(buf, [(0, S, w.rms)], "CAT", bounds, vis)
             for s_ in range(len(all_groups)):
                 lo, hi = all_bounds[s_], all_bounds[s_ + 1]
                 self._lora_gemm(buf, buf.CAT[:, lo:hi], w.out, L[p + ".out"], [0, hi - lo], [s_], buf.X[:, lo:hi],
