@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define UG_ABI_VERSION 4
+#define UG_ABI_VERSION 5
 
 typedef enum {
   UG_OK = 0,
@@ -110,6 +110,11 @@ typedef struct ug_gemm_args {
   int32_t qk_d;               /* heads * head_dim */
   float qk_eps;
   int32_t reserved2;
+  /* Per-segment gates: when != 0, rows of segment i of the row-segment table (lora_nseg / lora_seg_bounds, usable without a
+   * LoRA update) take their gate vector from gate + i * gate_seg_stride (+ b * gate_batch_stride): the per-stream
+   * `gate_msa` / `gate_mlp` of the P-variant's image and condition streams (UniCombineTransformerBlock.pyc L121-132, L222-230)
+   * in ONE launch over all streams instead of one under-filled launch per stream. */
+  int64_t gate_seg_stride;
 } ug_gemm_args;
 
 int ug_gemm_bf16(const ug_gemm_args* args, void* stream);

@@ -32,7 +32,7 @@ class GemmArgs(C.Structure):
         ("lora_b", C.c_void_p), ("lora_rank", C.c_int32), ("lora_block_n", C.c_int32), ("lora_nseg", C.c_int32),
         ("lora_seg_bounds", C.c_int32 * (UG_MAX_SEGMENTS + 1)), ("lora_seg_group", C.c_int32 * UG_MAX_SEGMENTS),
         ("qk_norm_weight", C.c_void_p), ("qk_cos_sin", C.c_void_p), ("qk_head_dim", C.c_int32), ("qk_d", C.c_int32),
-        ("qk_eps", C.c_float), ("reserved2", C.c_int32),
+        ("qk_eps", C.c_float), ("reserved2", C.c_int32), ("gate_seg_stride", C.c_int64),
     ]
 
 

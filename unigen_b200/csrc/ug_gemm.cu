@@ -22,6 +22,7 @@ struct GemmParams {
   long long bias_bs;
   const float* gate;
   long long gate_bs;
+  long long gate_seg_stride;  // != 0: rows of segment i (lora_bounds) use gate + i * gate_seg_stride
   float alpha;
   int act;
   const __nv_bfloat16* res;
@@ -64,8 +65,15 @@ __device__ __forceinline__ int lora_group_of(const GemmParams& p, int r) {
   return g;
 }
 
+__device__ __forceinline__ int seg_index_of(const GemmParams& p, int r) {
+  int g = 0;
+  for (int s = 0; s < p.lora_nseg; ++s)
+    if (r >= p.lora_bounds[s] && r < p.lora_bounds[s + 1]) g = s;
+  return g;
+}
+
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], int b, int r, int col0,
-                                               int lora_g) {
+                                               int lora_g, const float* gate_row) {
   const long long c_off = (long long)b * p.c_bs + (long long)r * p.c_rs;
   const long long r_off = (long long)b * p.res_bs + (long long)r * p.res_rs;
   // low-rank down-projection of this row for the sub-linear (fused q|k|v ...) the 32-column chunk belongs to
@@ -115,8 +123,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 #pragma unroll
       for (int i = 0; i < 8; ++i) x[i] = gelu_tanh(x[i]);
     }
-    if (p.gate) {
-      const float* g = p.gate + (long long)b * p.gate_bs + c;
+    if (gate_row) {
+      const float* g = gate_row + c;
       float4 g0 = *reinterpret_cast<const float4*>(g), g1 = *reinterpret_cast<const float4*>(g + 4);
       x[0] *= g0.x * p.alpha; x[1] *= g0.y * p.alpha; x[2] *= g0.z * p.alpha; x[3] *= g0.w * p.alpha;
       x[4] *= g1.x * p.alpha; x[5] *= g1.y * p.alpha; x[6] *= g1.z * p.alpha; x[7] *= g1.w * p.alpha;
@@ -328,6 +336,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
       const int lora_g = p.lora_t ? lora_group_of(p, r) : -1;
+      // gate vector of this row: per sample, and per row segment when gate_seg_stride is set (once per tile, not per chunk)
+      const float* gate_row = p.gate ? p.gate + (long long)b * p.gate_bs + (p.gate_seg_stride ? seg_index_of(p, r) * p.gate_seg_stride : 0)
+                                     : nullptr;
       auto release_acc = [&]() {
         // accumulator stage fully read: hand it back to the MMA warp before doing the last stores
         tc_fence_before();
@@ -374,7 +385,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           tmem_ld_wait();
           if (ch == BN / 32 - 1) release_acc();
           const int col0 = n0 + ch * 32;
-          if (r < p.rows && col0 < p.n) epilogue_chunk(p, v, b, r, col0, lora_g);
+          if (r < p.rows && col0 < p.n) epilogue_chunk(p, v, b, r, col0, lora_g, gate_row);
         }
       }
     }
@@ -427,7 +438,7 @@ static int launch_gemm(const ug_gemm_args& a, cudaStream_t stream) {
   p.total_tiles = p.m_tiles * p.n_tiles * a.batch;
   p.c = (__nv_bfloat16*)a.c; p.c_rs = a.c_row_stride; p.c_bs = a.c_batch_stride;
   p.bias = (const __nv_bfloat16*)a.bias; p.bias_bs = a.bias_batch_stride;
-  p.gate = a.gate; p.gate_bs = a.gate_batch_stride;
+  p.gate = a.gate; p.gate_bs = a.gate_batch_stride; p.gate_seg_stride = a.gate_seg_stride;
   p.alpha = a.alpha; p.act = a.act;
   p.res = (const __nv_bfloat16*)a.residual; p.res_rs = a.res_row_stride; p.res_bs = a.res_batch_stride;
   p.w_batched = w_batched ? 1 : 0;
@@ -483,6 +494,10 @@ extern "C" int ug_gemm_bf16(const ug_gemm_args* args, void* stream) {
   }
   if (a.bias) UG_CHECK_ARG((reinterpret_cast<uintptr_t>(a.bias) & 15) == 0 && a.bias_batch_stride % 8 == 0, "gemm: bias alignment");
   if (a.gate) UG_CHECK_ARG((reinterpret_cast<uintptr_t>(a.gate) & 15) == 0 && a.gate_batch_stride % 4 == 0, "gemm: gate alignment");
+  if (a.gate_seg_stride) {
+    UG_CHECK_ARG(a.gate && a.gate_seg_stride % 4 == 0 && a.lora_nseg >= 1 && a.lora_nseg <= UG_MAX_SEGMENTS,
+                 "gemm: gate_seg_stride needs a gate and the row-segment table (lora_nseg / lora_seg_bounds)");
+  }
   UG_CHECK_ARG(a.act == UG_ACT_NONE || a.act == UG_ACT_GELU_TANH, "gemm: unknown activation %d", a.act);
   if (a.qk_norm_weight) {
     UG_CHECK_ARG(a.qk_head_dim == 64 || a.qk_head_dim == 128, "gemm: fused QK-norm needs head_dim 64 or 128 (got %d)", a.qk_head_dim);

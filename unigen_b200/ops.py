@@ -79,7 +79,7 @@ def device_check() -> None:
 def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
          gate: Optional[torch.Tensor] = None, alpha: float = 1.0, act: int = UG_ACT_NONE,
          residual: Optional[torch.Tensor] = None, variant: int = 0, lora: Optional[dict] = None,
-         qk_norm: Optional[dict] = None) -> torch.Tensor:
+         qk_norm: Optional[dict] = None, gate_seg_stride: int = 0, seg_bounds: Optional[Sequence[int]] = None) -> torch.Tensor:
     """out[b,r,:] = residual + alpha * gate[b,:] * act(a[b,r,:] @ w^T + bias (+ switched LoRA update)).
     a: [B,R,K] view, w: [N,K] or [B,N,K]. lora = dict(t=fp32 [B,R,n_blocks*rank] from lora_down, b=bf16 [groups,N,rank]
     (pre-scaled), rank, block_n, seg_bounds, seg_group) applies adapter group seg_group[i] to rows of segment i."""
@@ -108,6 +108,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, b
             gate = gate.unsqueeze(0)
         g.gate, g.gate_batch_stride = gate.data_ptr(), gate.stride(0)
     g.alpha, g.act = float(alpha), int(act)
+    if gate_seg_stride:
+        # per-segment gates: segment i of the row-segment table reads gate + i * gate_seg_stride
+        g.gate_seg_stride = int(gate_seg_stride)
+        sb = seg_bounds if seg_bounds is not None else (lora["seg_bounds"] if lora is not None else None)
+        if gate is None or sb is None:
+            raise UgError("gemm: gate_seg_stride needs gate and seg_bounds (or a lora segment table)")
+        g.lora_nseg = len(sb) - 1
+        for i, v in enumerate(sb):
+            g.lora_seg_bounds[i] = int(v)
     if residual is not None:
         r3 = _view3(_dev(residual, "gemm.residual", BF16), "gemm.residual")
         g.residual, g.res_row_stride, g.res_batch_stride = r3.data_ptr(), r3.stride(1), r3.stride(0)

@@ -166,10 +166,11 @@ class UniCombineFlux(torch.nn.Module):
         ops.gemv(pooled, w.p1[0], w.p1[1], out=tmp, silu_out=True)
         ops.gemv(tmp, w.p2[0], w.p2[1], out=out, accumulate=True)
 
-    def _mod_vectors(self, buf, w, lora: Optional[_LoraPair], temb, group: int, n_chunks: int):
+    def _mod_vectors(self, buf, w, lora: Optional[_LoraPair], temb, group: int, n_chunks: int, out: Optional[torch.Tensor] = None):
         """AdaLN `linear(silu(temb))` with the LoRA of `group` (enable_lora on norm1.linear / norm.linear)."""
         D = self.inner_dim
-        out = torch.empty(temb.shape[0], n_chunks * D, device=self.device_, dtype=torch.float32)
+        if out is None:
+            out = torch.empty(temb.shape[0], n_chunks * D, device=self.device_, dtype=torch.float32)
         ops.gemv(temb, w[0], w[1], out=out, silu_in=True)
         if lora is not None and group >= 0:
             rp = lora.rank
@@ -247,9 +248,12 @@ class UniCombineFlux(torch.nn.Module):
         for i, w in enumerate(self.double):  # ---- block_forward ----
             p = f"transformer_blocks.{i}"
             L = self.lora
-            m_img = self._mod_vectors(buf, w.norm1, L[p + ".norm1"], buf.temb, 0, 6)
+            # the image / condition streams' AdaLN vectors live in ONE [1+n, B, 6D] table so that the gated GEMMs below can
+            # cover all of them in a single launch (ug_gemm_args.gate_seg_stride)
+            modd = torch.empty(1 + n, B, 6 * D, device=dev, dtype=torch.float32)
+            m_img = self._mod_vectors(buf, w.norm1, L[p + ".norm1"], buf.temb, 0, 6, out=modd[0])
             m_txt = self._mod_vectors(buf, w.norm1_ctx, None, buf.temb, -1, 6)
-            m_c = [self._mod_vectors(buf, w.norm1, L[p + ".norm1"], buf.ctemb, 1 + j, 6) for j in range(n)]
+            m_c = [self._mod_vectors(buf, w.norm1, L[p + ".norm1"], buf.ctemb, 1 + j, 6, out=modd[1 + j]) for j in range(n)]
             mods = [m_txt, m_img] + m_c
             for s_ in range(nseg):
                 ops.ln_modulate(seg(s_), buf.NX[:, bounds[s_]:bounds[s_ + 1]], mods[s_][0], mods[s_][1])
@@ -257,19 +261,16 @@ class UniCombineFlux(torch.nn.Module):
             self._lora_gemm(buf, buf.NX[:, T:], w.qkv, L[p + ".qkv"], img_cond_bounds, img_cond_groups, buf.QKV[:, T:])
             self._attention(buf, [(0, T, w.rms_ctx), (T, S, w.rms)], "AO", bounds, vis)
             ops.gemm(buf.AO[:, :T], w.to_add_out[0], out=seg(0), bias=w.to_add_out[1], gate=m_txt[2], residual=seg(0), variant=gv)
-            for s_ in range(1, nseg):  # to_out[0] switched per segment, each with its own gate
-                rows = bounds[s_ + 1] - bounds[s_]
-                self._lora_gemm(buf, buf.AO[:, bounds[s_]:bounds[s_ + 1]], w.to_out, L[p + ".to_out"], [0, rows], [s_ - 1],
-                                seg(s_), gate=mods[s_][2], residual=seg(s_))
+            # to_out[0]: LoRA group AND gate switched per stream inside one launch over [img | c_1 .. c_n]
+            self._lora_gemm(buf, buf.AO[:, T:], w.to_out, L[p + ".to_out"], img_cond_bounds, img_cond_groups, buf.X[:, T:],
+                            gate=m_img[2], gate_seg_stride=B * 6 * D, residual=buf.X[:, T:])
             for s_ in range(nseg):
                 ops.ln_modulate(seg(s_), buf.NX[:, bounds[s_]:bounds[s_ + 1]], mods[s_][3], mods[s_][4])
             ops.gemm(buf.NX[:, :T], w.ffc1[0], out=buf.FF[:, :T], bias=w.ffc1[1], act=UG_ACT_GELU_TANH, variant=gv)
             ops.gemm(buf.FF[:, :T], w.ffc2[0], out=seg(0), bias=w.ffc2[1], gate=m_txt[5], residual=seg(0), variant=gv)
             ops.gemm(buf.NX[:, T:], w.ff1[0], out=buf.FF[:, T:], bias=w.ff1[1], act=UG_ACT_GELU_TANH, variant=gv)
-            for s_ in range(1, nseg):
-                rows = bounds[s_ + 1] - bounds[s_]
-                self._lora_gemm(buf, buf.FF[:, bounds[s_]:bounds[s_ + 1]], w.ff2, L[p + ".ff2"], [0, rows], [s_ - 1], seg(s_),
-                                gate=mods[s_][5], residual=seg(s_))
+            self._lora_gemm(buf, buf.FF[:, T:], w.ff2, L[p + ".ff2"], img_cond_bounds, img_cond_groups, buf.X[:, T:],
+                            gate=m_img[5], gate_seg_stride=B * 6 * D, residual=buf.X[:, T:])
             self._rec(f"double.{i}.hidden", seg(1)); self._rec(f"double.{i}.context", seg(0))
             for j in range(n):
                 self._rec(f"double.{i}.cond{j}", seg(2 + j))
@@ -277,8 +278,9 @@ class UniCombineFlux(torch.nn.Module):
         for i, w in enumerate(self.single):  # ---- single_block_forward ----
             p = f"single_transformer_blocks.{i}"
             L = self.lora
-            m_x = self._mod_vectors(buf, w.norm, L[p + ".norm"], buf.temb, 0, 3)
-            m_c = [self._mod_vectors(buf, w.norm, L[p + ".norm"], buf.ctemb, 1 + j, 3) for j in range(n)]
+            mods_t = torch.empty(1 + n, B, 3 * D, device=dev, dtype=torch.float32)
+            m_x = self._mod_vectors(buf, w.norm, L[p + ".norm"], buf.temb, 0, 3, out=mods_t[0])
+            m_c = [self._mod_vectors(buf, w.norm, L[p + ".norm"], buf.ctemb, 1 + j, 3, out=mods_t[1 + j]) for j in range(n)]
             mods = [m_x] + m_c
             for s_ in range(len(all_groups)):
                 lo, hi = all_bounds[s_], all_bounds[s_ + 1]
@@ -286,10 +288,8 @@ class UniCombineFlux(torch.nn.Module):
             self._lora_gemm(buf, buf.NX, w.qkv, L[p + ".qkv"], all_bounds, all_groups, buf.QKV)
             self._lora_gemm(buf, buf.NX, w.mlp, L[p + ".mlp"], all_bounds, all_groups, buf.CAT[:, :, D:], act=UG_ACT_GELU_TANH)
             self._attention(buf, [(0, S, w.rms)], "CAT", bounds, vis)
-            for s_ in range(len(all_groups)):
-                lo, hi = all_bounds[s_], all_bounds[s_ + 1]
-                self._lora_gemm(buf, buf.CAT[:, lo:hi], w.out, L[p + ".out"], [0, hi - lo], [s_], buf.X[:, lo:hi],
-                                gate=mods[s_][2], residual=buf.X[:, lo:hi])
+            self._lora_gemm(buf, buf.CAT, w.out, L[p + ".out"], all_bounds, all_groups, buf.X, gate=m_x[2],
+                            gate_seg_stride=B * 3 * D, residual=buf.X)
             self._rec(f"single.{i}.hidden", buf.X[:, :T + N])
             for j in range(n):
                 self._rec(f"single.{i}.cond{j}", seg(2 + j))
