@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define UG_ABI_VERSION 5
+#define UG_ABI_VERSION 6
 
 typedef enum {
   UG_OK = 0,
@@ -115,6 +115,17 @@ typedef struct ug_gemm_args {
    * `gate_msa` / `gate_mlp` of the P-variant's image and condition streams (UniCombineTransformerBlock.pyc L121-132, L222-230)
    * in ONE launch over all streams instead of one under-filled launch per stream. */
   int64_t gate_seg_stride;
+  /* Second operand pair (K extension): the accumulator receives  A @ W^T + A2 @ W2^T  before the epilogue, both on the
+   * tensor cores. A2: bf16 [batch, rows, k2] (a2_row_stride / a2_batch_stride), W2: bf16 [n, k2] shared by all batches.
+   * Used for the switched LoRA update of the P-variant: A2 = the down-projection laid out in one 64-column block per
+   * adapter group with zeros outside the row's own group (ug_lora_down_wide), W2 = [B_0 | B_1 | ...] (pre-scaled), so a
+   * row only meets its own adapter's B and no tile-alignment of the segments is required. a2 == NULL: off. */
+  const void* a2;
+  int64_t a2_row_stride, a2_batch_stride;
+  const void* w2;
+  int64_t w2_row_stride;
+  int32_t k2;
+  int32_t reserved3;
 } ug_gemm_args;
 
 int ug_gemm_bf16(const ug_gemm_args* args, void* stream);
@@ -126,6 +137,14 @@ int ug_lora_down(const void* x, int64_t x_row_stride, int64_t x_batch_stride, co
                  int64_t t_row_stride, int64_t t_batch_stride, int32_t batch, int32_t rows, int32_t k,
                  int32_t rank_total, int32_t nseg, const int32_t* seg_bounds_host, const int32_t* seg_group_host,
                  void* stream);
+/* Same down-projection written for the K-extension form of the update (ug_gemm_args.a2): t_wide bf16 [batch, rows,
+ * groups * block] with block >= rank_total a multiple of 64; row r holds x[r] @ A[g(r)]^T in columns
+ * [g(r) * block, g(r) * block + rank_total) and ZEROS everywhere else (peft computes lora_A's output in the model dtype,
+ * so the bf16 rounding of t matches the reference). */
+int ug_lora_down_wide(const void* x, int64_t x_row_stride, int64_t x_batch_stride, const void* a_stack, void* t_wide,
+                      int64_t t_row_stride, int64_t t_batch_stride, int32_t batch, int32_t rows, int32_t k,
+                      int32_t rank_total, int32_t groups, int32_t block, int32_t nseg, const int32_t* seg_bounds_host,
+                      const int32_t* seg_group_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Joint attention (tcgen05 / TMEM / TMA), softmax(Q K^T * scale + mask) V per head, non-causal.

@@ -55,6 +55,50 @@ def test_gemm_switched_lora_epilogue_fused_qkv(ug, variant, rank):
     assert torch.equal(out[:, :40], plain[:, :40]) and not torch.equal(out[:, 40:], plain[:, 40:])
 
 
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_gemm_k_extension_switched_lora_on_tensor_cores(ug, variant):
+    """The same switched update as above, as a K extension of the main GEMM: A2 = ug_lora_down_wide (one 64-column block per
+    adapter group, zeros outside the row's own group), W2 = [B_0 | B_1 | B_2] — segment bounds need NOT be tile-aligned.
+    Also exercises per-segment gates (gate_seg_stride) and the residual in the same launch."""
+    torch.manual_seed(1)
+    D, rank, bounds, groups = 384, 4, [0, 40, 300, 420, 555], [-1, 0, 1, 2]
+    S, G, blk = bounds[-1], 3, 64
+    x = bf(torch.randn(2, S, D))
+    W, bias = bf(torch.randn(3 * D, D) / math.sqrt(D)), bf(torch.randn(3 * D))
+    A = bf(torch.randn(G, 3, rank, D) / math.sqrt(D))
+    Bm = bf(torch.randn(G, 3, D, rank) * 0.5 / math.sqrt(rank))
+    gates = torch.randn(4, 2, 3 * D)
+    res = bf(torch.randn(2, S, 3 * D))
+    lin = x @ W.t() + bias
+    for s in range(4):
+        g = groups[s]
+        rows = slice(bounds[s], bounds[s + 1])
+        if g >= 0:
+            for sub in range(3):
+                t = bf(x[:, rows] @ A[g, sub].t())  # peft: lora_A output in the model dtype
+                lin[:, rows, sub * D:(sub + 1) * D] += t @ Bm[g, sub].t()
+    want = res.clone()
+    for s in range(4):
+        rows = slice(bounds[s], bounds[s + 1])
+        want[:, rows] += gates[s][:, None, :] * lin[:, rows]
+    xd = x.cuda().to(torch.bfloat16)
+    a_stack = A.reshape(G, 3 * rank, D).cuda().to(torch.bfloat16)
+    bw = torch.zeros(3 * D, G * blk)
+    for g in range(G):
+        for sub in range(3):
+            bw[sub * D:(sub + 1) * D, g * blk + sub * rank:g * blk + (sub + 1) * rank] = Bm[g, sub]
+    tw = torch.full((2, S, G * blk), 7.0, device="cuda", dtype=torch.bfloat16)
+    ug.lora_down_wide(xd, a_stack, bounds, groups, out=tw, block=blk)
+    twc = tw.float().cpu()
+    assert twc[:, :40].abs().max() == 0 and twc[:, 40:300, blk:].abs().max() == 0 and twc[:, 40:300, 3 * rank:blk].abs().max() == 0
+    assert (twc[:, 300:420, blk:blk + 3 * rank] - bf(x[:, 300:420] @ A[1].reshape(3 * rank, D).t())).abs().max() < 2e-2
+    gd = gates.cuda().contiguous()
+    out = ug.gemm(xd, W.cuda().to(torch.bfloat16), bias=bias.cuda().to(torch.bfloat16), variant=variant, a2=tw,
+                  w2=bw.cuda().to(torch.bfloat16), gate=gd[0], gate_seg_stride=gd.stride(0), seg_bounds=bounds,
+                  residual=res.cuda().to(torch.bfloat16))
+    assert rel_l2(out, want) < 6e-3
+
+
 def _setup(n_cond=2, strict=False, seed=1):
     from oracle import unigen_oracle as O
     from unigen_b200.model import FluxArch
@@ -75,9 +119,11 @@ def _setup(n_cond=2, strict=False, seed=1):
     return cfg, inp, types_, oracle, model
 
 
+@pytest.mark.parametrize("lora_mode", ["mma", "epilogue"])
 @pytest.mark.parametrize("n_cond,strict", [(1, False), (2, False), (2, True)])
-def test_pvariant_forward_matches_oracle(n_cond, strict):
+def test_pvariant_forward_matches_oracle(n_cond, strict, lora_mode):
     cfg, inp, types_, oracle, model = _setup(n_cond, strict)
+    model.lora_mode = lora_mode
     args = (inp["hidden_states"], inp["condition_hidden_states"], inp["condition_ids"], types_, inp["encoder_hidden_states"],
             inp["pooled_projections"], inp["timestep"], inp["img_ids"], inp["txt_ids"])
     want = oracle.forward(*args)

@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--side", type=int, default=1024)
     ap.add_argument("--strict", action="store_true")
+    ap.add_argument("--lora-mode", default="mma", choices=["mma", "epilogue"])
     args = ap.parse_args()
     from unigen_b200 import ops
     from unigen_b200.model import FluxArch
@@ -44,6 +45,7 @@ def main():
             sd[f"{name}.lora_A.{a}.weight"] = torch.randn(4, in_f, device="cuda", generator=g) / in_f ** 0.5
             sd[f"{name}.lora_B.{a}.weight"] = torch.randn(out_f, 4, device="cuda", generator=g) * 0.25
     model.load_state_dict(sd, adapters=adapters, condition_types=types_)
+    model.lora_mode = args.lora_mode
     grid = args.side // 16
     ids = torch.zeros(grid, grid, 3, device="cuda")
     ids[..., 1] += torch.arange(grid, device="cuda")[:, None]
@@ -73,7 +75,7 @@ def main():
     print(json.dumps({"workload": f"cfg4 P-variant: {S} tokens ({args.conds} conditions), LoRA rank 4 switched per segment, "
                                   f"{'strict' if args.strict else 'reference'} visibility mask",
                       "ms_per_step": ms, "steps_per_s": 1e3 / ms, "tflop_per_step": (gemm + attn) / 1e12,
-                      "model_tflops": (gemm + attn) / ms / 1e9, "gpu_launches_per_step": ops.launch_count() // args.steps,
+                      "model_tflops": (gemm + attn) / ms / 1e9, "gpu_launches_per_step": ops.launch_count() // args.steps, "lora_mode": args.lora_mode,
                       "finite": bool(torch.isfinite(out.float()).all())}))
 
 

@@ -43,6 +43,8 @@ def main():
     ap.add_argument("--side", type=int, default=1024)
     ap.add_argument("--text", type=int, default=333)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--attn-variant", type=int, default=0)
+    ap.add_argument("--gemm-variant", type=int, default=0)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -58,6 +60,7 @@ def main():
     model.init_condition_block(condition_nums=1, control_params=shipped_control_params())
     model.init_random_(seed=0)
     model.use_cuda_graph = not args.no_graph
+    model.attn_variant, model.gemm_variant = args.attn_variant, args.gemm_variant
     B, lat = args.batch, args.side // 8
     N, T, D = (lat // 2) ** 2, args.text, model.inner_dim
     g = torch.Generator().manual_seed(1234 + rank)
@@ -112,7 +115,7 @@ def main():
                     "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()), "d2h_bytes_per_step": vel.numel() * 2},
             "tflop_per_step_per_sample_executed": (gf + af) / 1e12, "tflop_per_step_per_sample_reference_algorithmic": (gr + ar) / 1e12,
             "model_tflops_per_gpu": B * (gf + af) / ms / 1e9, "gpu_launches_per_step": launches // args.steps,
-            "cuda_graph": model.use_cuda_graph, "finite": bool(torch.isfinite(out.float()).all())}))
+            "cuda_graph": model.use_cuda_graph, "attn_variant": args.attn_variant, "gemm_variant": args.gemm_variant, "finite": bool(torch.isfinite(out.float()).all())}))
     if world > 1:
         dist.destroy_process_group()
 

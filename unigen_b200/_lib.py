@@ -33,6 +33,8 @@ class GemmArgs(C.Structure):
         ("lora_seg_bounds", C.c_int32 * (UG_MAX_SEGMENTS + 1)), ("lora_seg_group", C.c_int32 * UG_MAX_SEGMENTS),
         ("qk_norm_weight", C.c_void_p), ("qk_cos_sin", C.c_void_p), ("qk_head_dim", C.c_int32), ("qk_d", C.c_int32),
         ("qk_eps", C.c_float), ("reserved2", C.c_int32), ("gate_seg_stride", C.c_int64),
+        ("a2", C.c_void_p), ("a2_row_stride", C.c_int64), ("a2_batch_stride", C.c_int64),
+        ("w2", C.c_void_p), ("w2_row_stride", C.c_int64), ("k2", C.c_int32), ("reserved3", C.c_int32),
     ]
 
 
@@ -76,6 +78,8 @@ SIGNATURES = {
     "ug_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _VP]),
     "ug_lora_down": (C.c_int, [_VP, _I64, _I64, _VP, _VP, _I64, _I64, _I32, _I32, _I32, _I32, _I32,
                                C.POINTER(C.c_int32), C.POINTER(C.c_int32), _VP]),
+    "ug_lora_down_wide": (C.c_int, [_VP, _I64, _I64, _VP, _VP, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32,
+                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32), _VP]),
     "ug_attention_bf16": (C.c_int, [C.POINTER(AttnArgs), _VP]),
     "ug_expand_segment_mask": (C.c_int, [_I32, _I32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), _VP, _VP]),
     "ug_ln_modulate": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _I64, _VP, _VP, _I64, _I32, _I32, _I32, _F32, _VP]),

@@ -551,7 +551,86 @@ __global__ void __launch_bounds__(256) lora_down_kernel(const __nv_bfloat16* __r
     }
   }
 }
+// Same projection, written as bf16 in the K-extension layout of ug_gemm_args.a2: [rows, groups * block], the row's own
+// group block holds x @ A_g^T (first rtot columns), everything else is zero.
+__global__ void __launch_bounds__(256) lora_down_wide_kernel(const __nv_bfloat16* __restrict__ x, long long x_rs, long long x_bs,
+                                                             const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ t,
+                                                             long long t_rs, long long t_bs, int batch, int rows, int k, int rtot,
+                                                             int groups, int block, LoraSegs segs) {
+  __shared__ float res_s[8][64];
+  const int warp_in_block = threadIdx.x >> 5;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp_global >= batch * rows) return;
+  const int b = warp_global / rows, r = warp_global % rows;
+  int g = -1;
+  for (int s = 0; s < segs.nseg; ++s)
+    if (r >= segs.bounds[s] && r < segs.bounds[s + 1]) g = segs.group[s];
+  float* res = res_s[warp_in_block];
+  if (g >= 0) {
+    const __nv_bfloat16* xr = x + (long long)b * x_bs + (long long)r * x_rs;
+    const __nv_bfloat16* ag = a + (long long)g * rtot * k;
+    for (int j0 = 0; j0 < rtot; j0 += 4) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int kk = lane * 8; kk < k; kk += 256) {
+        float xf[8];
+        unpack8(*reinterpret_cast<const uint4*>(xr + kk), xf);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j0 + j < rtot) {
+            float af[8];
+            unpack8(*reinterpret_cast<const uint4*>(ag + (long long)(j0 + j) * k + kk), af);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[j] += xf[i] * af[i];
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = warp_sum(acc[j]);
+      if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j0 + j < rtot) res[j0 + j] = acc[j];
+      }
+    }
+  }
+  __syncwarp();
+  __nv_bfloat16* tp = t + (long long)b * t_bs + (long long)r * t_rs;
+  const int width = groups * block;
+  for (int c0 = lane * 8; c0 < width; c0 += 256) {
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i, j = c % block;
+      f[i] = (g >= 0 && c / block == g && j < rtot) ? res[j] : 0.f;
+    }
+    *reinterpret_cast<uint4*>(tp + c0) = pack8(f);
+  }
+}
 }  // namespace ug
+
+extern "C" int ug_lora_down_wide(const void* x, int64_t x_rs, int64_t x_bs, const void* a_stack, void* t_wide, int64_t t_rs,
+                                 int64_t t_bs, int32_t batch, int32_t rows, int32_t k, int32_t rank_total, int32_t groups,
+                                 int32_t block, int32_t nseg, const int32_t* seg_bounds, const int32_t* seg_group, void* stream) {
+  UG_CHECK_ARG(x && a_stack && t_wide && seg_bounds && seg_group, "lora_down_wide: null pointer");
+  UG_CHECK_ARG(batch >= 1 && rows >= 1 && k >= 8 && k % 8 == 0 && rank_total >= 1 && rank_total <= 64, "lora_down_wide: bad shape");
+  UG_CHECK_ARG(groups >= 1 && block >= rank_total && block % 64 == 0, "lora_down_wide: block (%d) must be a multiple of 64 >= rank_total (%d)",
+               block, rank_total);
+  UG_CHECK_ARG(nseg >= 1 && nseg <= UG_MAX_SEGMENTS, "lora_down_wide: nseg %d out of range", nseg);
+  UG_CHECK_ARG(x_rs % 8 == 0 && x_bs % 8 == 0 && t_rs % 8 == 0 && t_bs % 8 == 0 && aligned16(x) && aligned16(a_stack) && aligned16(t_wide),
+               "lora_down_wide: alignment");
+  ug::LoraSegs segs;
+  segs.nseg = nseg;
+  for (int i = 0; i <= UG_MAX_SEGMENTS; ++i) segs.bounds[i] = i <= nseg ? seg_bounds[i] : rows;
+  for (int i = 0; i < UG_MAX_SEGMENTS; ++i) segs.group[i] = i < nseg ? seg_group[i] : -1;
+  const long long warps = (long long)batch * rows;
+  const int grid = (int)((warps * 32 + 255) / 256);
+  ug::lora_down_wide_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const __nv_bfloat16*)x, x_rs, x_bs, (const __nv_bfloat16*)a_stack, (__nv_bfloat16*)t_wide, t_rs, t_bs, batch, rows, k, rank_total,
+      groups, block, segs);
+  UG_CHECK_LAUNCH("lora_down_wide");
+  return UG_OK;
+}
 
 extern "C" int ug_lora_down(const void* x, int64_t x_rs, int64_t x_bs, const void* a_stack, float* t, int64_t t_rs,
                             int64_t t_bs, int32_t batch, int32_t rows, int32_t k, int32_t rank_total, int32_t nseg,

@@ -16,6 +16,7 @@ namespace ug {
 struct GemmParams {
   int rows, n, k, batch;
   int m_tiles, n_tiles, k_blocks, total_tiles;
+  int k1_blocks;  // K blocks of the first operand pair (A, W); blocks [k1_blocks, k_blocks) come from the second pair (A2, W2)
   __nv_bfloat16* c;
   long long c_rs, c_bs;
   const __nv_bfloat16* bias;
@@ -214,7 +215,7 @@ __device__ __forceinline__ float chunk_sumsq(const GemmParams& p, const uint32_t
 template <int kCta, int BN, int kStages>
 __global__ void __launch_bounds__(192, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ CUtensorMap tma_w2, const GemmParams p) {
   using Cfg = GemmCfg<kCta, BN, kStages>;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte alignment; the offset is identical in both CTAs of a pair.
@@ -234,6 +235,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_w);
+    if (p.k1_blocks < p.k_blocks) {
+      tma_prefetch_desc(&tma_a2);
+      tma_prefetch_desc(&tma_w2);
+    }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -269,14 +274,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (lane == 0) {
           void* sa = smem_a + stage * Cfg::A_BYTES;
           void* sb = smem_b + stage * Cfg::B_BYTES;
+          // second operand pair (K extension: C += A2 @ W2^T accumulates into the same TMEM tile)
+          const bool second = kb >= p.k1_blocks;
+          const CUtensorMap* ma = second ? &tma_a2 : &tma_a;
+          const CUtensorMap* mw = second ? &tma_w2 : &tma_w;
+          const int kc = (second ? kb - p.k1_blocks : kb) * Cfg::BK;
           if constexpr (kCta == 1) {
             mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-            tma_load_3d(sa, &tma_a, &full[stage], kb * Cfg::BK, row0, b);
-            tma_load_3d(sb, &tma_w, &full[stage], kb * Cfg::BK, wrow0, wb);
+            tma_load_3d(sa, ma, &full[stage], kc, row0, b);
+            tma_load_3d(sb, mw, &full[stage], kc, wrow0, second ? 0 : wb);
           } else {
             if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
-            tma_load_3d_2sm(sa, &tma_a, &full[stage], kb * Cfg::BK, row0, b);
-            tma_load_3d_2sm(sb, &tma_w, &full[stage], kb * Cfg::BK, wrow0, wb);
+            tma_load_3d_2sm(sa, ma, &full[stage], kc, row0, b);
+            tma_load_3d_2sm(sb, mw, &full[stage], kc, wrow0, second ? 0 : wb);
           }
         }
         __syncwarp();
@@ -430,11 +440,32 @@ static int launch_gemm(const ug_gemm_args& a, cudaStream_t stream) {
     int st = encode_tmap_bf16(&tma_w, a.w, 3, dims, strides, box);
     if (st != UG_OK) return st;
   }
+  CUtensorMap tma_a2 = tma_a, tma_w2 = tma_w;
+  int k2_blocks = 0;
+  if (a.a2) {
+    {
+      uint64_t dims[3] = {(uint64_t)a.k2, (uint64_t)a.rows, (uint64_t)a.batch};
+      uint64_t bs = a.batch > 1 ? (uint64_t)a.a2_batch_stride : (uint64_t)a.rows * a.a2_row_stride;
+      uint64_t strides[2] = {(uint64_t)a.a2_row_stride * 2, bs * 2};
+      uint32_t box[3] = {(uint32_t)Cfg::BK, (uint32_t)Cfg::BM, 1};
+      int st = encode_tmap_bf16(&tma_a2, a.a2, 3, dims, strides, box);
+      if (st != UG_OK) return st;
+    }
+    {
+      uint64_t dims[3] = {(uint64_t)a.k2, (uint64_t)a.n, 1};
+      uint64_t strides[2] = {(uint64_t)a.w2_row_stride * 2, (uint64_t)a.n * a.w2_row_stride * 2};
+      uint32_t box[3] = {(uint32_t)Cfg::BK, (uint32_t)Cfg::BN_LOAD, 1};
+      int st = encode_tmap_bf16(&tma_w2, a.w2, 3, dims, strides, box);
+      if (st != UG_OK) return st;
+    }
+    k2_blocks = (a.k2 + Cfg::BK - 1) / Cfg::BK;
+  }
   GemmParams p;
   p.rows = a.rows; p.n = a.n; p.k = a.k; p.batch = a.batch;
   p.m_tiles = (a.rows + Cfg::BM * kCta - 1) / (Cfg::BM * kCta);
   p.n_tiles = (a.n + BN - 1) / BN;
-  p.k_blocks = (a.k + Cfg::BK - 1) / Cfg::BK;
+  p.k1_blocks = (a.k + Cfg::BK - 1) / Cfg::BK;
+  p.k_blocks = p.k1_blocks + k2_blocks;
   p.total_tiles = p.m_tiles * p.n_tiles * a.batch;
   p.c = (__nv_bfloat16*)a.c; p.c_rs = a.c_row_stride; p.c_bs = a.c_batch_stride;
   p.bias = (const __nv_bfloat16*)a.bias; p.bias_bs = a.bias_batch_stride;
@@ -465,7 +496,7 @@ static int launch_gemm(const ug_gemm_args& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tma_a, tma_w, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tma_a, tma_w, tma_a2, tma_w2, p);
   if (e != cudaSuccess) {
     set_error("gemm: launch failed: %s", cudaGetErrorString(e));
     return UG_ERR_CUDA;
@@ -516,6 +547,13 @@ extern "C" int ug_gemm_bf16(const ug_gemm_args* args, void* stream) {
     UG_CHECK_ARG(a.lora_t_row_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(a.lora_t) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(a.lora_b) & 7) == 0,
                  "gemm: LoRA operand alignment");
+  }
+  if (a.a2) {
+    UG_CHECK_ARG(a.w2 && a.k2 >= 8 && a.k2 % 8 == 0, "gemm: second operand pair needs w2 and k2 (%d) a positive multiple of 8", a.k2);
+    UG_CHECK_ARG(a.a2_row_stride % 8 == 0 && a.w2_row_stride % 8 == 0 && a.a2_row_stride >= a.k2 && a.w2_row_stride >= a.k2 &&
+                     (a.batch == 1 || a.a2_batch_stride % 8 == 0),
+                 "gemm: second operand pair strides must be multiples of 8 elements and cover k2");
+    UG_CHECK_ARG(!a.qk_norm_weight, "gemm: the second operand pair does not compose with the fused QK-norm epilogue");
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int variant = a.variant;

@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import UG_ACT_GELU_TANH, UG_ACT_NONE, AttnArgs, GemmArgs, QkvScatterArgs, UgError, check
 
-__all__ = ["gemm", "lora_down", "attention", "attention_peer", "qkv_scatter", "peer_bcast_rows", "peer_barrier", "expand_segment_mask", "ln_modulate", "qk_rmsnorm_rope", "rope_table", "gemv",
+__all__ = ["gemm", "lora_down", "lora_down_wide", "attention", "attention_peer", "qkv_scatter", "peer_bcast_rows", "peer_barrier", "expand_segment_mask", "ln_modulate", "qk_rmsnorm_rope", "rope_table", "gemv",
            "timestep_embedding", "add", "copy", "to_bf16", "to_f32", "moe_route", "moe_gather_modulate",
            "moe_combine", "ln_modulate_slots", "gated_add_slots", "unpatchify", "euler_step", "cfg_combine", "pack_latents", "unpack_latents", "launch_count", "reset_launch_count", "UG_ACT_NONE", "UG_ACT_GELU_TANH", "UgError"]
 
@@ -79,7 +79,8 @@ def device_check() -> None:
 def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
          gate: Optional[torch.Tensor] = None, alpha: float = 1.0, act: int = UG_ACT_NONE,
          residual: Optional[torch.Tensor] = None, variant: int = 0, lora: Optional[dict] = None,
-         qk_norm: Optional[dict] = None, gate_seg_stride: int = 0, seg_bounds: Optional[Sequence[int]] = None) -> torch.Tensor:
+         qk_norm: Optional[dict] = None, gate_seg_stride: int = 0, seg_bounds: Optional[Sequence[int]] = None,
+         a2: Optional[torch.Tensor] = None, w2: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[b,r,:] = residual + alpha * gate[b,:] * act(a[b,r,:] @ w^T + bias (+ switched LoRA update)).
     a: [B,R,K] view, w: [N,K] or [B,N,K]. lora = dict(t=fp32 [B,R,n_blocks*rank] from lora_down, b=bf16 [groups,N,rank]
     (pre-scaled), rank, block_n, seg_bounds, seg_group) applies adapter group seg_group[i] to rows of segment i."""
@@ -135,6 +136,14 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, b
             g.lora_seg_bounds[i] = int(v)
         for i, v in enumerate(sg):
             g.lora_seg_group[i] = int(v)
+    if a2 is not None:
+        # second operand pair: accumulator = a @ w^T + a2 @ w2^T (K extension on the tensor cores)
+        a23 = _view3(_dev(a2, "gemm.a2", BF16), "gemm.a2")
+        _dev(w2, "gemm.w2", BF16)
+        if a23.shape[:2] != (B, R) or w2.dim() != 2 or w2.shape[0] != N or w2.shape[1] != a23.shape[2] or w2.stride(1) != 1:
+            raise UgError(f"gemm: a2 {tuple(a23.shape)} / w2 {tuple(w2.shape)} do not match a {tuple(a.shape)} / n {N}")
+        g.a2, g.a2_row_stride, g.a2_batch_stride = a23.data_ptr(), a23.stride(1), a23.stride(0)
+        g.w2, g.w2_row_stride, g.k2 = w2.data_ptr(), w2.stride(0), a23.shape[2]
     if qk_norm is not None:
         # fused per-head RMSNorm + RoPE epilogue of a q|k|v projection: dict(weight=[2,dh] bf16, head_dim, d, cos_sin, eps)
         wq = _dev(qk_norm["weight"], "gemm.qk_norm.weight", BF16)
@@ -191,6 +200,25 @@ def _attn_args(q, k, v, heads, head_dim, seg_bounds, seg_visible, scale, variant
         a.n_seg, a.seg_bounds, a.seg_visible = n, sb, sv
     a.variant = variant
     return a, keep
+
+
+def lora_down_wide(x: torch.Tensor, a_stack: torch.Tensor, seg_bounds: Sequence[int], seg_group: Sequence[int],
+                   out: torch.Tensor, block: int = 64) -> torch.Tensor:
+    """bf16 out[b, r, g(r)*block : g(r)*block + rank_total] = x[b,r,:] @ a_stack[g(r)]^T, zeros elsewhere
+    (out: [B, rows, groups*block]) — the A2 operand of gemm(..., a2=out, w2=[B_0 | B_1 | ...])."""
+    x3 = _view3(_dev(x, "lora_down_wide.x", BF16), "lora_down_wide.x")
+    o3 = _view3(_dev(out, "lora_down_wide.out", BF16), "lora_down_wide.out")
+    _dev(a_stack, "lora_down_wide.a", BF16)
+    B, R, K = x3.shape
+    G, RT, K2 = a_stack.shape
+    if K2 != K or not a_stack.is_contiguous() or o3.shape[2] != G * block or o3.shape[1] != R:
+        raise UgError("lora_down_wide: a_stack must be contiguous [groups, rank_total, K] and out [B, rows, groups*block]")
+    n = len(seg_group)
+    sb = (C.c_int32 * (n + 1))(*[int(v) for v in seg_bounds])
+    sg = (C.c_int32 * n)(*[int(v) for v in seg_group])
+    check(_lib.load().ug_lora_down_wide(x3.data_ptr(), x3.stride(1), x3.stride(0), a_stack.data_ptr(), o3.data_ptr(), o3.stride(1),
+                                        o3.stride(0), B, R, K, RT, G, block, n, sb, sg, _stream()), "ug_lora_down_wide")
+    return out
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, heads: int, head_dim: int,

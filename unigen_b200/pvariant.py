@@ -27,6 +27,7 @@ from .ops import UG_ACT_GELU_TANH
 
 DOUBLE_LORA = ("norm1.linear", "attn.to_q", "attn.to_k", "attn.to_v", "attn.to_out.0", "ff.net.2")
 SINGLE_LORA = ("norm.linear", "proj_mlp", "proj_out", "attn.to_q", "attn.to_k", "attn.to_v")
+LORA_BLOCK = 64  # columns per adapter group in the K-extension operand (one 128-byte swizzle row of bf16)
 
 
 class _LoraPair:
@@ -36,6 +37,20 @@ class _LoraPair:
         self.rank, self.n_sub, self.n_each = rank, n_sub, n_each
         self.a = torch.zeros(groups, n_sub * rank, k, device=device, dtype=BF16)
         self.b = torch.zeros(groups, n_sub * n_each, rank, device=device, dtype=BF16)
+        self.bw: Optional[torch.Tensor] = None
+
+    def build_wide(self):
+        """W2 operand of the K-extension form: [n_sub * n_each, groups * 64], block g = B_g with sub-linear j's columns at
+        [j * rank, (j + 1) * rank) of the block (matching the column order of the stacked down-projection A_g)."""
+        G, n_tot, r = self.b.shape
+        if self.n_sub * r > LORA_BLOCK:
+            raise ops.UgError(f"stacked LoRA rank {self.n_sub * r} exceeds the {LORA_BLOCK}-column K-extension block")
+        bw = torch.zeros(n_tot, G * LORA_BLOCK, device=self.b.device, dtype=BF16)
+        for g in range(G):
+            for j in range(self.n_sub):
+                rows = slice(j * self.n_each, (j + 1) * self.n_each)
+                bw[rows, g * LORA_BLOCK + j * r:g * LORA_BLOCK + (j + 1) * r] = self.b[g, rows]
+        self.bw = bw
 
 
 class UniCombineFlux(torch.nn.Module):
@@ -69,6 +84,9 @@ class UniCombineFlux(torch.nn.Module):
         self._buf_key = None
         self.gemm_variant = 0
         self.attn_variant = 0
+        # "mma": the switched low-rank update rides the main GEMM's tensor-core loop as a K extension (A2 / W2 operand pair);
+        # "epilogue": it is applied per output element on the CUDA cores in the epilogue (kept for comparison)
+        self.lora_mode = "mma"
 
     @property
     def dtype(self):
@@ -115,6 +133,7 @@ class UniCombineFlux(torch.nn.Module):
         def mk(names, k, n_each):
             p = _LoraPair(self.device_, self.groups, R, k, n_each, len(names))
             fill(p, names)
+            p.build_wide()
             return p
 
         def mk_vec(name, k, n):  # AdaLN linears run as GEMVs: rank padded to a multiple of 8 (GEMV inner-dim granularity)
@@ -149,7 +168,7 @@ class UniCombineFlux(torch.nn.Module):
         z = lambda *s, dt=BF16: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
         self._buf = types.SimpleNamespace(
             X=z(B, S, D), NX=z(B, S, D), QKV=z(B, S, 3 * D), AO=z(B, S, D), FF=z(B, S, 4 * D), CAT=z(B, S, 5 * D),
-            LT=z(B, S, 3 * self.R, dt=torch.float32), temb=z(B, D, dt=torch.float32), ctemb=z(B, D, dt=torch.float32),
+            LT=z(B, S, 3 * self.R, dt=torch.float32), LTW=z(B, S, self.groups * LORA_BLOCK), temb=z(B, D, dt=torch.float32), ctemb=z(B, D, dt=torch.float32),
             tmp=z(B, D, dt=torch.float32), ltmp=z(B, 16, dt=torch.float32), NO=None,
             rope=z(S, self.arch.attention_head_dim, dt=torch.float32))
         self._buf_key = key
@@ -181,6 +200,11 @@ class UniCombineFlux(torch.nn.Module):
 
     def _lora_gemm(self, buf, x, w, pair: _LoraPair, seg_bounds, seg_group, out, **kw):
         """Main GEMM with the switched low-rank update fused into its epilogue."""
+        if self.lora_mode == "mma":
+            tw = buf.LTW[:, :x.shape[1]]
+            ops.lora_down_wide(x, pair.a, seg_bounds, seg_group, out=tw, block=LORA_BLOCK)
+            return ops.gemm(x, w[0], out=out, bias=w[1], variant=self.gemm_variant, a2=tw, w2=pair.bw,
+                            seg_bounds=seg_bounds if kw.get("gate_seg_stride") else None, **kw)
         rt = pair.n_sub * pair.rank
         t = buf.LT[:, :x.shape[1], :rt]
         ops.lora_down(x, pair.a, seg_bounds, seg_group, out=t)
