@@ -746,10 +746,11 @@ class PVariantOracle:
     den = adapters - condition_types act on the text/image rows. scaling[a] = lora_alpha/r (1.0 when alpha == r)."""
 
     def __init__(self, cfg: FluxConfig, sd: Dict[str, Tensor], adapters: List[str], scaling: Optional[Dict[str, float]] = None,
-                 strict_mask: bool = False):
+                 strict_mask: bool = False, add_cond_attn: bool = False):
         self.cfg, self.sd, self.adapters = cfg, sd, list(adapters)
         self.scaling = scaling or {a: 1.0 for a in adapters}
         self.strict_mask = strict_mask
+        self.add_cond_attn = add_cond_attn  # model_config['add_cond_attn'] (UniCombineTransformerBlock.pyc L201-202)
         self.trace: Dict[str, Tensor] = {}
         self.record = False
 
@@ -767,7 +768,7 @@ class PVariantOracle:
         return y
 
     def forward(self, hidden_states, condition_latents, condition_ids, condition_types, encoder_hidden_states,
-                pooled_projections, timestep, img_ids, txt_ids, c_t: float = 0.0):
+                pooled_projections, timestep, img_ids, txt_ids, c_t: float = 0.0, return_condition_latents: bool = False):
         cfg, sd = self.cfg, self.sd
         H = cfg.num_attention_heads
         den = [a for a in self.adapters if a not in condition_types]
@@ -822,9 +823,12 @@ class PVariantOracle:
             ot, oh = O[:, :T], O[:, T:T + N]
             h = h + e[2][:, None] * self.lin(a + ".to_out.0", oh, den)
             enc = enc + et[2][:, None] * linear(sd, a + ".to_add_out", ot)
-            for j in range(n):
+            for j in range(n):  # pyc L198-202
                 oc = O[:, bounds[2 + j]:bounds[3 + j]]
-                conds[j] = conds[j] + ec[j][2][:, None] * self.lin(a + ".to_out.0", oc, sets[j])
+                gated = ec[j][2][:, None] * self.lin(a + ".to_out.0", oc, sets[j])
+                conds[j] = conds[j] + gated
+                if self.add_cond_attn:
+                    h = h + gated
             # feed-forward: ff.net.2 is the switched linear (L222-230)
             def ff(x, sh, sc, gate, active):
                 y = gelu_tanh(linear(sd, p + ".ff.net.0.proj", layer_norm(x) * (1 + sc[:, None]) + sh[:, None]))
@@ -861,6 +865,8 @@ class PVariantOracle:
         h = x[:, T:]
         out = linear(sd, "proj_out", ada_layer_norm_continuous(sd, "norm_out", h, temb))
         self._rec("velocity", out)
+        if return_condition_latents:  # 2DModel L203-209: the condition streams after the last single block, un-projected
+            return out, conds
         return out
 
 

@@ -188,3 +188,27 @@ def test_forward_rejects_missing_control_init_and_cpu_device():
         m(torch.zeros(1, 16, 64), encoder_hidden_states=torch.zeros(1, 8, 4096))
     with pytest.raises(ValueError):
         m.init_condition_block(condition_nums=1, control_params=dict(use_rope=False, use_modulate=False))
+
+
+def test_checkpoint_loader_feeds_the_native_model(tmp_path):
+    """unigen_b200.checkpoint: base weights from a sharded safetensors `transformer/` folder + the control branch from
+    `<module>_weights_0.bin` files (src/hook.py) == loading the same state dict directly."""
+    from safetensors.torch import save_file
+    from unigen_b200 import checkpoint as ck
+    from unigen_b200.model import FluxArch, UniGenFlux, canonical_control_params
+    cfg, sd, inp, oracle, model = _setup()
+    dev_inp = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()}
+    want = model(**dev_inp)[0].clone()
+    ctrl = tuple(model.trainable_control_modules)
+    base = {k: v.contiguous() for k, v in sd.items() if not k.startswith(ctrl)}
+    keys = sorted(base)
+    d = tmp_path / "transformer"
+    d.mkdir()
+    save_file({k: base[k] for k in keys[::2]}, str(d / "diffusion_pytorch_model-00001-of-00002.safetensors"))
+    save_file({k: base[k] for k in keys[1::2]}, str(d / "diffusion_pytorch_model-00002-of-00002.safetensors"))
+    ck.save_modules(model, str(tmp_path / "ckpt"), list(ctrl))
+    fresh = UniGenFlux(FluxArch.tiny(), device="cuda")
+    fresh.init_condition_block(condition_nums=1, control_params=canonical_control_params())
+    res = ck.load_pretrained(fresh, base=str(d), control=str(tmp_path / "ckpt"))
+    assert not res.unexpected_keys and all(not k.startswith(ctrl) for k in res.missing_keys)
+    assert torch.equal(fresh(**dev_inp)[0], want)

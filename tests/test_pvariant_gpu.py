@@ -152,3 +152,24 @@ def test_pvariant_strict_mask_differs_and_condition_streams_are_isolated():
         model(*[cu(a) for a in base])
         same = torch.equal(model.trace["single.3.cond0"], c0)
         assert same == strict
+
+
+def test_add_cond_attn_and_return_condition_latents():
+    """model_config['add_cond_attn'] (pyc L201-202: gated condition attention outputs are also added to the image stream)
+    and `return_condition_latents` (2DModel L203-209)."""
+    from oracle import unigen_oracle as O
+    cfg, inp, types_, oracle, model = _setup(2, False)
+    oracle.add_cond_attn = model.add_cond_attn = True
+    args = (inp["hidden_states"], inp["condition_hidden_states"], inp["condition_ids"], types_, inp["encoder_hidden_states"],
+            inp["pooled_projections"], inp["timestep"], inp["img_ids"], inp["txt_ids"])
+    want, want_c = oracle.forward(*args, return_condition_latents=True)
+    plain = O.PVariantOracle(cfg, oracle.sd, oracle.adapters, oracle.scaling).forward(*args)
+    assert rel_l2(want, plain) > 1e-2  # the option changes the result
+    cu = lambda v: [t.cuda() for t in v] if isinstance(v, list) and torch.is_tensor(v[0]) else (v.cuda() if torch.is_tensor(v) else v)  # noqa: E731
+    model.trace = {}
+    got, got_c = model(*[cu(a) for a in args], return_condition_latents=True)
+    bad = {k: rel_l2(model.trace[k], v) for k, v in oracle.trace.items() if k in model.trace and rel_l2(model.trace[k], v) > 1e-2}
+    assert not bad, bad
+    assert rel_l2(got, want) < 1e-2 and len(got_c) == 2
+    for g, w in zip(got_c, want_c):
+        assert rel_l2(g, w) < 1e-2

@@ -87,6 +87,7 @@ class UniCombineFlux(torch.nn.Module):
         # "mma": the switched low-rank update rides the main GEMM's tensor-core loop as a K extension (A2 / W2 operand pair);
         # "epilogue": it is applied per output element on the CUDA cores in the epilogue (kept for comparison)
         self.lora_mode = "mma"
+        self.add_cond_attn = False  # model_config['add_cond_attn'] (UniCombineTransformerBlock.pyc L201-202)
 
     @property
     def dtype(self):
@@ -227,7 +228,9 @@ class UniCombineFlux(torch.nn.Module):
     # ---------------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, hidden_states, condition_latents, condition_ids, condition_types, encoder_hidden_states,
-                pooled_projections, timestep, img_ids, txt_ids, c_t: float = 0.0, **kwargs):
+                pooled_projections, timestep, img_ids, txt_ids, c_t: float = 0.0, return_condition_latents: bool = False,
+                **kwargs):
+        """`return_condition_latents` (2DModel L203-209): also return the condition streams after the last single block."""
         a, D = self.arch, self.inner_dim
         H, dh = a.num_attention_heads, a.attention_head_dim
         dev = self.device_
@@ -286,8 +289,22 @@ class UniCombineFlux(torch.nn.Module):
             self._attention(buf, [(0, T, w.rms_ctx), (T, S, w.rms)], "AO", bounds, vis)
             ops.gemm(buf.AO[:, :T], w.to_add_out[0], out=seg(0), bias=w.to_add_out[1], gate=m_txt[2], residual=seg(0), variant=gv)
             # to_out[0]: LoRA group AND gate switched per stream inside one launch over [img | c_1 .. c_n]
-            self._lora_gemm(buf, buf.AO[:, T:], w.to_out, L[p + ".to_out"], img_cond_bounds, img_cond_groups, buf.X[:, T:],
-                            gate=m_img[2], gate_seg_stride=B * 6 * D, residual=buf.X[:, T:])
+            if not self.add_cond_attn:
+                self._lora_gemm(buf, buf.AO[:, T:], w.to_out, L[p + ".to_out"], img_cond_bounds, img_cond_groups, buf.X[:, T:],
+                                gate=m_img[2], gate_seg_stride=B * 6 * D, residual=buf.X[:, T:])
+            else:
+                # add_cond_attn (pyc L201-202): the GATED condition attention outputs are also added into the image stream, so
+                # they are materialised once (gated, no residual) and added to both streams
+                if any(m != N for m in ncs):
+                    raise ops.UgError("add_cond_attn adds condition attention outputs to the image stream: needs Nc == N")
+                g_out = buf.NX[:, T:]  # free until the MLP's LayerNorm pass
+                self._lora_gemm(buf, buf.AO[:, T:], w.to_out, L[p + ".to_out"], img_cond_bounds, img_cond_groups, g_out,
+                                gate=m_img[2], gate_seg_stride=B * 6 * D)
+                ops.add(seg(1), g_out[:, :N], seg(1))
+                for j in range(n):
+                    gj = g_out[:, img_cond_bounds[1 + j]:img_cond_bounds[2 + j]]
+                    ops.add(seg(2 + j), gj, seg(2 + j))
+                    ops.add(seg(1), gj, seg(1))
             for s_ in range(nseg):
                 ops.ln_modulate(seg(s_), buf.NX[:, bounds[s_]:bounds[s_ + 1]], mods[s_][3], mods[s_][4])
             ops.gemm(buf.NX[:, :T], w.ffc1[0], out=buf.FF[:, :T], bias=w.ffc1[1], act=UG_ACT_GELU_TANH, variant=gv)
@@ -324,4 +341,6 @@ class UniCombineFlux(torch.nn.Module):
         ops.ln_modulate(seg(1), no, e[:, D:], e[:, :D])  # AdaLayerNormContinuous: scale first, then shift
         out = ops.gemm(no, self.proj_out_w[0], bias=self.proj_out_w[1], variant=gv)
         self._rec("velocity", out)
+        if return_condition_latents:
+            return out, [seg(2 + j).clone() for j in range(n)]
         return out
