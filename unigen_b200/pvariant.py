@@ -87,6 +87,8 @@ class UniCombineFlux(torch.nn.Module):
         # "mma": the switched low-rank update rides the main GEMM's tensor-core loop as a K extension (A2 / W2 operand pair);
         # "epilogue": it is applied per output element on the CUDA cores in the epilogue (kept for comparison)
         self.lora_mode = "mma"
+        self.overlap_mod_gemv = True  # AdaLN GEMVs (HBM-bound) on a side stream under the tensor-core-bound blocks
+        self._side_stream = torch.cuda.Stream(device=self.device_)
         self.add_cond_attn = False  # model_config['add_cond_attn'] (UniCombineTransformerBlock.pyc L201-202)
 
     @property
@@ -170,7 +172,7 @@ class UniCombineFlux(torch.nn.Module):
         self._buf = types.SimpleNamespace(
             X=z(B, S, D), NX=z(B, S, D), QKV=z(B, S, 3 * D), AO=z(B, S, D), FF=z(B, S, 4 * D), CAT=z(B, S, 5 * D),
             LT=z(B, S, 3 * self.R, dt=torch.float32), LTW=z(B, S, self.groups * LORA_BLOCK), temb=z(B, D, dt=torch.float32), ctemb=z(B, D, dt=torch.float32),
-            tmp=z(B, D, dt=torch.float32), ltmp=z(B, 16, dt=torch.float32), NO=None,
+            tmp=z(B, D, dt=torch.float32), ltmp=z(B, 16, dt=torch.float32), ltmp2=z(B, 16, dt=torch.float32), NO=None,
             rope=z(S, self.arch.attention_head_dim, dt=torch.float32))
         self._buf_key = key
         return self._buf
@@ -186,18 +188,24 @@ class UniCombineFlux(torch.nn.Module):
         ops.gemv(pooled, w.p1[0], w.p1[1], out=tmp, silu_out=True)
         ops.gemv(tmp, w.p2[0], w.p2[1], out=out, accumulate=True)
 
-    def _mod_vectors(self, buf, w, lora: Optional[_LoraPair], temb, group: int, n_chunks: int, out: Optional[torch.Tensor] = None):
-        """AdaLN `linear(silu(temb))` with the LoRA of `group` (enable_lora on norm1.linear / norm.linear)."""
-        D = self.inner_dim
-        if out is None:
-            out = torch.empty(temb.shape[0], n_chunks * D, device=self.device_, dtype=torch.float32)
-        ops.gemv(temb, w[0], w[1], out=out, silu_in=True)
-        if lora is not None and group >= 0:
-            rp = lora.rank
-            t = buf.ltmp[:, :rp]
-            ops.gemv(temb, lora.a[group], None, out=t, silu_in=True)
-            ops.gemv(t, lora.b[group], None, out=out, accumulate=True)
-        return [out[:, i * D:(i + 1) * D] for i in range(n_chunks)]
+    def _mod_table(self, w, lora: Optional[_LoraPair], tembs: torch.Tensor, n_chunks: int, ltmp: torch.Tensor) -> torch.Tensor:
+        """AdaLN `linear(silu(temb))` of ALL streams of one block in one pass over the weights: tembs fp32 [G, B, D] (row 0 =
+        temb for the denoising group, rows 1.. = cond_temb for the condition groups) -> fp32 [G, B, n_chunks * D]; group g
+        additionally gets its switched LoRA update (enable_lora on norm1.linear / norm.linear, pyc L154-156, L168-170, L251-253)."""
+        G, B, D = tembs.shape
+        out = torch.empty(G, B, n_chunks * D, device=self.device_, dtype=torch.float32)
+        ops.gemv(tembs.view(G * B, D), w[0], w[1], out=out.view(G * B, n_chunks * D), silu_in=True)
+        if lora is not None:
+            t = ltmp[:B, :lora.rank]
+            for g in range(G):
+                ops.gemv(tembs[g], lora.a[g], None, out=t, silu_in=True)
+                ops.gemv(t, lora.b[g], None, out=out[g], accumulate=True)
+        return out
+
+    @staticmethod
+    def _chunks(row: torch.Tensor, n_chunks: int) -> List[torch.Tensor]:
+        D = row.shape[-1] // n_chunks
+        return [row[:, i * D:(i + 1) * D] for i in range(n_chunks)]
 
     def _lora_gemm(self, buf, x, w, pair: _LoraPair, seg_bounds, seg_group, out, **kw):
         """Main GEMM with the switched low-rank update fused into its epilogue."""
@@ -272,15 +280,45 @@ class UniCombineFlux(torch.nn.Module):
         all_bounds = [0, T + N] + bounds[3:]                   # single blocks: [txt|img] share the denoising adapters
         all_groups = list(range(0, 1 + n))
 
+        # ---- AdaLN vectors of every block and stream (temb / cond_temb are step constants): block 0 on the main stream, the
+        # rest — HBM-bound weight streaming — on a side stream under the tensor-core-bound blocks ----
+        L = self.lora
+        tembs = torch.empty(1 + n, B, D, device=dev, dtype=torch.float32)
+        tembs[0].copy_(buf.temb)
+        for j in range(n):
+            tembs[1 + j].copy_(buf.ctemb)
+        dbl_mods, sgl_mods = [None] * len(self.double), [None] * len(self.single)
+
+        def mods_double(i, ltmp):
+            w, p = self.double[i], f"transformer_blocks.{i}"
+            dbl_mods[i] = (self._mod_table(w.norm1_ctx, None, tembs[:1], 6, ltmp)[0], self._mod_table(w.norm1, L[p + ".norm1"], tembs, 6, ltmp))
+
+        def mods_single(i, ltmp):
+            w, p = self.single[i], f"single_transformer_blocks.{i}"
+            sgl_mods[i] = self._mod_table(w.norm, L[p + ".norm"], tembs, 3, ltmp)
+
+        mods_double(0, buf.ltmp)
+        main_stream = torch.cuda.current_stream()
+        side = self._side_stream if self.overlap_mod_gemv else None
+        if side is not None:
+            side.wait_stream(main_stream)
+        with torch.cuda.stream(side if side is not None else main_stream):
+            for i in range(1, len(self.double)):
+                mods_double(i, buf.ltmp2)
+            for i in range(len(self.single)):
+                mods_single(i, buf.ltmp2)
+        mods_joined = side is None
+
         for i, w in enumerate(self.double):  # ---- block_forward ----
             p = f"transformer_blocks.{i}"
-            L = self.lora
+            if i == 1 and not mods_joined:
+                main_stream.wait_stream(side)
+                mods_joined = True
             # the image / condition streams' AdaLN vectors live in ONE [1+n, B, 6D] table so that the gated GEMMs below can
             # cover all of them in a single launch (ug_gemm_args.gate_seg_stride)
-            modd = torch.empty(1 + n, B, 6 * D, device=dev, dtype=torch.float32)
-            m_img = self._mod_vectors(buf, w.norm1, L[p + ".norm1"], buf.temb, 0, 6, out=modd[0])
-            m_txt = self._mod_vectors(buf, w.norm1_ctx, None, buf.temb, -1, 6)
-            m_c = [self._mod_vectors(buf, w.norm1, L[p + ".norm1"], buf.ctemb, 1 + j, 6, out=modd[1 + j]) for j in range(n)]
+            m_txt = self._chunks(dbl_mods[i][0], 6)
+            m_img = self._chunks(dbl_mods[i][1][0], 6)
+            m_c = [self._chunks(dbl_mods[i][1][1 + j], 6) for j in range(n)]
             mods = [m_txt, m_img] + m_c
             for s_ in range(nseg):
                 ops.ln_modulate(seg(s_), buf.NX[:, bounds[s_]:bounds[s_ + 1]], mods[s_][0], mods[s_][1])
@@ -316,12 +354,12 @@ class UniCombineFlux(torch.nn.Module):
             for j in range(n):
                 self._rec(f"double.{i}.cond{j}", seg(2 + j))
 
+        if not mods_joined:
+            main_stream.wait_stream(side)
         for i, w in enumerate(self.single):  # ---- single_block_forward ----
             p = f"single_transformer_blocks.{i}"
-            L = self.lora
-            mods_t = torch.empty(1 + n, B, 3 * D, device=dev, dtype=torch.float32)
-            m_x = self._mod_vectors(buf, w.norm, L[p + ".norm"], buf.temb, 0, 3, out=mods_t[0])
-            m_c = [self._mod_vectors(buf, w.norm, L[p + ".norm"], buf.ctemb, 1 + j, 3, out=mods_t[1 + j]) for j in range(n)]
+            m_x = self._chunks(sgl_mods[i][0], 3)
+            m_c = [self._chunks(sgl_mods[i][1 + j], 3) for j in range(n)]
             mods = [m_x] + m_c
             for s_ in range(len(all_groups)):
                 lo, hi = all_bounds[s_], all_bounds[s_ + 1]
