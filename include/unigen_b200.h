@@ -191,6 +191,14 @@ int ug_ln_modulate(const void* x, int64_t x_row_stride, int64_t x_batch_stride, 
                    int64_t o_batch_stride, const float* shift, const float* scale, int64_t mod_batch_stride,
                    int32_t batch, int32_t rows, int32_t d, float eps, void* stream);
 
+/* ug_ln_modulate with one modulation vector per ROW SEGMENT: rows [seg_bounds[i], seg_bounds[i+1]) of every sample use
+ * shift/scale + i * mod_seg_stride (+ b * mod_batch_stride) — the text / image / condition streams of a P-variant block
+ * (each with its own AdaLN vectors, UniCombineTransformerBlock.pyc L152-170, L207-218) normalised in ONE launch. */
+int ug_ln_modulate_segs(const void* x, int64_t x_row_stride, int64_t x_batch_stride, void* out, int64_t o_row_stride,
+                        int64_t o_batch_stride, const float* shift, const float* scale, int64_t mod_batch_stride,
+                        int64_t mod_seg_stride, int32_t nseg, const int32_t* seg_bounds_host, int32_t batch, int32_t rows,
+                        int32_t d, float eps, void* stream);
+
 /* Per-token AdaLN on capacity-slot buffers — the SD3.5 transformer-block experts run `SD3SingleTransformerBlock` on the
  * dispatched (1, C, D) chunks with a PER-TOKEN (1, C, D) temb (src/UniGenUtils.py:354-363,386-414 with a 3-D `emb`;
  * src/UniGenTransformer.py:256-258). A dispatched temb row is the temb of the sample the slot's token came from, or 0 for

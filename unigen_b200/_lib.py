@@ -83,6 +83,8 @@ SIGNATURES = {
     "ug_attention_bf16": (C.c_int, [C.POINTER(AttnArgs), _VP]),
     "ug_expand_segment_mask": (C.c_int, [_I32, _I32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), _VP, _VP]),
     "ug_ln_modulate": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _I64, _VP, _VP, _I64, _I32, _I32, _I32, _F32, _VP]),
+    "ug_ln_modulate_segs": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _I64, _VP, _VP, _I64, _I64, _I32, C.POINTER(C.c_int32), _I32, _I32,
+                                      _I32, _F32, _VP]),
     "ug_ln_modulate_slots": (C.c_int, [_VP, _I64, _VP, _I64, _VP, _VP, _I64, _I64, _VP, _I32, _I32, _I32, _I32, _I32, _F32, _VP]),
     "ug_gated_add_slots": (C.c_int, [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
     "ug_qk_rmsnorm_rope": (C.c_int, [_VP, _I64, _I64, _I32, _I32, _I32, _I32, _VP, _I32, _F32, _VP, _VP]),

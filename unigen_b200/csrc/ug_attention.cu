@@ -31,6 +31,10 @@ struct AttnParams {
   // rank's head columns) + (q % o_rows_per_rank) * o_rs.  o_rows_per_rank == 0: plain local output `o`.
   int o_rows_per_rank;
   __nv_bfloat16* o_peer[UG_MAX_PEERS];
+  // CTA order: 0 = query tile fastest (grid = (q_tiles, heads, batch): concurrently running CTAs share a head's K/V in L2);
+  // 1 = head fastest (grid = (heads, q_tiles, batch)): with few CTAs per SM and a segment mask, the query tiles with the
+  // most visible keys (text / image rows come first) all start in the first wave instead of trailing in the last one
+  int head_fastest;
 };
 
 __device__ __forceinline__ __nv_bfloat16* o_row_ptr(const AttnParams& p, int b, int q_row, int head, int dh) {
@@ -111,7 +115,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int qt = p.head_fastest ? blockIdx.y : blockIdx.x, head = p.head_fastest ? blockIdx.x : blockIdx.y, b = blockIdx.z;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_q);
@@ -447,7 +451,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int qt = p.head_fastest ? blockIdx.y : blockIdx.x, head = p.head_fastest ? blockIdx.x : blockIdx.y, b = blockIdx.z;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_q);
@@ -793,7 +797,9 @@ static int launch_attention(const ug_attn_args& a, const PeerO* peer, cudaStream
   p.scale_log2 = a.scale * 1.4426950408889634f;
   int st = fill_segments(p, a.seq, a.n_seg, a.seg_bounds, a.seg_visible);
   if (st != UG_OK) return st;
-  dim3 grid((a.seq + kBlockQ - 1) / kBlockQ, a.heads, a.batch);
+  const int q_tiles = (a.seq + kBlockQ - 1) / kBlockQ;
+  p.head_fastest = ((long long)q_tiles * a.heads * a.batch < 4LL * num_sms()) ? 1 : 0;
+  dim3 grid(p.head_fastest ? a.heads : q_tiles, p.head_fastest ? q_tiles : a.heads, a.batch);
   kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], p);
   UG_CHECK_LAUNCH("attention");
   return UG_OK;
@@ -832,7 +838,9 @@ static int launch_attention2(const ug_attn_args& a, const PeerO* peer, cudaStrea
   p.scale_log2 = a.scale * 1.4426950408889634f;
   int st = fill_segments(p, a.seq, a.n_seg, a.seg_bounds, a.seg_visible);
   if (st != UG_OK) return st;
-  dim3 grid((a.seq + 255) / 256, a.heads, a.batch);
+  const int q_tiles = (a.seq + 255) / 256;
+  p.head_fastest = ((long long)q_tiles * a.heads * a.batch < 4LL * num_sms()) ? 1 : 0;
+  dim3 grid(p.head_fastest ? a.heads : q_tiles, p.head_fastest ? q_tiles : a.heads, a.batch);
   kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], p);
   UG_CHECK_LAUNCH("attention2");
   return UG_OK;

@@ -26,6 +26,11 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // LayerNorm (no affine) + (1 + scale) * x + shift.  One warp per row, row kept in registers (d <= 8*32*kMaxV).
 // Algorithmic HBM bytes per row: 2*d (read) + 2*d (write).
 // ---------------------------------------------------------------------------------------------------
+struct RowSegs {
+  int nseg;
+  int bounds[UG_MAX_SEGMENTS + 1];
+};
+
 template <int kMaxV>
 __global__ void __launch_bounds__(256) ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long x_rs,
                                                           long long x_bs, __nv_bfloat16* __restrict__ out,
@@ -35,13 +40,20 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const __nv_bfloat16* _
                                                           int rows, int d, float eps,
                                                           const int* __restrict__ slot_token = nullptr, int capacity = 1,
                                                           int tokens_per_batch = 1, int empty_index = 0,
-                                                          long long mod_es = 0) {
+                                                          long long mod_es = 0, RowSegs segs = RowSegs{0, {0}},
+                                                          long long mod_seg_stride = 0) {
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp_global >= batch * rows) return;
   const int b = warp_global / rows, r = warp_global % rows;
   // modulation row: the sample index b, or (slot mode) expert e = r / capacity and the sample the slot's token came from
   long long mod_off = (long long)b * mod_bs;
+  if (segs.nseg > 0) {  // per-row-segment modulation vectors (the P-variant's text / image / condition streams in one launch)
+    int si = 0;
+    for (int s = 0; s < segs.nseg; ++s)
+      if (r >= segs.bounds[s] && r < segs.bounds[s + 1]) si = s;
+    mod_off += (long long)si * mod_seg_stride;
+  }
   if (slot_token) {
     const int token = slot_token[r];
     mod_off = (long long)(r / capacity) * mod_es + (long long)(token < 0 ? empty_index : token / tokens_per_batch) * mod_bs;
@@ -105,9 +117,13 @@ __global__ void __launch_bounds__(256) qk_rmsnorm_rope_kernel(__nv_bfloat16* __r
   // 16 bytes (8 elements) per lane: a head spans LPH lanes, a warp covers HPW heads per pass; kUnroll passes are
   // loaded before any is reduced so that enough bytes are in flight to approach HBM bandwidth.
   constexpr int LPH = kDh / 8, HPW = 32 / LPH, kUnroll = 4;
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // one warp per (row, chunk of HPW * kUnroll heads): more warps (and 16-byte accesses) in flight than one warp per row
+  const int chunks = (heads + HPW * kUnroll - 1) / (HPW * kUnroll);
+  const long long wg = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp_global >= batch * rows) return;
+  if (wg >= (long long)batch * rows * chunks) return;
+  const int chunk = (int)(wg % chunks);
+  const int warp_global = (int)(wg / chunks);
   const int b = warp_global / rows, r = warp_global % rows;
   __nv_bfloat16* row = x + (long long)b * bs + (long long)r * rs;
   const int sub = lane / LPH, e0 = (lane % LPH) * 8;  // head slot inside the pass, first element inside the head
@@ -117,7 +133,8 @@ __global__ void __launch_bounds__(256) qk_rmsnorm_rope_kernel(__nv_bfloat16* __r
     const float4 t0 = *reinterpret_cast<const float4*>(t), t1 = *reinterpret_cast<const float4*>(t + 4);
     cs[0] = t0.x; sn[0] = t0.y; cs[1] = t0.z; sn[1] = t0.w; cs[2] = t1.x; sn[2] = t1.y; cs[3] = t1.z; sn[3] = t1.w;
   }
-  for (int h0 = 0; h0 < heads; h0 += HPW * kUnroll) {
+  {
+    const int h0 = chunk * HPW * kUnroll;
     uint4 u[kUnroll];
 #pragma unroll
     for (int k = 0; k < kUnroll; ++k) {
@@ -337,7 +354,8 @@ using namespace ug;
 static int launch_ln_modulate(const void* x, int64_t x_rs, int64_t x_bs, void* out, int64_t o_rs, int64_t o_bs,
                               const float* shift, const float* scale, int64_t mod_bs, int32_t batch, int32_t rows, int32_t d,
                               float eps, const int32_t* slot_token, int32_t capacity, int32_t tokens_per_batch,
-                              int32_t empty_index, int64_t mod_es, void* stream, const char* name) {
+                              int32_t empty_index, int64_t mod_es, void* stream, const char* name,
+                              ug::RowSegs segs = ug::RowSegs{0, {0}}, int64_t mod_seg_stride = 0) {
   UG_CHECK_ARG(x && out && shift && scale, "%s: null pointer", name);
   UG_CHECK_ARG(batch >= 1 && rows >= 1 && d >= 8 && d % 8 == 0, "%s: bad shape batch %d rows %d d %d", name, batch, rows, d);
   UG_CHECK_ARG(x_rs % 8 == 0 && o_rs % 8 == 0 && x_bs % 8 == 0 && o_bs % 8 == 0 && mod_bs % 4 == 0 && mod_es % 4 == 0 &&
@@ -353,7 +371,7 @@ static int launch_ln_modulate(const void* x, int64_t x_rs, int64_t x_bs, void* o
   auto s = reinterpret_cast<cudaStream_t>(stream);
   auto xp = (const __nv_bfloat16*)x;
   auto op = (__nv_bfloat16*)out;
-#define UG_LN_LAUNCH(V) ln_modulate_kernel<V><<<grid, block, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, batch, rows, d, eps, slot_token, capacity, tokens_per_batch, empty_index, mod_es)
+#define UG_LN_LAUNCH(V) ln_modulate_kernel<V><<<grid, block, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, batch, rows, d, eps, slot_token, capacity, tokens_per_batch, empty_index, mod_es, segs, mod_seg_stride)
   if (d <= 8 * 32 * 2) UG_LN_LAUNCH(2);
   else if (d <= 8 * 32 * 6) UG_LN_LAUNCH(6);
   else if (d <= 8 * 32 * 12) UG_LN_LAUNCH(12);
@@ -368,6 +386,17 @@ extern "C" int ug_ln_modulate(const void* x, int64_t x_rs, int64_t x_bs, void* o
                               int32_t d, float eps, void* stream) {
   return launch_ln_modulate(x, x_rs, x_bs, out, o_rs, o_bs, shift, scale, mod_bs, batch, rows, d, eps, nullptr, 1, 1, 0, 0, stream,
                             "ln_modulate");
+}
+
+extern "C" int ug_ln_modulate_segs(const void* x, int64_t x_rs, int64_t x_bs, void* out, int64_t o_rs, int64_t o_bs,
+                                   const float* shift, const float* scale, int64_t mod_bs, int64_t mod_seg_stride, int32_t nseg,
+                                   const int32_t* seg_bounds, int32_t batch, int32_t rows, int32_t d, float eps, void* stream) {
+  UG_CHECK_ARG(seg_bounds && nseg >= 1 && nseg <= UG_MAX_SEGMENTS && mod_seg_stride % 4 == 0, "ln_modulate_segs: bad segment table");
+  ug::RowSegs segs;
+  segs.nseg = nseg;
+  for (int i = 0; i <= UG_MAX_SEGMENTS; ++i) segs.bounds[i] = i <= nseg ? seg_bounds[i] : rows;
+  return launch_ln_modulate(x, x_rs, x_bs, out, o_rs, o_bs, shift, scale, mod_bs, batch, rows, d, eps, nullptr, 1, 1, 0, 0, stream,
+                            "ln_modulate_segs", segs, mod_seg_stride);
 }
 
 extern "C" int ug_ln_modulate_slots(const void* x, int64_t x_rs, void* out, int64_t o_rs, const float* shift, const float* scale,
@@ -404,7 +433,8 @@ extern "C" int ug_qk_rmsnorm_rope(void* x, int64_t rs, int64_t bs, int32_t batch
   UG_CHECK_ARG(batch >= 1 && rows >= 1 && heads >= 1, "qk_rmsnorm_rope: bad shape");
   if (heads_per_weight <= 0) heads_per_weight = heads;
   UG_CHECK_ARG(rs % 8 == 0 && bs % 8 == 0 && aligned16(x) && aligned16(w) && (!cos_sin || aligned16(cos_sin)), "qk_rmsnorm_rope: alignment");
-  const long long warps = (long long)batch * rows;
+  const int heads_per_warp = (32 / (head_dim >= 8 ? head_dim / 8 : 1)) * 4;
+  const long long warps = (long long)batch * rows * ((heads + heads_per_warp - 1) / heads_per_warp);
   const int block = 256;
   const int grid = (int)((warps * 32 + block - 1) / block);
   auto s = reinterpret_cast<cudaStream_t>(stream);

@@ -77,7 +77,11 @@ __global__ void __launch_bounds__(256) qkv_scatter_kernel(const __nv_bfloat16* _
                                                           const float* __restrict__ cos_sin, PeerPtrs t, long long dst_offset,
                                                           int seq_total, int dst_row0) {
   constexpr int LPH = kDh / 8, HPW = 32 / LPH, kUnroll = 4;
-  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // one warp per (row, chunk of HPW * kUnroll heads): a row is spread over several warps so that enough 16-byte stores are
+  // in flight to cover the NVLink latency even when a rank owns only a few hundred rows
+  const int chunks = (3 * heads + HPW * kUnroll - 1) / (HPW * kUnroll);
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int r = wg / chunks, chunk = wg % chunks;
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
   const __nv_bfloat16* row = qkv + (long long)r * rs;
@@ -91,7 +95,8 @@ __global__ void __launch_bounds__(256) qkv_scatter_kernel(const __nv_bfloat16* _
     cs[0] = t0.x; sn[0] = t0.y; cs[1] = t0.z; sn[1] = t0.w; cs[2] = t1.x; sn[2] = t1.y; cs[3] = t1.z; sn[3] = t1.w;
   }
   const int total_heads = 3 * heads;
-  for (int h0 = 0; h0 < total_heads; h0 += HPW * kUnroll) {
+  {
+    const int h0 = chunk * HPW * kUnroll;
     uint4 u[kUnroll];
 #pragma unroll
     for (int k = 0; k < kUnroll; ++k) {
@@ -255,7 +260,9 @@ extern "C" int ug_qkv_scatter(const ug_peer_table* table, const ug_qkv_scatter_a
                "qkv_scatter: alignment");
   UG_CHECK_ARG(a->dst_row0 >= 0 && a->dst_row0 + a->rows <= a->seq_total, "qkv_scatter: rows [%d, %d) outside the %d-row sequence",
                a->dst_row0, a->dst_row0 + a->rows, a->seq_total);
-  const int grid = (int)(((long long)a->rows * 32 + 255) / 256);
+  const int heads_per_warp = (32 / (a->head_dim / 8)) * 4;
+  const long long warps = (long long)a->rows * ((3 * a->heads + heads_per_warp - 1) / heads_per_warp);
+  const int grid = (int)((warps * 32 + 255) / 256);
   auto s = reinterpret_cast<cudaStream_t>(stream);
   auto q = (const __nv_bfloat16*)a->qkv;
   auto w = (const __nv_bfloat16*)a->norm_weight;

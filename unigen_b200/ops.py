@@ -14,7 +14,7 @@ from ._lib import UG_ACT_GELU_TANH, UG_ACT_NONE, AttnArgs, GemmArgs, QkvScatterA
 
 __all__ = ["gemm", "lora_down", "lora_down_wide", "attention", "attention_peer", "qkv_scatter", "peer_bcast_rows", "peer_barrier", "expand_segment_mask", "ln_modulate", "qk_rmsnorm_rope", "rope_table", "gemv",
            "timestep_embedding", "add", "copy", "to_bf16", "to_f32", "moe_route", "moe_gather_modulate",
-           "moe_combine", "ln_modulate_slots", "gated_add_slots", "unpatchify", "euler_step", "cfg_combine", "pack_latents", "unpack_latents", "launch_count", "reset_launch_count", "UG_ACT_NONE", "UG_ACT_GELU_TANH", "UgError"]
+           "moe_combine", "ln_modulate_segs", "ln_modulate_slots", "gated_add_slots", "unpatchify", "euler_step", "cfg_combine", "pack_latents", "unpack_latents", "launch_count", "reset_launch_count", "UG_ACT_NONE", "UG_ACT_GELU_TANH", "UgError"]
 
 BF16 = torch.bfloat16
 
@@ -297,6 +297,20 @@ def ln_modulate(x: torch.Tensor, out: torch.Tensor, shift: torch.Tensor, scale: 
     check(_lib.load().ug_ln_modulate(x3.data_ptr(), x3.stride(1), x3.stride(0), o3.data_ptr(), o3.stride(1), o3.stride(0),
                                      shift.data_ptr(), scale.data_ptr(), shift.stride(0), B, R, D, float(eps), _stream()),
           "ug_ln_modulate")
+    return out
+
+
+def ln_modulate_segs(x: torch.Tensor, out: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, seg_bounds: Sequence[int],
+                     mod_seg_stride: int, eps: float = 1e-6) -> torch.Tensor:
+    """ln_modulate with per-row-segment vectors: segment i uses shift/scale + i * mod_seg_stride (fp32 [B, D] views of row 0)."""
+    x3, o3 = _view3(_dev(x, "ln.x", BF16), "ln.x"), _view3(_dev(out, "ln.out", BF16), "ln.out")
+    _dev(shift, "ln.shift", torch.float32), _dev(scale, "ln.scale", torch.float32)
+    B, R, D = x3.shape
+    n = len(seg_bounds) - 1
+    sb = (C.c_int32 * (n + 1))(*[int(v) for v in seg_bounds])
+    check(_lib.load().ug_ln_modulate_segs(x3.data_ptr(), x3.stride(1), x3.stride(0), o3.data_ptr(), o3.stride(1), o3.stride(0),
+                                          shift.data_ptr(), scale.data_ptr(), shift.stride(0), int(mod_seg_stride), n, sb, B, R, D,
+                                          float(eps), _stream()), "ug_ln_modulate_segs")
     return out
 
 

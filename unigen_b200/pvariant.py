@@ -188,12 +188,14 @@ class UniCombineFlux(torch.nn.Module):
         ops.gemv(pooled, w.p1[0], w.p1[1], out=tmp, silu_out=True)
         ops.gemv(tmp, w.p2[0], w.p2[1], out=out, accumulate=True)
 
-    def _mod_table(self, w, lora: Optional[_LoraPair], tembs: torch.Tensor, n_chunks: int, ltmp: torch.Tensor) -> torch.Tensor:
+    def _mod_table(self, w, lora: Optional[_LoraPair], tembs: torch.Tensor, n_chunks: int, ltmp: torch.Tensor,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """AdaLN `linear(silu(temb))` of ALL streams of one block in one pass over the weights: tembs fp32 [G, B, D] (row 0 =
         temb for the denoising group, rows 1.. = cond_temb for the condition groups) -> fp32 [G, B, n_chunks * D]; group g
         additionally gets its switched LoRA update (enable_lora on norm1.linear / norm.linear, pyc L154-156, L168-170, L251-253)."""
         G, B, D = tembs.shape
-        out = torch.empty(G, B, n_chunks * D, device=self.device_, dtype=torch.float32)
+        if out is None:
+            out = torch.empty(G, B, n_chunks * D, device=self.device_, dtype=torch.float32)
         ops.gemv(tembs.view(G * B, D), w[0], w[1], out=out.view(G * B, n_chunks * D), silu_in=True)
         if lora is not None:
             t = ltmp[:B, :lora.rank]
@@ -291,7 +293,12 @@ class UniCombineFlux(torch.nn.Module):
 
         def mods_double(i, ltmp):
             w, p = self.double[i], f"transformer_blocks.{i}"
-            dbl_mods[i] = (self._mod_table(w.norm1_ctx, None, tembs[:1], 6, ltmp)[0], self._mod_table(w.norm1, L[p + ".norm1"], tembs, 6, ltmp))
+            # ONE [2 + n, B, 6D] table per block: row 0 = text stream (norm1_context), row 1 = image, rows 2.. = conditions, so
+            # that ug_ln_modulate_segs / the gated GEMMs address every stream's vectors with a constant row stride
+            tab = torch.empty(2 + n, B, 6 * D, device=dev, dtype=torch.float32)
+            self._mod_table(w.norm1_ctx, None, tembs[:1], 6, ltmp, out=tab[:1])
+            self._mod_table(w.norm1, L[p + ".norm1"], tembs, 6, ltmp, out=tab[1:])
+            dbl_mods[i] = (tab[0], tab[1:])
 
         def mods_single(i, ltmp):
             w, p = self.single[i], f"single_transformer_blocks.{i}"
@@ -320,8 +327,7 @@ class UniCombineFlux(torch.nn.Module):
             m_img = self._chunks(dbl_mods[i][1][0], 6)
             m_c = [self._chunks(dbl_mods[i][1][1 + j], 6) for j in range(n)]
             mods = [m_txt, m_img] + m_c
-            for s_ in range(nseg):
-                ops.ln_modulate(seg(s_), buf.NX[:, bounds[s_]:bounds[s_ + 1]], mods[s_][0], mods[s_][1])
+            ops.ln_modulate_segs(buf.X, buf.NX, m_txt[0], m_txt[1], bounds, B * 6 * D)
             ops.gemm(buf.NX[:, :T], w.add_qkv[0], out=buf.QKV[:, :T], bias=w.add_qkv[1], variant=gv)
             self._lora_gemm(buf, buf.NX[:, T:], w.qkv, L[p + ".qkv"], img_cond_bounds, img_cond_groups, buf.QKV[:, T:])
             self._attention(buf, [(0, T, w.rms_ctx), (T, S, w.rms)], "AO", bounds, vis)
@@ -343,8 +349,7 @@ class UniCombineFlux(torch.nn.Module):
                     gj = g_out[:, img_cond_bounds[1 + j]:img_cond_bounds[2 + j]]
                     ops.add(seg(2 + j), gj, seg(2 + j))
                     ops.add(seg(1), gj, seg(1))
-            for s_ in range(nseg):
-                ops.ln_modulate(seg(s_), buf.NX[:, bounds[s_]:bounds[s_ + 1]], mods[s_][3], mods[s_][4])
+            ops.ln_modulate_segs(buf.X, buf.NX, m_txt[3], m_txt[4], bounds, B * 6 * D)
             ops.gemm(buf.NX[:, :T], w.ffc1[0], out=buf.FF[:, :T], bias=w.ffc1[1], act=UG_ACT_GELU_TANH, variant=gv)
             ops.gemm(buf.FF[:, :T], w.ffc2[0], out=seg(0), bias=w.ffc2[1], gate=m_txt[5], residual=seg(0), variant=gv)
             ops.gemm(buf.NX[:, T:], w.ff1[0], out=buf.FF[:, T:], bias=w.ff1[1], act=UG_ACT_GELU_TANH, variant=gv)
@@ -361,9 +366,7 @@ class UniCombineFlux(torch.nn.Module):
             m_x = self._chunks(sgl_mods[i][0], 3)
             m_c = [self._chunks(sgl_mods[i][1 + j], 3) for j in range(n)]
             mods = [m_x] + m_c
-            for s_ in range(len(all_groups)):
-                lo, hi = all_bounds[s_], all_bounds[s_ + 1]
-                ops.ln_modulate(buf.X[:, lo:hi], buf.NX[:, lo:hi], mods[s_][0], mods[s_][1])
+            ops.ln_modulate_segs(buf.X, buf.NX, m_x[0], m_x[1], all_bounds, B * 3 * D)
             self._lora_gemm(buf, buf.NX, w.qkv, L[p + ".qkv"], all_bounds, all_groups, buf.QKV)
             self._lora_gemm(buf, buf.NX, w.mlp, L[p + ".mlp"], all_bounds, all_groups, buf.CAT[:, :, D:], act=UG_ACT_GELU_TANH)
             self._attention(buf, [(0, S, w.rms)], "CAT", bounds, vis)
