@@ -232,3 +232,102 @@ def test_moe_gather_experts_combine_matches_dense_einsum(ug):
     assert rel_l2(out_h.cpu(), want_h) < 1e-2
     dropped = (r["slot"] < 0)
     assert dropped.any() and out_h[dropped].abs().max() == 0  # dropped tokens are exact zeros
+
+
+def test_ln_modulate_segs_equals_per_segment_calls(ug):
+    B, D, bounds = 2, 384, [0, 33, 200, 201, 333]
+    x = rnd(B, bounds[-1], D, scale=2.0)
+    table = torch.randn(4, B, 6 * D, device="cuda")
+    got = ug.ln_modulate_segs(x, torch.empty_like(x), table[0][:, 3 * D:4 * D], table[0][:, 4 * D:5 * D], bounds, B * 6 * D)
+    want = torch.empty_like(x)
+    for s in range(4):
+        ug.ln_modulate(x[:, bounds[s]:bounds[s + 1]], want[:, bounds[s]:bounds[s + 1]], table[s][:, 3 * D:4 * D], table[s][:, 4 * D:5 * D])
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("H,dh", [(24, 128), (5, 128), (24, 64), (9, 64)])
+def test_qk_rmsnorm_rope_many_heads(ug, H, dh):
+    """More heads than one warp pass covers (one warp per (row, head chunk)), incl. a ragged last chunk."""
+    S = 77
+    axes = (16, 56, 56) if dh == 128 else (8, 28, 28)
+    ids = torch.stack([torch.zeros(S), torch.arange(S) // 9, torch.arange(S) % 9], 1).float().cuda()
+    table = ug.rope_table(ids, axes)
+    qk = rnd(1, S, 2 * H * dh)
+    w = (1 + 0.1 * torch.randn(2, dh)).to(torch.bfloat16).cuda()
+    x = qk.float().reshape(S, 2, H, dh)
+    y = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * w.float()[None, :, None, :]
+    cs = table.view(S, dh // 2, 2)
+    y0, y1 = y[..., 0::2], y[..., 1::2]
+    c, s_ = cs[:, None, None, :, 0], cs[:, None, None, :, 1]
+    want = torch.stack([y0 * c - y1 * s_, y1 * c + y0 * s_], -1).reshape(1, S, 2 * H * dh)
+    ug.qk_rmsnorm_rope(qk, 2 * H, dh, w, table, heads_per_weight=H)
+    assert rel_l2(qk, want) < 4e-3
+
+
+def _pools(P, nbytes):
+    from unigen_b200 import _lib
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device="cuda") for _ in range(P)]
+    tables = []
+    for r in range(P):
+        t = _lib.PeerTable()
+        t.world, t.rank = P, r
+        for i in range(P):
+            t.base[i] = bufs[i].data_ptr()
+        tables.append(t)
+    return bufs, tables
+
+
+@pytest.mark.parametrize("P", [1, 2, 4, 8])
+@pytest.mark.parametrize("segmented", [False, True])
+def test_ulysses_peer_exchange_emulated_ranks(ug, P, segmented):
+    """The fused exchange kernels with P EMULATED ranks on one GPU (every "peer pool" is a local buffer, the ranks run one
+    after the other): qkv_scatter + attention_peer with the uniform and the segment-sharded row maps reproduce the
+    unsharded qk_rmsnorm_rope + (masked) attention bit for bit."""
+    from oracle import unigen_oracle as O
+    H, dh = 8, 64
+    D, hd = H * dh, H * dh // P
+    gb = [0, 64, 320, 448, 576] if segmented else [0, 576]      # global segment bounds, every bound a multiple of 8
+    vis = O.pvariant_visibility(2) if segmented else None
+    S = gb[-1]
+    qkv = rnd(S, 3 * D)
+    w = (1 + 0.1 * torch.randn(2, dh)).to(torch.bfloat16).cuda()
+    ids = torch.stack([torch.zeros(S), torch.arange(S) // 24, torch.arange(S) % 24], 1).float().cuda()
+    rope = ug.rope_table(ids, (8, 28, 28))
+    # unsharded reference with the same kernels (variant pinned: the auto choice depends on the head count)
+    ref_qkv = qkv.clone().unsqueeze(0)
+    ug.qk_rmsnorm_rope(ref_qkv[:, :, :2 * D], 2 * H, dh, w, rope, heads_per_weight=H)
+    want = torch.zeros(1, S, D, device="cuda", dtype=torch.bfloat16)
+    ug.attention(ref_qkv[:, :, :D], ref_qkv[:, :, D:2 * D], ref_qkv[:, :, 2 * D:], want, H, dh, seg_bounds=gb if segmented else None,
+                 seg_visible=vis, variant=1)
+    off_recv, off_ao = 4096, 4096 + 3 * S * hd * 2
+    bufs, tables = _pools(P, off_ao + (S // P) * D * 2 + 4096)
+    # local rows of rank r: its shard of every segment, in segment order
+    local = [[(gb[s] + r * (gb[s + 1] - gb[s]) // P, (gb[s + 1] - gb[s]) // P) for s in range(len(gb) - 1)] for r in range(P)]
+    for r in range(P):
+        for row0, n in local[r]:
+            ug.qkv_scatter(tables[r], qkv[row0:row0 + n], H, dh, w, rope[row0:row0 + n].contiguous(), off_recv, S, row0)
+    for r in range(P):
+        recv = bufs[r][off_recv:off_recv + 3 * S * hd * 2].view(torch.bfloat16).view(3, 1, S, hd)
+        ug.attention_peer(tables[r], recv[0], recv[1], recv[2], H // P, dh, off_ao, D, 0 if segmented else S // P,
+                          seg_bounds=gb if segmented else None, seg_visible=vis, variant=1)
+    torch.cuda.synchronize()
+    got = torch.empty_like(want)
+    for r in range(P):
+        ao = bufs[r][off_ao:off_ao + (S // P) * D * 2].view(torch.bfloat16).view(S // P, D)
+        lo = 0
+        for row0, n in local[r]:
+            got[0, row0:row0 + n] = ao[lo:lo + n]
+            lo += n
+    assert torch.equal(got, want)
+    # broadcast gather + barrier (world 1 table: the flag round trip on the local pool)
+    src = rnd(S // P, 64)
+    for r in range(P):
+        ug.peer_bcast_rows(tables[r], src, off_recv, 64, r * (S // P))
+    full = bufs[P - 1][off_recv:off_recv + S * 64 * 2].view(torch.bfloat16).view(S, 64)
+    assert all(torch.equal(full[r * (S // P):(r + 1) * (S // P)], src) for r in range(P))
+    b1, t1 = _pools(1, 8192)
+    for _ in range(3):
+        ug.peer_barrier(t1[0])
+    torch.cuda.synchronize()
+    ctrl = b1[0][:264].view(torch.int32)
+    assert ctrl[64].item() == 3 and ctrl[0].item() == 3 and ctrl[65].item() == 0  # epoch, own flag, no watchdog trip

@@ -217,6 +217,7 @@ class SequenceParallelUniGenFlux(UniGenFlux):
         key = (N, T)
         if self._pool_key != key:
             if self._pool is not None:
+                self._graphs.clear()  # captured graphs hold pointers into the old pool
                 self._pool.close()
             sizes = [("RECV", 3 * S * (D // P) * 2), ("AO", Smax * D * 2), ("CAT", S * 5 * D * 2), ("X", S * D * 2),
                      ("OUTF", S * a.in_channels * 2)]
@@ -456,6 +457,7 @@ class SequenceParallelUniCombineFlux(UniCombineFlux):
         S = S_loc * P
         if self._pool_key != S_loc:
             if self._pool is not None:
+                self._graphs.clear()  # captured graphs hold pointers into the old pool
                 self._pool.close()
             n_max = S  # velocity rows <= S
             sizes = [("RECV", 3 * S * (D // P) * 2), ("AO", S_loc * D * 2), ("CAT", S_loc * 5 * D * 2), ("OUTF", n_max * a.in_channels * 2)]
