@@ -390,7 +390,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         }
       }
     }
-    if (p.o_rows_per_rank != 0) __threadfence_system();  // peer stores: visible before the following flag barrier
   }
 
   tc_fence_before();
@@ -714,7 +713,6 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         }
       }
     }
-    if (p.o_rows_per_rank != 0) __threadfence_system();  // peer stores: visible before the following flag barrier
   }
 
   tc_fence_before();

@@ -16,6 +16,7 @@ namespace ug {
 struct GemmParams {
   int rows, n, k, batch;
   int m_tiles, n_tiles, k_blocks, total_tiles;
+  int group_m;    // tile walk: m-tiles (x batch) are swept in bands of group_m, n-tiles inside a band (L2 reuse for tall A)
   int k1_blocks;  // K blocks of the first operand pair (A, W); blocks [k1_blocks, k_blocks) come from the second pair (A2, W2)
   __nv_bfloat16* c;
   long long c_rs, c_bs;
@@ -212,6 +213,19 @@ __device__ __forceinline__ float chunk_sumsq(const GemmParams& p, const uint32_t
   return ss;
 }
 
+// Persistent tile walk. Band b covers m-indices [b * group_m, ...): inside a band the m index runs fastest, then n, so the
+// CTAs running at the same time share group_m A row-tiles and a handful of W column-tiles. group_m = all m-tiles gives the
+// plain m-fastest order (best when A fits in L2); a small band keeps tall-A problems (M = 16 k rows: A alone exceeds what L2
+// can hold next to the streaming C writes, and every n-wave re-read it from HBM: 4.7 GB per launch) inside L2.
+__device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int mb_count, int& mb, int& nt) {
+  const int band = p.group_m * p.n_tiles;
+  const int g = tile / band, in_band = tile - g * band;
+  const int first = g * p.group_m;
+  const int size = min(mb_count - first, p.group_m);
+  mb = first + in_band % size;
+  nt = in_band / size;
+}
+
 template <int kCta, int BN, int kStages>
 __global__ void __launch_bounds__(192, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
@@ -264,7 +278,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = unit; tile < p.total_tiles; tile += num_units) {
-      const int mb = tile % mb_count, nt = tile / mb_count;
+      int mb, nt;
+      tile_coords(p, tile, mb_count, mb, nt);
       const int b = mb / p.m_tiles, mt = mb % p.m_tiles;
       const int row0 = mt * (Cfg::BM * kCta) + (int)cta_rank * Cfg::BM;
       const int wrow0 = nt * BN + (int)cta_rank * Cfg::BN_LOAD;
@@ -336,7 +351,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int row_local = q * 32 + lane;
     int it = 0;
     for (int tile = unit; tile < p.total_tiles; tile += num_units, ++it) {
-      const int mb = tile % mb_count, nt = tile / mb_count;
+      int mb, nt;
+      tile_coords(p, tile, mb_count, mb, nt);
       const int b = mb / p.m_tiles, mt = mb % p.m_tiles;
       const int r = mt * (Cfg::BM * kCta) + (int)cta_rank * Cfg::BM + row_local;
       const int n0 = nt * BN;
@@ -464,6 +480,19 @@ static int launch_gemm(const ug_gemm_args& a, cudaStream_t stream) {
   p.rows = a.rows; p.n = a.n; p.k = a.k; p.batch = a.batch;
   p.m_tiles = (a.rows + Cfg::BM * kCta - 1) / (Cfg::BM * kCta);
   p.n_tiles = (a.n + BN - 1) / BN;
+  {
+    // A bytes one sweep over all m-tiles touches; above ~40 MB it no longer survives in the 126 MB L2 between n-waves
+    const long long a_bytes = (long long)a.batch * a.rows * (a.k + (a.a2 ? a.k2 : 0)) * 2;
+    const int mb_all = p.m_tiles * a.batch;
+    p.group_m = mb_all;
+    if (a_bytes > (40LL << 20) && !(a.w_batch_stride != 0 && a.batch > 1)) {
+      // band of A row-tiles worth ~24 MB: it stays in L2 while the band sweeps every n-tile, so A is read from HBM once
+      const long long tile_bytes = (long long)Cfg::BM * kCta * (a.k + (a.a2 ? a.k2 : 0)) * 2;
+      long long gm = (24LL << 20) / tile_bytes;
+      gm = gm < 2 ? 2 : (gm > 16 ? 16 : gm);
+      p.group_m = gm < mb_all ? (int)gm : mb_all;
+    }
+  }
   p.k1_blocks = (a.k + Cfg::BK - 1) / Cfg::BK;
   p.k_blocks = p.k1_blocks + k2_blocks;
   p.total_tiles = p.m_tiles * p.n_tiles * a.batch;

@@ -32,7 +32,9 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   return v;
 }
 
-// One block; thread r < world signals rank r and waits for rank r's signal of the same epoch. A rank that never arrives
+// One block; thread r < world signals rank r and waits for rank r's signal of the same epoch. Every peer store of the kernels
+// launched before it on this stream happens-before this kernel (stream order); the system-scope fence + release store make
+// them visible to a peer that acquires the flag, so the producing kernels need no fence of their own. A rank that never arrives
 // (a bug, or a dead peer) must not hang the GPU: after ~2 s of spinning the error word is set and the kernel returns.
 __global__ void peer_barrier_kernel(PeerPtrs t) {
   __shared__ unsigned int epoch;
@@ -145,7 +147,8 @@ __global__ void __launch_bounds__(256) qkv_scatter_kernel(const __nv_bfloat16* _
       *reinterpret_cast<uint4*>(dst) = outv;
     }
   }
-  __threadfence_system();
+  // no per-thread system fence here (it cost ~45 % of this kernel's stall samples): the stores are ordered before the
+  // following ug_peer_barrier by stream order, and that kernel's fence + release store publishes them to the peers
 }
 
 // dst pool rows [dst_row0, dst_row0 + rows) of EVERY rank <- src rows (16-byte vectors; blockIdx.y = destination rank)
@@ -159,7 +162,6 @@ __global__ void __launch_bounds__(256) peer_bcast_rows_kernel(const __nv_bfloat1
     const long long r = i / nvec;
     *reinterpret_cast<uint4*>(dst + r * d_rs + 8 * v) = *reinterpret_cast<const uint4*>(src + r * s_rs + 8 * v);
   }
-  __threadfence_system();
 }
 
 static int to_ptrs(const ug_peer_table* t, PeerPtrs* p, const char* name) {
