@@ -88,6 +88,22 @@ __device__ __forceinline__ int classify_tile(const AttnParams& p, int qt, int kt
   return needed | (partial << 1);
 }
 
+// Key tiles a query tile has to visit, built by all 32 lanes of one warp (lane l classifies tiles l, l + 32, ...; a ballot
+// + prefix count compacts them in order). A single thread doing this serially cost tens of microseconds per CTA at 132 key
+// tiles x 5 segments — a large fraction of a short (condition-row) CTA's lifetime.
+__device__ __forceinline__ int build_tile_list(const AttnParams& p, int qt, int block_q, uint16_t* tile_list, int lane) {
+  const int total = (p.seq + kBlockKV - 1) / kBlockKV;
+  int n = 0;
+  for (int k0 = 0; k0 < total; k0 += 32) {
+    const int kt = k0 + lane;
+    const int f = kt < total ? classify_tile(p, qt, kt, block_q) : 0;
+    const unsigned int m = __ballot_sync(0xffffffffu, f & 1);
+    if (f & 1) tile_list[n + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(kt | ((f >> 1) << 15));
+    n += __popc(m);
+  }
+  return n;
+}
+
 template <int kDh, bool kPInTmem>
 __global__ void __launch_bounds__(192, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
@@ -132,14 +148,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       mbar_init(&pv_done[s], 1);
     }
     fence_mbar_init();
-    // key tiles this query tile has to visit
-    const int total = (p.seq + kBlockKV - 1) / kBlockKV;
-    int n = 0;
-    for (int kt = 0; kt < total; ++kt) {
-      const int f = classify_tile(p, qt, kt);
-      if (f & 1) tile_list[n++] = (uint16_t)(kt | ((f >> 1) << 15));
-    }
-    *n_tiles_smem = n;
+  }
+  if (warp == 0) {
+    const int n = build_tile_list(p, qt, kBlockQ, tile_list, lane);
+    if (lane == 0) *n_tiles_smem = n;
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
@@ -467,13 +479,10 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       mbar_init(&pv_done[s], 1);
     }
     fence_mbar_init();
-    const int total = (p.seq + kBlockKV - 1) / kBlockKV;
-    int n = 0;
-    for (int kt = 0; kt < total; ++kt) {
-      const int f = classify_tile(p, qt, kt, kBlockQ2);
-      if (f & 1) tile_list[n++] = (uint16_t)(kt | ((f >> 1) << 15));
-    }
-    *n_tiles_smem = n;
+  }
+  if (warp == 0) {
+    const int n = build_tile_list(p, qt, kBlockQ2, tile_list, lane);
+    if (lane == 0) *n_tiles_smem = n;
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
