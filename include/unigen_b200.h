@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define UG_ABI_VERSION 6
+#define UG_ABI_VERSION 7
 
 typedef enum {
   UG_OK = 0,
@@ -125,7 +125,11 @@ typedef struct ug_gemm_args {
   const void* w2;
   int64_t w2_row_stride;
   int32_t k2;
-  int32_t reserved3;
+  /* Grouped projection mask: when != 0 (a multiple of 32), output columns are blocks of colmask_block columns and row r keeps
+   * only block lora_seg_group[segment(r)] (-1: none); every other column is written as zero. With W = the adapter groups'
+   * lora_A matrices stacked one block per group this IS ug_lora_down_wide on the tensor cores:
+   * t_wide = x @ [A_0; A_1; ...]^T masked to the row's own group. Composes with no other epilogue op. */
+  int32_t colmask_block;
 } ug_gemm_args;
 
 int ug_gemm_bf16(const ug_gemm_args* args, void* stream);

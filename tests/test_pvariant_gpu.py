@@ -92,6 +92,13 @@ def test_gemm_k_extension_switched_lora_on_tensor_cores(ug, variant):
     twc = tw.float().cpu()
     assert twc[:, :40].abs().max() == 0 and twc[:, 40:300, blk:].abs().max() == 0 and twc[:, 40:300, 3 * rank:blk].abs().max() == 0
     assert (twc[:, 300:420, blk:blk + 3 * rank] - bf(x[:, 300:420] @ A[1].reshape(3 * rank, D).t())).abs().max() < 2e-2
+    # the down-projection on the tensor cores (masked grouped GEMM) writes the same operand
+    aw = torch.zeros(G * blk, D)
+    for g in range(G):
+        aw[g * blk:g * blk + 3 * rank] = A[g].reshape(3 * rank, D)
+    tw2 = torch.full_like(tw, 5.0)
+    ug.gemm(xd, aw.cuda().to(torch.bfloat16), out=tw2, variant=variant, colmask=dict(block=blk, seg_bounds=bounds, seg_group=groups))
+    assert (tw2.float() - tw.float()).abs().max() < 3e-2 and torch.equal(tw2 == 0, tw == 0)
     gd = gates.cuda().contiguous()
     out = ug.gemm(xd, W.cuda().to(torch.bfloat16), bias=bias.cuda().to(torch.bfloat16), variant=variant, a2=tw,
                   w2=bw.cuda().to(torch.bfloat16), gate=gd[0], gate_seg_stride=gd.stride(0), seg_bounds=bounds,
@@ -119,11 +126,12 @@ def _setup(n_cond=2, strict=False, seed=1):
     return cfg, inp, types_, oracle, model
 
 
-@pytest.mark.parametrize("lora_mode", ["mma", "epilogue"])
+@pytest.mark.parametrize("lora_mode", ["mma", "mma-simt-down", "epilogue"])
 @pytest.mark.parametrize("n_cond,strict", [(1, False), (2, False), (2, True)])
 def test_pvariant_forward_matches_oracle(n_cond, strict, lora_mode):
     cfg, inp, types_, oracle, model = _setup(n_cond, strict)
-    model.lora_mode = lora_mode
+    model.lora_mode = lora_mode.split("-")[0]
+    model.lora_down_mode = "simt" if lora_mode.endswith("simt-down") else "mma"
     args = (inp["hidden_states"], inp["condition_hidden_states"], inp["condition_ids"], types_, inp["encoder_hidden_states"],
             inp["pooled_projections"], inp["timestep"], inp["img_ids"], inp["txt_ids"])
     want = oracle.forward(*args)

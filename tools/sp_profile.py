@@ -15,7 +15,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 OPS = ["gemm", "attention", "attention_peer", "qkv_scatter", "peer_barrier", "peer_bcast_rows", "ln_modulate", "qk_rmsnorm_rope",
-       "gemv", "lora_down", "add", "copy", "moe_route", "moe_gather_modulate", "moe_combine", "rope_table", "to_bf16"]
+       "gemv", "lora_down", "lora_down_wide", "ln_modulate_segs", "add", "copy", "moe_route", "moe_gather_modulate", "moe_combine", "rope_table", "to_bf16"]
 
 
 def main():

@@ -34,7 +34,7 @@ class GemmArgs(C.Structure):
         ("qk_norm_weight", C.c_void_p), ("qk_cos_sin", C.c_void_p), ("qk_head_dim", C.c_int32), ("qk_d", C.c_int32),
         ("qk_eps", C.c_float), ("reserved2", C.c_int32), ("gate_seg_stride", C.c_int64),
         ("a2", C.c_void_p), ("a2_row_stride", C.c_int64), ("a2_batch_stride", C.c_int64),
-        ("w2", C.c_void_p), ("w2_row_stride", C.c_int64), ("k2", C.c_int32), ("reserved3", C.c_int32),
+        ("w2", C.c_void_p), ("w2_row_stride", C.c_int64), ("k2", C.c_int32), ("colmask_block", C.c_int32),
     ]
 
 

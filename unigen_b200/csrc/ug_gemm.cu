@@ -24,6 +24,7 @@ struct GemmParams {
   long long bias_bs;
   const float* gate;
   long long gate_bs;
+  int colmask_block;           // != 0: output columns outside block lora_group(row) (blocks of colmask_block columns) are zeroed
   long long gate_seg_stride;  // != 0: rows of segment i (lora_bounds) use gate + i * gate_seg_stride
   float alpha;
   int act;
@@ -361,7 +362,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-      const int lora_g = p.lora_t ? lora_group_of(p, r) : -1;
+      const int lora_g = (p.lora_t || p.colmask_block) ? lora_group_of(p, r) : -1;
       // gate vector of this row: per sample, and per row segment when gate_seg_stride is set (once per tile, not per chunk)
       const float* gate_row = p.gate ? p.gate + (long long)b * p.gate_bs + (p.gate_seg_stride ? seg_index_of(p, r) * p.gate_seg_stride : 0)
                                      : nullptr;
@@ -411,7 +412,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           tmem_ld_wait();
           if (ch == BN / 32 - 1) release_acc();
           const int col0 = n0 + ch * 32;
-          if (r < p.rows && col0 < p.n) epilogue_chunk(p, v, b, r, col0, lora_g, gate_row);
+          if (p.colmask_block && col0 / p.colmask_block != lora_g) {
+            // grouped down-projection: a row keeps only the column block of its own adapter group
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0u;
+            if (r < p.rows && col0 < p.n) epilogue_chunk(p, v, b, r, col0, -1, nullptr);
+          } else if (r < p.rows && col0 < p.n) epilogue_chunk(p, v, b, r, col0, p.lora_t ? lora_g : -1, gate_row);
         }
       }
     }
@@ -498,7 +504,7 @@ static int launch_gemm(const ug_gemm_args& a, cudaStream_t stream) {
   p.total_tiles = p.m_tiles * p.n_tiles * a.batch;
   p.c = (__nv_bfloat16*)a.c; p.c_rs = a.c_row_stride; p.c_bs = a.c_batch_stride;
   p.bias = (const __nv_bfloat16*)a.bias; p.bias_bs = a.bias_batch_stride;
-  p.gate = a.gate; p.gate_bs = a.gate_batch_stride; p.gate_seg_stride = a.gate_seg_stride;
+  p.gate = a.gate; p.gate_bs = a.gate_batch_stride; p.gate_seg_stride = a.gate_seg_stride; p.colmask_block = a.colmask_block;
   p.alpha = a.alpha; p.act = a.act;
   p.res = (const __nv_bfloat16*)a.residual; p.res_rs = a.res_row_stride; p.res_bs = a.res_batch_stride;
   p.w_batched = w_batched ? 1 : 0;
@@ -576,6 +582,11 @@ extern "C" int ug_gemm_bf16(const ug_gemm_args* args, void* stream) {
     UG_CHECK_ARG(a.lora_t_row_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(a.lora_t) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(a.lora_b) & 7) == 0,
                  "gemm: LoRA operand alignment");
+  }
+  if (a.colmask_block) {
+    UG_CHECK_ARG(a.colmask_block % 32 == 0 && a.lora_nseg >= 1 && a.lora_nseg <= UG_MAX_SEGMENTS && !a.bias && !a.gate && !a.residual &&
+                     a.act == UG_ACT_NONE && !a.lora_t,
+                 "gemm: colmask_block must be a multiple of 32, needs the row-segment table and composes with no other epilogue op");
   }
   if (a.a2) {
     UG_CHECK_ARG(a.w2 && a.k2 >= 8 && a.k2 % 8 == 0, "gemm: second operand pair needs w2 and k2 (%d) a positive multiple of 8", a.k2);

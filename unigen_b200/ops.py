@@ -80,7 +80,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, b
          gate: Optional[torch.Tensor] = None, alpha: float = 1.0, act: int = UG_ACT_NONE,
          residual: Optional[torch.Tensor] = None, variant: int = 0, lora: Optional[dict] = None,
          qk_norm: Optional[dict] = None, gate_seg_stride: int = 0, seg_bounds: Optional[Sequence[int]] = None,
-         a2: Optional[torch.Tensor] = None, w2: Optional[torch.Tensor] = None) -> torch.Tensor:
+         a2: Optional[torch.Tensor] = None, w2: Optional[torch.Tensor] = None, colmask: Optional[dict] = None) -> torch.Tensor:
     """out[b,r,:] = residual + alpha * gate[b,:] * act(a[b,r,:] @ w^T + bias (+ switched LoRA update)).
     a: [B,R,K] view, w: [N,K] or [B,N,K]. lora = dict(t=fp32 [B,R,n_blocks*rank] from lora_down, b=bf16 [groups,N,rank]
     (pre-scaled), rank, block_n, seg_bounds, seg_group) applies adapter group seg_group[i] to rows of segment i."""
@@ -131,6 +131,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, b
         g.lora_t, g.lora_t_row_stride, g.lora_t_batch_stride = t3.data_ptr(), t3.stride(1), t3.stride(0)
         g.lora_b, g.lora_rank, g.lora_block_n = lb.data_ptr(), int(lora["rank"]), int(lora.get("block_n", 0))
         sb, sg = lora["seg_bounds"], lora["seg_group"]
+        g.lora_nseg = len(sg)
+        for i, v in enumerate(sb):
+            g.lora_seg_bounds[i] = int(v)
+        for i, v in enumerate(sg):
+            g.lora_seg_group[i] = int(v)
+    if colmask is not None:
+        # grouped projection: row r keeps only column block seg_group[segment(r)] (dict(block, seg_bounds, seg_group))
+        g.colmask_block = int(colmask["block"])
+        sb, sg = colmask["seg_bounds"], colmask["seg_group"]
         g.lora_nseg = len(sg)
         for i, v in enumerate(sb):
             g.lora_seg_bounds[i] = int(v)

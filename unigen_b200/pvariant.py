@@ -51,6 +51,11 @@ class _LoraPair:
                 rows = slice(j * self.n_each, (j + 1) * self.n_each)
                 bw[rows, g * LORA_BLOCK + j * r:g * LORA_BLOCK + (j + 1) * r] = self.b[g, rows]
         self.bw = bw
+        # stacked down-projection for the tensor-core form: [groups * 64, K], group g's lora_A rows at the top of block g
+        aw = torch.zeros(G * LORA_BLOCK, self.a.shape[2], device=self.a.device, dtype=BF16)
+        for g in range(G):
+            aw[g * LORA_BLOCK:g * LORA_BLOCK + self.a.shape[1]] = self.a[g]
+        self.aw = aw
 
 
 class UniCombineFlux(torch.nn.Module):
@@ -87,6 +92,7 @@ class UniCombineFlux(torch.nn.Module):
         # "mma": the switched low-rank update rides the main GEMM's tensor-core loop as a K extension (A2 / W2 operand pair);
         # "epilogue": it is applied per output element on the CUDA cores in the epilogue (kept for comparison)
         self.lora_mode = "mma"
+        self.lora_down_mode = "mma"  # "mma": tensor-core down-projection (masked grouped GEMM); "simt": ug_lora_down_wide
         self.overlap_mod_gemv = True  # AdaLN GEMVs (HBM-bound) on a side stream under the tensor-core-bound blocks
         self._side_stream = torch.cuda.Stream(device=self.device_)
         self.add_cond_attn = False  # model_config['add_cond_attn'] (UniCombineTransformerBlock.pyc L201-202)
@@ -213,7 +219,11 @@ class UniCombineFlux(torch.nn.Module):
         """Main GEMM with the switched low-rank update fused into its epilogue."""
         if self.lora_mode == "mma":
             tw = buf.LTW[:, :x.shape[1]]
-            ops.lora_down_wide(x, pair.a, seg_bounds, seg_group, out=tw, block=LORA_BLOCK)
+            if self.lora_down_mode == "mma" and x.shape[-1] >= 256:
+                # down-projection on the tensor cores too: x @ [A_0; A_1; ...]^T, each row masked to its own group's block
+                ops.gemm(x, pair.aw, out=tw, variant=self.gemm_variant, colmask=dict(block=LORA_BLOCK, seg_bounds=seg_bounds, seg_group=seg_group))
+            else:
+                ops.lora_down_wide(x, pair.a, seg_bounds, seg_group, out=tw, block=LORA_BLOCK)
             return ops.gemm(x, w[0], out=out, bias=w[1], variant=self.gemm_variant, a2=tw, w2=pair.bw,
                             seg_bounds=seg_bounds if kw.get("gate_seg_stride") else None, **kw)
         rt = pair.n_sub * pair.rank
