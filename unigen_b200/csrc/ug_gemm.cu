@@ -8,6 +8,8 @@
 // W tile; the leader CTA issues the MMAs, commits are multicast to both CTAs.
 //
 // Replaces every nn.Linear call on the reference path.
+#include <cstdlib>
+
 #include "ug_host.h"
 #include "ug_ptx.cuh"
 
@@ -609,11 +611,22 @@ extern "C" int ug_gemm_bf16(const ug_gemm_args* args, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int variant = a.variant;
   if (variant == 0) {
-    // auto: narrow tiles when a 128x256 grid would leave most SMs idle
-    const long long tiles256 = (long long)a.batch * ((a.rows + 127) / 128) * ((a.n + 255) / 256);
-    // big problems: the 2-CTA pair tile halves the per-SM W traffic (measured 2 % faster per cfg3 step than 1-CTA
-    // 128x256 at equal tensor throughput: less smem / L2 energy under the 1 kW power cap)
-    variant = (a.n <= 128 || tiles256 < num_sms()) ? 3 : 2;
+    // auto: estimate each variant's time as  waves x tile area / (SMs per tile x relative tile efficiency)  and take the
+    // smallest — wave quantisation and the padding of a partial last row tile decide for small M (text stream, per-rank
+    // shards of sequence parallelism: M = 576 at P = 8), the 2-CTA pair tile (half the per-SM W traffic, measured 2 % faster per
+    // cfg3 step under the 1 kW power cap) wins whenever the grid fills the machine
+    const int sms = num_sms();
+    struct Cand { int v, tm, tn; double rate; int units; };
+    // relative per-SM tile throughput from profiles/r01_probe_gemm_v1.log (large problems: 1371 / 1349 / ~900 TFLOP/s)
+    const Cand cands[3] = {{2, 256, 256, 2.0, sms / 2}, {1, 128, 256, 0.98, sms}, {3, 128, 128, 0.67, sms}};
+    double best = 0.0;
+    for (const Cand& c : cands) {
+      const long long tiles = (long long)a.batch * ((a.rows + c.tm - 1) / c.tm) * ((a.n + c.tn - 1) / c.tn);
+      const long long waves = (tiles + c.units - 1) / c.units;
+      const double t = (double)waves * c.tm * c.tn / c.rate;
+      if (variant == 0 || t < best) { best = t; variant = c.v; }
+    }
+    if (a.n <= 128) variant = 3;
   }
   switch (variant) {
     case 1: return launch_gemm<1, 256, 4>(a, s);
