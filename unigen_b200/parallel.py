@@ -268,9 +268,8 @@ class SequenceParallelUniGenFlux(UniGenFlux):
 
     def _gather_rows(self, local: torch.Tensor, name: str, full: torch.Tensor):
         """all-gather of [s_loc, d] row shards into the [S, d] buffer `name` of every rank."""
-        row0, s_loc, _ = self._sp_rows if self.exchange == "peer" else (0, 0, 0)
         if self.exchange == "peer":
-            ops.peer_bcast_rows(self._pool.table, local[0], self._off[name], full.shape[-1], row0)
+            ops.peer_bcast_rows(self._pool.table, local[0], self._off[name], full.shape[-1], self._sp_rows[0])
             self._pool.barrier()
         else:
             dist.all_gather_into_tensor(full.view(-1), local.reshape(-1), group=self.sp_group)

@@ -17,16 +17,15 @@ Data layout in HBM (bf16 unless noted)
   NX / NX2 / QKV / QKV2 / AO / AO2 / FF   per-block scratch sized for the longest joint sequence (shared_expert[1]: 2N+T)
   PAT   [B, N, C*p*p] patchified latents: PatchEmbed's Conv2d(k=p, s=p) is ONE tcgen05 GEMM with the flattened conv
         weight, the cropped sincos table rides in the epilogue as the residual operand (batch stride 0)
-  AH/AC [E*C, D]     capacity-slot buffers of the transformer-block experts; all E experts run as ONE batched GEMM /
+  SL[2] [E*C, D]     capacity-slot buffers of the transformer-block experts; all E experts run as ONE batched GEMM /
         attention launch per op (weights stacked [E, ., .]); per-token AdaLN = a (samples+1)-row table per expert
         indexed through slot_token (row B = the all-zero temb of empty slots, which DO take part in the attention)
   MOD   fp32         AdaLN vectors of all 48 blocks, computed once per step
 """
 from __future__ import annotations
 
-import math
 import types
-from typing import Any, Dict, List, Optional
+from typing import Any, Dict, Optional
 
 import torch
 
