@@ -182,6 +182,7 @@ class SequenceParallelUniGenFlux(UniGenFlux):
         if self.arch.num_attention_heads % self.sp_world:
             raise ops.UgError(f"{self.arch.num_attention_heads} heads are not divisible by {self.sp_world} ranks")
         self.exchange = exchange
+        self.sp_prestage = True  # shared-expert blocks of the CoMoE pre-stage sequence-parallel too (peer exchange only)
         self._sp_active = False
         self._xchg = None
         self._pool: Optional[PeerPool] = None
@@ -219,17 +220,26 @@ class SequenceParallelUniGenFlux(UniGenFlux):
             if self._pool is not None:
                 self._graphs.clear()  # captured graphs hold pointers into the old pool
                 self._pool.close()
-            sizes = [("RECV", 3 * S * (D // P) * 2), ("AO", Smax * D * 2), ("CAT", S * 5 * D * 2), ("X", S * D * 2),
-                     ("OUTF", S * a.in_channels * 2)]
+            sizes = [("RECV", 3 * Smax * (D // P) * 2), ("AO", Smax * D * 2), ("CAT", S * 5 * D * 2), ("X", S * D * 2),
+                     ("OUTF", S * a.in_channels * 2), ("HC", 2 * N * D * 2)]
             self._off, total = pool_layout(sizes)
             self._pool = PeerPool(self.sp_group, total, self.device_)
             self._pool_key = key
-            self._recv = self._pool.view(self._off["RECV"], (3, 1, S, D // P))
             self._outf = self._pool.view(self._off["OUTF"], (1, S, a.in_channels))
         pool = self._pool
         buf.AO, buf.CAT, buf.X = (pool.view(self._off["AO"], (1, Smax, D)), pool.view(self._off["CAT"], (1, S, 5 * D)),
                                   pool.view(self._off["X"], (1, S, D)))
+        buf.HC = pool.view(self._off["HC"], (1, 2 * N, D))
+        self._set_sp_rows(S)
+
+    def _set_sp_rows(self, S: int):
+        """Contiguous row sharding of an S-row joint sequence: (first global row, rows per rank, S) + the matching view of
+        the receive buffer (q, k, v of ALL S tokens for this rank's heads)."""
+        if S % self.sp_world:
+            raise ops.UgError(f"joint sequence {S} is not divisible by the sequence-parallel world size {self.sp_world}")
+        s_loc = S // self.sp_world
         self._sp_rows = (self.sp_rank * s_loc, s_loc, S)
+        self._recv = self._pool.view(self._off["RECV"], (3, 1, S, self.inner_dim // self.sp_world))
 
     def _peer_attention(self, o_name: str, o_row_stride: int):
         """barrier -> attention over this rank's heads of all tokens, output rows stored into their owners' `o_name` buffer ->
@@ -265,6 +275,86 @@ class SequenceParallelUniGenFlux(UniGenFlux):
         self._scatter(buf.QKV[0, :S], rms, rope[:S] if rope is not None else None, 0)
         self._peer_attention("CAT", 5 * self.inner_dim)  # `out` is the first D columns of the (peer-mapped) CAT rows
         return out
+
+    def _prestage_sp(self, buf, N, T, x_img, cond_tokens, pooled, cond_pooled, rts_uniform, mods_s0, mods_s1, cond_index,
+                     txt_ids, img_ids, cond_ids):
+        """CoMoE pre-stage with the two shared-expert blocks SEQUENCE-PARALLEL (they are 95 % of its FLOPs: joint blocks over
+        2N and T + 2N tokens); gate / routing / modulated experts stay replicated on the gathered residual stream, so routing is
+        bit-identical to the single-GPU run. Row shards of the shared blocks' joint sequences are contiguous:
+        shared[0] = [cond | image] (2N rows), shared[1] = [text | image | cond] (T + 2N rows); their outputs are re-gathered
+        into the peer-mapped HC buffer by peer stores because the two blocks (and the main blocks) shard differently."""
+        a = self.arch
+        D, E, C, P, r = self.inner_dim, self.expert_nums, buf.capacity, self.sp_world, self.sp_rank
+        gv = self.gemm_variant
+        B = 1
+        ops.gemm(cond_tokens, self.control_x_embedder_w[0], out=buf.COND, bias=self.control_x_embedder_w[1], variant=gv)
+        ops.rope_table(torch.cat([cond_ids, img_ids], 0), a.axes_dims_rope, a.theta, out=buf.rope0)
+        ops.rope_table(torch.cat([txt_ids, img_ids, cond_ids], 0), a.axes_dims_rope, a.theta, out=buf.rope1)
+        ops.add(x_img, buf.COND, buf.G.view(B, N, D))
+        route = ops.moe_route(buf.G, self.gate_wg, rts_uniform, C)
+        ops.gemv(cond_pooled, self.exp_mod_w[0], self.exp_mod_b[0], out=buf.MODC.view(B, E * D))
+        ops.gemv(pooled, self.exp_mod_w[1], self.exp_mod_b[1], out=buf.MODH.view(B, E * D))
+        ops.moe_gather_modulate(buf.COND.view(B * N, D), route["slot_token"], buf.MODC, E, C, N, out=buf.A)
+        ops.gemm(buf.A.view(E, C, D), self.exp_w[0], out=buf.YC.view(E, C, D), bias=self.exp_b[0], variant=gv)
+        ops.copy(x_img, buf.EH.view(B, N, D))
+        ops.moe_gather_modulate(buf.EH, route["slot_token"], buf.MODH, E, C, N, addend=buf.YC, out=buf.A)
+        ops.gemm(buf.A.view(E, C, D), self.exp_w[1], out=buf.YH.view(E, C, D), bias=self.exp_b[1], variant=gv)
+
+        def shard(S, n_first):
+            """rank's rows of an S-row joint sequence [first stream (n_first rows) | second stream]: (row0, rows, rows of the
+            first stream, first local row inside the second stream)."""
+            rows = S // P
+            row0 = r * rows
+            f_loc = min(max(n_first - row0, 0), rows)
+            return row0, rows, f_loc, max(row0 - n_first, 0)
+
+        main_rows = self._sp_rows
+        loc = self._sp_buf
+        if "HL" not in loc:
+            loc["HL"] = torch.empty(1, (T + 2 * N) // P + 1, D, device=self.device_, dtype=torch.bfloat16)
+        self._sp_active = True
+        try:
+            # ---- shared[0]: context = condition tokens, sample = image tokens, temb = this condition's temb ----
+            S0 = 2 * N
+            self._set_sp_rows(S0)
+            row0, rows, c_loc, i0 = shard(S0, N)
+            s_loc = rows - c_loc
+            out_c, out_s = loc["HL"][:, :c_loc], loc["HL"][:, c_loc:rows]
+            self._double_block(buf, self.shared[0], mods_s0[0], mods_s0[1], x_img[:, i0:i0 + s_loc], buf.COND[:, row0:row0 + c_loc],
+                               out_s, out_c, buf.rope0[row0:row0 + rows])
+            # HC = [shared hidden (N) | shared cond (N)] on every rank
+            if s_loc:
+                ops.peer_bcast_rows(self._pool.table, out_s[0], self._off["HC"], D, i0)
+            if c_loc:
+                ops.peer_bcast_rows(self._pool.table, out_c[0], self._off["HC"], D, N + row0)
+            self._pool.barrier()
+            # ---- shared[1]: context = control text, sample = [hidden | cond], temb = control_temb, context output discarded ----
+            S1 = T + 2 * N
+            self._set_sp_rows(S1)
+            row0, rows, t_loc, h0 = shard(S1, T)
+            h_loc = rows - t_loc
+            hl = loc["HL"][:, :h_loc]
+            self._double_block(buf, self.shared[1], mods_s1[0], mods_s1[1], buf.HC[:, h0:h0 + h_loc], buf.CENC[:, row0:row0 + t_loc],
+                               hl, None, buf.rope1[row0:row0 + rows])
+            self._pool.barrier()  # every rank has finished READING its HC rows before anyone overwrites them
+            if h_loc:
+                ops.peer_bcast_rows(self._pool.table, hl[0], self._off["HC"], D, h0)
+            self._pool.barrier()
+        finally:
+            self._sp_active = False
+            self._sp_rows = main_rows
+            self._set_sp_rows(main_rows[2])
+        hc_h, hc_c = buf.HC[:, :N], buf.HC[:, N:]
+        ops.moe_combine(buf.YH, route, C, buf.EH)
+        ops.moe_combine(buf.YC, route, C, buf.EC)
+        if cond_index == 0:
+            ops.add(hc_h, buf.EH.view(B, N, D), buf.CIN)
+        else:
+            ops.add(buf.CIN, hc_h, buf.CIN)
+            ops.add(buf.CIN, buf.EH.view(B, N, D), buf.CIN)
+        ops.add(buf.CIN, hc_c, buf.CIN)
+        ops.add(buf.CIN, buf.EC.view(B, N, D), buf.CIN)
+        return route
 
     def _gather_rows(self, local: torch.Tensor, name: str, full: torch.Tensor):
         """all-gather of [s_loc, d] row shards into the [S, d] buffer `name` of every rank."""
@@ -385,8 +475,12 @@ class SequenceParallelUniGenFlux(UniGenFlux):
                     x_txt, x_img = buf.X[:, :T], buf.X[:, T:]
                     ops.gemm(x_txt, self.control_context_embedder_w[0], out=buf.CENC, bias=self.control_context_embedder_w[1], variant=gv)
                     for c in range(n_cond):
-                        route = self._prestage(buf, B, N, T, x_img, cs[c], pooled, cond_pooled[c], rts_uniform[c], mods_s0[c],
-                                               mods_s1, c, txt_ids, img_ids, condition_ids[c])
+                        if self.exchange == "peer" and self.sp_prestage and (2 * N) % P == 0 and (T + 2 * N) % P == 0:
+                            route = self._prestage_sp(buf, N, T, x_img, cs[c], pooled, cond_pooled[c], rts_uniform[c], mods_s0[c],
+                                                      mods_s1, c, txt_ids, img_ids, condition_ids[c])
+                        else:
+                            route = self._prestage(buf, B, N, T, x_img, cs[c], pooled, cond_pooled[c], rts_uniform[c], mods_s0[c],
+                                                   mods_s1, c, txt_ids, img_ids, condition_ids[c])
                     self._sp_active = True
                     ctrl_in = buf.CIN[:, i0:i0 + n_img]
                     cenc_loc = buf.CENC[:, row0:row0 + t_loc]
