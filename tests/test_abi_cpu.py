@@ -66,3 +66,30 @@ def test_product_package_never_imports_the_oracle():
     for f in (ROOT / "unigen_b200").glob("*.py"):
         src = f.read_text()
         assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_struct_offsets_match_a_compiled_probe(tmp_path):
+    """sizeof / offsetof of every ABI struct as gcc lays them out == the ctypes mirrors the Python host side passes."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from unigen_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    structs = {"ug_gemm_args": _lib.GemmArgs, "ug_attn_args": _lib.AttnArgs, "ug_peer_table": _lib.PeerTable,
+               "ug_qkv_scatter_args": _lib.QkvScatterArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
+    for name, cls in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'  printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(out[name]) == C.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(out[f"{name}.{field}"]) == getattr(cls, field).offset, (name, field)

@@ -64,7 +64,7 @@ def consolidate_zero_checkpoint(ckpt_dir: str, tag: Optional[str] = None) -> Dic
     optim_files = sorted(glob.glob(os.path.join(d, "*_optim_states.pt")), key=_natural)
     if not optim_files:
         raise FileNotFoundError(f"no *_optim_states.pt under {d}")
-    optim = [torch.load(f, map_location="cpu", weights_only=False)["optimizer_state_dict"] for f in optim_files]
+    optim = [_torch_load(f)["optimizer_state_dict"] for f in optim_files]
     stage = optim[0][ZERO_STAGE]
     world = optim[0][PARTITION_COUNT]
     world = max(world) if isinstance(world, (list, tuple)) else world
@@ -77,7 +77,7 @@ def consolidate_zero_checkpoint(ckpt_dir: str, tag: Optional[str] = None) -> Dic
     model_files = sorted(glob.glob(os.path.join(d, "*_model_states.pt")), key=_natural)
     if not model_files:
         raise FileNotFoundError(f"no *_model_states.pt under {d}")
-    states = [torch.load(f, map_location="cpu", weights_only=False) for f in model_files]
+    states = [_torch_load(f) for f in model_files]
     s0 = states[0]
     out: "OrderedDict[str, Tensor]" = OrderedDict()
     for name in s0.get(BUFFER_NAMES, []):
@@ -120,6 +120,15 @@ def consolidate_zero_checkpoint(ckpt_dir: str, tag: Optional[str] = None) -> Dic
     return out
 
 
+def _torch_load(path: str):
+    """Plain tensor files load with `weights_only=True`; DeepSpeed shards / older pickles that carry python objects fall back
+    to the full unpickler the reference itself uses (`torch.load(path)`, infer.py:133) — only open checkpoints you trust."""
+    try:
+        return torch.load(path, map_location="cpu", weights_only=True)
+    except Exception:  # noqa: BLE001  (pickle.UnpicklingError / RuntimeError depending on the torch version)
+        return torch.load(path, map_location="cpu", weights_only=False)
+
+
 def _read_safetensors_dir(path: str) -> Dict[str, Tensor]:
     from safetensors.torch import load_file
     files = sorted(glob.glob(os.path.join(path, "*.safetensors")), key=_natural)
@@ -143,20 +152,20 @@ def read_state_dict(path: str) -> Dict[str, Tensor]:
             tag = f.read().strip()
         merged = os.path.join(path, tag, "pytorch_model_fp32.bin")  # script/infer.sh:44-46
         if os.path.exists(merged):
-            return torch.load(merged, map_location="cpu", weights_only=False)
+            return _torch_load(merged)
         return consolidate_zero_checkpoint(path, tag)
     if os.path.isfile(path):
         if path.endswith(".safetensors"):
             from safetensors.torch import load_file
             return load_file(path)
-        sd = torch.load(path, map_location="cpu", weights_only=False)
+        sd = _torch_load(path)
         return sd.get("state_dict", sd) if isinstance(sd, dict) else sd
     if os.path.isdir(path):
         bins = sorted(glob.glob(os.path.join(path, "*_weights_*.bin")), key=_natural)  # src/hook.py:19-25
         if bins and not glob.glob(os.path.join(path, "*.safetensors")):
             out: Dict[str, Tensor] = {}
             for f in bins:
-                out.update(torch.load(f, map_location="cpu", weights_only=False))
+                out.update(_torch_load(f))
             return out
         return _read_safetensors_dir(path)
     raise FileNotFoundError(path)
