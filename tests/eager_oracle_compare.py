@@ -4,8 +4,8 @@ run as plain PyTorch on the B200 — bf16 weights / activations, cuBLASLt `F.lin
 names), so one run gives (1) the torch-eager step time next to the native step time and (2) a FULL-SIZE parity check
 (cosine / rel-L2 of the velocity, routing agreement) that the CPU oracle cannot deliver at 18.7 B parameters.
 
-python tools/bench_eager_oracle.py [--workload cfg3|cfg2|tiny] [--steps 3]   -> one JSON line
-(test / measurement infrastructure: imports oracle/, never used by the product path)"""
+python tests/eager_oracle_compare.py [--workload cfg3|cfg2|tiny|cfg5] [--steps 3]   -> one JSON line
+(lives under tests/ because it imports oracle/: checker infrastructure, never used by the product path; not collected by pytest)"""
 import argparse
 import json
 import sys
