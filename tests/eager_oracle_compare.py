@@ -62,21 +62,23 @@ def main_sd3(args):
     with torch.no_grad():
         ms_eager, out_eager = timed(lambda: oracle.forward(**einp), args.steps)
     vel_eager = out_eager[0].float()
-    print(json.dumps({"workload": f"cfg5 architecture (SD3.5-medium UniGenSD3), forward batch {B}", "tokens": {"image": N, "condition": N, "text": T},
+    rec = ({"workload": f"cfg5 architecture (SD3.5-medium UniGenSD3), forward batch {B}", "tokens": {"image": N, "condition": N, "text": T},
                       "native_ms_per_step": ms_native, "torch_eager_bf16_ms_per_step": ms_eager, "speedup_vs_torch_eager": ms_eager / ms_native,
                       "eager_stack": f"torch {torch.__version__}: F.linear / F.conv2d (cuBLASLt, cuDNN) + F.scaled_dot_product_attention, bf16, oracle op order",
                       "full_size_parity": {"cosine": F.cosine_similarity(vel_native.flatten(), vel_eager.flatten(), dim=0).item(),
                                            "rel_l2": ((vel_native - vel_eager).norm() / vel_eager.norm()).item(),
                                            "routing_agreement": (route_native.long() == oracle.trace["moe.expert_idx"].long()).float().mean().item(),
-                                           "note": "both sides bf16 end to end (48 blocks deep): bf16-vs-bf16 drift, not the fp32-oracle bar"}}))
+                                           "note": "both sides bf16 end to end (48 blocks deep): bf16-vs-bf16 drift, not the fp32-oracle bar"}})
+    print(json.dumps(rec))
+    return rec
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="cfg3")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--batch", type=int, default=2)
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     if args.workload == "cfg5":
         return main_sd3(args)
     from oracle import unigen_oracle as O
@@ -130,11 +132,13 @@ def main():
     cos = F.cosine_similarity(vel_native.flatten(), vel_eager.flatten(), dim=0).item()
     rel = ((vel_native - vel_eager).norm() / vel_eager.norm()).item()
     agree = (route_native.long() == oracle.trace["moe.expert_idx"].long()).float().mean().item()
-    print(json.dumps({"workload": args.workload, "tokens": {"image": N, "condition": N, "text": T},
+    rec = ({"workload": args.workload, "tokens": {"image": N, "condition": N, "text": T},
                       "native_ms_per_step": ms_native, "torch_eager_bf16_ms_per_step": ms_eager, "speedup_vs_torch_eager": ms_eager / ms_native,
                       "eager_stack": f"torch {torch.__version__}: F.linear (cuBLASLt) + F.scaled_dot_product_attention, bf16, oracle op order",
                       "full_size_parity": {"cosine": cos, "rel_l2": rel, "routing_agreement": agree,
-                                           "note": "both sides bf16 end to end (57 + 28 blocks deep): bf16-vs-bf16 drift, not the fp32-oracle bar"}}))
+                                           "note": "both sides bf16 end to end (57 + 28 blocks deep): bf16-vs-bf16 drift, not the fp32-oracle bar"}})
+    print(json.dumps(rec))
+    return rec
 
 
 if __name__ == "__main__":
