@@ -26,3 +26,12 @@ def test_flux_cfg3_full_size_matches_eager_oracle():
     rec = E.main(["--workload", "cfg3", "--steps", "1"])
     par = rec["full_size_parity"]
     assert par["cosine"] >= 0.999 and par["routing_agreement"] >= 0.98, rec
+
+
+def test_pvariant_cfg4_full_size_matches_eager_oracle():
+    """cfg4, P-variant reading: 16 896 tokens (512 text + 4096 image + 3 x 4096 condition), LoRA rank 4 switched per segment,
+    reference visibility mask, against the PVariantOracle run as torch-eager bf16 (masked SDPA) on the same weights."""
+    import eager_oracle_compare as E
+    rec = E.main(["--workload", "cfg4p", "--steps", "1"])
+    par = rec["full_size_parity"]
+    assert par["cosine"] >= 0.999 and par["rel_l2"] < 5e-2, rec
