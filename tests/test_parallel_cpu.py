@@ -63,3 +63,17 @@ def test_ulysses_exchange_equals_unsharded_attention_world2():
         ret = m.dict()
         mp.spawn(_worker, args=(world, 29533, S, H, dh, ret), nprocs=world, join=True)
         assert len(ret) == world and max(ret.values()) < 1e-5, dict(ret)
+
+
+def test_pool_layout_is_aligned_ordered_and_deterministic():
+    """Peer pools must have IDENTICAL offsets on every rank: the layout is a pure function of the size list."""
+    from unigen_b200._lib import UG_PEER_HEADER_BYTES
+    from unigen_b200.parallel import pool_layout
+    sizes = [("RECV", 3 * 8704 * 384 * 2), ("AO", 8704 * 3072 * 2), ("CAT", 4608 * 15360 * 2), ("X", 4608 * 3072 * 2), ("OUTF", 4608 * 64 * 2 + 2)]
+    off, total = pool_layout(sizes)
+    assert pool_layout(sizes) == (off, total)
+    prev_end = UG_PEER_HEADER_BYTES
+    for name, nbytes in sizes:
+        assert off[name] % 256 == 0 and off[name] >= prev_end
+        prev_end = off[name] + nbytes
+    assert total >= prev_end and total % 256 == 0
