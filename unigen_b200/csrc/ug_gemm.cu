@@ -1,8 +1,9 @@
 // Dense bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (accumulators in TMEM,
 // double-buffered) -> fused epilogue from TMEM (bias / GELU-tanh / gate * alpha / residual) -> HBM.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..5 = epilogue
-// (warp w reads TMEM lanes 32*(w%4)..+31, the hardware lane-quarter rule of tcgen05.ld).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..9 = epilogue
+// (warp w reads TMEM lanes 32*(w%4)..+31, the hardware lane-quarter rule of tcgen05.ld; the two warps that share a lane
+// quarter split the tile's columns, which halves the epilogue latency per tile — it matters when the K loop is short).
 // Persistent: grid = min(tiles, SMs); tiles are walked m-fastest so concurrently running CTAs share W tiles in L2.
 // kCta == 2 pairs two SMs on a 256 x BN tile (cta_group::2): each CTA loads its own 128 A rows and HALF of the
 // W tile; the leader CTA issues the MMAs, commits are multicast to both CTAs.
@@ -46,6 +47,9 @@ struct GemmParams {
   int qk_dh, qk_d;
   float qk_eps;
 };
+
+constexpr int kEpiWarps = 8;                     // 4 or 8
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 
 template <int kCta, int BN, int kStages>
 struct GemmCfg {
@@ -241,7 +245,7 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int m
 }
 
 template <int kCta, int BN, int kStages>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                  const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ CUtensorMap tma_w2, const GemmParams p) {
   using Cfg = GemmCfg<kCta, BN, kStages>;
@@ -273,7 +277,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4 * kCta);  // one arrive per epilogue warp per CTA
+      mbar_init(&tmem_empty[s], kEpiWarps * kCta);  // one arrive per epilogue warp per CTA
     }
     fence_mbar_init();
   }
@@ -360,8 +364,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
     }
   } else {
-    // ------------------------------ epilogue (warps 2..5) ------------------------------
+    // ------------------------------ epilogue (warps 2..) ------------------------------
     const int q = warp & 3;
+    const int col_half = (warp - 2) >> 2;  // 0 / 1 with 8 epilogue warps: which half of the tile's columns this warp converts
     const int row_local = q * 32 + lane;
     int it = 0;
     for (int tile = unit; tile < p.total_tiles; tile += num_units, ++it) {
@@ -391,8 +396,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       if (p.qk_w) {
         // ---- QKV projection: per-head RMSNorm (two passes over the TMEM columns of a head) + RoPE, fused ----
         const int cph = p.qk_dh >> 5;  // 32-column chunks per head
+        // the two warps of a lane quarter split the tile's heads when half a tile holds whole heads; otherwise the first
+        // one converts the whole tile and the second only hands its share of the accumulator back
+        constexpr int kHalf = BN / (kEpiWarps / 4);
+        const bool split = (kHalf % p.qk_dh) == 0;
+        const int c_lo = split ? col_half * kHalf : 0;
+        const int c_hi = split ? c_lo + kHalf : (col_half == 0 ? BN : 0);
+        if (c_hi == 0) release_acc();
 #pragma unroll 1
-        for (int c_h = 0; c_h < BN; c_h += p.qk_dh) {
+        for (int c_h = c_lo; c_h < c_hi; c_h += p.qk_dh) {
           const int col_h = n0 + c_h;
           const bool active = col_h < p.n;             // warp-uniform
           const int which = active ? col_h / p.qk_d : 2;  // 0 = q head, 1 = k head, 2 = v head
@@ -413,17 +425,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             uint32_t v[32];
             tmem_ld_32x32(taddr + c_h + ch * 32, v);
             tmem_ld_wait();
-            if (c_h + p.qk_dh >= BN && ch == cph - 1) release_acc();
+            if (c_h + p.qk_dh >= c_hi && ch == cph - 1) release_acc();
             if (r < p.rows && active) epilogue_qkv_chunk(p, v, b, r, col_h + ch * 32, ch * 32, which, rstd);
           }
         }
       } else {
+        constexpr int kChunksPerWarp = (BN / 32) / (kEpiWarps / 4);
+        const int ch0 = col_half * kChunksPerWarp;
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
+        for (int ch = ch0; ch < ch0 + kChunksPerWarp; ++ch) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + ch * 32, v);
           tmem_ld_wait();
-          if (ch == BN / 32 - 1) release_acc();
+          if (ch == ch0 + kChunksPerWarp - 1) release_acc();
           const int col0 = n0 + ch * 32;
           if (p.colmask_block && col0 / p.colmask_block != lora_g) {
             // grouped down-projection: a row keeps only the column block of its own adapter group
@@ -534,7 +548,7 @@ static int launch_gemm(const ug_gemm_args& a, cudaStream_t stream) {
   if (units > p.total_tiles) units = p.total_tiles;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(units * kCta);
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
