@@ -106,6 +106,91 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const __nv_bfloat16* _
   }
 }
 
+// Same op, TWO warps per row (adjacent warps 2i, 2i+1 of a block; partial sums meet in shared memory). With one warp per
+// row and the row in registers a 3072-wide pass needs ~80 registers per thread -> 24 resident warps per SM -> 4608 rows take
+// 1.3 waves and the HBM pipe idles through the partial second wave; half the row per warp halves the registers, doubles the
+// resident rows' worth of loads in flight and shortens the tail.
+template <int kMaxV>
+__global__ void __launch_bounds__(256, 4) ln_modulate2_kernel(const __nv_bfloat16* __restrict__ x, long long x_rs,
+                                                           long long x_bs, __nv_bfloat16* __restrict__ out,
+                                                           long long o_rs, long long o_bs,
+                                                           const float* __restrict__ shift,
+                                                           const float* __restrict__ scale, long long mod_bs, int batch,
+                                                           int rows, int d, float eps, const int* __restrict__ slot_token,
+                                                           int capacity, int tokens_per_batch, int empty_index,
+                                                           long long mod_es, RowSegs segs, long long mod_seg_stride) {
+  __shared__ float red_sum[8], red_var[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row_global = (long long)blockIdx.x * 4 + (warp >> 1);
+  const bool valid = row_global < (long long)batch * rows;
+  const int b = valid ? (int)(row_global / rows) : 0, r = valid ? (int)(row_global % rows) : 0;
+  const int l64 = (warp & 1) * 32 + lane;
+  long long mod_off = (long long)b * mod_bs;
+  if (segs.nseg > 0) {
+    int si = 0;
+    for (int s = 0; s < segs.nseg; ++s)
+      if (r >= segs.bounds[s] && r < segs.bounds[s + 1]) si = s;
+    mod_off += (long long)si * mod_seg_stride;
+  }
+  if (slot_token && valid) {
+    const int token = slot_token[r];
+    mod_off = (long long)(r / capacity) * mod_es + (long long)(token < 0 ? empty_index : token / tokens_per_batch) * mod_bs;
+  }
+  const uint4* xp = reinterpret_cast<const uint4*>(x + (long long)b * x_bs + (long long)r * x_rs);
+  const int nvec = d >> 3;
+  uint4 buf[kMaxV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int v = l64 + 64 * i;
+    if (valid && v < nvec) {
+      buf[i] = xp[v];
+      float f[8];
+      unpack8(buf[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += f[j];
+    }
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red_sum[warp] = sum;
+  __syncthreads();
+  const float mean = (red_sum[warp] + red_sum[warp ^ 1]) / (float)d;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int v = l64 + 64 * i;
+    if (valid && v < nvec) {
+      float f[8];
+      unpack8(buf[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { float t = f[j] - mean; var += t * t; }
+    }
+  }
+  var = warp_sum(var);
+  if (lane == 0) red_var[warp] = var;
+  __syncthreads();
+  const float rstd = rsqrtf((red_var[warp] + red_var[warp ^ 1]) / (float)d + eps);
+  if (!valid) return;
+  uint4* op = reinterpret_cast<uint4*>(out + (long long)b * o_bs + (long long)r * o_rs);
+  const float* sh = shift + mod_off;
+  const float* sc = scale + mod_off;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int v = l64 + 64 * i;
+    if (v < nvec) {
+      float f[8];
+      unpack8(buf[i], f);
+      const float4 s0 = *reinterpret_cast<const float4*>(sc + 8 * v), s1 = *reinterpret_cast<const float4*>(sc + 8 * v + 4);
+      const float4 h0 = *reinterpret_cast<const float4*>(sh + 8 * v), h1 = *reinterpret_cast<const float4*>(sh + 8 * v + 4);
+      const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      const float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * (1.f + s[j]) + h[j];
+      op[v] = pack8(f);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Per-head RMSNorm (learned weight) + interleaved-pair RoPE, in place. One warp per token row, looping heads.
 // ---------------------------------------------------------------------------------------------------
@@ -372,10 +457,14 @@ static int launch_ln_modulate(const void* x, int64_t x_rs, int64_t x_bs, void* o
   auto xp = (const __nv_bfloat16*)x;
   auto op = (__nv_bfloat16*)out;
 #define UG_LN_LAUNCH(V) ln_modulate_kernel<V><<<grid, block, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, batch, rows, d, eps, slot_token, capacity, tokens_per_batch, empty_index, mod_es, segs, mod_seg_stride)
+  const int grid2 = (int)((warps + 3) / 4);  // two warps per row, four rows per 256-thread block
+#define UG_LN2_LAUNCH(V) ln_modulate2_kernel<V><<<grid2, block, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, batch, rows, d, eps, slot_token, capacity, tokens_per_batch, empty_index, mod_es, segs, mod_seg_stride)
   if (d <= 8 * 32 * 2) UG_LN_LAUNCH(2);
-  else if (d <= 8 * 32 * 6) UG_LN_LAUNCH(6);
+  else if (d <= 8 * 64 * 3) UG_LN2_LAUNCH(3);
+  else if (d <= 8 * 64 * 6) UG_LN2_LAUNCH(6);
   else if (d <= 8 * 32 * 12) UG_LN_LAUNCH(12);
   else UG_LN_LAUNCH(16);
+#undef UG_LN2_LAUNCH
 #undef UG_LN_LAUNCH
   UG_CHECK_LAUNCH(name);
   return UG_OK;
