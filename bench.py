@@ -212,6 +212,7 @@ def run_native(args):
     model.init_random_(seed=0)
     model.gemm_variant, model.attn_variant = args.gemm_variant, args.attn_variant
     model.use_cuda_graph = not args.no_graph
+    model.overlap_text_stream = not args.no_text_overlap
     E = model.expert_nums
 
     # synthetic inputs of the named shape, one distinct set per rank, resident in pinned host memory
@@ -442,6 +443,7 @@ def main():
     ap.add_argument("--attn-variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-text-overlap", action="store_true", help="text-stream GEMMs on the main stream (A/B of the two-stream double block)")
     args = ap.parse_args()
     if args.workload in ("cfg4p", "cfg5"):
         if args.impl == "reference":

@@ -128,6 +128,8 @@ class _DenoiserBase(torch.nn.Module):
         self.attn_variant = 0
         self.overlap_mod_gemv = True  # AdaLN GEMVs (HBM-bound) on a side stream under the tensor-core-bound blocks
         self._side_stream = torch.cuda.Stream(device=self.device_)
+        self.overlap_text_stream = True  # text-stream GEMMs of the double blocks on a second stream beside the image stream's
+        self._text_stream = torch.cuda.Stream(device=self.device_)
         self.trace: Optional[Dict[str, torch.Tensor]] = None  # set to {} to record per-block intermediates
 
     @property
@@ -394,15 +396,33 @@ class UniGenFlux(_DenoiserBase):
         sh_a, sc_a, g_a, sh_m, sc_m, g_m = mod_smp
         csh_a, csc_a, cg_a, csh_m, csc_m, cg_m = mod_ctx
         nx_c, nx_s = buf.NX[:, :n_ctx], buf.NX[:, n_ctx:S]
+        # The text stream's GEMMs are small (M = 512 at cfg3: 24-96 tiles for 148 SMs); issued on a second stream they run
+        # beside the image stream's GEMMs (disjoint rows of NX / QKV / FF) and fill the SMs those leave idle in their last wave.
+        main = torch.cuda.current_stream()
+        side = self._text_stream if (self.overlap_text_stream and ctx_out is not None and n_ctx and n_smp
+                                     and not getattr(self, "_sp_active", False)) else None
         if n_ctx:
-            ops.ln_modulate(ctx_in, nx_c, csh_a, csc_a)
-            ops.gemm(nx_c, w.add_qkv[0], out=buf.QKV[:, :n_ctx], bias=w.add_qkv[1], variant=gv,
-                     qk_norm=self._qk_norm(w.rms_ctx, rope[:n_ctx] if rope is not None else None))
+            if side is not None:
+                side.wait_stream(main)
+            with torch.cuda.stream(side if side is not None else main):
+                ops.ln_modulate(ctx_in, nx_c, csh_a, csc_a)
+                ops.gemm(nx_c, w.add_qkv[0], out=buf.QKV[:, :n_ctx], bias=w.add_qkv[1], variant=gv,
+                         qk_norm=self._qk_norm(w.rms_ctx, rope[:n_ctx] if rope is not None else None))
         if n_smp:
             ops.ln_modulate(smp_in, nx_s, sh_a, sc_a)
             ops.gemm(nx_s, w.qkv[0], out=buf.QKV[:, n_ctx:S], bias=w.qkv[1], variant=gv,
                      qk_norm=self._qk_norm(w.rms, rope[n_ctx:S] if rope is not None else None))
+        if side is not None:
+            main.wait_stream(side)
         ao = self._joint_attention(buf, B, n_ctx, n_smp, w.rms_ctx, w.rms, rope)
+        if ctx_out is not None and n_ctx:
+            if side is not None:
+                side.wait_stream(main)
+            with torch.cuda.stream(side if side is not None else main):
+                ops.gemm(ao[:, :n_ctx], w.to_add_out[0], out=ctx_out, bias=w.to_add_out[1], gate=cg_a, residual=ctx_in, variant=gv)
+                ops.ln_modulate(ctx_out, nx_c, csh_m, csc_m)
+                ops.gemm(nx_c, w.ffc1[0], out=buf.FF[:, :n_ctx], bias=w.ffc1[1], act=UG_ACT_GELU_TANH, variant=gv)
+                ops.gemm(buf.FF[:, :n_ctx], w.ffc2[0], out=ctx_out, bias=w.ffc2[1], gate=cg_m, residual=ctx_out, variant=gv)
         if n_smp:
             # h = h + gate_msa * to_out(attn)
             ops.gemm(ao[:, n_ctx:S], w.to_out[0], out=smp_out, bias=w.to_out[1], gate=g_a, residual=smp_in, variant=gv)
@@ -410,11 +430,8 @@ class UniGenFlux(_DenoiserBase):
             ops.ln_modulate(smp_out, nx_s, sh_m, sc_m)
             ops.gemm(nx_s, w.ff1[0], out=buf.FF[:, n_ctx:S], bias=w.ff1[1], act=UG_ACT_GELU_TANH, variant=gv)
             ops.gemm(buf.FF[:, n_ctx:S], w.ff2[0], out=smp_out, bias=w.ff2[1], gate=g_m, residual=smp_out, variant=gv)
-        if ctx_out is not None and n_ctx:
-            ops.gemm(ao[:, :n_ctx], w.to_add_out[0], out=ctx_out, bias=w.to_add_out[1], gate=cg_a, residual=ctx_in, variant=gv)
-            ops.ln_modulate(ctx_out, nx_c, csh_m, csc_m)
-            ops.gemm(nx_c, w.ffc1[0], out=buf.FF[:, :n_ctx], bias=w.ffc1[1], act=UG_ACT_GELU_TANH, variant=gv)
-            ops.gemm(buf.FF[:, :n_ctx], w.ffc2[0], out=ctx_out, bias=w.ffc2[1], gate=cg_m, residual=ctx_out, variant=gv)
+        if side is not None:
+            main.wait_stream(side)
 
     def _single_attention(self, buf, S: int, rms: torch.Tensor, rope, out: torch.Tensor):
         """(RMSNorm(q,k)+RoPE in place on the QKV rows unless fused into the projection GEMM) + attention over rows [0, S) ->
