@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define UG_ABI_VERSION 7
+#define UG_ABI_VERSION 8
 
 typedef enum {
   UG_OK = 0,
@@ -242,8 +242,11 @@ int ug_gemv(const float* x, int64_t x_stride, const void* w, const void* bias, f
             int32_t batch, int32_t n, int32_t k, int32_t silu_in, int32_t silu_out, int32_t accumulate,
             void* stream);
 
-/* Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0): out[b] = [cos(t*f) | sin(t*f)]. */
-int ug_timestep_embedding(const float* t, int32_t batch, int32_t dim, float* out, void* stream);
+/* Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0): out[b] = [cos(s*f) | sin(s*f)], s = scale * t[b * t_stride]
+ * (SURVEY.md §A.4). `scale` folds the `timestep * 1000` / `guidance * 1000` of UniGenFlux.forward
+ * (src/UniGenTransformer.py:1217-1220) into the kernel; t_stride = 0 broadcasts one device-resident value (entry i of the
+ * sigma table of a graph-captured denoise loop) to every sample. */
+int ug_timestep_embedding(const float* t, int64_t t_stride, int32_t batch, int32_t dim, float scale, float* out, void* stream);
 
 /* out = a + b (bf16, same [batch, rows, d] view conventions). `hidden_states+condition_hidden_states`
  * (src/UniGenTransformer.py:979,1089) and the weave add (:1141,1166). */
@@ -293,6 +296,11 @@ int ug_moe_combine(const void* y, const int32_t* expert_idx, const int32_t* slot
  * ---------------------------------------------------------------------------------------------------- */
 /* FlowMatchEulerDiscreteScheduler.step: latents <- bf16(float(latents) + (sigma_next - sigma) * float(velocity)), n elements. */
 int ug_euler_step(void* latents_bf16, const void* velocity_bf16, float sigma, float sigma_next, int64_t n, void* stream);
+/* Same update with the schedule resident on the device: sigma = sigmas[step], sigma_next = sigmas[step + 1] (fp32 table of
+ * num_steps + 1 entries, src/UniGenPipeline.py:989-1006) are read by the kernel, so a whole sampling loop captured in ONE CUDA
+ * graph needs no host value between steps. */
+int ug_euler_step_table(void* latents_bf16, const void* velocity_bf16, const float* sigmas_dev, int32_t step, int64_t n,
+                        void* stream);
 /* classifier-free guidance (src/UniGenPipeline.py:405-412): out = uncond + guidance_scale * (text - uncond). */
 int ug_cfg_combine(const void* uncond_bf16, const void* text_bf16, float guidance_scale, void* out_bf16, int64_t n, void* stream);
 /* FluxPipeline._pack_latents (unpack = 0): (B, C, H, W) -> (B, (H/2)(W/2), 4C); _unpack_latents (unpack = 1): inverse. */
@@ -319,10 +327,16 @@ int ug_peer_export(const void* dev_ptr, uint8_t handle[UG_PEER_HANDLE_BYTES]);
 int ug_peer_open(const uint8_t handle[UG_PEER_HANDLE_BYTES], void** peer_ptr);
 int ug_peer_close(void* peer_ptr);
 /* Device-side barrier of all ranks on `stream` (release/acquire flags in the control blocks; no host sync; graph-capturable).
- * Every rank must issue the same sequence of barriers. A rank that waits ~2 s sets the error word instead of hanging. */
+ * Every rank must issue the same sequence of barriers, and the ranks must be host-synchronised (e.g. a process-group
+ * barrier) before the first one. A rank that waits longer than the timeout (default 20 s, env UG_PEER_TIMEOUT_MS or
+ * ug_peer_set_timeout_ms) sets the STICKY error word to 1 + the rank that did not arrive instead of hanging; later barriers
+ * then no longer wait. Everything computed after the word was set is invalid: poll it with ug_peer_error(_async). */
 int ug_peer_barrier(const ug_peer_table* table, void* stream);
+int ug_peer_set_timeout_ms(int64_t milliseconds);
 /* Reads the local error word (synchronous cudaMemcpy): 0 = every barrier so far completed. */
 int ug_peer_error(const ug_peer_table* table, int32_t* error_host);
+/* Stream-ordered, graph-capturable copy of the error word into PINNED host memory (no host sync). */
+int ug_peer_error_async(const ug_peer_table* table, int32_t* error_host_pinned, void* stream);
 
 /* seq-shard x all heads -> all tokens x head-shard, fused with the per-token QK-RMSNorm + RoPE pass:
  * reads `rows` local rows of the fused q|k|v projection ([rows, 3*heads*head_dim] bf16), normalises / rotates the q and k

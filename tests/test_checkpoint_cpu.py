@@ -135,3 +135,26 @@ def test_load_pretrained_and_save_modules_roundtrip(tmp_path):
     torch.save({"x_embedder.weight": base["x_embedder.weight"]}, tmp_path / "partial.bin")
     with pytest.raises(RuntimeError):
         ck.load_pretrained(model, base=str(tmp_path / "partial.bin"))
+
+
+class _NotATensor:  # a python object inside a checkpoint: needs the full (code-executing) unpickler
+    pass
+
+
+def test_full_unpickler_is_an_explicit_opt_in(tmp_path):
+    """A file that is not a plain tensor container raises instead of silently retrying with `weights_only=False`
+    (arbitrary code execution from an untrusted control checkpoint); `trust_pickle=True` is the caller's opt-in.
+    A corrupt file raises either way."""
+    import pickle
+    f = tmp_path / "model.bin"
+    torch.save({"w": torch.ones(2), "extra": _NotATensor()}, f)
+    with pytest.raises(pickle.UnpicklingError, match="trust_pickle"):
+        ck.read_state_dict(str(f))
+    sd = ck.read_state_dict(str(f), trust_pickle=True)
+    assert torch.equal(sd["w"], torch.ones(2))
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(b"not a checkpoint")
+    with pytest.raises(Exception):
+        ck.read_state_dict(str(bad))
+    with pytest.raises(Exception):
+        ck.read_state_dict(str(bad), trust_pickle=True)

@@ -212,3 +212,31 @@ def test_checkpoint_loader_feeds_the_native_model(tmp_path):
     res = ck.load_pretrained(fresh, base=str(d), control=str(tmp_path / "ckpt"))
     assert not res.unexpected_keys and all(not k.startswith(ctrl) for k in res.missing_keys)
     assert torch.equal(fresh(**dev_inp)[0], want)
+
+
+def test_cuda_graph_replay_survives_alternating_shapes():
+    """a graph captured for shape A holds raw pointers into A's workspace; running shape B in between
+    must neither free nor overwrite it. Alternating two (N, T) shapes with use_cuda_graph=True stays bit-equal to eager,
+    also after the workspace cache evicts and re-creates a shape."""
+    from oracle import unigen_oracle as O
+    cfg, sd, inp_a, oracle, model = _setup()
+    inp_b = O.make_inputs(cfg, 192, 320, text_len=77)
+    for k in ("hidden_states", "condition_hidden_states", "encoder_hidden_states"):
+        inp_b[k] = inp_b[k].to(torch.bfloat16).float()
+    dev = lambda inp: {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()}  # noqa: E731
+    a, b = dev(inp_a), dev(inp_b)
+    eager = [model(**a)[0].clone(), model(**b)[0].clone()]
+    model.use_cuda_graph = True
+    for rnd in range(3):
+        for want, x in zip(eager, (a, b)):
+            assert torch.equal(model(**x)[0], want), rnd
+    assert len(model._graphs) == 2 and len(model._workspaces) == 2
+    # forward hands out copies: the first result survives a second call
+    first = model(**a)[0]
+    model(**b)
+    assert torch.equal(first, eager[0])
+    # eviction: with room for ONE workspace, shape A's graph is dropped with its buffers and rebuilt on return
+    model.max_workspaces = 1
+    for want, x in zip(eager + eager, (a, b, a, b)):
+        assert torch.equal(model(**x)[0], want)
+    assert len(model._workspaces) == 1 and len(model._graphs) == 1

@@ -11,6 +11,7 @@ LIB_PATH = PKG_DIR / "libunigen_b200.so"
 UG_ACT_NONE = 0
 UG_ACT_GELU_TANH = 1
 UG_MAX_SEGMENTS = 8
+UG_ABI_VERSION = 8  # include/unigen_b200.h; checked against ug_abi_version() of the loaded library
 
 
 class UgError(RuntimeError):
@@ -90,7 +91,7 @@ SIGNATURES = {
     "ug_qk_rmsnorm_rope": (C.c_int, [_VP, _I64, _I64, _I32, _I32, _I32, _I32, _VP, _I32, _F32, _VP, _VP]),
     "ug_rope_table": (C.c_int, [_VP, _I32, C.POINTER(C.c_int32), _F32, _VP, _VP]),
     "ug_gemv": (C.c_int, [_VP, _I64, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
-    "ug_timestep_embedding": (C.c_int, [_VP, _I32, _I32, _VP, _VP]),
+    "ug_timestep_embedding": (C.c_int, [_VP, _I64, _I32, _I32, _F32, _VP, _VP]),
     "ug_add_bf16": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP]),
     "ug_copy_bf16": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP]),
     "ug_cast_f32_to_bf16": (C.c_int, [_VP, _VP, _I64, _VP]),
@@ -99,6 +100,7 @@ SIGNATURES = {
     "ug_moe_gather_modulate": (C.c_int, [_VP, _VP, _VP, _I64, _I64, _VP, _VP, _I32, _I32, _I32, _I32, _VP]),
     "ug_moe_combine": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP]),
     "ug_euler_step": (C.c_int, [_VP, _VP, _F32, _F32, _I64, _VP]),
+    "ug_euler_step_table": (C.c_int, [_VP, _VP, _VP, _I32, _I64, _VP]),
     "ug_cfg_combine": (C.c_int, [_VP, _VP, _F32, _VP, _I64, _VP]),
     "ug_pack_latents": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
     "ug_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -108,6 +110,8 @@ SIGNATURES = {
     "ug_peer_close": (C.c_int, [_VP]),
     "ug_peer_barrier": (C.c_int, [C.POINTER(PeerTable), _VP]),
     "ug_peer_error": (C.c_int, [C.POINTER(PeerTable), C.POINTER(C.c_int32)]),
+    "ug_peer_set_timeout_ms": (C.c_int, [_I64]),
+    "ug_peer_error_async": (C.c_int, [C.POINTER(PeerTable), _VP, _VP]),
     "ug_qkv_scatter": (C.c_int, [C.POINTER(PeerTable), C.POINTER(QkvScatterArgs), _VP]),
     "ug_attention_bf16_peer": (C.c_int, [C.POINTER(AttnArgs), C.POINTER(PeerTable), _I64, _I32, _VP]),
     "ug_peer_bcast_rows": (C.c_int, [C.POINTER(PeerTable), _VP, _I64, _I32, _I32, _I64, _I64, _I32, _VP]),
@@ -131,6 +135,10 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library drift apart
         fn.restype = res
         fn.argtypes = args
+    got = int(lib.ug_abi_version())
+    if got != UG_ABI_VERSION:
+        raise UgError(f"{LIB_PATH} reports ABI version {got}, this package binds version {UG_ABI_VERSION}: stale build — "
+                      "rebuild with `python -c 'import __graft_entry__ as g; g.build()'`")
     _lib = lib
     return lib
 

@@ -22,6 +22,7 @@ import glob
 import json
 import math
 import os
+import pickle
 import re
 import types
 from collections import OrderedDict
@@ -52,7 +53,7 @@ def _zero3_partition(numel: int, world: int):
     return math.ceil(numel / world), (world - rem) if rem else 0
 
 
-def consolidate_zero_checkpoint(ckpt_dir: str, tag: Optional[str] = None) -> Dict[str, Tensor]:
+def consolidate_zero_checkpoint(ckpt_dir: str, tag: Optional[str] = None, trust_pickle: bool = False) -> Dict[str, Tensor]:
     """fp32 state dict from the rank shards of a DeepSpeed ZeRO-2 / ZeRO-3 checkpoint.
     Layout read: `<dir>/<tag>/*_optim_states.pt` (optimizer_state_dict: zero_stage, partition_count, fp32 flat groups) and
     `<dir>/<tag>/*_model_states.pt` (module buffers, param_shapes per optimizer group, frozen_param_shapes / fragments,
@@ -64,7 +65,7 @@ def consolidate_zero_checkpoint(ckpt_dir: str, tag: Optional[str] = None) -> Dic
     optim_files = sorted(glob.glob(os.path.join(d, "*_optim_states.pt")), key=_natural)
     if not optim_files:
         raise FileNotFoundError(f"no *_optim_states.pt under {d}")
-    optim = [_torch_load(f)["optimizer_state_dict"] for f in optim_files]
+    optim = [_torch_load(f, trust_pickle)["optimizer_state_dict"] for f in optim_files]
     stage = optim[0][ZERO_STAGE]
     world = optim[0][PARTITION_COUNT]
     world = max(world) if isinstance(world, (list, tuple)) else world
@@ -77,7 +78,7 @@ def consolidate_zero_checkpoint(ckpt_dir: str, tag: Optional[str] = None) -> Dic
     model_files = sorted(glob.glob(os.path.join(d, "*_model_states.pt")), key=_natural)
     if not model_files:
         raise FileNotFoundError(f"no *_model_states.pt under {d}")
-    states = [_torch_load(f) for f in model_files]
+    states = [_torch_load(f, trust_pickle) for f in model_files]
     s0 = states[0]
     out: "OrderedDict[str, Tensor]" = OrderedDict()
     for name in s0.get(BUFFER_NAMES, []):
@@ -120,13 +121,19 @@ def consolidate_zero_checkpoint(ckpt_dir: str, tag: Optional[str] = None) -> Dic
     return out
 
 
-def _torch_load(path: str):
-    """Plain tensor files load with `weights_only=True`; DeepSpeed shards / older pickles that carry python objects fall back
-    to the full unpickler the reference itself uses (`torch.load(path)`, infer.py:133) — only open checkpoints you trust."""
+def _torch_load(path: str, trust_pickle: bool = False):
+    """`torch.load(..., weights_only=True)`: tensors and plain containers only. DeepSpeed rank shards (`*_optim_states.pt`,
+    `*_model_states.pt`) and older pickles carry python objects and need the full unpickler the reference itself uses
+    (`torch.load(path)`, infer.py:133) — that executes code from the file, so it is taken ONLY with `trust_pickle=True`
+    (an explicit opt-in of the caller), never as a silent retry; a truncated / corrupt file raises either way."""
+    if trust_pickle:
+        return torch.load(path, map_location="cpu", weights_only=False)
     try:
         return torch.load(path, map_location="cpu", weights_only=True)
-    except Exception:  # noqa: BLE001  (pickle.UnpicklingError / RuntimeError depending on the torch version)
-        return torch.load(path, map_location="cpu", weights_only=False)
+    except pickle.UnpicklingError as e:
+        raise pickle.UnpicklingError(
+            f"{path} is not a plain tensor file ({e}); if it is a DeepSpeed shard or an older pickle from a source you trust, "
+            "pass trust_pickle=True") from e
 
 
 def _read_safetensors_dir(path: str) -> Dict[str, Tensor]:
@@ -145,40 +152,41 @@ def _read_safetensors_dir(path: str) -> Dict[str, Tensor]:
     return out
 
 
-def read_state_dict(path: str) -> Dict[str, Tensor]:
-    """Branch order of infer.py:124-141."""
+def read_state_dict(path: str, trust_pickle: bool = False) -> Dict[str, Tensor]:
+    """Branch order of infer.py:124-141. `trust_pickle` (default off) allows the full unpickler for files that are not plain
+    tensor containers (DeepSpeed ZeRO rank shards always need it)."""
     if os.path.isdir(path) and os.path.exists(os.path.join(path, "latest")):
         with open(os.path.join(path, "latest")) as f:
             tag = f.read().strip()
         merged = os.path.join(path, tag, "pytorch_model_fp32.bin")  # script/infer.sh:44-46
         if os.path.exists(merged):
-            return _torch_load(merged)
-        return consolidate_zero_checkpoint(path, tag)
+            return _torch_load(merged, trust_pickle)
+        return consolidate_zero_checkpoint(path, tag, trust_pickle)
     if os.path.isfile(path):
         if path.endswith(".safetensors"):
             from safetensors.torch import load_file
             return load_file(path)
-        sd = _torch_load(path)
+        sd = _torch_load(path, trust_pickle)
         return sd.get("state_dict", sd) if isinstance(sd, dict) else sd
     if os.path.isdir(path):
         bins = sorted(glob.glob(os.path.join(path, "*_weights_*.bin")), key=_natural)  # src/hook.py:19-25
         if bins and not glob.glob(os.path.join(path, "*.safetensors")):
             out: Dict[str, Tensor] = {}
             for f in bins:
-                out.update(_torch_load(f))
+                out.update(_torch_load(f, trust_pickle))
             return out
         return _read_safetensors_dir(path)
     raise FileNotFoundError(path)
 
 
-def load_pretrained(model, base: Optional[str] = None, control: Optional[str] = None):
+def load_pretrained(model, base: Optional[str] = None, control: Optional[str] = None, trust_pickle: bool = False):
     """`cls.from_pretrained(<base>/transformer)` + `load_state_dict(<control ckpt>, strict=False)` (infer.py:115-141).
     Base keys must all be present in the base checkpoint (a missing block would silently run on zeros otherwise); the
     control checkpoint is loaded non-strictly exactly like the reference and its load result is returned."""
     own = set(model.state_dict().keys())
     result = types.SimpleNamespace(missing_keys=[], unexpected_keys=[])
     if base is not None:
-        sd = read_state_dict(base)
+        sd = read_state_dict(base, trust_pickle)
         ctrl_prefixes = tuple(getattr(model, "trainable_control_modules", {}) or ())
         need = [k for k in own if not k.startswith(ctrl_prefixes)] if ctrl_prefixes else list(own)
         missing = [k for k in need if k not in sd]
@@ -186,7 +194,7 @@ def load_pretrained(model, base: Optional[str] = None, control: Optional[str] = 
             raise RuntimeError(f"base checkpoint {base} lacks {len(missing)} base-model keys, e.g. {missing[:4]}")
         model.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
     if control is not None:
-        sd = read_state_dict(control)
+        sd = read_state_dict(control, trust_pickle)
         result = model.load_state_dict(sd, strict=False)
     return result
 

@@ -776,15 +776,8 @@ template <int kDh, bool kPInTmem>
 static int launch_attention(const ug_attn_args& a, const PeerO* peer, cudaStream_t stream) {
   using Cfg = AttnCfg<kDh, kPInTmem>;
   auto kern = attention_kernel<kDh, kPInTmem>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("attention: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-      return UG_ERR_CUDA;
-    }
-    attr_done = true;
-  }
+  static bool attr_done[64] = {false};
+  if (int st = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done, "attention"); st != UG_OK) return st;
   CUtensorMap maps[3];
   const void* ptrs[3] = {a.q, a.k, a.v};
   const int64_t rs[3] = {a.q_row_stride, a.k_row_stride, a.v_row_stride};
@@ -817,15 +810,8 @@ template <int kDh, int kPolyMod>
 static int launch_attention2(const ug_attn_args& a, const PeerO* peer, cudaStream_t stream) {
   using Cfg = Attn2Cfg<kDh>;
   auto kern = attention2_kernel<kDh, kPolyMod>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("attention2: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-      return UG_ERR_CUDA;
-    }
-    attr_done = true;
-  }
+  static bool attr_done[64] = {false};
+  if (int st = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done, "attention2"); st != UG_OK) return st;
   CUtensorMap maps[3];
   const void* ptrs[3] = {a.q, a.k, a.v};
   const int64_t rs[3] = {a.q_row_stride, a.k_row_stride, a.v_row_stride};

@@ -353,14 +353,15 @@ __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, 
   }
 }
 
-__global__ void timestep_embedding_kernel(const float* __restrict__ t, int batch, int dim, float* __restrict__ out) {
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, long long t_stride, int batch, int dim, float scale,
+                                          float* __restrict__ out) {
   const int half = dim / 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= batch * half) return;
   const int b = idx / half, j = idx % half;
   // exponent = -ln(10000) * j / (half - downscale_freq_shift), downscale_freq_shift = 0
   const float freq = expf(-logf(10000.f) * (float)j / (float)half);
-  const float a = t[b] * freq;
+  const float a = (t[(long long)b * t_stride] * scale) * freq;
   // flip_sin_to_cos=True -> [cos | sin]
   out[b * dim + j] = cosf(a);
   out[b * dim + half + j] = sinf(a);
@@ -572,10 +573,11 @@ extern "C" int ug_gemv(const float* x, int64_t x_stride, const void* w, const vo
   return UG_OK;
 }
 
-extern "C" int ug_timestep_embedding(const float* t, int32_t batch, int32_t dim, float* out, void* stream) {
-  UG_CHECK_ARG(t && out && batch >= 1 && dim >= 2 && dim % 2 == 0, "timestep_embedding: bad arguments");
+extern "C" int ug_timestep_embedding(const float* t, int64_t t_stride, int32_t batch, int32_t dim, float scale, float* out,
+                                     void* stream) {
+  UG_CHECK_ARG(t && out && batch >= 1 && dim >= 2 && dim % 2 == 0 && t_stride >= 0, "timestep_embedding: bad arguments");
   const int total = batch * dim / 2;
-  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t, batch, dim, out);
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t, t_stride, batch, dim, scale, out);
   UG_CHECK_LAUNCH("timestep_embedding");
   return UG_OK;
 }

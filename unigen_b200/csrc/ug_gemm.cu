@@ -462,15 +462,8 @@ template <int kCta, int BN, int kStages>
 static int launch_gemm(const ug_gemm_args& a, cudaStream_t stream) {
   using Cfg = GemmCfg<kCta, BN, kStages>;
   auto kern = gemm_bf16_kernel<kCta, BN, kStages>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("gemm: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-      return UG_ERR_CUDA;
-    }
-    attr_done = true;
-  }
+  static bool attr_done[64] = {false};
+  if (int st = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done, "gemm"); st != UG_OK) return st;
   CUtensorMap tma_a, tma_w;
   {
     uint64_t dims[3] = {(uint64_t)a.k, (uint64_t)a.rows, (uint64_t)a.batch};

@@ -16,11 +16,15 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 
-int num_sms() {
-  static int cached[64] = {0};
+int current_device_slot() {
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) dev = 0;
+  return (dev < 0 || dev >= 64) ? 0 : dev;
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  const int dev = current_device_slot();
   if (cached[dev] == 0) {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;

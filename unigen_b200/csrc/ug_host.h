@@ -15,6 +15,22 @@ namespace ug {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int num_sms();
+int current_device_slot();  // cudaGetDevice() clamped to [0, 64): index into per-device caches
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: opt in once per device the kernel is
+// launched on, not once per process (a process may drive cuda:1 after cuda:0).
+template <typename Kernel>
+int ensure_dynamic_smem(Kernel kern, int bytes, bool (&done)[64], const char* name) {
+  const int dev = current_device_slot();
+  if (done[dev]) return UG_OK;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(smem=%d) failed: %s", name, bytes, cudaGetErrorString(e));
+    return UG_ERR_CUDA;
+  }
+  done[dev] = true;
+  return UG_OK;
+}
 
 // Encode a (up to 4-D) bf16 tiled tensor map with 128-byte swizzle. dims/box innermost-first; strides in
 // BYTES for dims 1..rank-1. Returns UG_OK or an error status (message set).

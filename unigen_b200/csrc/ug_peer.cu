@@ -13,6 +13,8 @@
 //                         no NCCL, capturable in a CUDA graph (the epoch counter lives in device memory).
 // Pool layout (every rank allocates the same size): bytes [0, UG_PEER_HEADER_BYTES) = control block (flags[src rank] u32 at
 // 0.., epoch u32 at 256, error u32 at 260), payload behind it at offsets the host chooses identically on all ranks.
+#include <cstdlib>
+
 #include "ug_host.h"
 #include "ug_ptx.cuh"
 
@@ -35,28 +37,48 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 // One block; thread r < world signals rank r and waits for rank r's signal of the same epoch. Every peer store of the kernels
 // launched before it on this stream happens-before this kernel (stream order); the system-scope fence + release store make
 // them visible to a peer that acquires the flag, so the producing kernels need no fence of their own. A rank that never arrives
-// (a bug, or a dead peer) must not hang the GPU: after ~2 s of spinning the error word is set and the kernel returns.
-__global__ void peer_barrier_kernel(PeerPtrs t) {
-  __shared__ unsigned int epoch;
+// (a bug, a dead peer, or host-side skew longer than the timeout) must not hang the GPU: after `timeout_ns` of spinning the
+// STICKY error word (ctrl[65]) is set and the kernel returns; once it is set, later barriers still signal their peers but do
+// not wait, so a failure costs one timeout, not one per barrier. The host surfaces the word (ug_peer_error; the sequence-parallel
+// modules raise on it) — results produced after it was set are invalid.
+__global__ void peer_barrier_kernel(PeerPtrs t, unsigned long long timeout_ns) {
+  __shared__ unsigned int epoch, failed;
   unsigned int* ctrl = reinterpret_cast<unsigned int*>(t.base[t.rank]);
   if (threadIdx.x == 0) {
     epoch = ctrl[64] + 1;
     ctrl[64] = epoch;
+    failed = ctrl[65];
   }
   __syncthreads();
   if ((int)threadIdx.x < t.world) {
     __threadfence_system();
     st_release_sys(reinterpret_cast<unsigned int*>(t.base[threadIdx.x]) + t.rank, epoch);
-    const unsigned int* mine = ctrl + threadIdx.x;
-    const long long t0 = clock64();
-    while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
-      if (clock64() - t0 > 4000000000LL) {
-        ctrl[65] = 1u;
-        break;
+    if (!failed) {
+      const unsigned int* mine = ctrl + threadIdx.x;
+      const uint64_t t0 = globaltimer_ns();
+      unsigned int spins = 0;
+      while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
+        if ((++spins & 0xffu) == 0 && globaltimer_ns() - t0 > timeout_ns) {
+          atomicExch(ctrl + 65, 1u + threadIdx.x);  // 1 + the rank that did not arrive
+          break;
+        }
       }
     }
     __threadfence_system();
   }
+}
+
+static unsigned long long g_peer_timeout_ns = 0;  // 0 = not initialised yet
+static unsigned long long peer_timeout_ns() {
+  if (g_peer_timeout_ns == 0) {
+    unsigned long long ms = 20000;  // default 20 s: covers graph instantiation / IO skew between ranks
+    if (const char* env = getenv("UG_PEER_TIMEOUT_MS")) {
+      const long long v = atoll(env);
+      if (v > 0) ms = (unsigned long long)v;
+    }
+    g_peer_timeout_ns = ms * 1000000ull;
+  }
+  return g_peer_timeout_ns;
 }
 
 __device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
@@ -233,8 +255,26 @@ extern "C" int ug_peer_barrier(const ug_peer_table* table, void* stream) {
   PeerPtrs t;
   int st = to_ptrs(table, &t, "peer_barrier");
   if (st != UG_OK) return st;
-  peer_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t);
+  peer_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t, peer_timeout_ns());
   UG_CHECK_LAUNCH("peer_barrier");
+  return UG_OK;
+}
+
+extern "C" int ug_peer_set_timeout_ms(int64_t ms) {
+  UG_CHECK_ARG(ms >= 1, "peer_set_timeout_ms: timeout must be positive");
+  g_peer_timeout_ns = (unsigned long long)ms * 1000000ull;
+  return UG_OK;
+}
+
+// Asynchronous read-out of the sticky error word into (pinned) host memory, stream-ordered and graph-capturable: the
+// sequence-parallel modules enqueue it at the end of every forward and test the host word before the next one.
+extern "C" int ug_peer_error_async(const ug_peer_table* table, int32_t* error_host_pinned, void* stream) {
+  PeerPtrs t;
+  int st = to_ptrs(table, &t, "peer_error_async");
+  if (st != UG_OK) return st;
+  UG_CHECK_ARG(error_host_pinned, "peer_error_async: null pointer");
+  UG_CUDA_CALL(cudaMemcpyAsync(error_host_pinned, t.base[t.rank] + 260, 4, cudaMemcpyDeviceToHost, reinterpret_cast<cudaStream_t>(stream)),
+               "peer_error_async: cudaMemcpyAsync");
   return UG_OK;
 }
 

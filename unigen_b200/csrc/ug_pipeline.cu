@@ -13,6 +13,13 @@ __global__ void __launch_bounds__(256) euler_step_kernel(__nv_bfloat16* __restri
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     x[i] = __float2bfloat16(__bfloat162float(x[i]) + dsigma * __bfloat162float(v[i]));
 }
+// same, sigma / sigma_next read from the device-resident schedule
+__global__ void __launch_bounds__(256) euler_step_table_kernel(__nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ v,
+                                                               const float* __restrict__ sigmas, int step, long long n) {
+  const float dsigma = sigmas[step + 1] - sigmas[step];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = __float2bfloat16(__bfloat162float(x[i]) + dsigma * __bfloat162float(v[i]));
+}
 // out = uncond + g * (text - uncond)
 __global__ void __launch_bounds__(256) cfg_combine_kernel(const __nv_bfloat16* __restrict__ uncond,
                                                           const __nv_bfloat16* __restrict__ text, float g,
@@ -71,6 +78,13 @@ extern "C" int ug_euler_step(void* latents, const void* velocity, float sigma, f
   euler_step_kernel<<<grid1d(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((__nv_bfloat16*)latents, (const __nv_bfloat16*)velocity,
                                                                                 sigma_next - sigma, n);
   UG_CHECK_LAUNCH("euler_step");
+  return UG_OK;
+}
+extern "C" int ug_euler_step_table(void* latents, const void* velocity, const float* sigmas_dev, int32_t step, int64_t n, void* stream) {
+  UG_CHECK_ARG(latents && velocity && sigmas_dev && step >= 0 && n >= 1, "euler_step_table: bad arguments");
+  euler_step_table_kernel<<<grid1d(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((__nv_bfloat16*)latents, (const __nv_bfloat16*)velocity,
+                                                                                      sigmas_dev, step, n);
+  UG_CHECK_LAUNCH("euler_step_table");
   return UG_OK;
 }
 extern "C" int ug_cfg_combine(const void* uncond, const void* text, float guidance_scale, void* out, int64_t n, void* stream) {

@@ -18,6 +18,7 @@ Data layout in HBM (bf16 unless noted)
 """
 from __future__ import annotations
 
+import collections
 import math
 import types
 from typing import Any, Dict, List, Optional, Sequence, Tuple
@@ -121,7 +122,11 @@ class _DenoiserBase(torch.nn.Module):
             raise ops.UgError(f"{type(self).__name__} (B200-native) needs a CUDA device: the hot path has no CPU fallback")
         self._ws = _Weights(self.device_)
         self._control_ready = False
-        self._buf_key = None
+        # one workspace per input shape, kept alive as long as a CUDA graph captured over it may be replayed (a graph holds
+        # raw pointers into X / QKV / AO / ...): least-recently-used shapes are evicted TOGETHER with their graphs
+        self._workspaces: "collections.OrderedDict[Any, Any]" = collections.OrderedDict()
+        self.max_workspaces = 4
+        self._buf = None
         self._graphs: Dict[Any, Any] = {}
         self.use_cuda_graph = False
         self.gemm_variant = 0
@@ -131,6 +136,7 @@ class _DenoiserBase(torch.nn.Module):
         self.overlap_text_stream = True  # text-stream GEMMs of the double blocks on a second stream beside the image stream's
         self._text_stream = torch.cuda.Stream(device=self.device_)
         self.trace: Optional[Dict[str, torch.Tensor]] = None  # set to {} to record per-block intermediates
+        self.clone_outputs = True  # forward returns copies, not views of the workspace / graph-static buffers
 
     @property
     def dtype(self):
@@ -210,12 +216,39 @@ class _DenoiserBase(torch.nn.Module):
         if self.trace is not None:
             self.trace[name] = t.detach().float().clone()
 
+    def _cached_workspace(self, key, make):
+        """Workspace for input shape `key` (built by `make()` on first use). Buffers of a shape stay where they are for as
+        long as the shape is cached, so a graph captured over them stays valid when other shapes run in between; when the
+        least-recently-used shape is evicted, the graphs captured over its buffers are dropped with it."""
+        ws = self._workspaces
+        b = ws.get(key)
+        if b is None:
+            while len(ws) >= max(int(self.max_workspaces), 1):
+                _, old = ws.popitem(last=False)
+                self._drop_graphs(old)
+            b = ws[key] = make()
+        else:
+            ws.move_to_end(key)
+        self._buf = b
+        return b
+
+    def _drop_graphs(self, buf=None):
+        """Forget the CUDA graphs captured over workspace `buf` (all graphs for None)."""
+        if buf is None:
+            self._graphs.clear()
+            return
+        for k in [k for k, g in self._graphs.items() if g[4] is buf]:
+            del self._graphs[k]
+
     def _run_staged(self, key, staged: Dict[str, Optional[torch.Tensor]], *args):
         """`self._forward_impl(*args, **staged)`, eagerly or as a replay of a CUDA graph captured over static copies of
-        the staged inputs (one graph per `key`)."""
+        the staged inputs (one graph per `key`). The graph record keeps the workspace it was captured over."""
         if not self.use_cuda_graph or self.trace is not None:
             return self._forward_impl(*args, **staged)
         g = self._graphs.get(key)
+        if g is not None and not any(g[4] is b for b in self._workspaces.values()):
+            del self._graphs[key]  # its workspace was evicted
+            g = None
         if g is None:
             static = {k: (v.clone() if v is not None else None) for k, v in staged.items()}
             self._forward_impl(*args, **static)  # warm-up: attribute setup, workspace allocation
@@ -223,8 +256,11 @@ class _DenoiserBase(torch.nn.Module):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 out = self._forward_impl(*args, **static)
-            g = self._graphs[key] = (graph, static, out, ops.launch_count_in_last_capture())
-        graph, static, out, n_launch = g
+            g = self._graphs[key] = (graph, static, out, ops.launch_count_in_last_capture(), self._buf)
+        graph, static, out, n_launch, buf = g
+        ws_key = next(k for k, b in self._workspaces.items() if b is buf)
+        self._workspaces.move_to_end(ws_key)
+        self._buf = buf
         for k, v in staged.items():
             if v is not None:
                 static[k].copy_(v)
@@ -329,9 +365,9 @@ class UniGenFlux(_DenoiserBase):
     # workspaces
     # ---------------------------------------------------------------------------------------------------------
     def _workspace(self, B: int, N: int, T: int):
-        key = (B, N, T)
-        if self._buf_key == key:
-            return self._buf
+        return self._cached_workspace((B, N, T), lambda: self._make_workspace(B, N, T))
+
+    def _make_workspace(self, B: int, N: int, T: int):
         D, dev = self.inner_dim, self.device_
         S = T + N
         Smax = T + 2 * N  # shared_expert[1] runs over [txt | img | cond]
@@ -351,12 +387,19 @@ class UniGenFlux(_DenoiserBase):
             rope0=z(2 * N, self.arch.attention_head_dim, dt=torch.float32),
             rope1=z(Smax, self.arch.attention_head_dim, dt=torch.float32),
             NO=z(B, N, D), OUT=z(B, N, self.arch.in_channels), capacity=C)
-        self._buf, self._buf_key = b, key
         return b
 
     # ---------------------------------------------------------------------------------------------------------
     # building blocks (each line = one kernel launch in libunigen_b200.so)
     # ---------------------------------------------------------------------------------------------------------
+    def _rope(self, out: torch.Tensor, *id_tables: torch.Tensor):
+        """FluxPosEmbed over `cat(id_tables)` written table by table into consecutive rows of `out` (no concat copy)."""
+        a, r0 = self.arch, 0
+        for ids in id_tables:
+            ops.rope_table(ids, a.axes_dims_rope, a.theta, out=out[r0:r0 + ids.shape[0]])
+            r0 += ids.shape[0]
+        return out
+
     def _attend(self, buf, S: int, out: torch.Tensor):
         """Joint attention over rows [0, S) of the fused QKV buffer (q/k already normalised + rotated) -> out [B, S, D].
         The sequence-parallel subclass replaces this with the Ulysses exchange (parallel.py)."""
@@ -469,8 +512,8 @@ class UniGenFlux(_DenoiserBase):
         D, E, C = self.inner_dim, self.expert_nums, buf.capacity
         gv = self.gemm_variant
         ops.gemm(cond_tokens, self.control_x_embedder_w[0], out=buf.COND, bias=self.control_x_embedder_w[1], variant=gv)
-        ops.rope_table(torch.cat([cond_ids, img_ids], 0), a.axes_dims_rope, a.theta, out=buf.rope0)
-        ops.rope_table(torch.cat([txt_ids, img_ids, cond_ids], 0), a.axes_dims_rope, a.theta, out=buf.rope1)
+        self._rope(buf.rope0, cond_ids, img_ids)
+        self._rope(buf.rope1, txt_ids, img_ids, cond_ids)
         # --- gate + Random-Token-Selection routing (DeepSpeed top1gating) ---
         g = buf.G.view(B, N, D)
         ops.add(h_img, buf.COND, g)
@@ -551,7 +594,14 @@ class UniGenFlux(_DenoiserBase):
             staged[f"u{c}"] = f32(u_list[c])
         key = (B, N, T, float(conditioning_scale), guidance is not None,
                tuple((k, v.dtype) for k, v in staged.items() if v is not None))
-        return self._run_staged(key, staged, float(conditioning_scale))
+        out, add_losses, add_outputs = self._run_staged(key, staged, float(conditioning_scale))
+        if self.clone_outputs:
+            # the velocity lives in the workspace (and, under graph replay, in the graph's static output): hand out a copy so
+            # that a second forward (cond / uncond passes held together) does not overwrite the first result
+            out = ops.copy(out, torch.empty(out.shape, device=out.device, dtype=out.dtype))
+            add_losses = {k: v.clone() for k, v in add_losses.items()}
+            add_outputs = {k: v.clone() for k, v in add_outputs.items()}
+        return out, add_losses, add_outputs
 
     def _forward_impl(self, conditioning_scale, hs, es, pooled, timestep, guidance, txt_ids, img_ids, **cond):
         a = self.arch
@@ -574,15 +624,15 @@ class UniGenFlux(_DenoiserBase):
         x_txt, x_img = buf.X[:, :T], buf.X[:, T:]
         ops.gemm(hs, self.x_embedder_w[0], out=x_img, bias=self.x_embedder_w[1], variant=gv)
         ops.gemm(es, self.context_embedder_w[0], out=x_txt, bias=self.context_embedder_w[1], variant=gv)
-        t_emb = ops.timestep_embedding(timestep * 1000.0)
-        g_emb = ops.timestep_embedding(guidance * 1000.0) if guidance is not None else None
+        t_emb = ops.timestep_embedding(timestep, scale=1000.0, batch=B)  # `timestep * 1000` (:1220) folded into the kernel
+        g_emb = ops.timestep_embedding(guidance, scale=1000.0, batch=B) if guidance is not None else None
         self._time_text(self.time_text, t_emb, pooled, buf.temb, buf.tmp, g_emb)
         ctrl_pooled = pooled if self.use_pooled_prompt_embeds else torch.zeros_like(pooled)
         self._time_text(self.control_time_text, t_emb, ctrl_pooled, buf.ctemb, buf.tmp, g_emb)      # control_temb
         for c in range(n_cond):  # condition_temb per condition and their sum (what the control blocks are modulated by)
             self._time_text(self.control_condition, t_emb, cond_pooled[c], buf.cdtemb_c[c], buf.tmp, g_emb)
             self._time_text(self.control_condition, t_emb, cond_pooled[c], buf.cdtemb, buf.tmp, g_emb, accumulate=c > 0)
-        ops.rope_table(torch.cat([txt_ids, img_ids], 0), a.axes_dims_rope, a.theta, out=buf.rope)
+        self._rope(buf.rope, txt_ids, img_ids)
         self._rec("temb", buf.temb); self._rec("x_embed", x_img); self._rec("context_embed", x_txt)
 
         # ---- every block's AdaLN vectors, once per step (temb / condition_temb are step constants) ----

@@ -14,7 +14,7 @@ from ._lib import UG_ACT_GELU_TANH, UG_ACT_NONE, AttnArgs, GemmArgs, QkvScatterA
 
 __all__ = ["gemm", "lora_down", "lora_down_wide", "attention", "attention_peer", "qkv_scatter", "peer_bcast_rows", "peer_barrier", "expand_segment_mask", "ln_modulate", "qk_rmsnorm_rope", "rope_table", "gemv",
            "timestep_embedding", "add", "copy", "to_bf16", "to_f32", "moe_route", "moe_gather_modulate",
-           "moe_combine", "ln_modulate_segs", "ln_modulate_slots", "gated_add_slots", "unpatchify", "euler_step", "cfg_combine", "pack_latents", "unpack_latents", "launch_count", "reset_launch_count", "UG_ACT_NONE", "UG_ACT_GELU_TANH", "UgError"]
+           "moe_combine", "ln_modulate_segs", "ln_modulate_slots", "gated_add_slots", "unpatchify", "euler_step", "euler_step_table", "cfg_combine", "pack_latents", "unpack_latents", "launch_count", "reset_launch_count", "UG_ACT_NONE", "UG_ACT_GELU_TANH", "UgError"]
 
 BF16 = torch.bfloat16
 
@@ -408,10 +408,20 @@ def gemv(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: Op
     return out
 
 
-def timestep_embedding(t: torch.Tensor, dim: int = 256) -> torch.Tensor:
-    t = _dev(t, "timestep").to(torch.float32).contiguous()
-    out = torch.empty(t.shape[0], dim, device=t.device, dtype=torch.float32)
-    check(_lib.load().ug_timestep_embedding(t.data_ptr(), t.shape[0], dim, out.data_ptr(), _stream()), "ug_timestep_embedding")
+def timestep_embedding(t: torch.Tensor, dim: int = 256, scale: float = 1.0, batch: Optional[int] = None,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Timesteps(dim)(scale * t). t: fp32 [B]; or a ONE-element device view broadcast to `batch` samples (entry i of a
+    device-resident sigma table: the whole-loop CUDA graph reads the step's timestep from memory)."""
+    t = _dev(t, "timestep").to(torch.float32)
+    if t.dim() != 1 or (t.shape[0] > 1 and t.stride(0) != 1):
+        t = t.reshape(-1).contiguous()
+    B = int(batch) if batch is not None else t.shape[0]
+    if t.shape[0] not in (1, B):
+        raise UgError(f"timestep_embedding: {t.shape[0]} timesteps for a batch of {B}")
+    if out is None:
+        out = torch.empty(B, dim, device=t.device, dtype=torch.float32)
+    check(_lib.load().ug_timestep_embedding(t.data_ptr(), 0 if t.shape[0] == 1 else 1, B, dim, float(scale), out.data_ptr(),
+                                            _stream()), "ug_timestep_embedding")
     return out
 
 
@@ -514,6 +524,18 @@ def euler_step(latents: torch.Tensor, velocity: torch.Tensor, sigma: float, sigm
         raise UgError("euler_step: contiguous tensors of equal size required")
     check(_lib.load().ug_euler_step(latents.data_ptr(), velocity.data_ptr(), float(sigma), float(sigma_next), latents.numel(),
                                     _stream()), "ug_euler_step")
+    return latents
+
+
+def euler_step_table(latents: torch.Tensor, velocity: torch.Tensor, sigmas: torch.Tensor, step: int) -> torch.Tensor:
+    """In place: latents <- latents + (sigmas[step + 1] - sigmas[step]) * velocity with the fp32 schedule read on the device."""
+    _dev(latents, "euler.latents", BF16), _dev(velocity, "euler.velocity", BF16), _dev(sigmas, "euler.sigmas", torch.float32)
+    if not (latents.is_contiguous() and velocity.is_contiguous() and sigmas.is_contiguous()) or latents.numel() != velocity.numel():
+        raise UgError("euler_step_table: contiguous tensors of equal size required")
+    if not 0 <= step < sigmas.numel() - 1:
+        raise UgError(f"euler_step_table: step {step} outside the {sigmas.numel()}-entry schedule")
+    check(_lib.load().ug_euler_step_table(latents.data_ptr(), velocity.data_ptr(), sigmas.data_ptr(), int(step), latents.numel(),
+                                          _stream()), "ug_euler_step_table")
     return latents
 
 

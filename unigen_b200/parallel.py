@@ -100,6 +100,8 @@ class PeerPool:
                 self._opened.append(peer.value)
         self._ptr = ptr.value
         self.local = torch.as_tensor(_CudaBuf(self._ptr, self.nbytes), device=self.device)
+        # pinned host mirror of the sticky barrier-error word, refreshed by `poll_error_async` (stream-ordered, no host sync)
+        self._err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         dist.barrier(group=group)  # nobody stores into a pool before every rank has mapped it
 
     def view(self, offset: int, shape, dtype=torch.bfloat16) -> torch.Tensor:
@@ -112,13 +114,45 @@ class PeerPool:
         ops.peer_barrier(self.table)
 
     def error(self) -> int:
+        """Synchronous read of the sticky barrier-error word (0 = every barrier so far completed)."""
         e = C.c_int32()
         _lib.check(_lib.load().ug_peer_error(C.byref(self.table), C.byref(e)), "ug_peer_error")
         return int(e.value)
 
+    def poll_error_async(self):
+        """Enqueue a copy of the error word into pinned host memory on the current stream (graph-capturable)."""
+        _lib.check(_lib.load().ug_peer_error_async(C.byref(self.table), self._err_host.data_ptr(), ops._stream()), "ug_peer_error_async")
+
+    def raise_on_error(self, sync: bool = False):
+        """Raise if a device-side barrier timed out (a rank never arrived: dead peer, or host skew beyond UG_PEER_TIMEOUT_MS).
+        sync=False tests the pinned mirror last refreshed by `poll_error_async` — call it after the stream was synchronised
+        (e.g. at the start of the next forward); sync=True reads the device word."""
+        e = self.error() if sync else int(self._err_host.item())
+        if e:
+            raise ops.UgError(f"sequence-parallel peer barrier timed out on rank {self.rank} waiting for rank {e - 1}: every result "
+                              "since then is invalid (the ranks must be host-synchronised before the first sequence-parallel "
+                              "forward; raise UG_PEER_TIMEOUT_MS if ranks legitimately skew by more than the timeout)")
+
+    def __del__(self):  # a dropped pool must not leak its cudaMalloc / IPC mappings (no collective here: peers may be gone)
+        try:
+            self._release()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _release(self):
+        lib = _lib.load()
+        for p in getattr(self, "_opened", []):
+            lib.ug_peer_close(C.c_void_p(p))
+        self._opened = []
+        if getattr(self, "_ptr", 0):
+            self.local = None
+            lib.ug_peer_free(C.c_void_p(self._ptr))
+            self._ptr = 0
+
     def close(self):
         lib = _lib.load()
         torch.cuda.synchronize(self.device)
+        err = self.error() if self._ptr else 0
         dist.barrier(group=self.group)
         for p in self._opened:
             lib.ug_peer_close(C.c_void_p(p))
@@ -127,6 +161,8 @@ class PeerPool:
             self.local = None
             lib.ug_peer_free(C.c_void_p(self._ptr))
             self._ptr = 0
+        if err:
+            raise ops.UgError(f"peer pool closed with barrier-error word {err} (rank {err - 1} did not arrive at a barrier)")
 
 
 class UlyssesExchange:
@@ -191,7 +227,21 @@ class SequenceParallelUniGenFlux(UniGenFlux):
     def _run_staged(self, key, staged, *args):
         if self.exchange != "peer":  # NCCL collectives stay out of graph capture: the staged-exchange baseline runs eagerly
             return self._forward_impl(*args, **staged)
+        if self._pool is not None:
+            self._pool.raise_on_error()  # barrier-error word mirrored at the end of the previous forward
         return super()._run_staged(key, staged, *args)
+
+    def check_peer_errors(self):
+        """Synchronise and raise if any device-side barrier of the forwards so far timed out (call once per denoise loop)."""
+        if self._pool is not None:
+            torch.cuda.synchronize(self.device_)
+            self._pool.raise_on_error(sync=True)
+
+    def close(self):
+        if self._pool is not None:
+            self._graphs.clear()
+            pool, self._pool, self._pool_key = self._pool, None, None
+            pool.close()
 
     # ---------------------------------------------------------------------------------------------------------
     # exchange = "nccl": staging copy + all_to_all_single around a local attention call
@@ -288,8 +338,8 @@ class SequenceParallelUniGenFlux(UniGenFlux):
         gv = self.gemm_variant
         B = 1
         ops.gemm(cond_tokens, self.control_x_embedder_w[0], out=buf.COND, bias=self.control_x_embedder_w[1], variant=gv)
-        ops.rope_table(torch.cat([cond_ids, img_ids], 0), a.axes_dims_rope, a.theta, out=buf.rope0)
-        ops.rope_table(torch.cat([txt_ids, img_ids, cond_ids], 0), a.axes_dims_rope, a.theta, out=buf.rope1)
+        self._rope(buf.rope0, cond_ids, img_ids)
+        self._rope(buf.rope1, txt_ids, img_ids, cond_ids)
         ops.add(x_img, buf.COND, buf.G.view(B, N, D))
         route = ops.moe_route(buf.G, self.gate_wg, rts_uniform, C)
         ops.gemv(cond_pooled, self.exp_mod_w[0], self.exp_mod_b[0], out=buf.MODC.view(B, E * D))
@@ -405,15 +455,15 @@ class SequenceParallelUniGenFlux(UniGenFlux):
             ops.gemm(hs[:, i0:i0 + n_img], self.x_embedder_w[0], out=xl_img, bias=self.x_embedder_w[1], variant=gv)
         if t_loc:
             ops.gemm(es[:, row0:row0 + t_loc], self.context_embedder_w[0], out=xl_txt, bias=self.context_embedder_w[1], variant=gv)
-        t_emb = ops.timestep_embedding(timestep * 1000.0)
-        g_emb = ops.timestep_embedding(guidance * 1000.0) if guidance is not None else None
+        t_emb = ops.timestep_embedding(timestep, scale=1000.0, batch=B)  # `timestep * 1000` (:1220) folded into the kernel
+        g_emb = ops.timestep_embedding(guidance, scale=1000.0, batch=B) if guidance is not None else None
         self._time_text(self.time_text, t_emb, pooled, buf.temb, buf.tmp, g_emb)
         ctrl_pooled = pooled if self.use_pooled_prompt_embeds else torch.zeros_like(pooled)
         self._time_text(self.control_time_text, t_emb, ctrl_pooled, buf.ctemb, buf.tmp, g_emb)
         for c in range(n_cond):
             self._time_text(self.control_condition, t_emb, cond_pooled[c], buf.cdtemb_c[c], buf.tmp, g_emb)
             self._time_text(self.control_condition, t_emb, cond_pooled[c], buf.cdtemb, buf.tmp, g_emb, accumulate=c > 0)
-        ops.rope_table(torch.cat([txt_ids, img_ids], 0), a.axes_dims_rope, a.theta, out=buf.rope)
+        self._rope(buf.rope, txt_ids, img_ids)
         rope_loc = buf.rope[row0:row0 + s_loc]
 
         # ---- AdaLN vectors of every block (replicated: step constants). Only what the first block pair and the pre-stage
@@ -514,6 +564,8 @@ class SequenceParallelUniGenFlux(UniGenFlux):
         ops.ln_modulate(XL, sb["NOL"], m_out[1], m_out[0])
         ops.gemm(sb["NOL"], self.proj_out_w[0], out=sb["OUTL"], bias=self.proj_out_w[1], variant=gv)
         self._gather_rows(sb["OUTL"], "OUTF", sb["OUTF"])
+        if self.exchange == "peer":
+            self._pool.poll_error_async()
         self._last_route = route
         ops.note_capture_launches(ops.launch_count() - n0)
         return sb["OUTF"][:, T:], dict(moe_loss=route["l_aux"][0] * 0.1), dict(expert_counts=route["exp_counts"])
@@ -584,13 +636,28 @@ class SequenceParallelUniCombineFlux(UniCombineFlux):
         n_loc = out_loc.shape[1]
         ops.peer_bcast_rows(self._pool.table, out_loc[0], self._off["OUTF"], self.arch.in_channels, self.sp_rank * n_loc)
         self._pool.barrier()
+        self._pool.poll_error_async()
         return self._pool.view(self._off["OUTF"], (1, N, self.arch.in_channels))
+
+    def check_peer_errors(self):
+        """Synchronise and raise if any device-side barrier of the forwards so far timed out (call once per denoise loop)."""
+        if self._pool is not None:
+            torch.cuda.synchronize(self.device_)
+            self._pool.raise_on_error(sync=True)
+
+    def close(self):
+        if self._pool is not None:
+            self._graphs.clear()
+            pool, self._pool, self._pool_key = self._pool, None, None
+            pool.close()
 
     @torch.no_grad()
     def forward(self, hidden_states, condition_latents, condition_ids, condition_types, encoder_hidden_states,
                 pooled_projections, timestep, img_ids, txt_ids, c_t: float = 0.0, **kwargs):
         P, r = self.sp_world, self.sp_rank
         dev = self.device_
+        if self._pool is not None:
+            self._pool.raise_on_error()  # barrier-error word mirrored at the end of the previous forward
 
         def shard(t, dim):
             n = t.shape[dim]
@@ -610,7 +677,7 @@ class SequenceParallelUniCombineFlux(UniCombineFlux):
                                        t["timestep"], t["img_ids"], t["txt_ids"], list(condition_types), c_t, N)
 
         if not self.use_cuda_graph or self.trace is not None:
-            return run(local)
+            return self._own(run(local))
         key = (tuple((k, tuple(v.shape), v.dtype) for k, v in local.items()), tuple(condition_types), float(c_t))
         g = self._graphs.get(key)
         if g is None:
@@ -627,4 +694,9 @@ class SequenceParallelUniCombineFlux(UniCombineFlux):
             static[k].copy_(v)
         graph.replay()
         ops.add_launches(n_launch)
-        return out
+        return self._own(out)
+
+    @staticmethod
+    def _own(out: torch.Tensor) -> torch.Tensor:
+        """The velocity is gathered into the peer pool (freed / rewritten by later forwards): return a copy the caller owns."""
+        return ops.copy(out, torch.empty(out.shape, device=out.device, dtype=out.dtype))

@@ -237,9 +237,9 @@ class UniGenSD3(_DenoiserBase):
 
     # ---------------------------------------------------------------------------------------------------------
     def _workspace(self, B: int, N: int, T: int):
-        key = (B, N, T)
-        if self._buf_key == key:
-            return self._buf
+        return self._cached_workspace((B, N, T), lambda: self._make_workspace(B, N, T))
+
+    def _make_workspace(self, B: int, N: int, T: int):
         a, D, dev = self.arch, self.inner_dim, self.device_
         S, Smax = N + T, 2 * N + T
         E = self.expert_nums
@@ -256,7 +256,6 @@ class UniGenSD3(_DenoiserBase):
             TE=[torch.zeros(B + 1, D, device=dev, dtype=torch.float32) for _ in (0, 1)],  # [temb rows | zero row]
             MOD=z(B, n_mod * D, dt=torch.float32), temb=z(B, D, dt=torch.float32), tmp=z(B, D, dt=torch.float32),
             PAT=z(B, N, kpe), NO=z(B, N, D), OUT=z(B, N, a.patch_size ** 2 * a.out_channels), capacity=C)
-        self._buf, self._buf_key = b, key
         return b
 
     def _patch_embed(self, buf, w: _PatchEmbedW, latents: torch.Tensor, out: torch.Tensor):
@@ -401,7 +400,14 @@ class UniGenSD3(_DenoiserBase):
                       pooled=f32(pooled_projections), cpooled=f32(condition_pooled_projections),
                       timestep=f32(timestep).reshape(-1).expand(B).contiguous(), u=f32(rts_uniform))
         key = (B, Hh, Ww, T, float(conditioning_scale), tuple((k, v.dtype) for k, v in staged.items()))
-        return self._run_staged(key, staged, float(conditioning_scale))
+        out, add_losses, add_outputs = self._run_staged(key, staged, float(conditioning_scale))
+        if self.clone_outputs:  # under graph replay `out` is the graph's static output: hand out a copy (see UniGenFlux.forward)
+            cp = torch.empty(out.shape, device=out.device, dtype=out.dtype)
+            ops.copy(out.view(B, 1, -1), cp.view(B, 1, -1))
+            out = cp
+            add_losses = {k: v.clone() for k, v in add_losses.items()}
+            add_outputs = {k: v.clone() for k, v in add_outputs.items()}
+        return out, add_losses, add_outputs
 
     def _forward_impl(self, conditioning_scale, hs, cs, es, pooled, cpooled, timestep, u):
         a, D = self.arch, self.inner_dim
