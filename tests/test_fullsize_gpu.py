@@ -35,3 +35,26 @@ def test_pvariant_cfg4_full_size_matches_eager_oracle():
     rec = E.main(["--workload", "cfg4p", "--steps", "1"])
     par = rec["full_size_parity"]
     assert par["cosine"] >= 0.999 and par["rel_l2"] < 5e-2, rec
+
+
+def _check_fp32_oracle_parity(rec):
+    tf = rec["teacher_forced"]
+    assert tf["max_rel_l2"] <= 1e-2, tf["worst"]
+    r = rec["routing_given_native_gate_input"]
+    assert r["bit_exact"], r
+    fr = rec["free_running"]
+    assert fr["cosine"] >= 0.999, fr
+
+
+def test_flux_cfg2_per_block_parity_vs_fp32_oracle_on_gpu():
+    """cfg2 (FLUX.1-schnell architecture, 512^2 + 1 condition: 1024 + 1024 + 512 tokens): every block of the weave against the
+    fp32 oracle evaluated on the native block input (rel-L2 <= 1e-2 per block), bit-exact routing given the native gate input,
+    final-velocity cosine >= 0.999 against the free-running fp32 oracle (tests/parity_fullsize.py)."""
+    import parity_fullsize as P
+    _check_fp32_oracle_parity(P.main(["--workload", "cfg2"]))
+
+
+def test_flux_cfg3_per_block_parity_vs_fp32_oracle_on_gpu():
+    """The BASELINE metric config (1024^2 + 1 condition: 4096 + 4096 + 512 tokens), same three checks."""
+    import parity_fullsize as P
+    _check_fp32_oracle_parity(P.main(["--workload", "cfg3"]))

@@ -65,6 +65,19 @@ def test_tiny_forward_matches_oracle_per_block():
     assert agree >= 0.99, agree
     assert abs(losses["moe_loss"].item() - want_losses["moe_loss"].item()) < 2e-3
     assert (outs["expert_counts"].cpu() - want_out["expert_counts"]).abs().sum() <= 4
+    # GIVEN the native bf16 gate input (exported in the trace) the routing is bit-exact: argmax, RTS top-C, slots, counts
+    from oracle import unigen_oracle as O
+    G = model.trace["moe.gate_input"].cpu()
+    assert torch.equal(G, (model.trace["double.0.base_hidden"].cpu() + model.trace["moe.cond_embed"].cpu()).to(torch.bfloat16).float())
+    logits = G.reshape(-1, G.shape[-1]) @ sd["moe.moe_layer.gate.wg.weight"].t()
+    C = O.moe_capacity(logits.shape[0], cfg.expert_nums)
+    _, _, _, counts, (idx_o, slot_o, prob_o) = O.top1gating(logits, C, inp["rts_uniform"])
+    top2 = logits.topk(2, dim=1).values
+    assert (top2[:, 0] - top2[:, 1]).min() > 1e-5, "seed produced a near-tie in the gate logits; pick another seed"
+    assert torch.equal(model.trace["moe.route.expert_idx"].cpu().long(), idx_o)
+    assert torch.equal(model.trace["moe.route.slot"].cpu().long(), slot_o)
+    assert torch.equal(model.trace["moe.route.exp_counts"].cpu(), counts)
+    assert torch.allclose(model.trace["moe.route.prob"].cpu(), prob_o, rtol=1e-5, atol=1e-6)
 
 
 def test_true_zero_linears_equal_bare_base_model():

@@ -34,6 +34,39 @@ def test_gemm_plain(ug, variant, shape):
     assert rel_l2(out, want) < 6e-3
 
 
+# the GEMM shapes of the BASELINE configs (SURVEY.md §7 minimum slice, (M, K, N)): q|k|v-sized, proj_mlp / ff1, proj_out of the
+# single blocks (K = 5D), ff2; the last one has A = 104 MB > 40 MB, which takes the banded tile walk (ug_gemm.cu group_m)
+REAL_SHAPES = [(4608, 3072, 3072), (4608, 3072, 12288), (4608, 15360, 3072), (4096, 12288, 3072), (16896, 3072, 3072)]
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("mkn", REAL_SHAPES)
+def test_gemm_real_shapes(ug, variant, mkn):
+    """fp32 torch matmul (TF32 off) on the same bf16 inputs; bias epilogue; rel-L2 <= 6e-3 (bf16 out, fp32 accumulate)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    M, K, N = mkn
+    a, w, bias = rnd(1, M, K), rnd(N, K, scale=K ** -0.5), rnd(N)
+    out = ug.gemm(a, w, bias=bias, variant=variant)
+    want = a[0].float() @ w.float().t() + bias.float()
+    assert rel_l2(out[0], want) < 6e-3
+    # no row / column was skipped or written twice by the (banded) persistent tile walk: every element is close, not just the norm
+    assert (out[0].float() - want).abs().max() < 0.15
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_gemm_real_shape_fused_epilogue(ug, variant):
+    """The gated-residual epilogue (`h + gate * (x W^T + b)`, in place) at the to_out / ff2 shape of cfg3."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    M, K, N = 4096, 12288, 3072
+    a, w, bias = rnd(1, M, K), rnd(N, K, scale=K ** -0.5), rnd(N)
+    gate = torch.randn(1, N, device="cuda")
+    h = rnd(1, M, N)
+    h0 = h.float().clone()
+    ug.gemm(a, w, out=h, bias=bias, gate=gate, residual=h, variant=variant)
+    want = h0 + gate[:, None] * (a.float() @ w.float().t() + bias.float())
+    assert rel_l2(h, want) < 6e-3
+
+
 @pytest.mark.parametrize("variant", [1, 2, 3])
 def test_gemm_fused_epilogue_strided(ug, variant):
     B, R, N, K = 3, 333, 640, 256

@@ -517,7 +517,13 @@ class UniGenFlux(_DenoiserBase):
         # --- gate + Random-Token-Selection routing (DeepSpeed top1gating) ---
         g = buf.G.view(B, N, D)
         ops.add(h_img, buf.COND, g)
+        tag = "moe" if cond_index == 0 and self.condition_nums == 1 else f"moe.cond{cond_index}"
+        # the gate sees the bf16 sum, exactly what `hidden_states + condition_hidden_states` is in the reference's bf16 run
+        self._rec(tag + ".cond_embed", buf.COND); self._rec(tag + ".gate_input", g)
         route = ops.moe_route(buf.G, self.gate_wg, rts_uniform, C)
+        if self.trace is not None:
+            for k in ("expert_idx", "slot", "prob", "slot_token", "exp_counts"):
+                self.trace[f"{tag}.route.{k}"] = route[k].detach().clone()
         # --- condition-modulated experts: cond' = Wc (s_c . cond) + bc ; hid' = Wh (s_h . (hid + cond')) + bh ---
         ops.gemv(cond_pooled, self.exp_mod_w[0], self.exp_mod_b[0], out=buf.MODC.view(B, E * D))
         ops.gemv(pooled, self.exp_mod_w[1], self.exp_mod_b[1], out=buf.MODH.view(B, E * D))
@@ -534,7 +540,6 @@ class UniGenFlux(_DenoiserBase):
         # --- combine (gate-probability weighted, dropped tokens -> 0) and sum: ctrl_in (+)= (hid + EH) + (cond + EC) ---
         ops.moe_combine(buf.YH, route, C, buf.EH)
         ops.moe_combine(buf.YC, route, C, buf.EC)
-        tag = "moe" if cond_index == 0 and self.condition_nums == 1 else f"moe.cond{cond_index}"
         self._rec(tag + ".expert_hidden", buf.EH.view(B, N, D)); self._rec(tag + ".expert_cond", buf.EC.view(B, N, D))
         self._rec(tag + ".shared_hidden", hc_h); self._rec(tag + ".shared_cond", hc_c)
         if cond_index == 0:
@@ -634,6 +639,9 @@ class UniGenFlux(_DenoiserBase):
             self._time_text(self.control_condition, t_emb, cond_pooled[c], buf.cdtemb, buf.tmp, g_emb, accumulate=c > 0)
         self._rope(buf.rope, txt_ids, img_ids)
         self._rec("temb", buf.temb); self._rec("x_embed", x_img); self._rec("context_embed", x_txt)
+        self._rec("control_temb", buf.ctemb); self._rec("condition_temb", buf.cdtemb)
+        for c in range(n_cond):
+            self._rec(f"condition_temb.{c}", buf.cdtemb_c[c])
 
         # ---- every block's AdaLN vectors, once per step (temb / condition_temb are step constants) ----
         # 13 GB of bf16 weights are streamed by HBM-bound GEMVs: only what the first double block and the pre-stage need
@@ -691,6 +699,7 @@ class UniGenFlux(_DenoiserBase):
             j = int(i / (len(self.double) / n_cd))
             if route is None:  # first control call: CoMoE pre-stage, control stream := sum_c (expert_hidden + expert_cond)
                 ops.gemm(x_txt, self.control_context_embedder_w[0], out=buf.CENC, bias=self.control_context_embedder_w[1], variant=gv)
+                self._rec("moe.control_context", buf.CENC)
                 for c in range(n_cond):
                     route = self._prestage(buf, B, N, T, x_img, cs[c], pooled, cond_pooled[c], rts_uniform[c], mods_s0[c],
                                            mods_s1, c, txt_ids, img_ids, condition_ids[c])
@@ -714,6 +723,7 @@ class UniGenFlux(_DenoiserBase):
                 j = int(i / (len(self.single) / n_cs))
                 self._single_block(buf, self.ctrl_single[j], m_csingle[j], buf.X, buf.CS, buf.rope)
                 wa = self.add_single[j]
+                self._rec(f"single.{i}.ctrl_hidden", buf.CS)
                 if self.single_block_control_method == "overall_add":
                     ops.gemm(buf.CS, wa[0], out=buf.X, bias=wa[1], alpha=float(conditioning_scale), residual=buf.X, variant=gv)
                 else:  # single_add: only the image rows receive the control signal
