@@ -253,3 +253,72 @@ def test_cuda_graph_replay_survives_alternating_shapes():
     for want, x in zip(eager + eager, (a, b, a, b)):
         assert torch.equal(model(**x)[0], want)
     assert len(model._workspaces) == 1 and len(model._graphs) == 1
+
+
+def test_from_pretrained_then_init_condition_block_like_infer_py(tmp_path):
+    """The construction contract of the reference (infer.py:115-141): `cls.from_pretrained(<root>/transformer)` ->
+    `.to(device, dtype)` -> `init_condition_block(condition_nums, condition_types, **cn_config.params)` ->
+    `load_state_dict(control ckpt, strict=False)`; the result equals loading the full state dict directly."""
+    import json
+    from safetensors.torch import save_file
+    from unigen_b200 import checkpoint as ck
+    from unigen_b200.model import UniGenFlux, canonical_control_params
+    cfg, sd, inp, oracle, model = _setup()
+    dev_inp = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()}
+    want = model(**dev_inp)[0].clone()
+    ctrl = tuple(model.trainable_control_modules)
+    root = tmp_path / "FLUX.1-tiny"
+    d = root / "transformer"
+    d.mkdir(parents=True)
+    (d / "config.json").write_text(json.dumps(dict(
+        _class_name="FluxTransformer2DModel", num_layers=cfg.num_layers, num_single_layers=cfg.num_single_layers,
+        attention_head_dim=cfg.attention_head_dim, num_attention_heads=cfg.num_attention_heads, in_channels=cfg.in_channels,
+        joint_attention_dim=cfg.joint_attention_dim, pooled_projection_dim=cfg.pooled_projection_dim, guidance_embeds=False,
+        axes_dims_rope=list(cfg.axes_dims_rope), patch_size=1)))
+    save_file({k: v.contiguous() for k, v in sd.items() if not k.startswith(ctrl)}, str(d / "diffusion_pytorch_model.safetensors"))
+    ck.save_modules(model, str(tmp_path / "ckpt"), list(ctrl))
+    m2 = UniGenFlux.from_pretrained(str(root), subfolder="transformer", torch_dtype=torch.bfloat16).to("cuda", dtype=torch.bfloat16)
+    assert m2.config.num_layers == cfg.num_layers and m2.config.in_channels == 64 and m2.dtype == torch.bfloat16
+    m2.init_condition_block(condition_nums=1, condition_types=["canny"], control_params=canonical_control_params())
+    res = m2.load_state_dict(ck.read_state_dict(str(tmp_path / "ckpt")), strict=False)
+    assert not res.unexpected_keys and all(not k.startswith(ctrl) for k in res.missing_keys)
+    m2.requires_grad_(False)
+    assert torch.equal(m2(**dev_inp)[0], want)
+    with pytest.raises(OSError):
+        UniGenFlux.from_pretrained(str(tmp_path / "nowhere"))
+    with pytest.raises(Exception):
+        m2.to("cpu")
+
+
+def test_use_shared_expert_false_and_use_transformer_params():
+    """control_params branches the shipped YAML does not select (VERDICT r1 missing #6): `use_shared_expert=False` — the control
+    stream is the routed experts' output alone (src/UniGenTransformer.py:1005-1024 skipped) — against the oracle; and
+    `use_transformer_params=True` (:777-803) — control blocks / embedders start as copies of the base model's."""
+    from oracle import unigen_oracle as O
+    from unigen_b200.model import FluxArch, UniGenFlux, canonical_control_params
+    cfg = O.FluxConfig.tiny()
+    cfg.use_shared_expert = False
+    sd = O.init_state_dict(cfg, seed=7)
+    sd = {k: (v if k.endswith("gate.wg.weight") else v.to(torch.bfloat16).float()) for k, v in sd.items() if not k.startswith("shared_expert")}
+    inp = O.make_inputs(cfg, 256, 256, text_len=512)
+    for k in ("hidden_states", "condition_hidden_states", "encoder_hidden_states"):
+        inp[k] = inp[k].to(torch.bfloat16).float()
+    oracle = O.UniGenFluxOracle(cfg, sd)
+    oracle.record = True
+    want = oracle.forward(**inp)[0]
+    params = dict(canonical_control_params(), use_shared_expert=False)
+    model = UniGenFlux(FluxArch.tiny(), device="cuda")
+    model.init_condition_block(condition_nums=1, control_params=params)
+    assert not any(k.startswith("shared_expert") for k in model.state_dict())
+    model.load_state_dict(sd, strict=True)
+    model.trace = {}
+    got = model(**{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()})[0]
+    assert rel_l2(model.trace["moe.ctrl_in"], oracle.trace["moe.ctrl_in"]) < 1e-2
+    assert rel_l2(got, want) < 1e-2
+    m3 = UniGenFlux(FluxArch.tiny(), device="cuda")
+    m3.init_random_(seed=3)
+    m3.init_condition_block(condition_nums=1, control_params=dict(canonical_control_params(), use_transformer_params=True))
+    v = m3.state_dict()
+    assert torch.equal(v["control_joint_trans_blocks.0.attn.to_q.weight"], v["transformer_blocks.0.attn.to_q.weight"])
+    assert torch.equal(v["control_single_trans_blocks.1.proj_mlp.weight"], v["single_transformer_blocks.1.proj_mlp.weight"])
+    assert torch.equal(v["control_condition_embed.text_embedder.linear_2.weight"], v["time_text_embed.text_embedder.linear_2.weight"])

@@ -136,9 +136,13 @@ def _torch_load(path: str, trust_pickle: bool = False):
             "pass trust_pickle=True") from e
 
 
-def _read_safetensors_dir(path: str) -> Dict[str, Tensor]:
+def _read_safetensors_dir(path: str, variant: Optional[str] = None) -> Dict[str, Tensor]:
     from safetensors.torch import load_file
     files = sorted(glob.glob(os.path.join(path, "*.safetensors")), key=_natural)
+    if variant is not None:  # diffusers naming: diffusion_pytorch_model.<variant>.safetensors / ...<variant>-00001-of-0000N...
+        files = [f for f in files if f".{variant}" in os.path.basename(f)]
+        if not files:
+            raise FileNotFoundError(f"no *.{variant}*.safetensors under {path}")
     index = glob.glob(os.path.join(path, "*.safetensors.index.json"))
     if index:  # HF sharded layout: only the shards the index names, each key from the shard it is mapped to
         with open(index[0]) as f:
@@ -152,7 +156,7 @@ def _read_safetensors_dir(path: str) -> Dict[str, Tensor]:
     return out
 
 
-def read_state_dict(path: str, trust_pickle: bool = False) -> Dict[str, Tensor]:
+def read_state_dict(path: str, trust_pickle: bool = False, variant: Optional[str] = None) -> Dict[str, Tensor]:
     """Branch order of infer.py:124-141. `trust_pickle` (default off) allows the full unpickler for files that are not plain
     tensor containers (DeepSpeed ZeRO rank shards always need it)."""
     if os.path.isdir(path) and os.path.exists(os.path.join(path, "latest")):
@@ -175,7 +179,7 @@ def read_state_dict(path: str, trust_pickle: bool = False) -> Dict[str, Tensor]:
             for f in bins:
                 out.update(_torch_load(f, trust_pickle))
             return out
-        return _read_safetensors_dir(path)
+        return _read_safetensors_dir(path, variant)
     raise FileNotFoundError(path)
 
 

@@ -298,6 +298,58 @@ class UniGenFlux(_DenoiserBase):
     # ---------------------------------------------------------------------------------------------------------
     # reference API: construction
     # ---------------------------------------------------------------------------------------------------------
+    _CONFIG_FIELDS = ("num_layers", "num_single_layers", "attention_head_dim", "num_attention_heads", "in_channels",
+                      "joint_attention_dim", "pooled_projection_dim", "guidance_embeds", "axes_dims_rope")
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, subfolder: Optional[str] = None, torch_dtype=None,
+                        device: Any = "cuda", revision: Optional[str] = None, variant: Optional[str] = None,
+                        trust_pickle: bool = False, **kwargs):
+        """`getattr(UniGenTransformer, basemodel).from_pretrained(f"{path}/transformer", revision=, variant=)` (infer.py:115-119,
+        diffusers ModelMixin.from_pretrained): reads `config.json` (FluxTransformer2DModel fields) and the base weights
+        (`diffusion_pytorch_model*.safetensors`, sharded or not) of a LOCAL diffusers transformer folder and returns the model
+        with the base weights resident on `device`. The control branch is added afterwards by `init_condition_block(...)` and
+        loaded with `load_state_dict(..., strict=False)`, exactly like the reference (infer.py:121-141). No hub download:
+        `pretrained_model_name_or_path` must be a directory (this process has no network by design)."""
+        import json
+        import os
+        from . import checkpoint
+        path = os.path.join(pretrained_model_name_or_path, subfolder) if subfolder else pretrained_model_name_or_path
+        cfg_file = os.path.join(path, "config.json")
+        if not os.path.isfile(cfg_file):
+            raise OSError(f"{path} does not contain config.json: from_pretrained needs a local diffusers transformer folder")
+        with open(cfg_file) as f:
+            cfg = json.load(f)
+        if torch_dtype not in (None, BF16):
+            import warnings
+            warnings.warn(f"torch_dtype={torch_dtype}: the B200-native path stores weights and activations in bf16 (fp32 accumulate)")
+        fields = {k: cfg[k] for k in cls._CONFIG_FIELDS if k in cfg}
+        fields.update({k: v for k, v in kwargs.items() if k in cls._CONFIG_FIELDS})
+        model = cls(FluxArch(**fields), device=device)
+        sd = checkpoint.read_state_dict(path, trust_pickle=trust_pickle, variant=variant)
+        own = model._ws.views
+        missing = [k for k in own if k not in sd]
+        if missing:
+            raise RuntimeError(f"{path} lacks {len(missing)} base-model keys, e.g. {missing[:4]}")
+        model.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
+        model.name_or_path = pretrained_model_name_or_path
+        return model
+
+    def to(self, *args, **kwargs):
+        """`transformer.to(accelerator.device, dtype=weight_dtype)` (infer.py:119): the weights already live on the CUDA device
+        the model was built on, in bf16. Another CUDA device / a CPU target is an error (no fallback), a dtype is a no-op."""
+        for a in list(args) + [kwargs.get("device")]:
+            if isinstance(a, (str, torch.device)) and a is not None:
+                d = torch.device(a)
+                if d.type != "cuda" or (d.index is not None and d.index != (self.device_.index or 0)):
+                    raise ops.UgError(f"the B200-native model lives on {self.device_}; moving it to {d} is not supported")
+        return self
+
+    def requires_grad_(self, requires_grad: bool = True):  # infer.py:143 `transformer.requires_grad_(False)`: inference-only path
+        if requires_grad:
+            raise ops.UgError("the B200-native path is forward-only (SURVEY.md §3.2: training is out of scope)")
+        return self
+
     def init_condition_block(self, condition_nums: int = 1, **kwargs):
         """reference src/UniGenTransformer.py:713-715 -> init_control_block(kwargs['control_params'])."""
         self.condition_nums = condition_nums
@@ -317,8 +369,7 @@ class UniGenFlux(_DenoiserBase):
             raise ValueError("Warning: please use rope or modulated")
         if get("use_consis_module", False):
             raise ops.UgError("use_consis_module is not supported by the B200-native path (SURVEY.md §A.1: left off)")
-        if not get("use_shared_expert", False):
-            raise ops.UgError("use_shared_expert=False is not covered by the B200-native path yet")
+        self.use_shared_expert = bool(get("use_shared_expert", False))  # :863 (False: the routed experts alone, :1024 skipped)
         dev = get("single_control_dev", 2)
         self.cn_joint_layers, self.cn_single_joint_layers = a.num_layers // dev, a.num_single_layers // dev
         self.single_block_control_method = get("single_block_control_method", "overall_add")
@@ -354,12 +405,35 @@ class UniGenFlux(_DenoiserBase):
                 ws.views[p + ".0.weight"], ws.views[p + ".0.bias"] = self.exp_w[br][e], self.exp_b[br][e]
                 ws.views[p + ".1.weight"] = self.exp_mod_w[br][e * D:(e + 1) * D]
                 ws.views[p + ".1.bias"] = self.exp_mod_b[br][e * D:(e + 1) * D]
-        self.shared = [_DoubleBlockW(ws, f"shared_expert.{s}", D, dh) for s in (0, 1)]
+        self.shared = [_DoubleBlockW(ws, f"shared_expert.{s}", D, dh) for s in (0, 1)] if self.use_shared_expert else []
         self.trainable_control_modules = {k: None for k in (
             "control_pos_embed_input", "control_time_text_embed", "control_condition_embed", "control_context_embedder",
             "control_x_embedder", "control_joint_trans_blocks", "controlnet_add_joint_blocks", "control_single_trans_blocks",
-            "controlnet_add_single_blocks", "moe", "shared_expert")}
+            "controlnet_add_single_blocks", "moe") + (("shared_expert",) if self.use_shared_expert else ())}
         self._control_ready = True
+        if get("use_transformer_params", False):
+            self.init_control_param()
+
+    @torch.no_grad()
+    def init_control_param(self):
+        """reference :790-803: the control branch starts from the base model's weights — both control time-text embedders copy
+        `time_text_embed`, control block j copies base block j (`load_state_dict(..., strict=False)` over the ModuleLists: the
+        first cn_*_layers blocks match by index). `control_x_embedder` loads its OWN state dict there (a no-op, kept)."""
+        v = self._ws.views
+
+        def copy_prefix(dst: str, src: str):
+            for k in [k for k in v if k.startswith(src + ".")]:
+                kd = dst + k[len(src):]
+                if kd in v and v[kd].shape == v[k].shape:
+                    v[kd].copy_(v[k])
+
+        copy_prefix("control_time_text_embed", "time_text_embed")
+        copy_prefix("control_condition_embed", "time_text_embed")
+        for j in range(self.cn_joint_layers):
+            copy_prefix(f"control_joint_trans_blocks.{j}", f"transformer_blocks.{j}")
+        for j in range(len(self.ctrl_single)):
+            copy_prefix(f"control_single_trans_blocks.{j}", f"single_transformer_blocks.{j}")
+        self._weights_loaded()
 
     # ---------------------------------------------------------------------------------------------------------
     # workspaces
@@ -535,12 +609,20 @@ class UniGenFlux(_DenoiserBase):
         ops.gemm(buf.A.view(E, C, D), self.exp_w[1], out=buf.YH.view(E, C, D), bias=self.exp_b[1], variant=gv)
         # --- shared experts (V2, :1013-1022) ---
         hc_h, hc_c = buf.HC[:, :N], buf.HC[:, N:]
-        self._double_block(buf, self.shared[0], mods_s0[0], mods_s0[1], h_img, buf.COND, hc_h, hc_c, buf.rope0)
-        self._double_block(buf, self.shared[1], mods_s1[0], mods_s1[1], buf.HC, buf.CENC, buf.HC, None, buf.rope1)
+        if self.use_shared_expert:
+            self._double_block(buf, self.shared[0], mods_s0[0], mods_s0[1], h_img, buf.COND, hc_h, hc_c, buf.rope0)
+            self._double_block(buf, self.shared[1], mods_s1[0], mods_s1[1], buf.HC, buf.CENC, buf.HC, None, buf.rope1)
         # --- combine (gate-probability weighted, dropped tokens -> 0) and sum: ctrl_in (+)= (hid + EH) + (cond + EC) ---
         ops.moe_combine(buf.YH, route, C, buf.EH)
         ops.moe_combine(buf.YC, route, C, buf.EC)
         self._rec(tag + ".expert_hidden", buf.EH.view(B, N, D)); self._rec(tag + ".expert_cond", buf.EC.view(B, N, D))
+        if not self.use_shared_expert:  # use_shared_expert=False (:1005): the control stream is the routed experts' output alone
+            if cond_index == 0:
+                ops.add(buf.EH.view(B, N, D), buf.EC.view(B, N, D), buf.CIN)
+            else:
+                ops.add(buf.CIN, buf.EH.view(B, N, D), buf.CIN)
+                ops.add(buf.CIN, buf.EC.view(B, N, D), buf.CIN)
+            return route
         self._rec(tag + ".shared_hidden", hc_h); self._rec(tag + ".shared_cond", hc_c)
         if cond_index == 0:
             ops.add(hc_h, buf.EH.view(B, N, D), buf.CIN)

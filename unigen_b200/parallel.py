@@ -658,6 +658,7 @@ class SequenceParallelUniCombineFlux(UniCombineFlux):
         dev = self.device_
         if self._pool is not None:
             self._pool.raise_on_error()  # barrier-error word mirrored at the end of the previous forward
+        self._sync_lora()  # outside any graph capture / replay: hook changes rewrite the operand stacks in place
 
         def shard(t, dim):
             n = t.shape[dim]

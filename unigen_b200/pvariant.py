@@ -22,6 +22,7 @@ from typing import Any, Dict, List, Optional, Sequence
 import torch
 
 from . import ops
+from .lora_switching_module import LoraLayer
 from .model import BF16, FluxArch, _DoubleBlockW, _SingleBlockW, _TimeTextW, _Weights
 from .ops import UG_ACT_GELU_TANH
 
@@ -38,6 +39,7 @@ class _LoraPair:
         self.a = torch.zeros(groups, n_sub * rank, k, device=device, dtype=BF16)
         self.b = torch.zeros(groups, n_sub * n_each, rank, device=device, dtype=BF16)
         self.bw: Optional[torch.Tensor] = None
+        self.aw: Optional[torch.Tensor] = None
 
     def build_wide(self):
         """W2 operand of the K-extension form: [n_sub * n_each, groups * 64], block g = B_g with sub-linear j's columns at
@@ -45,14 +47,15 @@ class _LoraPair:
         G, n_tot, r = self.b.shape
         if self.n_sub * r > LORA_BLOCK:
             raise ops.UgError(f"stacked LoRA rank {self.n_sub * r} exceeds the {LORA_BLOCK}-column K-extension block")
-        bw = torch.zeros(n_tot, G * LORA_BLOCK, device=self.b.device, dtype=BF16)
+        # (re)built IN PLACE after the first call so that captured CUDA graphs keep valid operand pointers
+        bw = self.bw.zero_() if self.bw is not None else torch.zeros(n_tot, G * LORA_BLOCK, device=self.b.device, dtype=BF16)
         for g in range(G):
             for j in range(self.n_sub):
                 rows = slice(j * self.n_each, (j + 1) * self.n_each)
                 bw[rows, g * LORA_BLOCK + j * r:g * LORA_BLOCK + (j + 1) * r] = self.b[g, rows]
         self.bw = bw
         # stacked down-projection for the tensor-core form: [groups * 64, K], group g's lora_A rows at the top of block g
-        aw = torch.zeros(G * LORA_BLOCK, self.a.shape[2], device=self.a.device, dtype=BF16)
+        aw = self.aw.zero_() if self.aw is not None else torch.zeros(G * LORA_BLOCK, self.a.shape[2], device=self.a.device, dtype=BF16)
         for g in range(G):
             aw[g * LORA_BLOCK:g * LORA_BLOCK + self.a.shape[1]] = self.a[g]
         self.aw = aw
@@ -106,67 +109,120 @@ class UniCombineFlux(torch.nn.Module):
 
     # ---------------------------------------------------------------------------------------------------------
     def load_state_dict(self, state_dict, adapters: Sequence[str] = (), condition_types: Sequence[str] = (),
-                        scaling: Optional[Dict[str, float]] = None, strict: bool = False):
+                        scaling: Optional[Dict[str, float]] = None, strict: bool = False,
+                        lora_alpha: Optional[Dict[str, float]] = None):
         """Base weights under diffusers names + PEFT LoRA weights `<linear>.lora_A/B.<adapter>.weight`. `condition_types`
         fixes which adapter belongs to which condition slot (group 1+i); every other adapter is a denoising adapter and is
-        stacked into group 0 — exactly the partition `enable_lora` makes at every call site of the predecessor."""
+        stacked into group 0 — exactly the partition `enable_lora` makes at every call site of the predecessor.
+        Every LoRA-wrapped linear gets a `LoraLayer` carrier (`self.lora_layers[name]`: `.active_adapters`, `.scaling`,
+        `.set_scale`) for the reference's hooks (unigen_b200.lora_switching_module.enable_lora); `lora_alpha[a]` (default r,
+        the UniCombine convention) gives the initial `scaling = lora_alpha / r`, `scaling=` overrides it directly."""
         a, D = self.arch, self.inner_dim
+        dev = self.device_
         with torch.no_grad():
             for k, v in state_dict.items():
                 if k in self._ws.views:
-                    self._ws.views[k].copy_(v.to(self.device_, self._ws.views[k].dtype))
+                    self._ws.views[k].copy_(v.to(dev, self._ws.views[k].dtype))
         self.condition_types = list(condition_types)
+        adapters = list(adapters)
         den = [x for x in adapters if x not in condition_types]
-        scaling = scaling or {x: 1.0 for x in adapters}
         R = max(self.rank * max(len(den), 1), self.rank)
         if R not in (4, 8, 12, 16):
             raise ops.UgError(f"stacked LoRA rank {R} not supported by the fused epilogue (4, 8, 12, 16)")
-        group_sets = [den] + [[t] for t in condition_types]
-        if len(group_sets) > self.groups:
+        self._group_sets = [den] + [[t] for t in condition_types]
+        if len(self._group_sets) > self.groups:
             raise ops.UgError("more conditions than max_conditions")
+        # raw low-rank weights per linear and adapter stay on the device: the scale tables are rebuilt from them whenever a
+        # hook (enable_lora / set_scale / set_adapter) changes a carrier
+        self._lora_raw: Dict[str, Dict[str, tuple]] = {}
+        self.lora_layers: Dict[str, LoraLayer] = {}
+        self._pair_of: Dict[str, str] = {}     # linear name -> key of the (fused) operand pair it belongs to
+        self._pair_names: Dict[str, List[str]] = {}
+        self._dirty = set()
 
-        def fill(pair: _LoraPair, names: Sequence[str]):
-            for s_i, name in enumerate(names):
-                for g, aset in enumerate(group_sets):
-                    off = 0
-                    for ad in aset:
-                        ka, kb = f"{name}.lora_A.{ad}.weight", f"{name}.lora_B.{ad}.weight"
-                        if ka not in state_dict:
-                            continue
-                        A, Bm = state_dict[ka].float(), state_dict[kb].float() * scaling[ad]
-                        r = A.shape[0]
-                        pair.a[g, s_i * pair.rank + off:s_i * pair.rank + off + r] = A.to(self.device_, BF16)
-                        pair.b[g, s_i * pair.n_each:(s_i + 1) * pair.n_each, off:off + r] = Bm.to(self.device_, BF16)
-                        off += r
+        def register(names: Sequence[str], key: str):
+            self._pair_names[key] = list(names)
+            for name in names:
+                raw, ranks = {}, {}
+                for ad in adapters:
+                    ka, kb = f"{name}.lora_A.{ad}.weight", f"{name}.lora_B.{ad}.weight"
+                    if ka in state_dict:
+                        raw[ad] = (state_dict[ka].to(dev, BF16), state_dict[kb].to(dev, BF16))
+                        ranks[ad] = raw[ad][0].shape[0]
+                self._lora_raw[name] = raw
+                alpha = {ad: float((lora_alpha or {}).get(ad, ranks[ad])) for ad in raw}
+                layer = LoraLayer(name, list(raw), ranks, alpha, on_change=self._lora_changed)
+                if scaling is not None:
+                    for ad in raw:
+                        layer.scaling[ad] = float(scaling.get(ad, layer.scaling[ad]))
+                self.lora_layers[name] = layer
+                self._pair_of[name] = key
 
-        def mk(names, k, n_each):
-            p = _LoraPair(self.device_, self.groups, R, k, n_each, len(names))
-            fill(p, names)
+        def mk(key, names, k, n_each):
+            register(names, key)
+            p = _LoraPair(dev, self.groups, R, k, n_each, len(names))
+            self._fill(p, names)
             p.build_wide()
             return p
 
-        def mk_vec(name, k, n):  # AdaLN linears run as GEMVs: rank padded to a multiple of 8 (GEMV inner-dim granularity)
+        def mk_vec(key, name, k, n):  # AdaLN linears run as GEMVs: rank padded to a multiple of 8 (GEMV inner-dim granularity)
+            register([name], key)
             Rp = (R + 7) // 8 * 8
-            p = _LoraPair(self.device_, self.groups, Rp, k, n, 1)
-            fill(p, [name])
+            p = _LoraPair(dev, self.groups, Rp, k, n, 1)
+            self._fill(p, [name])
             return p
 
         L = self.lora = {}
-        L["x_embedder"] = mk(["x_embedder"], a.in_channels, D)
+        L["x_embedder"] = mk("x_embedder", ["x_embedder"], a.in_channels, D)
         for i in range(a.num_layers):
             p = f"transformer_blocks.{i}"
-            L[p + ".norm1"] = mk_vec(p + ".norm1.linear", D, 6 * D)
-            L[p + ".qkv"] = mk([p + ".attn.to_q", p + ".attn.to_k", p + ".attn.to_v"], D, D)
-            L[p + ".to_out"] = mk([p + ".attn.to_out.0"], D, D)
-            L[p + ".ff2"] = mk([p + ".ff.net.2"], 4 * D, D)
+            L[p + ".norm1"] = mk_vec(p + ".norm1", p + ".norm1.linear", D, 6 * D)
+            L[p + ".qkv"] = mk(p + ".qkv", [p + ".attn.to_q", p + ".attn.to_k", p + ".attn.to_v"], D, D)
+            L[p + ".to_out"] = mk(p + ".to_out", [p + ".attn.to_out.0"], D, D)
+            L[p + ".ff2"] = mk(p + ".ff2", [p + ".ff.net.2"], 4 * D, D)
         for i in range(a.num_single_layers):
             p = f"single_transformer_blocks.{i}"
-            L[p + ".norm"] = mk_vec(p + ".norm.linear", D, 3 * D)
-            L[p + ".qkv"] = mk([p + ".attn.to_q", p + ".attn.to_k", p + ".attn.to_v"], D, D)
-            L[p + ".mlp"] = mk([p + ".proj_mlp"], D, 4 * D)
-            L[p + ".out"] = mk([p + ".proj_out"], 5 * D, D)
+            L[p + ".norm"] = mk_vec(p + ".norm", p + ".norm.linear", D, 3 * D)
+            L[p + ".qkv"] = mk(p + ".qkv", [p + ".attn.to_q", p + ".attn.to_k", p + ".attn.to_v"], D, D)
+            L[p + ".mlp"] = mk(p + ".mlp", [p + ".proj_mlp"], D, 4 * D)
+            L[p + ".out"] = mk(p + ".out", [p + ".proj_out"], 5 * D, D)
         self.R = R
+        self._dirty.clear()
         return types.SimpleNamespace(missing_keys=[], unexpected_keys=[])
+
+    def _fill(self, pair: _LoraPair, names: Sequence[str]):
+        """(Re)write a pair's stacked operands IN PLACE from the raw adapter weights and the carriers' current scales:
+        group g's B block = B_a * effective_scale(a) for the adapters a of that group (0 for an inactive / disabled adapter)."""
+        pair.a.zero_()
+        pair.b.zero_()
+        for s_i, name in enumerate(names):
+            layer, raw = self.lora_layers[name], self._lora_raw[name]
+            for g, aset in enumerate(self._group_sets):
+                off = 0
+                for ad in aset:
+                    if ad not in raw:
+                        continue
+                    A, Bm = raw[ad]
+                    r = A.shape[0]
+                    pair.a[g, s_i * pair.rank + off:s_i * pair.rank + off + r] = A
+                    pair.b[g, s_i * pair.n_each:(s_i + 1) * pair.n_each, off:off + r] = (Bm.float() * layer.effective_scale(ad)).to(BF16)
+                    off += r
+
+    def _lora_changed(self, name: str):
+        self._dirty.add(self._pair_of[name])
+
+    def _sync_lora(self):
+        """Apply pending hook changes (enable_lora / set_scale / set_adapter on a carrier) to the operand stacks."""
+        for key in sorted(self._dirty):
+            pair = self.lora[key]
+            self._fill(pair, self._pair_names[key])
+            if pair.bw is not None:
+                pair.build_wide()
+        self._dirty.clear()
+
+    def lora_modules(self) -> List[LoraLayer]:
+        """The LoRA carriers of every switched linear, in registration order — what the reference passes to `enable_lora`."""
+        return list(self.lora_layers.values())
 
     # ---------------------------------------------------------------------------------------------------------
     def _workspace(self, B, S):
@@ -256,6 +312,7 @@ class UniCombineFlux(torch.nn.Module):
         dev = self.device_
         if list(condition_types) != self.condition_types[:len(condition_types)]:
             raise ops.UgError(f"condition_types {list(condition_types)} do not match the loaded adapters {self.condition_types}")
+        self._sync_lora()  # scale tables follow the LoRA hooks (lora_switching_module.enable_lora / LoraLayer.set_scale)
         n = len(condition_latents)
         B, N, _ = hidden_states.shape
         T = encoder_hidden_states.shape[1]
