@@ -242,6 +242,32 @@ int ug_gemv(const float* x, int64_t x_stride, const void* w, const void* bias, f
             int32_t batch, int32_t n, int32_t k, int32_t silu_in, int32_t silu_out, int32_t accumulate,
             void* stream);
 
+/* Grouped small-M linear: every job j is an independent ug_gemv  out_j[b, :] = W_j @ f(x_j[b, :]) + bias_j  and ONE launch
+ * streams all of them — the AdaLN `linear(silu(temb))` of every block of a denoise step (temb / condition_temb are step
+ * constants, SURVEY.md §7 step 4: "compute ALL blocks' shift / scale / gate vectors in one batched pass at step start").
+ * The job table lives in DEVICE memory (built once per workspace; nothing is copied at launch, so the call is graph-capturable).
+ * Work unit = a group of 4 consecutive output rows; job j owns groups [first_group_j, first_group_j + ceil(n_j / 4)) of the
+ * launch-wide list (first_group ascending, total_groups = their sum). [group_begin, group_end) selects the part THIS call
+ * computes: the whole list on one GPU, rank r's 1/world share under sequence parallelism — there `peers` is the pool table and
+ * every job's `out` is a BYTE OFFSET into the pools: each result is stored into every rank's pool, which all-gathers the table
+ * (follow with ug_peer_barrier). n_j, k_j multiples of 8; x rows 16-byte aligned; batch <= 8. */
+#define UG_MAX_GEMV_JOBS 256
+struct ug_peer_table;
+typedef struct ug_gemv_job {
+  const void* w;      /* bf16 [n, k], contiguous */
+  const void* bias;   /* bf16 [n] or NULL */
+  const float* x;     /* fp32 [batch, k] */
+  float* out;         /* fp32 [batch, n]; with a peer table: byte offset into every rank's pool, cast to a pointer */
+  int64_t x_stride, out_stride; /* elements */
+  int32_t n, k;
+  int32_t first_group;
+  int32_t flags;      /* bit 0: f = SiLU */
+} ug_gemv_job;
+int ug_gemv_grouped(const ug_gemv_job* jobs_dev, int32_t n_jobs, int32_t total_groups, int32_t batch, int32_t group_begin,
+                    int32_t group_end, const struct ug_peer_table* peers_or_null, void* stream);
+/* out = x * sigmoid(x), fp32, n elements — `silu(temb)` once per step instead of once per AdaLN linear. */
+int ug_silu_f32(const float* x, float* out, int64_t n, void* stream);
+
 /* Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0): out[b] = [cos(s*f) | sin(s*f)], s = scale * t[b * t_stride]
  * (SURVEY.md §A.4). `scale` folds the `timestep * 1000` / `guidance * 1000` of UniGenFlux.forward
  * (src/UniGenTransformer.py:1217-1220) into the kernel; t_stride = 0 broadcasts one device-resident value (entry i of the

@@ -364,3 +364,53 @@ def test_ulysses_peer_exchange_emulated_ranks(ug, P, segmented):
     torch.cuda.synchronize()
     ctrl = b1[0][:264].view(torch.int32)
     assert ctrl[64].item() == 3 and ctrl[0].item() == 3 and ctrl[65].item() == 0  # epoch, own flag, no watchdog trip
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 8])
+def test_gemv_grouped_one_launch_equals_per_job_gemv(ug, B):
+    """Every AdaLN linear of a step in ONE launch (device-resident job table): same numbers as one ug_gemv per job; sharding the
+    group list over emulated ranks with a "peer pool" output reproduces the unsharded table on every rank."""
+    from unigen_b200 import _lib
+    torch.manual_seed(3)
+    shapes = [(1152, 384), (2304, 384), (768, 768), (6144, 3072), (40, 384), (9216, 3072)]  # (n, k); 40: ragged last group
+    xs = [torch.randn(B, 384, device="cuda"), torch.randn(B, 768, device="cuda"), torch.randn(B, 3072, device="cuda")]
+    xof = {384: xs[0], 768: xs[1], 3072: xs[2]}
+    total = sum(n for n, _ in shapes)
+    out = torch.zeros(B, total, device="cuda")
+    jobs, want, c0 = [], [], 0
+    for j, (n, k) in enumerate(shapes):
+        w, b = rnd(n, k, scale=k ** -0.5), (rnd(n) if j % 2 == 0 else None)
+        silu_in = j % 3 != 1
+        jobs.append((w, b, xof[k], out[:, c0:c0 + n], silu_in))
+        want.append(ug.gemv(xof[k], w, b, silu_in=silu_in))
+        ref = (torch.nn.functional.silu(xof[k]) if silu_in else xof[k]) @ w.float().t() + (b.float() if b is not None else 0)
+        assert rel_l2(want[-1], ref) < 1e-5
+        c0 += n
+    plan = ug.GemvPlan(jobs, "cuda")
+    assert plan.total_groups == sum((n + 3) // 4 for n, _ in shapes)
+    ug.gemv_grouped(plan)
+    assert rel_l2(out, torch.cat(want, 1)) < 1e-5  # fp32 summation order differs slightly from the per-job kernel
+    # emulated sequence-parallel ranks: each computes its share of the groups and stores into EVERY "pool"
+    P = 4
+    nbytes = 4096 + B * total * 4
+    pools = [torch.zeros(nbytes, dtype=torch.uint8, device="cuda") for _ in range(P)]
+    for r in range(P):
+        t = _lib.PeerTable()
+        t.world, t.rank = P, r
+        for i in range(P):
+            t.base[i] = pools[i].data_ptr()
+
+        class Pool:  # what GemvPlan needs of a parallel.PeerPool
+            local, nbytes, table = pools[r], nbytes, t
+
+        view = pools[r][4096:].view(torch.float32).view(B, total)
+        pj, c0 = [], 0
+        for (w, b, x, _, s_), (n, k) in zip(jobs, shapes):
+            pj.append((w, b, x, view[:, c0:c0 + n], s_))
+            c0 += n
+        ug.gemv_grouped(ug.GemvPlan(pj, "cuda", pool=Pool), rank=r, world=P)
+    torch.cuda.synchronize()
+    for r in range(P):
+        assert torch.equal(pools[r][4096:].view(torch.float32).view(B, total), out)
+    y = torch.empty_like(xs[2])
+    assert torch.allclose(ug.silu(xs[2], y), torch.nn.functional.silu(xs[2]), rtol=1e-6, atol=1e-7)

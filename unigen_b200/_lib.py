@@ -54,6 +54,15 @@ class QkvScatterArgs(C.Structure):
                 ("dst_offset", C.c_int64), ("seq_total", C.c_int32), ("dst_row0", C.c_int32)]
 
 
+UG_MAX_GEMV_JOBS = 256
+
+
+class GemvJob(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("bias", C.c_void_p), ("x", C.c_void_p), ("out", C.c_void_p),
+                ("x_stride", C.c_int64), ("out_stride", C.c_int64), ("n", C.c_int32), ("k", C.c_int32),
+                ("first_group", C.c_int32), ("flags", C.c_int32)]
+
+
 class AttnArgs(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p),
@@ -91,6 +100,8 @@ SIGNATURES = {
     "ug_qk_rmsnorm_rope": (C.c_int, [_VP, _I64, _I64, _I32, _I32, _I32, _I32, _VP, _I32, _F32, _VP, _VP]),
     "ug_rope_table": (C.c_int, [_VP, _I32, C.POINTER(C.c_int32), _F32, _VP, _VP]),
     "ug_gemv": (C.c_int, [_VP, _I64, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "ug_gemv_grouped": (C.c_int, [_VP, _I32, _I32, _I32, _I32, _I32, C.POINTER(PeerTable), _VP]),
+    "ug_silu_f32": (C.c_int, [_VP, _VP, _I64, _VP]),
     "ug_timestep_embedding": (C.c_int, [_VP, _I64, _I32, _I32, _F32, _VP, _VP]),
     "ug_add_bf16": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP]),
     "ug_copy_bf16": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP]),

@@ -353,6 +353,130 @@ __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Grouped small-M linear: ONE launch streams the weights of MANY independent linears (every AdaLN `linear(silu(temb))` of a
+// denoise step: 117 matrices, ~10 GB of bf16 at cfg3) at HBM speed. The per-linear launches of gemv_kernel covered 4608
+// warps each (< 1 wave of a B200) and paid a launch + tail per 57-113 MB; here a grid that fills every SM walks the
+// concatenated list of 4-row groups of all jobs, 16 independent 16-byte weight loads in flight per lane (batch 1).
+// With a peer table the output rows are stored into EVERY rank's pool (job.out = byte offset): the sequence-parallel ranks
+// each compute 1/P of the groups and the table is all-gathered by the stores themselves.
+// ---------------------------------------------------------------------------------------------------
+struct GemvPeers {
+  int world;
+  uint8_t* base[UG_MAX_PEERS];
+};
+
+// U consecutive 256-element K chunks of 4 weight rows: all 4 * U 16-byte loads are issued before the first FMA.
+template <int kB, int U>
+__device__ __forceinline__ void gemv_chunks(const __nv_bfloat16* __restrict__ w0, const __nv_bfloat16* __restrict__ w1,
+                                            const __nv_bfloat16* __restrict__ w2, const __nv_bfloat16* __restrict__ w3,
+                                            const float* __restrict__ x, long long x_stride, int kk, int batch, bool silu_in,
+                                            float (&acc)[4][kB]) {
+  uint4 wv[U][4];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    wv[u][0] = *reinterpret_cast<const uint4*>(w0 + kk + 256 * u);
+    wv[u][1] = *reinterpret_cast<const uint4*>(w1 + kk + 256 * u);
+    wv[u][2] = *reinterpret_cast<const uint4*>(w2 + kk + 256 * u);
+    wv[u][3] = *reinterpret_cast<const uint4*>(w3 + kk + 256 * u);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+#pragma unroll
+    for (int b = 0; b < kB; ++b) {
+      if (b < batch) {
+        const float* xp = x + (long long)b * x_stride + kk + 256 * u;
+        const float4 a = *reinterpret_cast<const float4*>(xp), c = *reinterpret_cast<const float4*>(xp + 4);
+        float xv[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        if (silu_in) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xv[j] = xv[j] / (1.f + expf(-xv[j]));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 p0 = unpack_bf16x2(wv[u][i].x), p1 = unpack_bf16x2(wv[u][i].y), p2 = unpack_bf16x2(wv[u][i].z),
+                       p3 = unpack_bf16x2(wv[u][i].w);
+          acc[i][b] += p0.x * xv[0] + p0.y * xv[1] + p1.x * xv[2] + p1.y * xv[3] + p2.x * xv[4] + p2.y * xv[5] + p3.x * xv[6] +
+                       p3.y * xv[7];
+        }
+      }
+    }
+  }
+}
+
+template <int kB, int kUnroll>
+__global__ void __launch_bounds__(256, 2) gemv_grouped_kernel(const ug_gemv_job* __restrict__ jobs, int n_jobs, int g_begin,
+                                                              int g_end, int batch, GemvPeers peers) {
+  constexpr int kRows = 4;
+  __shared__ int first_group[UG_MAX_GEMV_JOBS + 1];
+  for (int i = threadIdx.x; i <= n_jobs; i += blockDim.x)
+    first_group[i] = i < n_jobs ? jobs[i].first_group : 0x7fffffff;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  for (int g = g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); g < g_end; g += warps_total) {
+    int lo = 0, hi = n_jobs - 1;  // last job whose first_group <= g
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (first_group[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    const ug_gemv_job* J = jobs + lo;
+    const int n = J->n, k = J->k;
+    const int n0 = (g - first_group[lo]) * kRows;
+    // a ragged last group re-reads row n - 1 instead of predicating the loads; only rows < n are stored
+    const __nv_bfloat16* wbase = reinterpret_cast<const __nv_bfloat16*>(J->w);
+    const __nv_bfloat16* w0 = wbase + (long long)min(n0, n - 1) * k;
+    const __nv_bfloat16* w1 = wbase + (long long)min(n0 + 1, n - 1) * k;
+    const __nv_bfloat16* w2 = wbase + (long long)min(n0 + 2, n - 1) * k;
+    const __nv_bfloat16* w3 = wbase + (long long)min(n0 + 3, n - 1) * k;
+    const float* x = J->x;
+    const long long x_stride = J->x_stride;
+    const bool silu_in = (J->flags & 1) != 0;
+    float acc[kRows][kB];
+#pragma unroll
+    for (int i = 0; i < kRows; ++i)
+#pragma unroll
+      for (int b = 0; b < kB; ++b) acc[i][b] = 0.f;
+    int kk = lane * 8;
+    for (; kk + 256 * (kUnroll - 1) < k; kk += 256 * kUnroll) gemv_chunks<kB, kUnroll>(w0, w1, w2, w3, x, x_stride, kk, batch, silu_in, acc);
+    for (; kk < k; kk += 256) gemv_chunks<kB, 1>(w0, w1, w2, w3, x, x_stride, kk, batch, silu_in, acc);
+#pragma unroll
+    for (int i = 0; i < kRows; ++i)
+#pragma unroll
+      for (int b = 0; b < kB; ++b) acc[i][b] = warp_sum(acc[i][b]);
+    if (lane == 0) {
+      const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(J->bias);
+      const long long out_stride = J->out_stride;
+#pragma unroll
+      for (int i = 0; i < kRows; ++i) {
+        if (n0 + i >= n) continue;
+        const float bv = bias ? __bfloat162float(bias[n0 + i]) : 0.f;
+#pragma unroll
+        for (int b = 0; b < kB; ++b) {
+          if (b >= batch) continue;
+          const float v = acc[i][b] + bv;
+          const long long off = (long long)b * out_stride + n0 + i;
+          if (peers.world == 0) {
+            J->out[off] = v;
+          } else {
+            const long long byte_off = (long long)reinterpret_cast<uintptr_t>(J->out);
+#pragma unroll
+            for (int r = 0; r < UG_MAX_PEERS; ++r)  // constant indices: the table stays in the parameter bank
+              if (r < peers.world) reinterpret_cast<float*>(peers.base[r] + byte_off)[off] = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) silu_f32_kernel(const float* __restrict__ x, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    out[i] = v / (1.f + expf(-v));
+  }
+}
+
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, long long t_stride, int batch, int dim, float scale,
                                           float* __restrict__ out) {
   const int half = dim / 2;
@@ -570,6 +694,46 @@ extern "C" int ug_gemv(const float* x, int64_t x_stride, const void* w, const vo
     else gemv_kernel<8><<<grid, block, 0, s>>>(x, x_stride, wp, bp, out, out_stride, b0, batch, n, k, silu_in, silu_out, accumulate);
     UG_CHECK_LAUNCH("gemv");
   }
+  return UG_OK;
+}
+
+extern "C" int ug_gemv_grouped(const ug_gemv_job* jobs_dev, int32_t n_jobs, int32_t total_groups, int32_t batch, int32_t group_begin,
+                               int32_t group_end, const ug_peer_table* peers, void* stream) {
+  UG_CHECK_ARG(jobs_dev && n_jobs >= 1 && n_jobs <= UG_MAX_GEMV_JOBS, "gemv_grouped: need 1..%d jobs (got %d)", UG_MAX_GEMV_JOBS, n_jobs);
+  UG_CHECK_ARG(batch >= 1 && batch <= 8, "gemv_grouped: batch %d outside [1, 8]", batch);
+  UG_CHECK_ARG(group_begin >= 0 && group_begin <= group_end && group_end <= total_groups, "gemv_grouped: group range [%d, %d) outside [0, %d)",
+               group_begin, group_end, total_groups);
+  UG_CHECK_ARG((reinterpret_cast<uintptr_t>(jobs_dev) & 7) == 0, "gemv_grouped: job table must be 8-byte aligned");
+  if (group_begin == group_end) return UG_OK;
+  ug::GemvPeers pp;
+  pp.world = 0;
+  for (int i = 0; i < UG_MAX_PEERS; ++i) pp.base[i] = nullptr;
+  if (peers) {
+    UG_CHECK_ARG(peers->world >= 1 && peers->world <= UG_MAX_PEERS, "gemv_grouped: bad peer world %d", peers->world);
+    pp.world = peers->world;
+    for (int i = 0; i < peers->world; ++i) {
+      UG_CHECK_ARG(peers->base[i], "gemv_grouped: null peer base %d", i);
+      pp.base[i] = reinterpret_cast<uint8_t*>(peers->base[i]);
+    }
+  }
+  const int groups = group_end - group_begin;
+  const int warps_per_block = 8;
+  int grid = (groups + warps_per_block - 1) / warps_per_block;
+  const int cap = num_sms() * 2;  // 2 resident blocks of 256 threads per SM (launch bounds of the kernel: up to 128 registers)
+  if (grid > cap) grid = cap;
+  auto s = reinterpret_cast<cudaStream_t>(stream);
+  if (batch == 1) gemv_grouped_kernel<1, 4><<<grid, 256, 0, s>>>(jobs_dev, n_jobs, group_begin, group_end, batch, pp);
+  else if (batch == 2) gemv_grouped_kernel<2, 2><<<grid, 256, 0, s>>>(jobs_dev, n_jobs, group_begin, group_end, batch, pp);
+  else if (batch <= 4) gemv_grouped_kernel<4, 1><<<grid, 256, 0, s>>>(jobs_dev, n_jobs, group_begin, group_end, batch, pp);
+  else gemv_grouped_kernel<8, 1><<<grid, 256, 0, s>>>(jobs_dev, n_jobs, group_begin, group_end, batch, pp);
+  UG_CHECK_LAUNCH("gemv_grouped");
+  return UG_OK;
+}
+
+extern "C" int ug_silu_f32(const float* x, float* out, int64_t n, void* stream) {
+  UG_CHECK_ARG(x && out && n >= 1, "silu_f32: bad arguments");
+  silu_f32_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, n);
+  UG_CHECK_LAUNCH("silu_f32");
   return UG_OK;
 }
 

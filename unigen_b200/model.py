@@ -448,24 +448,84 @@ class UniGenFlux(_DenoiserBase):
         E = self.expert_nums
         C = ops.moe_capacity(B * N, E)
         z = lambda *s, dt=BF16: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
-        n_mod = (6 * 2 * (self.arch.num_layers + self.cn_joint_layers + 1 + self.condition_nums) + 3 * (self.arch.num_single_layers + self.cn_single_joint_layers) + 2)
+        n_mod = (6 * 2 * (self.arch.num_layers + self.cn_joint_layers + 1 + self.condition_nums) + 3 * (self.arch.num_single_layers + len(self.ctrl_single)) + 2)
         b = types.SimpleNamespace(
             X=z(B, S, D), NX=z(B, Smax, D), QKV=z(B, Smax, 3 * D), AO=z(B, Smax, D), FF=z(B, Smax, 4 * D),
             CAT=z(B, S, 5 * D), CH=z(B, N, D), CS=z(B, S, D), CENC=z(B, T, D), COND=z(B, N, D), HC=z(B, 2 * N, D),
             G=z(B * N, D), A=z(E * C, D), YC=z(E * C, D), YH=z(E * C, D), EH=z(B * N, D), EC=z(B * N, D), CIN=z(B, N, D),
-            MOD=z(B, n_mod * D, dt=torch.float32), temb=z(B, D, dt=torch.float32), tmp=z(B, D, dt=torch.float32),
-            ctemb=z(B, D, dt=torch.float32), cdtemb=z(B, D, dt=torch.float32),
-            cdtemb_c=[z(B, D, dt=torch.float32) for _ in range(self.condition_nums)],
+            MOD=z(B, n_mod * D, dt=torch.float32), n_mod=n_mod, tmp=z(B, D, dt=torch.float32),
+            # step-constant conditioning vectors [temb | control_temb | sum_c condition_temb | condition_temb_c ...] and their SiLU
+            TEMBS=z(3 + self.condition_nums, B, D, dt=torch.float32), STEMBS=z(3 + self.condition_nums, B, D, dt=torch.float32),
             MODC=z(B, E, D, dt=torch.float32), MODH=z(B, E, D, dt=torch.float32),
             rope=z(S, self.arch.attention_head_dim, dt=torch.float32),
             rope0=z(2 * N, self.arch.attention_head_dim, dt=torch.float32),
             rope1=z(Smax, self.arch.attention_head_dim, dt=torch.float32),
             NO=z(B, N, D), OUT=z(B, N, self.arch.in_channels), capacity=C)
+        b.temb, b.ctemb, b.cdtemb = b.TEMBS[0], b.TEMBS[1], b.TEMBS[2]
+        b.cdtemb_c = [b.TEMBS[3 + c] for c in range(self.condition_nums)]
+        b.mod_plans = None
         return b
 
     # ---------------------------------------------------------------------------------------------------------
     # building blocks (each line = one kernel launch in libunigen_b200.so)
     # ---------------------------------------------------------------------------------------------------------
+    def _conditioning_vectors(self, buf, B, timestep, guidance, pooled, cond_pooled):
+        """temb / control_temb / condition_temb (per condition and summed, :1048-1049, :1314-1319) into buf.TEMBS, then ONE SiLU pass
+        over all of them (every AdaLN linear consumes silu(temb))."""
+        n_cond = self.condition_nums
+        t_emb = ops.timestep_embedding(timestep, scale=1000.0, batch=B)  # `timestep * 1000` (:1220) folded into the kernel
+        g_emb = ops.timestep_embedding(guidance, scale=1000.0, batch=B) if guidance is not None else None
+        self._time_text(self.time_text, t_emb, pooled, buf.temb, buf.tmp, g_emb)
+        ctrl_pooled = pooled if self.use_pooled_prompt_embeds else torch.zeros_like(pooled)
+        self._time_text(self.control_time_text, t_emb, ctrl_pooled, buf.ctemb, buf.tmp, g_emb)      # control_temb
+        for c in range(n_cond):  # condition_temb per condition and their sum (what the control blocks are modulated by)
+            self._time_text(self.control_condition, t_emb, cond_pooled[c], buf.cdtemb_c[c], buf.tmp, g_emb)
+            self._time_text(self.control_condition, t_emb, cond_pooled[c], buf.cdtemb, buf.tmp, g_emb, accumulate=c > 0)
+        ops.silu(buf.TEMBS, buf.STEMBS)
+
+    def _mod_plans(self, buf, pool=None):
+        """AdaLN job tables of this workspace (ops.GemvPlan: device-resident, built once): `early` = the linears the first
+        block pair and the CoMoE pre-stage need, `late` = all others, `all` = both (sequence parallelism: one sharded launch
+        writing into every rank's peer-mapped MOD). Also the fp32 [B, D] chunk views of MOD every block reads."""
+        key = (buf.MOD.data_ptr(), id(pool))
+        mp = buf.mod_plans
+        if mp is not None and mp.key == key:
+            return mp
+        D, n_cond = self.inner_dim, self.condition_nums
+        s_temb, s_ctemb, s_cdtemb = buf.STEMBS[0], buf.STEMBS[1], buf.STEMBS[2]
+        slot = [0]
+        early, late = [], []
+
+        def job(w, x, n_chunks, dst):
+            s0 = slot[0]
+            slot[0] += n_chunks
+            region = buf.MOD[:, s0 * D:(s0 + n_chunks) * D]
+            dst.append((w[0], w[1], x, region, False))
+            return [region[:, i * D:(i + 1) * D] for i in range(n_chunks)]
+
+        mp = types.SimpleNamespace(key=key)
+        mp.m_double = [(job(w.norm1, s_temb, 6, early if i == 0 else late), job(w.norm1_ctx, s_temb, 6, early if i == 0 else late))
+                       for i, w in enumerate(self.double)]
+        mp.m_cdouble = [(job(w.norm1, s_cdtemb, 6, early if j == 0 else late), job(w.norm1_ctx, s_cdtemb, 6, early if j == 0 else late))
+                        for j, w in enumerate(self.ctrl_double)]
+        mp.m_single = [job(w.norm, s_temb, 3, late) for w in self.single]
+        mp.m_csingle = [job(w.norm, s_cdtemb, 3, late) for w in self.ctrl_single]
+        mp.mods_s0, mp.mods_s1 = [None] * n_cond, None
+        if self.use_shared_expert:  # shared_expert[0] is modulated by THIS condition's temb, shared_expert[1] by control_temb
+            mp.mods_s0 = [(job(self.shared[0].norm1, buf.STEMBS[3 + c], 6, early), job(self.shared[0].norm1_ctx, buf.STEMBS[3 + c], 6, early))
+                          for c in range(n_cond)]
+            mp.mods_s1 = (job(self.shared[1].norm1, s_ctemb, 6, early), job(self.shared[1].norm1_ctx, s_ctemb, 6, early))
+        mp.m_out = job(self.norm_out_w, s_temb, 2, late)  # AdaLayerNormContinuous: (scale, shift)
+        assert slot[0] <= buf.n_mod, (slot[0], buf.n_mod)
+        dev = self.device_
+        if pool is None:
+            mp.early, mp.late, mp.all = ops.GemvPlan(early, dev), ops.GemvPlan(late, dev), None
+        else:
+            mp.early = mp.late = None
+            mp.all = ops.GemvPlan(early + late, dev, pool=pool)
+        buf.mod_plans = mp
+        return mp
+
     def _rope(self, out: torch.Tensor, *id_tables: torch.Tensor):
         """FluxPosEmbed over `cat(id_tables)` written table by table into consecutive rows of `out` (no concat copy)."""
         a, r0 = self.arch, 0
@@ -711,62 +771,26 @@ class UniGenFlux(_DenoiserBase):
         x_txt, x_img = buf.X[:, :T], buf.X[:, T:]
         ops.gemm(hs, self.x_embedder_w[0], out=x_img, bias=self.x_embedder_w[1], variant=gv)
         ops.gemm(es, self.context_embedder_w[0], out=x_txt, bias=self.context_embedder_w[1], variant=gv)
-        t_emb = ops.timestep_embedding(timestep, scale=1000.0, batch=B)  # `timestep * 1000` (:1220) folded into the kernel
-        g_emb = ops.timestep_embedding(guidance, scale=1000.0, batch=B) if guidance is not None else None
-        self._time_text(self.time_text, t_emb, pooled, buf.temb, buf.tmp, g_emb)
-        ctrl_pooled = pooled if self.use_pooled_prompt_embeds else torch.zeros_like(pooled)
-        self._time_text(self.control_time_text, t_emb, ctrl_pooled, buf.ctemb, buf.tmp, g_emb)      # control_temb
-        for c in range(n_cond):  # condition_temb per condition and their sum (what the control blocks are modulated by)
-            self._time_text(self.control_condition, t_emb, cond_pooled[c], buf.cdtemb_c[c], buf.tmp, g_emb)
-            self._time_text(self.control_condition, t_emb, cond_pooled[c], buf.cdtemb, buf.tmp, g_emb, accumulate=c > 0)
+        self._conditioning_vectors(buf, B, timestep, guidance, pooled, cond_pooled)
         self._rope(buf.rope, txt_ids, img_ids)
         self._rec("temb", buf.temb); self._rec("x_embed", x_img); self._rec("context_embed", x_txt)
         self._rec("control_temb", buf.ctemb); self._rec("condition_temb", buf.cdtemb)
         for c in range(n_cond):
             self._rec(f"condition_temb.{c}", buf.cdtemb_c[c])
 
-        # ---- every block's AdaLN vectors, once per step (temb / condition_temb are step constants) ----
-        # 13 GB of bf16 weights are streamed by HBM-bound GEMVs: only what the first double block and the pre-stage need
-        # is computed on the main stream; the rest runs on a side stream UNDER the tensor-core-bound block kernels.
-        nd, ncd, ns, ncs_ = len(self.double), len(self.ctrl_double), len(self.single), len(self.ctrl_single)
-        s_d, s_cd = 0, 12 * nd
-        s_s, s_cs = s_cd + 12 * ncd, s_cd + 12 * ncd + 3 * ns
-        s_sh = s_cs + 3 * ncs_
-        s_out = s_sh + 12 * n_cond + 12
-        m_double, m_cdouble = [None] * nd, [None] * ncd
-        m_single, m_csingle = [None] * ns, [None] * ncs_
-
-        def mod_double(i):
-            w = self.double[i]
-            m_double[i] = (self._mods(buf, s_d + 12 * i, 6, w.norm1, buf.temb), self._mods(buf, s_d + 12 * i + 6, 6, w.norm1_ctx, buf.temb))
-
-        def mod_cdouble(j):
-            w = self.ctrl_double[j]
-            m_cdouble[j] = (self._mods(buf, s_cd + 12 * j, 6, w.norm1, buf.cdtemb),
-                            self._mods(buf, s_cd + 12 * j + 6, 6, w.norm1_ctx, buf.cdtemb))
-
-        mod_double(0)
-        mod_cdouble(0)
-        mods_s0 = []
-        for c in range(n_cond):  # shared_expert[0] is modulated by THIS condition's temb, shared_expert[1] by control_temb
-            mods_s0.append((self._mods(buf, s_sh + 12 * c, 6, self.shared[0].norm1, buf.cdtemb_c[c]),
-                            self._mods(buf, s_sh + 12 * c + 6, 6, self.shared[0].norm1_ctx, buf.cdtemb_c[c])))
-        mods_s1 = (self._mods(buf, s_sh + 12 * n_cond, 6, self.shared[1].norm1, buf.ctemb),
-                   self._mods(buf, s_sh + 12 * n_cond + 6, 6, self.shared[1].norm1_ctx, buf.ctemb))
+        # ---- every block's AdaLN vectors, once per step (temb / condition_temb are step constants): ~10 GB of bf16 weights
+        # streamed by TWO grouped-GEMV launches — what the first block pair and the pre-stage need on the main stream, the rest
+        # on a side stream UNDER the tensor-core-bound block kernels ----
+        mp = self._mod_plans(buf)
+        m_double, m_cdouble, m_single, m_csingle = mp.m_double, mp.m_cdouble, mp.m_single, mp.m_csingle
+        mods_s0, mods_s1, m_out = mp.mods_s0, mp.mods_s1, mp.m_out
+        ops.gemv_grouped(mp.early)
         main_stream = torch.cuda.current_stream()
         side = self._side_stream if self.overlap_mod_gemv else None
         if side is not None:
             side.wait_stream(main_stream)
         with torch.cuda.stream(side if side is not None else main_stream):
-            for i in range(1, nd):
-                mod_double(i)
-            for j in range(1, ncd):
-                mod_cdouble(j)
-            for i, w in enumerate(self.single):
-                m_single[i] = self._mods(buf, s_s + 3 * i, 3, w.norm, buf.temb)
-            for j, w in enumerate(self.ctrl_single):
-                m_csingle[j] = self._mods(buf, s_cs + 3 * j, 3, w.norm, buf.cdtemb)
-            m_out = self._mods(buf, s_out, 2, self.norm_out_w, buf.temb)  # AdaLayerNormContinuous: (scale, shift)
+            ops.gemv_grouped(mp.late)
         mods_joined = side is None
 
         # ---- 19 x [base double -> control double -> add] (:1124-1141) ----

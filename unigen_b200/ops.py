@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import UG_ACT_GELU_TANH, UG_ACT_NONE, AttnArgs, GemmArgs, QkvScatterArgs, UgError, check
 
-__all__ = ["gemm", "lora_down", "lora_down_wide", "attention", "attention_peer", "qkv_scatter", "peer_bcast_rows", "peer_barrier", "expand_segment_mask", "ln_modulate", "qk_rmsnorm_rope", "rope_table", "gemv",
+__all__ = ["gemm", "lora_down", "lora_down_wide", "attention", "attention_peer", "qkv_scatter", "peer_bcast_rows", "peer_barrier", "expand_segment_mask", "ln_modulate", "qk_rmsnorm_rope", "rope_table", "gemv", "GemvPlan", "gemv_grouped", "silu",
            "timestep_embedding", "add", "copy", "to_bf16", "to_f32", "moe_route", "moe_gather_modulate",
            "moe_combine", "ln_modulate_segs", "ln_modulate_slots", "gated_add_slots", "unpatchify", "euler_step", "euler_step_table", "cfg_combine", "pack_latents", "unpack_latents", "launch_count", "reset_launch_count", "UG_ACT_NONE", "UG_ACT_GELU_TANH", "UgError"]
 
@@ -405,6 +405,71 @@ def gemv(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: Op
     check(_lib.load().ug_gemv(x.data_ptr(), x.stride(0), w.data_ptr(), bias.data_ptr() if bias is not None else 0,
                               out.data_ptr(), out.stride(0), B, N, K, int(silu_in), int(silu_out), int(accumulate),
                               _stream()), "ug_gemv")
+    return out
+
+
+class GemvPlan:
+    """Device-resident job table of `gemv_grouped` (ug_gemv_job[]): built once per workspace, launched every step.
+    jobs: sequence of (w bf16 [n, k], bias bf16 [n] | None, x fp32 [B, k], out fp32 [B, n] view, silu_in). With `pool` (a
+    parallel.PeerPool) every `out` must be a view INTO that pool: its byte offset is stored instead of the pointer and the
+    launch writes each result into every rank's pool."""
+
+    def __init__(self, jobs, device, pool=None):
+        if not 1 <= len(jobs) <= _lib.UG_MAX_GEMV_JOBS:
+            raise UgError(f"gemv_grouped: 1..{_lib.UG_MAX_GEMV_JOBS} jobs per plan (got {len(jobs)})")
+        self.more = None
+        B_all = jobs[0][2].shape[0]
+        if B_all > 8:  # the kernel holds <= 8 batch rows in registers per weight pass: further rows are a second plan
+            self.more = GemvPlan([(w, b, x[8:], out[8:], s_) for w, b, x, out, s_ in jobs], device, pool)
+            jobs = [(w, b, x[:8], out[:8], s_) for w, b, x, out, s_ in jobs]
+        arr = (_lib.GemvJob * len(jobs))()
+        self.keep, self.pool, g, self.batch = [], pool, 0, None
+        for j, (w, bias, x, out, silu_in) in enumerate(jobs):
+            _dev(w, "gemv_grouped.w", BF16), _dev(x, "gemv_grouped.x", torch.float32), _dev(out, "gemv_grouped.out", torch.float32)
+            n, k = w.shape
+            B = x.shape[0]
+            self.batch = B if self.batch is None else self.batch
+            if B != self.batch or B > 8:
+                raise UgError("gemv_grouped: every job needs the same batch (<= 8)")
+            if not w.is_contiguous() or x.shape != (B, k) or out.shape != (B, n) or x.stride(1) != 1 or out.stride(1) != 1 or k % 8 or n % 8:
+                raise UgError(f"gemv_grouped: job {j}: w [n,k] contiguous, x [B,k], out [B,n] with unit inner strides, n / k multiples of 8")
+            if x.data_ptr() % 16 or (x.stride(0) * 4) % 16 or w.data_ptr() % 16:
+                raise UgError(f"gemv_grouped: job {j}: x rows / w must be 16-byte aligned")
+            a = arr[j]
+            a.w, a.bias, a.x = w.data_ptr(), (_dev(bias, "gemv_grouped.bias", BF16).data_ptr() if bias is not None else None), x.data_ptr()
+            if pool is not None:
+                off = out.data_ptr() - pool.local.data_ptr()
+                if off < 0 or off + ((B - 1) * out.stride(0) + n) * 4 > pool.nbytes:
+                    raise UgError(f"gemv_grouped: job {j}: with a peer pool every output must be a view into the pool")
+                a.out = off
+            else:
+                a.out = out.data_ptr()
+            a.x_stride, a.out_stride, a.n, a.k, a.first_group, a.flags = x.stride(0), out.stride(0), n, k, g, int(bool(silu_in))
+            g += (n + 3) // 4
+            self.keep.append((w, bias, x, out))
+        self.n_jobs, self.total_groups = len(jobs), g
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self.table = raw.to(device)
+        self.weight_bytes = sum(w.numel() * 2 for w, _, _, _ in self.keep)
+
+
+def gemv_grouped(plan: GemvPlan, rank: int = 0, world: int = 1) -> None:
+    """One launch over `plan`; (rank, world) selects this rank's contiguous share of the 4-row groups (sequence parallelism:
+    the plan was built with the peer pool, results land in every rank's pool — follow with a pool barrier)."""
+    G = plan.total_groups
+    lo, hi = (G * rank) // world, (G * (rank + 1)) // world
+    peers = C.byref(plan.pool.table) if plan.pool is not None else None
+    check(_lib.load().ug_gemv_grouped(plan.table.data_ptr(), plan.n_jobs, G, plan.batch, lo, hi, peers, _stream()), "ug_gemv_grouped")
+    if plan.more is not None:
+        gemv_grouped(plan.more, rank, world)
+
+
+def silu(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out = x * sigmoid(x) (fp32, contiguous, same numel)."""
+    _dev(x, "silu.x", torch.float32), _dev(out, "silu.out", torch.float32)
+    if not (x.is_contiguous() and out.is_contiguous()) or x.numel() != out.numel():
+        raise UgError("silu: contiguous fp32 tensors of equal size required")
+    check(_lib.load().ug_silu_f32(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "ug_silu_f32")
     return out
 
 

@@ -271,7 +271,7 @@ class SequenceParallelUniGenFlux(UniGenFlux):
                 self._graphs.clear()  # captured graphs hold pointers into the old pool
                 self._pool.close()
             sizes = [("RECV", 3 * Smax * (D // P) * 2), ("AO", Smax * D * 2), ("CAT", S * 5 * D * 2), ("X", S * D * 2),
-                     ("OUTF", S * a.in_channels * 2), ("HC", 2 * N * D * 2)]
+                     ("OUTF", S * a.in_channels * 2), ("HC", 2 * N * D * 2), ("MOD", buf.n_mod * D * 4)]
             self._off, total = pool_layout(sizes)
             self._pool = PeerPool(self.sp_group, total, self.device_)
             self._pool_key = key
@@ -280,6 +280,7 @@ class SequenceParallelUniGenFlux(UniGenFlux):
         buf.AO, buf.CAT, buf.X = (pool.view(self._off["AO"], (1, Smax, D)), pool.view(self._off["CAT"], (1, S, 5 * D)),
                                   pool.view(self._off["X"], (1, S, D)))
         buf.HC = pool.view(self._off["HC"], (1, 2 * N, D))
+        buf.MOD = pool.view(self._off["MOD"], (1, buf.n_mod * D), dtype=torch.float32)  # AdaLN table: written by every rank's share
         self._set_sp_rows(S)
 
     def _set_sp_rows(self, S: int):
@@ -455,56 +456,31 @@ class SequenceParallelUniGenFlux(UniGenFlux):
             ops.gemm(hs[:, i0:i0 + n_img], self.x_embedder_w[0], out=xl_img, bias=self.x_embedder_w[1], variant=gv)
         if t_loc:
             ops.gemm(es[:, row0:row0 + t_loc], self.context_embedder_w[0], out=xl_txt, bias=self.context_embedder_w[1], variant=gv)
-        t_emb = ops.timestep_embedding(timestep, scale=1000.0, batch=B)  # `timestep * 1000` (:1220) folded into the kernel
-        g_emb = ops.timestep_embedding(guidance, scale=1000.0, batch=B) if guidance is not None else None
-        self._time_text(self.time_text, t_emb, pooled, buf.temb, buf.tmp, g_emb)
-        ctrl_pooled = pooled if self.use_pooled_prompt_embeds else torch.zeros_like(pooled)
-        self._time_text(self.control_time_text, t_emb, ctrl_pooled, buf.ctemb, buf.tmp, g_emb)
-        for c in range(n_cond):
-            self._time_text(self.control_condition, t_emb, cond_pooled[c], buf.cdtemb_c[c], buf.tmp, g_emb)
-            self._time_text(self.control_condition, t_emb, cond_pooled[c], buf.cdtemb, buf.tmp, g_emb, accumulate=c > 0)
+        self._conditioning_vectors(buf, B, timestep, guidance, pooled, cond_pooled)
         self._rope(buf.rope, txt_ids, img_ids)
         rope_loc = buf.rope[row0:row0 + s_loc]
 
-        # ---- AdaLN vectors of every block (replicated: step constants). Only what the first block pair and the pre-stage
-        # need is computed on the main stream; the other 13 GB of weight streaming runs on a side stream under the blocks ----
-        nd, ncd, ns, ncs_ = len(self.double), len(self.ctrl_double), len(self.single), len(self.ctrl_single)
-        s_cd, s_s = 12 * nd, 12 * nd + 12 * ncd
-        s_cs = s_s + 3 * ns
-        s_sh = s_cs + 3 * ncs_
-        s_out = s_sh + 12 * n_cond + 12
-        m_double, m_cdouble, m_single, m_csingle, mods_s0 = [None] * nd, [None] * ncd, [None] * ns, [None] * ncs_, []
-
-        def mod_double(i):
-            w = self.double[i]
-            m_double[i] = (self._mods(buf, 12 * i, 6, w.norm1, buf.temb), self._mods(buf, 12 * i + 6, 6, w.norm1_ctx, buf.temb))
-
-        def mod_cdouble(j):
-            w = self.ctrl_double[j]
-            m_cdouble[j] = (self._mods(buf, s_cd + 12 * j, 6, w.norm1, buf.cdtemb), self._mods(buf, s_cd + 12 * j + 6, 6, w.norm1_ctx, buf.cdtemb))
-
-        mod_double(0)
-        mod_cdouble(0)
-        for c in range(n_cond):
-            mods_s0.append((self._mods(buf, s_sh + 12 * c, 6, self.shared[0].norm1, buf.cdtemb_c[c]),
-                            self._mods(buf, s_sh + 12 * c + 6, 6, self.shared[0].norm1_ctx, buf.cdtemb_c[c])))
-        mods_s1 = (self._mods(buf, s_sh + 12 * n_cond, 6, self.shared[1].norm1, buf.ctemb),
-                   self._mods(buf, s_sh + 12 * n_cond + 6, 6, self.shared[1].norm1_ctx, buf.ctemb))
+        # ---- AdaLN vectors of every block (step constants). exchange="peer": the ~10 GB weight stream is SHARDED — every rank
+        # runs 1/P of the grouped-GEMV work list and stores its results into every rank's peer-mapped MOD table (the all-gather
+        # is the stores themselves), one barrier; exchange="nccl" (baseline): replicated, as on one GPU ----
         main_stream = torch.cuda.current_stream()
-        side = self._side_stream if self.overlap_mod_gemv else None
-        if side is not None:
-            side.wait_stream(main_stream)
-        with torch.cuda.stream(side if side is not None else main_stream):
-            for i in range(1, nd):
-                mod_double(i)
-            for j in range(1, ncd):
-                mod_cdouble(j)
-            for i, w in enumerate(self.single):
-                m_single[i] = self._mods(buf, s_s + 3 * i, 3, w.norm, buf.temb)
-            for j, w in enumerate(self.ctrl_single):
-                m_csingle[j] = self._mods(buf, s_cs + 3 * j, 3, w.norm, buf.cdtemb)
-            m_out = self._mods(buf, s_out, 2, self.norm_out_w, buf.temb)
-        mods_joined = side is None
+        if self.exchange == "peer":
+            mp = self._mod_plans(buf, pool=self._pool)
+            ops.gemv_grouped(mp.all, rank, P)
+            self._pool.barrier()
+            side, mods_joined = None, True
+        else:
+            mp = self._mod_plans(buf)
+            ops.gemv_grouped(mp.early)
+            side = self._side_stream if self.overlap_mod_gemv else None
+            if side is not None:
+                side.wait_stream(main_stream)
+            with torch.cuda.stream(side if side is not None else main_stream):
+                ops.gemv_grouped(mp.late)
+            mods_joined = side is None
+        m_double, m_cdouble, m_single, m_csingle = mp.m_double, mp.m_cdouble, mp.m_single, mp.m_csingle
+        mods_s0, mods_s1, m_out = mp.mods_s0, mp.mods_s1, mp.m_out
+        nd = len(self.double)
 
         # ---- double blocks on token shards ----
         route = None

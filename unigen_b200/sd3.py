@@ -258,6 +258,34 @@ class UniGenSD3(_DenoiserBase):
             PAT=z(B, N, kpe), NO=z(B, N, D), OUT=z(B, N, a.patch_size ** 2 * a.out_channels), capacity=C)
         return b
 
+    def _sd3_mod_plans(self, buf, B: int):
+        """Job tables (ops.GemvPlan) of every block's AdaLN linear `linear(silu(temb))` for this workspace + the MOD chunk views."""
+        mp = getattr(buf, "mod_plans", None)
+        if mp is not None:
+            return mp
+        D = self.inner_dim
+        control_temb, condition_temb = buf.TE[0][:B], buf.TE[1][:B]
+        slot, early, late = [0], [], []
+
+        def job(w, x, n_chunks, dst):
+            s0 = slot[0]
+            slot[0] += n_chunks
+            region = buf.MOD[:, s0 * D:(s0 + n_chunks) * D]
+            dst.append((w[0], w[1], x, region, True))  # SiLU applied on the fly (three distinct temb vectors)
+            return [region[:, i * D:(i + 1) * D] for i in range(n_chunks)]
+
+        def pair(w, x, dst):
+            return job(w.norm1, x, w.n1, dst), job(w.norm1_ctx, x, w.n1c, dst)
+
+        mp = types.SimpleNamespace()
+        mp.m_base = [pair(w, buf.temb, early if i == 0 else late) for i, w in enumerate(self.blocks)]
+        mp.m_ctrl = [pair(w, condition_temb, early if j == 0 else late) for j, w in enumerate(self.ctrl_blocks)]
+        mp.mods_s0, mp.mods_s1 = pair(self.shared[0], condition_temb, early), pair(self.shared[1], control_temb, early)
+        mp.m_out = job(self.norm_out_w, buf.temb, 2, late)  # AdaLayerNormContinuous: (scale, shift)
+        mp.early, mp.late = ops.GemvPlan(early, self.device_), ops.GemvPlan(late, self.device_)
+        buf.mod_plans = mp
+        return mp
+
     def _patch_embed(self, buf, w: _PatchEmbedW, latents: torch.Tensor, out: torch.Tensor):
         """PatchEmbed.forward: patchify (ug_pack_latents) -> conv-as-GEMM + bias + cropped sincos table (residual operand)."""
         B, C, H, W = latents.shape
@@ -431,31 +459,17 @@ class UniGenSD3(_DenoiserBase):
         self._time_text(self.control_condition, t_emb, cpooled, condition_temb, buf.tmp)
         self._rec("temb", buf.temb); self._rec("x_embed", x_img); self._rec("context_embed", x_txt)
 
-        # ---- AdaLN vectors of every block, once per step; all but the first pair + pre-stage on a side stream ----
-        slot = [0]
-
-        def mods(w: _JointBlockW, temb):
-            s0 = slot[0]
-            slot[0] += w.n1 + w.n1c
-            return lambda: (self._mods(buf, s0, w.n1, w.norm1, temb), self._mods(buf, s0 + w.n1, w.n1c, w.norm1_ctx, temb))
-
-        jobs_base = [mods(w, buf.temb) for w in self.blocks]
-        jobs_ctrl = [mods(w, condition_temb) for w in self.ctrl_blocks]
-        job_s0, job_s1 = mods(self.shared[0], condition_temb), mods(self.shared[1], control_temb)
-        s_out = slot[0]
-        m_base, m_ctrl = [None] * len(self.blocks), [None] * len(self.ctrl_blocks)
-        m_base[0], m_ctrl[0] = jobs_base[0](), jobs_ctrl[0]()
-        mods_s0, mods_s1 = job_s0(), job_s1()
+        # ---- AdaLN vectors of every block, once per step: two grouped-GEMV launches (device-resident job tables) — the first
+        # block pair + pre-stage on the main stream, everything else on a side stream under the tensor-core-bound blocks ----
+        mp = self._sd3_mod_plans(buf, B)
+        m_base, m_ctrl, mods_s0, mods_s1, m_out = mp.m_base, mp.m_ctrl, mp.mods_s0, mp.mods_s1, mp.m_out
+        ops.gemv_grouped(mp.early)
         main_stream = torch.cuda.current_stream()
         side = self._side_stream if self.overlap_mod_gemv else None
         if side is not None:
             side.wait_stream(main_stream)
         with torch.cuda.stream(side if side is not None else main_stream):
-            for i in range(1, len(self.blocks)):
-                m_base[i] = jobs_base[i]()
-            for j in range(1, len(self.ctrl_blocks)):
-                m_ctrl[j] = jobs_ctrl[j]()
-            m_out = self._mods(buf, s_out, 2, self.norm_out_w, buf.temb)  # AdaLayerNormContinuous: (scale, shift)
+            ops.gemv_grouped(mp.late)
         joined = side is None
 
         # ---- 24 x [base MMDiT block -> control block -> zero-linear add] (:583-623) ----
