@@ -873,8 +873,9 @@ class PVariantOracle:
 # ------------------------------------------------------------------------------------------------------------------
 # denoise-loop glue (callers of the path)
 # ------------------------------------------------------------------------------------------------------------------
-def calculate_shift(image_seq_len, base_seq_len=256, max_seq_len=4096, base_shift=0.5, max_shift=1.16):
-    """diffusers pipeline_flux.calculate_shift (src/UniGenPipeline.py:991-997)."""
+def calculate_shift(image_seq_len, base_seq_len=256, max_seq_len=4096, base_shift=0.5, max_shift=1.15):
+    """diffusers pipeline_flux.calculate_shift as called at src/UniGenPipeline.py:991-997: the reference passes
+    `scheduler.config.get("max_shift", 1.15)` (and base 256 / 4096 / 0.5)."""
     m = (max_shift - base_shift) / (max_seq_len - base_seq_len)
     return image_seq_len * m + (base_shift - m * base_seq_len)
 

@@ -53,3 +53,91 @@ def test_four_step_denoise_matches_oracle_loop():
     rel = ((got - want).norm() / want.norm()).item()
     cos = torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0).item()
     assert rel < 1e-2 and cos >= 0.999, (rel, cos)
+
+
+def _tiny_flux(seed=0, guidance=False):
+    from oracle import unigen_oracle as O
+    from unigen_b200.model import FluxArch, UniGenFlux, canonical_control_params
+    cfg = O.FluxConfig.tiny()
+    cfg.guidance_embeds = guidance
+    sd = O.init_state_dict(cfg, seed=seed)
+    sd = {k: (v if k.endswith("gate.wg.weight") else v.to(torch.bfloat16).float()) for k, v in sd.items()}
+    inp = O.make_inputs(cfg, 256, 256, text_len=512)
+    for k in ("hidden_states", "condition_hidden_states", "encoder_hidden_states"):
+        inp[k] = inp[k].to(torch.bfloat16).float()
+    model = UniGenFlux(FluxArch(num_layers=2, num_single_layers=4, attention_head_dim=64, num_attention_heads=6,
+                                axes_dims_rope=(8, 28, 28), guidance_embeds=guidance), device="cuda")
+    model.init_condition_block(condition_nums=1, control_params=canonical_control_params())
+    model.load_state_dict(sd)
+    return cfg, sd, {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()}, model
+
+
+def test_whole_loop_is_one_cuda_graph_and_equals_the_stepwise_loop():
+    """(f)1: the 4-step loop replays as ONE CUDA graph (sigma / timestep / RTS tables on the device, Euler update and the
+    true-CFG combine in-graph) and is bit-identical to the same loop launched kernel by kernel and to a python loop over
+    `transformer(...)` through the public API with the scheduler kernels called step by step."""
+    from unigen_b200 import ops, pipeline as PL
+    cfg, sd, inp, model = _tiny_flux()
+    g = torch.Generator().manual_seed(5)
+    steps = 4
+    rts = [[torch.rand(256, cfg.expert_nums, generator=g).cuda() for _ in range(2)] for _ in range(steps)]
+    neg_es = torch.randn(1, 512, 4096, generator=g).to(torch.bfloat16).cuda()
+    neg_pool = torch.randn(1, 768, generator=g).cuda()
+    args = (inp["hidden_states"], inp["condition_hidden_states"], inp["encoder_hidden_states"], inp["pooled_projections"],
+            inp["condition_pooled_projections"], inp["img_ids"], inp["txt_ids"], inp["condition_ids"])
+    for cfg_kw in (dict(), dict(true_cfg_scale=3.0, negative_encoder_hidden_states=neg_es, negative_pooled_projections=neg_pool)):
+        eager = PL.denoise(model, *args, num_inference_steps=steps, rts_uniform=rts, graph_loop=False, **cfg_kw)
+        n_before = len(PL._loop_graphs(model).graphs)
+        ops.reset_launch_count()
+        graphed = [PL.denoise(model, *args, num_inference_steps=steps, rts_uniform=rts, graph_loop=True, **cfg_kw) for _ in range(2)]
+        assert len(PL._loop_graphs(model).graphs) == n_before + 1          # one graph per (shape, steps, flags) ...
+        assert torch.equal(graphed[0], eager) and torch.equal(graphed[1], eager)  # ... replayed once per image
+        # python reference loop: per-step forward through the public API + the scheduler kernels with HOST sigma values
+        sig = torch.tensor(PL.flow_match_sigmas(steps, 256), dtype=torch.float32)
+        x = inp["hidden_states"].to(torch.bfloat16).clone()
+        for i in range(steps):
+            t = ((sig[i] * 1000.0) / 1000.0).reshape(1).cuda()
+            kw = dict(condition_hidden_states=inp["condition_hidden_states"], pooled_projections=inp["pooled_projections"],
+                      condition_pooled_projections=inp["condition_pooled_projections"], timestep=t, img_ids=inp["img_ids"],
+                      txt_ids=inp["txt_ids"], condition_ids=inp["condition_ids"])
+            v = model(hidden_states=x, encoder_hidden_states=inp["encoder_hidden_states"], rts_uniform=rts[i][0], **kw)[0]
+            if cfg_kw:
+                kw["pooled_projections"] = neg_pool
+                vn = model(hidden_states=x, encoder_hidden_states=neg_es, rts_uniform=rts[i][1], **kw)[0]
+                v = ops.cfg_combine(vn, v, 3.0)
+            ops.euler_step(x, v.contiguous(), sig[i].item(), sig[i + 1].item())
+        assert torch.equal(x, eager)
+
+
+def test_pipeline_call_shaped_entry():
+    """`UniGenFLUXPipeline.__call__`-shaped entry (src/UniGenPipeline.py:810-1134) == denoise() on the same latents; prompts
+    without a text encoder and pixel output without a VAE fail loudly."""
+    from unigen_b200 import pipeline as PL
+    from unigen_b200.condition import Condition
+    from unigen_b200.ops import UgError
+    cfg, sd, inp, model = _tiny_flux(guidance=True)
+    pipe = PL.UniGenFLUXPipeline(model)
+    g = torch.Generator().manual_seed(9)
+    rts = [torch.rand(256, cfg.expert_nums, generator=g).cuda() for _ in range(2)]
+    lat = inp["hidden_states"].to(torch.bfloat16)
+    cond = Condition("canny", inp["condition_hidden_states"].to(torch.bfloat16), height=256, width=256)
+    out = pipe(prompt_embeds=inp["encoder_hidden_states"], pooled_prompt_embeds=inp["pooled_projections"], control_image=cond,
+               condition_pooled_prompt_embeds=inp["condition_pooled_projections"], height=256, width=256, num_inference_steps=2,
+               guidance_scale=3.5, latents=lat, rts_uniform=rts, output_type="latent")
+    want = PL.denoise(model, lat, inp["condition_hidden_states"], inp["encoder_hidden_states"], inp["pooled_projections"],
+                      inp["condition_pooled_projections"], inp["img_ids"], inp["txt_ids"], inp["condition_ids"], num_inference_steps=2,
+                      guidance=torch.full([1], 3.5).cuda(), rts_uniform=rts)
+    assert torch.equal(out.images, want)
+    # fresh latents from a generator: shape (B, N, 64), reproducible
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    a = pipe(prompt_embeds=inp["encoder_hidden_states"], pooled_prompt_embeds=inp["pooled_projections"],
+             control_image=inp["condition_hidden_states"].to(torch.bfloat16), condition_types=["canny"],
+             condition_pooled_prompt_embeds=inp["condition_pooled_projections"], height=256, width=256, num_inference_steps=1,
+             generator=gen, rts_uniform=rts[:1], return_dict=False)[0]
+    assert a.shape == (1, 256, 64) and torch.isfinite(a.float()).all()
+    with pytest.raises(UgError):
+        pipe(prompt="a photo", control_image=cond, condition_pooled_prompt_embeds=inp["condition_pooled_projections"])
+    with pytest.raises(UgError):
+        pipe(prompt_embeds=inp["encoder_hidden_states"], pooled_prompt_embeds=inp["pooled_projections"], control_image=cond,
+             condition_pooled_prompt_embeds=inp["condition_pooled_projections"], height=256, width=256, num_inference_steps=1,
+             latents=lat, output_type="pil")

@@ -166,3 +166,41 @@ def test_rejects_unsupported_configurations():
         m.init_condition_block(condition_nums=1, control_params=dict(shipped_control_params(), use_rope=True))
     with pytest.raises(AssertionError):
         m.init_condition_block(condition_nums=1, control_params=None)
+
+
+def test_sd3_cfg_loop_is_one_cuda_graph_and_equals_the_stepwise_loop():
+    """`UniGenSD3Pipeline.__call__` loop (src/UniGenPipeline.py:377-412): batch-doubled classifier-free guidance with the
+    combine `uncond + g * (text - uncond)` (:405-407) and the Euler update inside ONE CUDA graph == the same loop stepped
+    through the public forward with the scheduler kernels called one by one."""
+    from unigen_b200 import ops, pipeline as PL
+    cfg, sd, inp, oracle, model = _setup()
+    d = _dev(inp)
+    steps, g_scale = 3, 5.0
+    gen = torch.Generator().manual_seed(3)
+    B, Cc, Hh, Ww = d["hidden_states"].shape
+    N = (Hh // 2) * (Ww // 2)
+    rts = [torch.rand(2 * B * N, cfg.expert_nums, generator=gen).cuda() for _ in range(steps)]
+    neg_es = torch.randn(d["encoder_hidden_states"].shape, generator=gen).to(torch.bfloat16).cuda()
+    neg_pool = torch.randn(d["pooled_projections"].shape, generator=gen).cuda()
+    lat = d["hidden_states"].to(torch.bfloat16)
+    kw = dict(num_inference_steps=steps, guidance_scale=g_scale, negative_encoder_hidden_states=neg_es,
+              negative_pooled_projections=neg_pool, rts_uniform=rts)
+    args = (lat, d["condition_hidden_states"], d["encoder_hidden_states"], d["pooled_projections"], d["condition_pooled_projections"])
+    eager = PL.denoise_sd3(model, *args, graph_loop=False, **kw)
+    graphed = [PL.denoise_sd3(model, *args, graph_loop=True, **kw) for _ in range(2)]
+    assert torch.equal(graphed[0], eager) and torch.equal(graphed[1], eager)
+    assert len(PL._loop_graphs(model).graphs) == 1
+    sig = torch.tensor(PL.flow_match_sigmas(steps, N, use_dynamic_shifting=False, shift=3.0), dtype=torch.float32)
+    x = lat.clone()
+    es2 = torch.cat([neg_es, d["encoder_hidden_states"].to(torch.bfloat16)], 0)
+    pool2 = torch.cat([neg_pool, d["pooled_projections"]], 0)
+    cs2 = torch.cat([d["condition_hidden_states"].to(torch.bfloat16)] * 2, 0)
+    cp2 = torch.cat([d["condition_pooled_projections"]] * 2, 0)
+    for i in range(steps):
+        t = (sig[i] * 1000.0).reshape(1).cuda()
+        out = model(hidden_states=torch.cat([x, x], 0), condition_hidden_states=cs2, encoder_hidden_states=es2, pooled_projections=pool2,
+                    condition_pooled_projections=cp2, timestep=t, rts_uniform=rts[i])[0]
+        v = ops.cfg_combine(out[:B], out[B:], g_scale)
+        ops.euler_step(x, v, sig[i].item(), sig[i + 1].item())
+    assert torch.equal(x, eager)
+    assert not torch.equal(eager, lat)

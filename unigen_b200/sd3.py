@@ -451,7 +451,7 @@ class UniGenSD3(_DenoiserBase):
         # ---- embeddings (:663-666) ----
         self._patch_embed(buf, self.pos_embed_w, hs, x_img)
         ops.gemm(es, self.context_embedder_w[0], out=x_txt, bias=self.context_embedder_w[1], variant=gv)
-        t_emb = ops.timestep_embedding(timestep)  # raw timestep: the SD3 forward does not rescale it
+        t_emb = ops.timestep_embedding(timestep, batch=B)  # raw timestep: the SD3 forward does not rescale it (1-element view: broadcast)
         self._time_text(self.time_text, t_emb, pooled, buf.temb, buf.tmp)
         ctrl_pooled = pooled if self.use_pooled_prompt_embeds else torch.zeros_like(pooled)
         control_temb, condition_temb = buf.TE[0][:B], buf.TE[1][:B]  # row B of TE stays 0: the temb of an empty slot
