@@ -63,11 +63,17 @@ def step_flops(D, H, N, T, n_double, n_single, n_cd_calls, n_cs_calls, E, in_ch=
     return g, a
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the committed `ncu --set full`
-# capture (profiles/prof_gemm2cta_r01.ncu-rep, summary profiles/r01_ncu_gemm_2cta_summary.txt)
-NCU_GEMM_TRAFFIC = {"bytes": 104.824064e6 + 84.813312e6,
-                    "note": "gemm_bf16_kernel<2,256,6> M=4608 N=12288 K=3072: algorithmic 28.3 MB (A) + 75.5 MB (W) + 113.2 MB (C) "
-                            "= 217 MB per launch; measured 189.6 MB (A partly served from L2)"}
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, read from the committed `ncu --set full`
+    summary of the CURRENT build (profiles/r02_ncu_traffic.json, written by tools/ncu_summary.py from the .ncu-rep of the same
+    command); None when no capture of this build is committed."""
+    f = ROOT / "profiles" / "r02_ncu_traffic.json"
+    try:
+        rec = json.loads(f.read_text())
+        g = rec["gemm"]
+        return float(g["dram_bytes_read"]) + float(g["dram_bytes_write"]), f"{f.name}: {g.get('note', '')}"
+    except Exception:  # noqa: BLE001
+        return None, "no committed ncu capture of this build"
 
 
 def sample_clocks(stop, out):
@@ -207,7 +213,14 @@ def run_native(args):
     n_cond = 3 if arch_name == "flux3" else 1
     B = args.batch
     N = (height // 16) * (width // 16)
-    model = UniGenFlux(arch, device=dev)
+    sp_leg = world > 1 and not args.no_sp and args.workload == "cfg3" and B == 1
+    if sp_leg:
+        # ONE set of weights serves both measurements: with sp_enabled=False the object is the plain single-GPU UniGenFlux
+        from unigen_b200.parallel import SequenceParallelUniGenFlux
+        model = SequenceParallelUniGenFlux(arch, device=dev, group=None, exchange="peer")
+        model.sp_enabled = False
+    else:
+        model = UniGenFlux(arch, device=dev)
     model.init_condition_block(condition_nums=n_cond, control_params=canonical_control_params())
     model.init_random_(seed=0)
     model.gemm_variant, model.attn_variant = args.gemm_variant, args.attn_variant
@@ -336,18 +349,68 @@ def run_native(args):
             tot[kname] = dict(ms=ms, flops=fl, launches=len(lst), tflops=fl / ms / 1e9 if ms > 0 else 0.0)
         gm = tot["gemm"]
         roof = {"bound": "tensor", "kernel": "ug::gemm_bf16_kernel (tcgen05)", "achieved": gm["tflops"], "peak": peak,
-                "unit": "TFLOP/s", "frac": gm["tflops"] / peak, "traffic": NCU_GEMM_TRAFFIC["bytes"],
-                "traffic_note": NCU_GEMM_TRAFFIC["note"], "peak_source": peak_src,
+                "unit": "TFLOP/s", "frac": gm["tflops"] / peak, "traffic": ncu_traffic()[0],
+                "traffic_note": ncu_traffic()[1], "peak_source": peak_src,
                 "flops_per_step": gm["flops"], "launches_per_step": gm["launches"], "ms_per_step_in_kernel": gm["ms"],
                 "attention": {"achieved": tot["attn"]["tflops"], "frac": tot["attn"]["tflops"] / peak,
                               "launches_per_step": tot["attn"]["launches"], "ms_per_step_in_kernel": tot["attn"]["ms"]}}
         kernel_share = {"gemm": gm["ms"] / ms_step, "attention": tot["attn"]["ms"] / ms_step}
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    model.use_cuda_graph = not args.no_graph
 
+    # ---- whole-loop CUDA graph ((f)1): `--loop K` denoise steps per graph launch through unigen_b200.pipeline.denoise ----
+    loop = None
+    if args.loop > 0:
+        from unigen_b200 import pipeline as PL
+        n_loops = max(1, -(-args.steps // args.loop))
+        largs = (resident["hidden_states"], resident["condition_hidden_states"], resident["encoder_hidden_states"],
+                 resident["pooled_projections"], resident["condition_pooled_projections"], resident["img_ids"], resident["txt_ids"],
+                 resident["condition_ids"])
+        run_loop = lambda: PL.denoise(model, *largs, num_inference_steps=args.loop, graph_loop=not args.no_graph)  # noqa: E731
+        for _ in range(2):
+            run_loop()
+        ms_loop = timed(run_loop, n_loops)
+        loop = {"steps_per_graph_launch": args.loop, "graph_launches_timed": n_loops, "ms_per_step": ms_loop / (n_loops * args.loop),
+                "value": world * B * n_loops * args.loop / (ms_loop / 1e3), "unit": "steps/s",
+                "note": "sigma / timestep / RTS tables on the device, Euler update in-graph: one graph launch per image, no host "
+                        "work between steps (fresh RTS draws and latents staged per launch)"}
+
+    # ---- same-box torch-eager bf16 comparator (cuBLASLt F.linear + flash SDPA, oracle op order) on the model's own weights ----
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager_baseline and B == 1:
+        try:
+            eager = gpu_eager_baseline(model, resident, arch_name, n_cond)
+        except Exception as e:  # noqa: BLE001
+            eager = {"ms_per_step": None, "error": f"{type(e).__name__}: {e}"[:300]}
+
+    line = None
+    if rank == 0:
+        line = assemble_line(args, model, arch, N, T, E, n_cond, B, world, desc, ms_step, ms_step_e2e, value, value_e2e, h2d_bytes,
+                             d2h_bytes, launches, clock_lines, roof, kernel_share, eager, loop)
+
+    # ---- sequence parallelism (north_star subsystem 4): ONE sample sharded over all N ranks. Runs LAST, under a watchdog: a
+    # hang or crash in this leg must not take the data-parallel line down ----
+    if world > 1 and not args.no_sp and B == 1 and args.workload == "cfg3":
+        def give_up():
+            if rank == 0:
+                print(json.dumps(dict(line, sp={"error": f"sequence-parallel legs exceeded {args.sp_timeout} s"})), flush=True)
+            os._exit(0)
+
+        timer = threading.Timer(args.sp_timeout, give_up)
+        timer.daemon = True
+        timer.start()
+        sp = run_sp_legs(args, model if sp_leg else None, resident, ms_step, timed, barrier, dev, rank, world)
+        timer.cancel()
+        if rank == 0:
+            line["sp"] = sp
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def assemble_line(args, model, arch, N, T, E, n_cond, B, world, desc, ms_step, ms_step_e2e, value, value_e2e, h2d_bytes, d2h_bytes,
+                  launches, clock_lines, roof, kernel_share, eager, loop):
     D, H = model.inner_dim, arch.num_attention_heads
     g_ex, a_ex = step_flops(D, H, N, T, arch.num_layers, arch.num_single_layers, arch.num_layers, arch.num_single_layers, E,
                             n_cond=n_cond)
@@ -371,16 +434,150 @@ def run_native(args):
                    "tflop_per_step_per_sample_reference_algorithmic": (g_alg + a_alg) / 1e12,
                    "model_tflops_per_gpu": (g_ex + a_ex) * B / (ms_step / 1e3) / 1e12,
                    "gemm_variant": args.gemm_variant, "attn_variant": args.attn_variant,
-                   "cuda_graph": not args.no_graph},
+                   "cuda_graph": not args.no_graph,
+                   "moe_pooling": "one routing pool of per_gpu_batch x N tokens per forward (the reference's single-device semantics, "
+                                  "src/UniGenUtils.py:89); data-parallel ranks route their own micro-batch (accelerate DP)",
+                   "gpu_eager_baseline": eager},
         "e2e": {"value": value_e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_step_e2e},
         "gpu_launches": launches,
         "clocks": summarize_clocks(clock_lines),
         "roofline": roof, "kernel_time_share": kernel_share, "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if loop is not None:
+        line["loop"] = loop
+    return line
+
+
+def gpu_eager_baseline(model, resident, arch_name, n_cond, steps: int = 3):
+    """The oracle restatement run as plain PyTorch bf16 on the same B200 and the SAME device-resident weights (the native
+    model's state dict carries the reference key names): the comparator SURVEY.md §8(d) calls "the real bar". Baseline leg only —
+    never on the product path."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import unigen_oracle as O
+    cfg = O.FluxConfig.tiny() if arch_name == "tiny" else O.FluxConfig.flux()
+    cfg.condition_nums = n_cond
+    manual = O.sdpa
+    O.sdpa = lambda q, k, v, mask=None: manual(q, k, v, mask) if mask is not None else F.scaled_dot_product_attention(q, k, v)
+    try:
+        oracle = O.UniGenFluxOracle(cfg, dict(model.state_dict()))
+        bf = torch.bfloat16
+        einp = {k: ([t.to(bf) if t.dtype == torch.float32 and k != "rts_uniform" and not k.endswith("ids") else t for t in v]
+                    if isinstance(v, list) else (v.to(bf) if v.dtype == torch.float32 and k != "rts_uniform" and not k.endswith("ids") else v))
+                for k, v in resident.items()}
+        with torch.no_grad():
+            for _ in range(2):
+                oracle.forward(**einp)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                oracle.forward(**einp)
+            e1.record()
+            torch.cuda.synchronize()
+    finally:
+        O.sdpa = manual
+    return {"ms_per_step": e0.elapsed_time(e1) / steps, "steps": steps,
+            "stack": f"torch {torch.__version__} eager bf16: F.linear (cuBLASLt) + F.scaled_dot_product_attention, oracle op order"}
+
+
+def build_pvariant(cls, dev, conds: int, **kw):
+    """Random-init Flux-arch P-variant model (UniCombineFlux or its sequence-parallel subclass) with rank-4 LoRA pairs for a
+    "denoise" adapter + one adapter per condition on every switched linear, and its synthetic cfg4 inputs (1024^2, T = 512)."""
+    import torch
+    from unigen_b200.model import FluxArch
+    from unigen_b200.pvariant import DOUBLE_LORA, SINGLE_LORA
+    arch = FluxArch()
+    T, grid = 512, 64
+    N = grid * grid
+    types_ = ["depth", "canny", "openpose"][:conds]
+    adapters = ["denoise"] + types_
+    model = cls(arch, device=dev, lora_rank=4, max_conditions=conds, **kw)
+    g = torch.Generator(device=dev).manual_seed(0)
+    with torch.no_grad():
+        for k, v in model._ws.views.items():
+            if "norm_q" in k or "norm_k" in k or "norm_added" in k:
+                v.fill_(1.0)
+            else:
+                fan = model._ws.views[k[:-4] + "weight"].shape[-1] if k.endswith(".bias") else v.shape[-1]
+                v.copy_((torch.rand(v.shape, device=dev, generator=g) * 2 - 1) / fan ** 0.5)
+    sd = {}
+    names = ["x_embedder"] + [f"transformer_blocks.{i}.{n}" for i in range(arch.num_layers) for n in DOUBLE_LORA] + \
+            [f"single_transformer_blocks.{i}.{n}" for i in range(arch.num_single_layers) for n in SINGLE_LORA]
+    for name in names:
+        out_f, in_f = model._ws.views[name + ".weight"].shape
+        for a in adapters:
+            sd[f"{name}.lora_A.{a}.weight"] = torch.randn(4, in_f, device=dev, generator=g) / in_f ** 0.5
+            sd[f"{name}.lora_B.{a}.weight"] = torch.randn(out_f, 4, device=dev, generator=g) * 0.25
+    model.load_state_dict(sd, adapters=adapters, condition_types=types_)
+    ids = torch.zeros(grid, grid, 3, device=dev)
+    ids[..., 1] += torch.arange(grid, device=dev)[:, None]
+    ids[..., 2] += torch.arange(grid, device=dev)[None, :]
+    ids = ids.reshape(N, 3)
+    rnd = lambda *s_: torch.randn(*s_, device=dev, generator=g).to(torch.bfloat16)  # noqa: E731
+    inputs = (rnd(1, N, 64), [rnd(1, N, 64) for _ in types_], [ids.clone() for _ in types_], types_, rnd(1, T, 4096),
+              torch.randn(1, 768, device=dev, generator=g), torch.tensor([0.5], device=dev), ids, torch.zeros(T, 3, device=dev))
+    return model, inputs, T + N + conds * N
+
+
+def run_sp_legs(args, model, resident, ms_dp_step, timed, barrier, dev, rank, world):
+    """Ulysses sequence parallelism with the exchange fused into the kernels over NVLink peer memory, measured under the driver's
+    plain `--gpus N`: (1) one cfg3 sample through SequenceParallelUniGenFlux, speed-up against the same object's single-GPU step
+    (= the data-parallel leg's per-rank step: same weights, same box); (2) one cfg4 P-variant sample (16 896 tokens, 3 switched
+    LoRA groups, visibility mask) through SequenceParallelUniCombineFlux against its own single-GPU step. Every rank passes the
+    same inputs; times are CUDA-event, max over ranks. A failure is reported in the record, it does not take the line down."""
+    import torch
+    import torch.distributed as dist
+    out = {"world": world, "exchange": "peer (qkv_scatter / attention epilogue / grouped-GEMV stores into NVLink peer memory, "
+                                       "device-side flag barriers, whole step = one CUDA graph per rank)"}
+    steps = max(args.steps, 3)
+
+    def same_on_all_ranks(v):
+        if torch.is_tensor(v):
+            v = v.clone()
+            dist.broadcast(v, 0)
+            return v
+        return [same_on_all_ranks(t) for t in v] if isinstance(v, list) else v
+
+    try:
+        if model is not None:
+            inp = {k: same_on_all_ranks(v) for k, v in resident.items()}
+            model.sp_enabled = True
+            model.use_cuda_graph = not args.no_graph
+            for _ in range(3):
+                model(**inp)
+            ms = timed(lambda: model(**inp), steps) / steps
+            model.check_peer_errors()
+            out["cfg3"] = {"ms_per_step": ms, "ms_per_step_n1": ms_dp_step, "speedup_vs_n1": ms_dp_step / ms,
+                           "steps_per_s": 1e3 / ms, "tokens": 4608 + 4096,
+                           "note": "n1 = the data-parallel leg's step of the same object (sp_enabled=False) in this process"}
+            model.sp_enabled = False
+            model.close()
+    except Exception as e:  # noqa: BLE001
+        out["cfg3"] = {"error": f"{type(e).__name__}: {e}"[:400]}
+    if args.no_sp_pvariant:
+        return out
+    try:
+        from unigen_b200.parallel import SequenceParallelUniCombineFlux
+        torch.cuda.empty_cache()
+        pv, pin, S = build_pvariant(SequenceParallelUniCombineFlux, dev, 3)
+        pin = tuple(same_on_all_ranks(v) for v in pin)
+        pv.sp_enabled = False
+        for _ in range(2):
+            pv(*pin)
+        ms1 = timed(lambda: pv(*pin), 3) / 3
+        pv.sp_enabled, pv.use_cuda_graph = True, not args.no_graph
+        for _ in range(3):
+            pv(*pin)
+        msp = timed(lambda: pv(*pin), steps) / steps
+        pv.check_peer_errors()
+        out["cfg4_pvariant"] = {"ms_per_step": msp, "ms_per_step_n1": ms1, "speedup_vs_n1": ms1 / msp, "steps_per_s": 1e3 / msp,
+                                "tokens": S, "note": "n1 = the same object with sp_enabled=False (eager launches) in this process"}
+        pv.close()
+    except Exception as e:  # noqa: BLE001
+        out["cfg4_pvariant"] = {"error": f"{type(e).__name__}: {e}"[:400]}
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -444,6 +641,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-text-overlap", action="store_true", help="text-stream GEMMs on the main stream (A/B of the two-stream double block)")
+    ap.add_argument("--no-sp", action="store_true", help="N > 1: skip the sequence-parallel legs (data-parallel measurement only)")
+    ap.add_argument("--sp-timeout", type=float, default=420.0, help="N > 1: seconds before the sequence-parallel legs are abandoned")
+    ap.add_argument("--no-sp-pvariant", action="store_true", help="N > 1: skip the cfg4 P-variant sequence-parallel leg")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the same-box torch-eager bf16 comparator")
+    ap.add_argument("--loop", type=int, default=0, help="also time the whole-loop CUDA graph: LOOP denoise steps per graph launch")
     args = ap.parse_args()
     if args.workload in ("cfg4p", "cfg5"):
         if args.impl == "reference":

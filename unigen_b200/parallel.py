@@ -218,6 +218,9 @@ class SequenceParallelUniGenFlux(UniGenFlux):
         if self.arch.num_attention_heads % self.sp_world:
             raise ops.UgError(f"{self.arch.num_attention_heads} heads are not divisible by {self.sp_world} ranks")
         self.exchange = exchange
+        # False: this object behaves exactly like the single-GPU UniGenFlux (own workspaces and graphs) — one set of weights
+        # serves both the batch-data-parallel and the sequence-parallel measurement of bench.py
+        self.sp_enabled = True
         self.sp_prestage = True  # shared-expert blocks of the CoMoE pre-stage sequence-parallel too (peer exchange only)
         self._sp_active = False
         self._xchg = None
@@ -225,11 +228,19 @@ class SequenceParallelUniGenFlux(UniGenFlux):
         self._pool_key = None
 
     def _run_staged(self, key, staged, *args):
+        if not self.sp_enabled:
+            return super()._run_staged((key, "local"), staged, *args)
         if self.exchange != "peer":  # NCCL collectives stay out of graph capture: the staged-exchange baseline runs eagerly
             return self._forward_impl(*args, **staged)
         if self._pool is not None:
             self._pool.raise_on_error()  # barrier-error word mirrored at the end of the previous forward
-        return super()._run_staged(key, staged, *args)
+        return super()._run_staged((key, "sp"), staged, *args)
+
+    def _workspace(self, B: int, N: int, T: int):
+        if not self.sp_enabled:
+            return super()._workspace(B, N, T)
+        # the sequence-parallel workspace re-points AO / CAT / X / HC / MOD into the peer pool: keep it apart from the local one
+        return self._cached_workspace((B, N, T, "sp"), lambda: self._make_workspace(B, N, T))
 
     def check_peer_errors(self):
         """Synchronise and raise if any device-side barrier of the forwards so far timed out (call once per denoise loop)."""
@@ -416,6 +427,8 @@ class SequenceParallelUniGenFlux(UniGenFlux):
             dist.all_gather_into_tensor(full.view(-1), local.reshape(-1), group=self.sp_group)
 
     def _forward_impl(self, conditioning_scale, hs, es, pooled, timestep, guidance, txt_ids, img_ids, **cond):
+        if not self.sp_enabled:
+            return UniGenFlux._forward_impl(self, conditioning_scale, hs, es, pooled, timestep, guidance, txt_ids, img_ids, **cond)
         a = self.arch
         P, rank = self.sp_world, self.sp_rank
         n_cond = self.condition_nums
@@ -569,9 +582,12 @@ class SequenceParallelUniCombineFlux(UniCombineFlux):
         self._pool_key = None
         self.use_cuda_graph = False
         self._graphs = {}
+        self.sp_enabled = True  # False: behaves exactly like the single-GPU UniCombineFlux (same weights; bench.py's 1-GPU leg)
 
     def _workspace(self, B, S_loc):
         buf = super()._workspace(B, S_loc)
+        if not self.sp_enabled:
+            return buf
         if B != 1:
             raise ops.UgError("sequence parallelism shards ONE sample across ranks (use batch data-parallelism for B > 1)")
         a, D, P = self.arch, self.inner_dim, self.sp_world
@@ -590,6 +606,8 @@ class SequenceParallelUniCombineFlux(UniCombineFlux):
         return buf
 
     def _attention(self, buf, parts, out_name: str, bounds, vis):
+        if not self.sp_enabled:
+            return super()._attention(buf, parts, out_name, bounds, vis)
         a, D, P, pool = self.arch, self.inner_dim, self.sp_world, self._pool
         H, dh = a.num_attention_heads, a.attention_head_dim
         gbounds = [b * P for b in bounds]
@@ -630,6 +648,9 @@ class SequenceParallelUniCombineFlux(UniCombineFlux):
     @torch.no_grad()
     def forward(self, hidden_states, condition_latents, condition_ids, condition_types, encoder_hidden_states,
                 pooled_projections, timestep, img_ids, txt_ids, c_t: float = 0.0, **kwargs):
+        if not self.sp_enabled:
+            return UniCombineFlux.forward(self, hidden_states, condition_latents, condition_ids, condition_types,
+                                          encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, c_t=c_t, **kwargs)
         P, r = self.sp_world, self.sp_rank
         dev = self.device_
         if self._pool is not None:

@@ -89,7 +89,7 @@ class UniCombineFlux(torch.nn.Module):
         self.lora: Dict[str, _LoraPair] = {}
         self.condition_types: List[str] = []
         self.trace: Optional[Dict[str, torch.Tensor]] = None
-        self._buf_key = None
+        self._bufs: Dict[Any, Any] = {}
         self.gemm_variant = 0
         self.attn_variant = 0
         # "mma": the switched low-rank update rides the main GEMM's tensor-core loop as a K extension (A2 / W2 operand pair);
@@ -227,16 +227,16 @@ class UniCombineFlux(torch.nn.Module):
     # ---------------------------------------------------------------------------------------------------------
     def _workspace(self, B, S):
         key = (B, S)
-        if self._buf_key == key:
+        if key in self._bufs:  # one workspace per shape, never freed while the model lives (captured graphs point into them)
+            self._buf = self._bufs[key]
             return self._buf
         D, dev = self.inner_dim, self.device_
         z = lambda *s, dt=BF16: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
-        self._buf = types.SimpleNamespace(
+        self._buf = self._bufs[key] = types.SimpleNamespace(
             X=z(B, S, D), NX=z(B, S, D), QKV=z(B, S, 3 * D), AO=z(B, S, D), FF=z(B, S, 4 * D), CAT=z(B, S, 5 * D),
             LT=z(B, S, 3 * self.R, dt=torch.float32), LTW=z(B, S, self.groups * LORA_BLOCK), temb=z(B, D, dt=torch.float32), ctemb=z(B, D, dt=torch.float32),
             tmp=z(B, D, dt=torch.float32), ltmp=z(B, 16, dt=torch.float32), ltmp2=z(B, 16, dt=torch.float32), NO=None,
             rope=z(S, self.arch.attention_head_dim, dt=torch.float32))
-        self._buf_key = key
         return self._buf
 
     def _rec(self, name, t):
