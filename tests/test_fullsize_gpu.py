@@ -37,6 +37,13 @@ def test_pvariant_cfg4_full_size_matches_eager_oracle():
     assert par["cosine"] >= 0.999 and par["rel_l2"] < 5e-2, rec
 
 
+def _parity_out(workload):
+    """UG_PARITY_OUT=<dir>: also keep the per-block record (profiles/r02_parity_<workload>.json is a copy of it)."""
+    import os
+    d = os.environ.get("UG_PARITY_OUT")
+    return ["--out", os.path.join(d, f"r02_parity_{workload}.json")] if d else []
+
+
 def _check_fp32_oracle_parity(rec):
     tf = rec["teacher_forced"]
     assert tf["max_rel_l2"] <= 1e-2, tf["worst"]
@@ -51,10 +58,10 @@ def test_flux_cfg2_per_block_parity_vs_fp32_oracle_on_gpu():
     fp32 oracle evaluated on the native block input (rel-L2 <= 1e-2 per block), bit-exact routing given the native gate input,
     final-velocity cosine >= 0.999 against the free-running fp32 oracle (tests/parity_fullsize.py)."""
     import parity_fullsize as P
-    _check_fp32_oracle_parity(P.main(["--workload", "cfg2"]))
+    _check_fp32_oracle_parity(P.main(["--workload", "cfg2"] + _parity_out("cfg2")))
 
 
 def test_flux_cfg3_per_block_parity_vs_fp32_oracle_on_gpu():
     """The BASELINE metric config (1024^2 + 1 condition: 4096 + 4096 + 512 tokens), same three checks."""
     import parity_fullsize as P
-    _check_fp32_oracle_parity(P.main(["--workload", "cfg3"]))
+    _check_fp32_oracle_parity(P.main(["--workload", "cfg3"] + _parity_out("cfg3")))

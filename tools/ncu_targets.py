@@ -1,0 +1,102 @@
+"""One launch of every hot kernel at its cfg3 shape inside a cudaProfilerStart/Stop window, for ONE `ncu --set full` capture:
+
+  ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof_r02_targets \\
+      python tools/ncu_targets.py [--workload cfg3|cfg5]
+
+cfg3 (Flux, D = 3072, dh = 128, S = 4608):  grouped AdaLN GEMV (the step's `late` job table, ~9 GB of weights), LN-modulate
+(4608 x 3072), q|k|v projection GEMM (N = 9216), QK-RMSNorm + RoPE (in place, 4608 x 6144), joint attention (24 heads),
+proj_mlp GEMM with the GELU epilogue (N = 12288), ff2-shaped GEMM with the gated-residual epilogue (K = 12288), proj_out of the
+single blocks (K = 15360). cfg5 (SD3.5-medium, D = 1536, dh = 64): attention at dh = 64 and the K = 1536 GEMMs.
+The model is built exactly as bench.py builds it, one warm-up forward allocates the workspace and job tables, and the window
+then launches the ops on the workspace buffers (ncu flushes caches between replays: these are cold-cache numbers; the in-situ
+bandwidth of the HBM-bound kernels is in bench.py's `roofline.hbm_bound_kernels`)."""
+import argparse
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5", "tiny"])
+    args = ap.parse_args()
+    from unigen_b200 import ops
+    from unigen_b200.ops import UG_ACT_GELU_TANH
+    dev = torch.device("cuda")
+    prof = torch.cuda.profiler
+    if args.workload == "cfg5":
+        from unigen_b200.sd3 import SD3Arch, UniGenSD3, shipped_control_params
+        model = UniGenSD3(SD3Arch(), device=dev)
+        model.init_condition_block(condition_nums=1, control_params=shipped_control_params())
+        model.init_random_(seed=0)
+        B, lat, T = 2, 128, 333
+        N = (lat // 2) ** 2
+        g = torch.Generator(device=dev).manual_seed(1234)
+        bf = torch.bfloat16
+        inp = dict(hidden_states=torch.randn(B, 16, lat, lat, device=dev, generator=g).to(bf),
+                   condition_hidden_states=torch.randn(B, 16, lat, lat, device=dev, generator=g).to(bf),
+                   encoder_hidden_states=torch.randn(B, T, 4096, device=dev, generator=g).to(bf),
+                   pooled_projections=torch.randn(B, 2048, device=dev, generator=g),
+                   condition_pooled_projections=torch.randn(B, 2048, device=dev, generator=g),
+                   timestep=torch.full((B,), 500.0, device=dev))
+        model(**inp)
+        torch.cuda.synchronize()
+        buf, D, S = model._buf, model.inner_dim, N + T
+        w = model.blocks[0]
+        a = model.arch
+        prof.start()
+        ops.gemm(buf.NX[:, :S], w.attn.qkv[0], out=buf.QKV[:, :S], bias=w.attn.qkv[1])
+        ops.attention(buf.QKV[:, :S, 0:D], buf.QKV[:, :S, D:2 * D], buf.QKV[:, :S, 2 * D:3 * D], buf.AO[:, :S], a.num_attention_heads,
+                      a.attention_head_dim)
+        torch.cuda.synchronize()
+        prof.stop()
+        return
+    from unigen_b200.model import FluxArch, UniGenFlux, canonical_control_params
+    tiny = args.workload == "tiny"
+    arch = FluxArch.tiny() if tiny else FluxArch()
+    side = 256 if tiny else 1024
+    model = UniGenFlux(arch, device=dev)
+    model.init_condition_block(condition_nums=1, control_params=canonical_control_params())
+    model.init_random_(seed=0)
+    T, grid = 512, side // 16
+    N = grid * grid
+    g = torch.Generator(device=dev).manual_seed(1234)
+    ids = torch.zeros(grid, grid, 3, device=dev)
+    ids[..., 1] += torch.arange(grid, device=dev)[:, None]
+    ids[..., 2] += torch.arange(grid, device=dev)[None, :]
+    ids = ids.reshape(N, 3)
+    bf = torch.bfloat16
+    inp = dict(hidden_states=torch.randn(1, N, 64, device=dev, generator=g).to(bf),
+               condition_hidden_states=torch.randn(1, N, 64, device=dev, generator=g).to(bf),
+               encoder_hidden_states=torch.randn(1, T, 4096, device=dev, generator=g).to(bf),
+               pooled_projections=torch.randn(1, 768, device=dev, generator=g),
+               condition_pooled_projections=torch.randn(1, 768, device=dev, generator=g), timestep=torch.tensor([0.75], device=dev),
+               img_ids=ids, txt_ids=torch.zeros(T, 3, device=dev), condition_ids=ids.clone())
+    model(**inp)
+    torch.cuda.synchronize()
+    buf, D, S = model._buf, model.inner_dim, T + N
+    H, dh = arch.num_attention_heads, arch.attention_head_dim
+    w = model.single[0]
+    mp = model._mod_plans(buf)
+    shift, scale, gate = mp.m_single[0]
+    x, nx, cat = buf.X, buf.NX[:, :S], buf.CAT[:, :S]
+    prof.start()
+    ops.gemv_grouped(mp.late)                                                                   # AdaLN weights, HBM-bound
+    ops.ln_modulate(x, nx, shift, scale)                                                        # HBM-bound
+    ops.gemm(nx, w.qkv[0], out=buf.QKV[:, :S], bias=w.qkv[1])                                   # N = 3D
+    ops.qk_rmsnorm_rope(buf.QKV[:, :S, :2 * D], 2 * H, dh, w.rms, buf.rope[:S], heads_per_weight=H)  # HBM-bound, in place
+    ops.attention(buf.QKV[:, :S, 0:D], buf.QKV[:, :S, D:2 * D], buf.QKV[:, :S, 2 * D:3 * D], cat[:, :, :D], H, dh)
+    ops.gemm(nx, w.mlp[0], out=cat[:, :, D:], bias=w.mlp[1], act=UG_ACT_GELU_TANH)              # N = 4D, GELU epilogue
+    ops.gemm(cat, w.out[0], out=buf.CS, bias=w.out[1], gate=gate, residual=x)                   # K = 5D, gated residual
+    dw = model.double[0]
+    ops.gemm(buf.FF[:, :N], dw.ff2[0], out=buf.CH, bias=dw.ff2[1], gate=gate, residual=buf.CH)  # K = 4D, in-place residual
+    torch.cuda.synchronize()
+    prof.stop()
+
+
+if __name__ == "__main__":
+    main()
