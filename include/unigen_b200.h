@@ -402,6 +402,64 @@ int ug_peer_bcast_rows(const ug_peer_table* table, const void* src, int64_t src_
 int ug_unpatchify(const void* tokens_bf16, void* image_bf16, int32_t batch, int32_t h, int32_t w, int32_t p, int32_t channels,
                   void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Whole-step handle: ONE denoise step of UniGenFlux (`UniGenFlux.forward`, src/UniGenTransformer.py:1182-1271, with
+ * base_forward :1106-1180, control_forward :1070-1104, preprocess_moe_forward :1028-1068, moe_forward :969-1026) sequenced inside
+ * the library, for hosts that are not Python (SURVEY.md §8(b) "what a C-ABI replacement must export"). The handle owns no device
+ * memory: weights are BORROWED pointers bound under the reference's state-dict names, the caller supplies one workspace.
+ *   ug_flux_create / ug_flux_destroy
+ *   ug_flux_bind_weight(handle, "transformer_blocks.0.attn.to_q.weight", ptr, dtype, shape, ndim)   dtype 0 = bf16, 1 = fp32
+ *       every key of the reference state dict (diffusers Flux names + control_*, controlnet_add_*, moe.*, shared_expert.*);
+ *       bf16 except `moe.moe_layer.gate.wg.weight` (fp32, as DeepSpeed evaluates the gate). Rows that one fused launch reads
+ *       must be CONTIGUOUS in memory: to_q|to_k|to_v (and add_q|k|v_proj) weights and biases of a block, norm_q|norm_k
+ *       (norm_added_q|k) weights, and the E experts' `.{br}.0` / `.{br}.1` linears stacked in expert order.
+ *   ug_flux_workspace_bytes(handle, batch, n_img, n_txt)
+ *   ug_flux_forward(handle, inputs, outputs, workspace, bytes, stream)
+ *       never allocates, never synchronises — except on the FIRST call with a new (workspace, shape), which uploads the AdaLN
+ *       job table and must therefore not run under stream capture; later calls are capturable into a CUDA graph.
+ * Numerics: the same kernels in the same order as the Python mirror (unigen_b200/model.py) — bit-identical results.
+ * ---------------------------------------------------------------------------------------------------- */
+#define UG_FLUX_MAX_CONDITIONS 4
+typedef struct ug_flux_desc {
+  int32_t num_layers, num_single_layers;     /* 19, 38 */
+  int32_t heads, head_dim;                   /* 24, 128 */
+  int32_t in_channels, joint_dim, pooled_dim; /* 64, 4096, 768 */
+  int32_t guidance_embeds;
+  int32_t axes_dims_rope[3];                 /* 16, 56, 56 */
+  float theta;                               /* 10000 */
+  int32_t n_ctrl_double, n_ctrl_single;      /* num_layers // single_control_dev, num_single_layers // single_control_dev (0: none) */
+  int32_t experts, condition_nums;           /* (condition_nums + 1) * expert_num_each_condition, 1 */
+  int32_t use_shared_expert, single_add, use_pooled_prompt_embeds; /* control_params (config/unigen.yaml) */
+} ug_flux_desc;
+typedef struct ug_flux ug_flux;
+typedef struct ug_flux_inputs {
+  int32_t batch, n_img, n_txt;
+  float conditioning_scale;
+  const void* hidden_states;         /* bf16 [batch, n_img, in_channels] */
+  const void* encoder_hidden_states; /* bf16 [batch, n_txt, joint_dim] */
+  const float* pooled_projections;   /* fp32 [batch, pooled_dim] */
+  const float* timestep;             /* fp32, already divided by 1000 as the pipeline passes it; element b at timestep[b * timestep_stride] */
+  int64_t timestep_stride;           /* 1, or 0 to broadcast one device-resident value (a sigma-table entry) */
+  const float* guidance;             /* fp32 [batch] or NULL */
+  const float* img_ids;              /* fp32 [n_img, 3] */
+  const float* txt_ids;              /* fp32 [n_txt, 3] */
+  const void* condition_hidden_states[UG_FLUX_MAX_CONDITIONS];       /* bf16 [batch, n_img, in_channels] per condition */
+  const float* condition_pooled_projections[UG_FLUX_MAX_CONDITIONS]; /* fp32 [batch, pooled_dim] */
+  const float* condition_ids[UG_FLUX_MAX_CONDITIONS];                /* fp32 [n_img, 3] */
+  const float* rts_uniform[UG_FLUX_MAX_CONDITIONS];                  /* fp32 [batch * n_img, experts]: the gate's uniform draw */
+} ug_flux_inputs;
+typedef struct ug_flux_outputs {
+  void* velocity;         /* bf16 [batch, n_img, in_channels] */
+  int64_t* expert_counts; /* int64 [experts] (last condition) */
+  float* l_aux;           /* fp32 [1]; moe_loss = 0.1 * l_aux */
+} ug_flux_outputs;
+int ug_flux_create(const ug_flux_desc* desc, ug_flux** handle);
+void ug_flux_destroy(ug_flux* handle);
+int ug_flux_bind_weight(ug_flux* handle, const char* name, const void* dev_ptr, int32_t dtype, const int64_t* shape, int32_t ndim);
+size_t ug_flux_workspace_bytes(const ug_flux* handle, int32_t batch, int32_t n_img, int32_t n_txt);
+int ug_flux_forward(ug_flux* handle, const ug_flux_inputs* inputs, const ug_flux_outputs* outputs, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,7 +34,8 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_struct_layouts_match_header_field_order():
     from unigen_b200 import _lib
     text = HEADER.read_text()
-    for struct, cls in (("ug_gemm_args", _lib.GemmArgs), ("ug_attn_args", _lib.AttnArgs), ("ug_gemv_job", _lib.GemvJob)):
+    for struct, cls in (("ug_gemm_args", _lib.GemmArgs), ("ug_attn_args", _lib.AttnArgs), ("ug_gemv_job", _lib.GemvJob),
+                        ("ug_flux_desc", _lib.FluxDesc), ("ug_flux_inputs", _lib.FluxInputs), ("ug_flux_outputs", _lib.FluxOutputs)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), text, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []

@@ -23,7 +23,7 @@ def _seed():
     torch.manual_seed(0)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("shape", [(1, 128, 256, 64), (1, 200, 384, 192), (1, 300, 64, 384), (2, 1000, 1152, 384),
                                    (1, 768, 384, 1920)])
 def test_gemm_plain(ug, variant, shape):
@@ -39,7 +39,7 @@ def test_gemm_plain(ug, variant, shape):
 REAL_SHAPES = [(4608, 3072, 3072), (4608, 3072, 12288), (4608, 15360, 3072), (4096, 12288, 3072), (16896, 3072, 3072)]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("mkn", REAL_SHAPES)
 def test_gemm_real_shapes(ug, variant, mkn):
     """fp32 torch matmul (TF32 off) on the same bf16 inputs; bias epilogue; rel-L2 <= 6e-3 (bf16 out, fp32 accumulate)."""
@@ -53,7 +53,7 @@ def test_gemm_real_shapes(ug, variant, mkn):
     assert (out[0].float() - want).abs().max() < 0.15
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
 def test_gemm_real_shape_fused_epilogue(ug, variant):
     """The gated-residual epilogue (`h + gate * (x W^T + b)`, in place) at the to_out / ff2 shape of cfg3."""
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -67,7 +67,7 @@ def test_gemm_real_shape_fused_epilogue(ug, variant):
     assert rel_l2(h, want) < 6e-3
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
 def test_gemm_fused_epilogue_strided(ug, variant):
     B, R, N, K = 3, 333, 640, 256
     a = rnd(B, R + 50, K + 64)[:, 50:, 64:]
@@ -83,18 +83,37 @@ def test_gemm_fused_epilogue_strided(ug, variant):
     assert out_full[:, :7].abs().max() == 0 and out_full[:, :, :64].abs().max() == 0  # no out-of-bounds writes
 
 
-def test_gemm_batched_weights_and_inplace_residual(ug):
+@pytest.mark.parametrize("variant", [0, 4, 5, 6])
+def test_gemm_batched_weights_and_inplace_residual(ug, variant):
+    """Stacked-expert GEMM (per-batch weights + bias) and the in-place gated residual; variants 4-6 = the smem-staged TMA-store
+    epilogue (residual slab TMA-loaded into the staging buffer, result TMA-stored over it)."""
     E, C, D = 6, 43, 384
     a, w, b = rnd(E, C, D), rnd(E, D, D, scale=D ** -0.5), rnd(E, D)
-    out = ug.gemm(a, w, bias=b)
+    out = ug.gemm(a, w, bias=b, variant=variant)
     want = torch.einsum("ecd,end->ecn", a.float(), w.float()) + b.float()[:, None]
     assert rel_l2(out, want) < 6e-3
     h = rnd(2, 300, 384)
     h0 = h.clone()
     x, w2 = rnd(2, 300, 512), rnd(384, 512, scale=512 ** -0.5)
     gate = torch.randn(2, 384, device="cuda")
-    ug.gemm(x, w2, out=h, gate=gate, residual=h)
+    ug.gemm(x, w2, out=h, gate=gate, residual=h, variant=variant)
     assert rel_l2(h, h0.float() + gate[:, None] * (x.float() @ w2.float().t())) < 6e-3
+
+
+@pytest.mark.parametrize("n", [8, 40, 64, 72, 200])
+def test_gemm_staged_epilogue_equals_direct_epilogue_bitwise(ug, n):
+    """Same accumulators, same epilogue arithmetic: the staged (TMA-store) epilogue must reproduce the direct one bit for bit,
+    also for output widths that end inside a 64-column staging slab / a 32-row lane quarter (hardware clipping)."""
+    B, R, K = 2, 333, 320
+    a, w, bias = rnd(B, R, K), rnd(n, K, scale=K ** -0.5), rnd(n)
+    gate, res = torch.randn(B, n, device="cuda"), rnd(B, R, n)
+    for direct, staged in ((1, 5), (2, 4), (3, 6)):
+        ref = torch.full((B, R + 2, n + 8), 7.0, device="cuda", dtype=torch.bfloat16)
+        got = ref.clone()
+        kw = dict(bias=bias, gate=gate, alpha=0.7, act=ug.UG_ACT_GELU_TANH, residual=res)
+        ug.gemm(a, w, out=ref[:, 1:-1, :n], variant=direct, **kw)
+        ug.gemm(a, w, out=got[:, 1:-1, :n], variant=staged, **kw)
+        assert torch.equal(got, ref)  # incl. the untouched guard rows / columns around the output view
 
 
 def test_gemm_rejects_bad_arguments(ug):
@@ -392,16 +411,16 @@ def test_gemv_grouped_one_launch_equals_per_job_gemv(ug, B):
     assert rel_l2(out, torch.cat(want, 1)) < 1e-5  # fp32 summation order differs slightly from the per-job kernel
     # emulated sequence-parallel ranks: each computes its share of the groups and stores into EVERY "pool"
     P = 4
-    nbytes = 4096 + B * total * 4
-    pools = [torch.zeros(nbytes, dtype=torch.uint8, device="cuda") for _ in range(P)]
+    pool_bytes = 4096 + B * total * 4
+    pools = [torch.zeros(pool_bytes, dtype=torch.uint8, device="cuda") for _ in range(P)]
     for r in range(P):
         t = _lib.PeerTable()
         t.world, t.rank = P, r
         for i in range(P):
             t.base[i] = pools[i].data_ptr()
 
-        class Pool:  # what GemvPlan needs of a parallel.PeerPool
-            local, nbytes, table = pools[r], nbytes, t
+        import types as _types
+        Pool = _types.SimpleNamespace(local=pools[r], nbytes=pool_bytes, table=t)  # what GemvPlan needs of a parallel.PeerPool
 
         view = pools[r][4096:].view(torch.float32).view(B, total)
         pj, c0 = [], 0

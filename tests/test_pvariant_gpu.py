@@ -233,11 +233,11 @@ def test_enable_lora_hook_rewrites_the_native_scale_tables_like_the_oracle():
         assert stub.scaling["canny"] == 0 and all(m.scaling == stub.scaling for m in mods)
         want1, got1 = oracle_out(), native_out()
     assert rel_l2(got1, want1) < 1e-2
-    assert rel_l2(want1, want0) > 2e-2 and rel_l2(got1, got0) > 2e-2  # switching canny off is visible on both sides
+    assert rel_l2(want1, want0) > 5e-3 and rel_l2(got1, got0) > 5e-3  # switching canny off is visible on both sides
     # after exit: denoise / depth (alpha == r) are restored exactly, canny comes back as saved * alpha / r = 4.0, not 2.0
     assert stub.scaling == {"denoise": 1.0, "depth": 1.0, "canny": 4.0} and all(m.scaling == stub.scaling for m in mods)
     want2, got2 = oracle_out(), native_out()
-    assert rel_l2(got2, want2) < 1e-2 and rel_l2(got2, got0) > 1e-2
+    assert rel_l2(got2, want2) < 1e-2 and rel_l2(got2, got0) > 5e-3
     # set_adapter: an adapter that is not active contributes nothing (peft applies active adapters only)
     for m in mods:
         m.set_adapter(["denoise", "depth"])

@@ -63,6 +63,30 @@ class GemvJob(C.Structure):
                 ("first_group", C.c_int32), ("flags", C.c_int32)]
 
 
+UG_FLUX_MAX_CONDITIONS = 4
+
+
+class FluxDesc(C.Structure):
+    _fields_ = [("num_layers", C.c_int32), ("num_single_layers", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
+                ("in_channels", C.c_int32), ("joint_dim", C.c_int32), ("pooled_dim", C.c_int32), ("guidance_embeds", C.c_int32),
+                ("axes_dims_rope", C.c_int32 * 3), ("theta", C.c_float), ("n_ctrl_double", C.c_int32), ("n_ctrl_single", C.c_int32),
+                ("experts", C.c_int32), ("condition_nums", C.c_int32), ("use_shared_expert", C.c_int32), ("single_add", C.c_int32),
+                ("use_pooled_prompt_embeds", C.c_int32)]
+
+
+class FluxInputs(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("n_img", C.c_int32), ("n_txt", C.c_int32), ("conditioning_scale", C.c_float),
+                ("hidden_states", C.c_void_p), ("encoder_hidden_states", C.c_void_p), ("pooled_projections", C.c_void_p),
+                ("timestep", C.c_void_p), ("timestep_stride", C.c_int64), ("guidance", C.c_void_p), ("img_ids", C.c_void_p),
+                ("txt_ids", C.c_void_p), ("condition_hidden_states", C.c_void_p * UG_FLUX_MAX_CONDITIONS),
+                ("condition_pooled_projections", C.c_void_p * UG_FLUX_MAX_CONDITIONS),
+                ("condition_ids", C.c_void_p * UG_FLUX_MAX_CONDITIONS), ("rts_uniform", C.c_void_p * UG_FLUX_MAX_CONDITIONS)]
+
+
+class FluxOutputs(C.Structure):
+    _fields_ = [("velocity", C.c_void_p), ("expert_counts", C.c_void_p), ("l_aux", C.c_void_p)]
+
+
 class AttnArgs(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p),
@@ -102,6 +126,11 @@ SIGNATURES = {
     "ug_gemv": (C.c_int, [_VP, _I64, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "ug_gemv_grouped": (C.c_int, [_VP, _I32, _I32, _I32, _I32, _I32, C.POINTER(PeerTable), _VP]),
     "ug_silu_f32": (C.c_int, [_VP, _VP, _I64, _VP]),
+    "ug_flux_create": (C.c_int, [C.POINTER(FluxDesc), C.POINTER(C.c_void_p)]),
+    "ug_flux_destroy": (None, [_VP]),
+    "ug_flux_bind_weight": (C.c_int, [_VP, C.c_char_p, _VP, _I32, C.POINTER(C.c_int64), _I32]),
+    "ug_flux_workspace_bytes": (C.c_size_t, [_VP, _I32, _I32, _I32]),
+    "ug_flux_forward": (C.c_int, [_VP, C.POINTER(FluxInputs), C.POINTER(FluxOutputs), _VP, C.c_size_t, _VP]),
     "ug_timestep_embedding": (C.c_int, [_VP, _I64, _I32, _I32, _F32, _VP, _VP]),
     "ug_add_bf16": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP]),
     "ug_copy_bf16": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP]),

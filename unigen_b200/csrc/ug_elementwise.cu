@@ -1,6 +1,9 @@
 // Fused elementwise family of the UniGen hot path (HBM-bound): LayerNorm+modulate, per-head RMSNorm+RoPE,
 // RoPE table, small-M linears (AdaLN / timestep / expert-modulation GEMVs), adds / copies / casts.
 // All kernels use 16-byte vector accesses and fp32 math; bf16 is storage only.
+#include <cstdlib>
+#include <cstring>
+
 #include "ug_host.h"
 #include "ug_ptx.cuh"
 
@@ -187,6 +190,97 @@ __global__ void __launch_bounds__(256, 4) ln_modulate2_kernel(const __nv_bfloat1
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * (1.f + s[j]) + h[j];
       op[v] = pack8(f);
+    }
+  }
+}
+
+// Same op for the plain per-sample form (no slots / row segments), kR rows per block: thread t owns the 16-byte column chunks
+// t, t + kThreads, ... of ALL kR rows, so the fp32 shift / scale vectors — 4 x the bytes of a bf16 row, and the same for every
+// row of a sample — are loaded ONCE per kR rows, and they are requested together with the rows (one memory latency per block
+// instead of two: in the two-warp kernel the modulation loads only issue after both reductions, ncu: 50 % of its stall samples
+// are long-scoreboard waits on `1 + scale`). kR * kChunks + 4 * kChunks 16-byte loads in flight per thread.
+template <int kThreads, int kChunks, int kR>
+__global__ void __launch_bounds__(kThreads) ln_modulate_rows_kernel(const __nv_bfloat16* __restrict__ x, long long x_rs, long long x_bs,
+                                                                    __nv_bfloat16* __restrict__ out, long long o_rs, long long o_bs,
+                                                                    const float* __restrict__ shift, const float* __restrict__ scale,
+                                                                    long long mod_bs, int rows, int d, float eps) {
+  constexpr int kWarps = kThreads / 32;
+  __shared__ float red[2][kR][kWarps];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * kR;
+  const __nv_bfloat16* xb = x + (long long)b * x_bs;
+  uint4 buf[kR][kChunks];
+#pragma unroll
+  for (int r = 0; r < kR; ++r) {
+    const int row = min(r0 + r, rows - 1);  // a ragged last block re-reads the last row; only rows < `rows` are stored
+    const uint4* xp = reinterpret_cast<const uint4*>(xb + (long long)row * x_rs);
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i) buf[r][i] = xp[t + kThreads * i];
+  }
+  float4 sc[kChunks][2], sh[kChunks][2];
+  const float* scp = scale + (long long)b * mod_bs;
+  const float* shp = shift + (long long)b * mod_bs;
+#pragma unroll
+  for (int i = 0; i < kChunks; ++i) {
+    const int c = 8 * (t + kThreads * i);
+    sc[i][0] = *reinterpret_cast<const float4*>(scp + c); sc[i][1] = *reinterpret_cast<const float4*>(scp + c + 4);
+    sh[i][0] = *reinterpret_cast<const float4*>(shp + c); sh[i][1] = *reinterpret_cast<const float4*>(shp + c + 4);
+  }
+  float mean[kR], rstd[kR];
+#pragma unroll
+  for (int r = 0; r < kR; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i) {
+      float f[8];
+      unpack8(buf[r][i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[j];
+    }
+    s = warp_sum(s);
+    if (lane == 0) red[0][r][warp] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kR; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += red[0][r][w];
+    mean[r] = s / (float)d;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i) {
+      float f[8];
+      unpack8(buf[r][i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float u = f[j] - mean[r]; v += u * u; }
+    }
+    v = warp_sum(v);
+    if (lane == 0) red[1][r][warp] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kR; ++r) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) v += red[1][r][w];
+    rstd[r] = rsqrtf(v / (float)d + eps);
+  }
+  __nv_bfloat16* ob = out + (long long)b * o_bs;
+#pragma unroll
+  for (int r = 0; r < kR; ++r) {
+    if (r0 + r >= rows) break;
+    uint4* op = reinterpret_cast<uint4*>(ob + (long long)(r0 + r) * o_rs);
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i) {
+      float f[8];
+      unpack8(buf[r][i], f);
+      const float s[8] = {sc[i][0].x, sc[i][0].y, sc[i][0].z, sc[i][0].w, sc[i][1].x, sc[i][1].y, sc[i][1].z, sc[i][1].w};
+      const float h[8] = {sh[i][0].x, sh[i][0].y, sh[i][0].z, sh[i][0].w, sh[i][1].x, sh[i][1].y, sh[i][1].z, sh[i][1].w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean[r]) * rstd[r] * (1.f + s[j]) + h[j];
+      op[t + kThreads * i] = pack8(f);
     }
   }
 }
@@ -550,6 +644,16 @@ __global__ void __launch_bounds__(256) gated_add_slots_kernel(__nv_bfloat16* __r
   }
 }
 
+// UG_LN_KERNEL=rows|warp: A/B switch between the kR-rows-per-block LayerNorm kernel and the one / two-warps-per-row kernels
+static inline bool ln_rows_kernel_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("UG_LN_KERNEL");
+    cached = (e && strcmp(e, "warp") == 0) ? 0 : 1;
+  }
+  return cached == 1;
+}
+
 static inline int grid_for(long long threads, int block) {
   long long g = (threads + block - 1) / block;
   const long long cap = (long long)num_sms() * 16;
@@ -581,6 +685,21 @@ static int launch_ln_modulate(const void* x, int64_t x_rs, int64_t x_bs, void* o
   auto s = reinterpret_cast<cudaStream_t>(stream);
   auto xp = (const __nv_bfloat16*)x;
   auto op = (__nv_bfloat16*)out;
+  if (!slot_token && segs.nseg == 0 && ln_rows_kernel_enabled() && batch <= 65535) {
+    // plain per-sample form: kR rows per block share one load of the modulation vectors
+    constexpr int kR = 4;
+    const dim3 g((unsigned)((rows + kR - 1) / kR), (unsigned)batch);
+    const int nvec = d >> 3;
+    bool done = true;
+    if (nvec == 3 * 128) ln_modulate_rows_kernel<128, 3, kR><<<g, 128, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, rows, d, eps);
+    else if (nvec == 3 * 64) ln_modulate_rows_kernel<64, 3, kR><<<g, 64, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, rows, d, eps);
+    else if (nvec == 2 * 128) ln_modulate_rows_kernel<128, 2, kR><<<g, 128, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, rows, d, eps);
+    else done = false;
+    if (done) {
+      UG_CHECK_LAUNCH(name);
+      return UG_OK;
+    }
+  }
 #define UG_LN_LAUNCH(V) ln_modulate_kernel<V><<<grid, block, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, batch, rows, d, eps, slot_token, capacity, tokens_per_batch, empty_index, mod_es, segs, mod_seg_stride)
   const int grid2 = (int)((warps + 3) / 4);  // two warps per row, four rows per 256-thread block
 #define UG_LN2_LAUNCH(V) ln_modulate2_kernel<V><<<grid2, block, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, batch, rows, d, eps, slot_token, capacity, tokens_per_batch, empty_index, mod_es, segs, mod_seg_stride)

@@ -10,11 +10,15 @@
 //
 // Replaces every nn.Linear call on the reference path.
 #include <cstdlib>
+#include <cstring>
 
 #include "ug_host.h"
 #include "ug_ptx.cuh"
 
 namespace ug {
+
+constexpr int kEpiWarps = 8;                     // 4 or 8
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 
 struct GemmParams {
   int rows, n, k, batch;
@@ -48,10 +52,7 @@ struct GemmParams {
   float qk_eps;
 };
 
-constexpr int kEpiWarps = 8;                     // 4 or 8
-constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
-
-template <int kCta, int BN, int kStages>
+template <int kCta, int BN, int kStages, bool kTmaEpi = false>
 struct GemmCfg {
   static constexpr int BM = 128;  // rows per CTA
   static constexpr int BK = 64;   // 64 bf16 = one 128-byte swizzle row
@@ -60,8 +61,15 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN_LOAD * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int BAR_BYTES = (2 * kStages + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + BAR_BYTES + 1024;
+  // smem-staged epilogue: every epilogue warp owns EPI_SLABS staging slabs of 32 rows x 64 bf16 columns (4 KB, 128B-swizzled:
+  // the box of one TMA store / one TMA residual load), one per 64-column slab of its share of the tile
+  static constexpr int EPI_SLABS = BN / (64 * (kEpiWarps / 4));
+  static constexpr int EPI_SLAB_BYTES = 32 * 128;
+  static constexpr int EPI_WARP_BYTES = EPI_SLABS * EPI_SLAB_BYTES;
+  static constexpr int EPI_BYTES = kTmaEpi ? kEpiWarps * EPI_WARP_BYTES : 0;
+  static constexpr int EPI_BARS = kTmaEpi ? kEpiWarps * EPI_SLABS : 0;
+  static constexpr int BAR_BYTES = (2 * kStages + 4 + EPI_BARS) * 8 + 16;
+  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
   static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
@@ -167,6 +175,45 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   }
 }
 
+// bias / GELU-tanh / gate * alpha / residual of 8 consecutive columns starting at c (c < p.n, c % 8 == 0) -> 8 bf16.
+// The residual arrives as the 16 bytes the staged epilogue read from its (TMA-loaded) shared-memory slab.
+__device__ __forceinline__ uint4 epilogue_group8(const GemmParams& p, const uint32_t* v8, int b, int c, const float* gate_row,
+                                                 const uint4& rv) {
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v8[i]);
+  if (p.bias) {
+    const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + (long long)b * p.bias_bs + c);
+    const float2 f0 = unpack_bf16x2(bv.x), f1 = unpack_bf16x2(bv.y), f2 = unpack_bf16x2(bv.z), f3 = unpack_bf16x2(bv.w);
+    x[0] += f0.x; x[1] += f0.y; x[2] += f1.x; x[3] += f1.y;
+    x[4] += f2.x; x[5] += f2.y; x[6] += f3.x; x[7] += f3.y;
+  }
+  if (p.act == UG_ACT_GELU_TANH) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = gelu_tanh(x[i]);
+  }
+  if (gate_row) {
+    const float* g = gate_row + c;
+    const float4 g0 = *reinterpret_cast<const float4*>(g), g1 = *reinterpret_cast<const float4*>(g + 4);
+    x[0] *= g0.x * p.alpha; x[1] *= g0.y * p.alpha; x[2] *= g0.z * p.alpha; x[3] *= g0.w * p.alpha;
+    x[4] *= g1.x * p.alpha; x[5] *= g1.y * p.alpha; x[6] *= g1.z * p.alpha; x[7] *= g1.w * p.alpha;
+  } else if (p.alpha != 1.0f) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] *= p.alpha;
+  }
+  if (p.res) {
+    const float2 f0 = unpack_bf16x2(rv.x), f1 = unpack_bf16x2(rv.y), f2 = unpack_bf16x2(rv.z), f3 = unpack_bf16x2(rv.w);
+    x[0] += f0.x; x[1] += f0.y; x[2] += f1.x; x[3] += f1.y;
+    x[4] += f2.x; x[5] += f2.y; x[6] += f3.x; x[7] += f3.y;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(x[0], x[1]);
+  o.y = pack_bf16x2(x[2], x[3]);
+  o.z = pack_bf16x2(x[4], x[5]);
+  o.w = pack_bf16x2(x[6], x[7]);
+  return o;
+}
+
 // bias (+ per-head RMSNorm weight * rstd + interleaved-pair RoPE for q / k columns) -> bf16.  c_in_head = column of the
 // first element of this 32-column chunk inside its head; `which` 0/1 = q/k head (normalised), 2 = v head (plain).
 __device__ __forceinline__ void epilogue_qkv_chunk(const GemmParams& p, const uint32_t (&v)[32], int b, int r, int col0,
@@ -244,21 +291,24 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int m
   nt = in_band / size;
 }
 
-template <int kCta, int BN, int kStages>
+template <int kCta, int BN, int kStages, bool kTmaEpi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
-                 const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ CUtensorMap tma_w2, const GemmParams p) {
-  using Cfg = GemmCfg<kCta, BN, kStages>;
+                 const __grid_constant__ CUtensorMap tma_a2, const __grid_constant__ CUtensorMap tma_w2,
+                 const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r, const GemmParams p) {
+  using Cfg = GemmCfg<kCta, BN, kStages, kTmaEpi>;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte alignment; the offset is identical in both CTAs of a pair.
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::STAGE_BYTES);
+  uint8_t* smem_epi = smem + kStages * Cfg::STAGE_BYTES;  // 1024-byte aligned (every stage is a multiple of 1 KB)
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
   uint64_t* empty = full + kStages;
   uint64_t* tmem_full = empty + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bars = tmem_empty + 2;  // [kEpiWarps][EPI_SLABS] (staged epilogue only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bars + Cfg::EPI_BARS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -278,6 +328,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], kEpiWarps * kCta);  // one arrive per epilogue warp per CTA
+    }
+    for (int s = 0; s < Cfg::EPI_BARS; ++s) mbar_init(&res_bars[s], 1);
+    if constexpr (kTmaEpi) {
+      tma_prefetch_desc(&tma_c);
+      if (p.res) tma_prefetch_desc(&tma_r);
     }
     fence_mbar_init();
   }
@@ -368,6 +423,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int q = warp & 3;
     const int col_half = (warp - 2) >> 2;  // 0 / 1 with 8 epilogue warps: which half of the tile's columns this warp converts
     const int row_local = q * 32 + lane;
+    uint32_t res_phase = 0;  // staged epilogue: parity bit per residual-slab barrier of this warp
+    (void)res_phase;
     int it = 0;
     for (int tile = unit; tile < p.total_tiles; tile += num_units, ++it) {
       int mb, nt;
@@ -377,8 +434,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int n0 = nt * BN;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after();
+      if constexpr (!kTmaEpi) {  // (the staged epilogue first issues its residual prefetch, then waits)
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
       const int lora_g = (p.lora_t || p.colmask_block) ? lora_group_of(p, r) : -1;
       // gate vector of this row: per sample, and per row segment when gate_seg_stride is set (once per tile, not per chunk)
@@ -393,7 +452,66 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           else mbar_arrive_cluster(&tmem_empty[as], 0);
         }
       };
-      if (p.qk_w) {
+      if constexpr (kTmaEpi) {
+        // ---- smem-staged epilogue: TMEM -> registers -> (bias / GELU / gate / residual) -> this warp's 128B-swizzled slab ->
+        // ONE TMA store per 32 x 64 slab (full 128-byte lines, rows / columns past the matrix edge clipped by the hardware).
+        // The residual slab is TMA-LOADED into the same staging buffer ahead of the accumulator (issued before the wait on
+        // tmem_full, so its latency hides behind the MMAs of this tile) instead of 16-byte loads strided over 32 rows. ----
+        const int ew = warp - 2;
+        uint8_t* slab0 = smem_epi + ew * Cfg::EPI_WARP_BYTES;
+        uint64_t* rbar = res_bars + ew * Cfg::EPI_SLABS;
+        const int r0 = mt * (Cfg::BM * kCta) + (int)cta_rank * Cfg::BM + q * 32;  // first row of this warp's lane quarter
+        const int cw0 = n0 + col_half * (BN / (kEpiWarps / 4));                    // first column of this warp's share
+        if (lane == 0) bulk_wait_group_read<0>();  // last tile's stores have drained their staging slabs
+        __syncwarp();
+        if (p.res && lane == 0) {
+#pragma unroll
+          for (int sl = 0; sl < Cfg::EPI_SLABS; ++sl) {
+            if (cw0 + 64 * sl < p.n) {
+              mbar_arrive_expect_tx(&rbar[sl], Cfg::EPI_SLAB_BYTES);
+              tma_load_3d(slab0 + sl * Cfg::EPI_SLAB_BYTES, &tma_r, &rbar[sl], cw0 + 64 * sl, r0, b);
+            }
+          }
+        }
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        constexpr int kChunksPerWarp = (BN / 32) / (kEpiWarps / 4);
+        const int ch0 = col_half * kChunksPerWarp;
+#pragma unroll 1
+        for (int sl = 0; sl < Cfg::EPI_SLABS; ++sl) {
+          const int cs0 = cw0 + 64 * sl;
+          const bool active = cs0 < p.n;  // warp-uniform
+          uint8_t* slab = slab0 + sl * Cfg::EPI_SLAB_BYTES;
+          if (p.res && active) {
+            mbar_wait(&rbar[sl], (res_phase >> sl) & 1u);
+            res_phase ^= 1u << sl;
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + (ch0 + 2 * sl + h) * 32, v);
+            tmem_ld_wait();
+            if (sl == Cfg::EPI_SLABS - 1 && h == 1) release_acc();
+            if (active) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int c = cs0 + 32 * h + 8 * j;
+                // row `lane` of the slab, 16-byte chunk (4 h + j) XOR-swizzled by the row's position in its 8-row atom
+                uint4* cell = reinterpret_cast<uint4*>(slab + lane * 128 + (((4 * h + j) ^ (lane & 7)) << 4));
+                if (c < p.n) *cell = epilogue_group8(p, &v[8 * j], b, c, gate_row, p.res ? *cell : make_uint4(0, 0, 0, 0));
+              }
+            }
+          }
+          if (active) {
+            fence_proxy_async_smem();  // generic-proxy writes of the slab -> visible to the TMA engine
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tma_c, slab, cs0, r0, b);
+              bulk_commit_group();
+            }
+          }
+        }
+      } else if (p.qk_w) {
         // ---- QKV projection: per-head RMSNorm (two passes over the TMEM columns of a head) + RoPE, fused ----
         const int cph = p.qk_dh >> 5;  // 32-column chunks per head
         // the two warps of a lane quarter split the tile's heads when half a tile holds whole heads; otherwise the first
@@ -450,6 +568,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   }
 
+  if constexpr (kTmaEpi) {
+    if (warp >= 2 && lane == 0) bulk_wait_group<0>();  // the last tile's TMA stores have completed before the CTA retires
+  }
   tc_fence_before();
   if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
@@ -458,10 +579,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   }
 }
 
-template <int kCta, int BN, int kStages>
+template <int kCta, int BN, int kStages, bool kTmaEpi = false>
 static int launch_gemm(const ug_gemm_args& a, cudaStream_t stream) {
-  using Cfg = GemmCfg<kCta, BN, kStages>;
-  auto kern = gemm_bf16_kernel<kCta, BN, kStages>;
+  using Cfg = GemmCfg<kCta, BN, kStages, kTmaEpi>;
+  auto kern = gemm_bf16_kernel<kCta, BN, kStages, kTmaEpi>;
   static bool attr_done[64] = {false};
   if (int st = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done, "gemm"); st != UG_OK) return st;
   CUtensorMap tma_a, tma_w;
@@ -501,6 +622,25 @@ static int launch_gemm(const ug_gemm_args& a, cudaStream_t stream) {
       if (st != UG_OK) return st;
     }
     k2_blocks = (a.k2 + Cfg::BK - 1) / Cfg::BK;
+  }
+  CUtensorMap tma_c = tma_a, tma_r = tma_a;
+  if constexpr (kTmaEpi) {
+    // output / residual as [n, rows, batch] with a 64-column x 32-row box: one epilogue warp's staging slab
+    uint32_t box[3] = {64, 32, 1};
+    {
+      uint64_t dims[3] = {(uint64_t)a.n, (uint64_t)a.rows, (uint64_t)a.batch};
+      uint64_t bs = a.batch > 1 ? (uint64_t)a.c_batch_stride : (uint64_t)a.rows * a.c_row_stride;
+      uint64_t strides[2] = {(uint64_t)a.c_row_stride * 2, bs * 2};
+      int st = encode_tmap_bf16(&tma_c, a.c, 3, dims, strides, box);
+      if (st != UG_OK) return st;
+    }
+    if (a.residual) {
+      uint64_t dims[3] = {(uint64_t)a.n, (uint64_t)a.rows, (uint64_t)a.batch};
+      uint64_t bs = a.batch > 1 ? (uint64_t)a.res_batch_stride : (uint64_t)a.rows * a.res_row_stride;
+      uint64_t strides[2] = {(uint64_t)a.res_row_stride * 2, bs * 2};
+      int st = encode_tmap_bf16(&tma_r, a.residual, 3, dims, strides, box);
+      if (st != UG_OK) return st;
+    }
   }
   GemmParams p;
   p.rows = a.rows; p.n = a.n; p.k = a.k; p.batch = a.batch;
@@ -551,13 +691,23 @@ static int launch_gemm(const ug_gemm_args& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tma_a, tma_w, tma_a2, tma_w2, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tma_a, tma_w, tma_a2, tma_w2, tma_c, tma_r, p);
   if (e != cudaSuccess) {
     set_error("gemm: launch failed: %s", cudaGetErrorString(e));
     return UG_ERR_CUDA;
   }
   count_launch();
   return UG_OK;
+}
+
+// UG_GEMM_EPILOGUE=direct|staged selects what variant 0 (auto) maps to (A/B switch; default below)
+static bool staged_epilogue_default() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("UG_GEMM_EPILOGUE");
+    cached = e ? (strcmp(e, "staged") == 0 ? 1 : 0) : 0;
+  }
+  return cached == 1;
 }
 
 }  // namespace ug
@@ -635,10 +785,21 @@ extern "C" int ug_gemm_bf16(const ug_gemm_args* args, void* stream) {
     }
     if (a.n <= 128) variant = 3;
   }
+  // epilogue flavour: variants 4 / 5 / 6 = tiles of 2 / 1 / 3 with the smem-staged TMA-store epilogue. The LoRA-in-epilogue,
+  // column-mask and fused QK-norm modes keep the direct epilogue (they need per-row state the staged path does not carry).
+  const bool special = a.lora_t || a.colmask_block || a.qk_norm_weight;
+  if (a.variant == 0 && !special && staged_epilogue_default()) variant = variant == 2 ? 4 : (variant == 1 ? 5 : 6);
+  if (variant >= 4 && variant <= 6) {
+    UG_CHECK_ARG(!special, "gemm: variants 4-6 (staged epilogue) do not compose with lora_t / colmask_block / qk_norm_weight");
+    UG_CHECK_ARG(!a.residual || a.res_batch_stride % 8 == 0 || a.batch == 1, "gemm: residual batch stride must be a multiple of 8");
+  }
   switch (variant) {
     case 1: return launch_gemm<1, 256, 4>(a, s);
     case 2: return launch_gemm<2, 256, 6>(a, s);
     case 3: return launch_gemm<1, 128, 6>(a, s);
+    case 4: return launch_gemm<2, 256, 5, true>(a, s);
+    case 5: return launch_gemm<1, 256, 3, true>(a, s);
+    case 6: return launch_gemm<1, 128, 6, true>(a, s);
     default:
       set_error("gemm: unknown variant %d", a.variant);
       return UG_ERR_INVALID;

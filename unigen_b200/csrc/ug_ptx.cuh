@@ -111,6 +111,24 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, ui
       : "memory");
 }
 
+// TMA store (shared::cta -> global, tile mode, bulk-group completion). OOB rows / columns of the box are clipped by the
+// hardware. The smem source must be made visible to the async proxy first (fence_proxy_async_smem after the writes).
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most kPending of this thread's bulk groups still READ their shared-memory source (the buffer may be reused)
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPending) : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // Cluster helpers
 // ----------------------------------------------------------------------------------------------
@@ -262,11 +280,16 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(h);
 }
-// GELU(approximate="tanh") as torch defines it.
+// GELU(approximate="tanh") as torch defines it: 0.5 x (1 + tanh(u)), u = sqrt(2/pi) (x + 0.044715 x^3). Evaluated in the
+// algebraically identical logistic form x / (1 + exp(-2u)) with one MUFU.EX2 and one MUFU.RCP (relative error ~1e-6, far below
+// bf16 resolution) instead of the ~25-instruction tanhf() — the GELU epilogue made the proj_mlp / ff1 GEMMs epilogue-bound
+// (tensor pipe 69 % active vs 76-81 % for the other projections, profiles/r02_ncu_targets_summary.txt).
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float inner = k0 * (x + k1 * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(inner));
+  const float u = k0 * (x + k1 * x * x * x);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * -2.885390081777927f));  // exp(-2u) = 2^(-2u log2 e)
+  return __fdividef(x, 1.0f + e);
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 // single MUFU.EX2 (flush-to-zero): exp2f() without the denormal-range fix-up sequence

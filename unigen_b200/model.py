@@ -229,6 +229,9 @@ class _DenoiserBase(torch.nn.Module):
             b = ws[key] = make()
         else:
             ws.move_to_end(key)
+            while len(ws) > max(int(self.max_workspaces), 1):  # the limit was lowered: trim, least recently used first
+                _, old = ws.popitem(last=False)
+                self._drop_graphs(old)
         self._buf = b
         return b
 

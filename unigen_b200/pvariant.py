@@ -87,6 +87,8 @@ class UniCombineFlux(torch.nn.Module):
         self.groups = 1 + max_conditions
         self.strict_mask = strict_mask
         self.lora: Dict[str, _LoraPair] = {}
+        self.lora_layers: Dict[str, LoraLayer] = {}
+        self._dirty: set = set()
         self.condition_types: List[str] = []
         self.trace: Optional[Dict[str, torch.Tensor]] = None
         self._bufs: Dict[Any, Any] = {}
