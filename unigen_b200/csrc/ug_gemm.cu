@@ -700,12 +700,13 @@ static int launch_gemm(const ug_gemm_args& a, cudaStream_t stream) {
   return UG_OK;
 }
 
-// UG_GEMM_EPILOGUE=direct|staged selects what variant 0 (auto) maps to (A/B switch; default below)
+// What variant 0 (auto) maps to: the smem-staged TMA-store epilogue (default: -2.4 % per cfg3 step in a same-box A/B,
+// profiles/r02_ab_epilogue_ln.txt), or the direct per-thread-store epilogue with UG_GEMM_EPILOGUE=direct (kept as the A/B arm).
 static bool staged_epilogue_default() {
   static int cached = -1;
   if (cached < 0) {
     const char* e = getenv("UG_GEMM_EPILOGUE");
-    cached = e ? (strcmp(e, "staged") == 0 ? 1 : 0) : 0;
+    cached = (e && strcmp(e, "direct") == 0) ? 0 : 1;
   }
   return cached == 1;
 }

@@ -229,11 +229,16 @@ class _DenoiserBase(torch.nn.Module):
             b = ws[key] = make()
         else:
             ws.move_to_end(key)
-            while len(ws) > max(int(self.max_workspaces), 1):  # the limit was lowered: trim, least recently used first
-                _, old = ws.popitem(last=False)
-                self._drop_graphs(old)
+            self._trim_workspaces()
         self._buf = b
         return b
+
+    def _trim_workspaces(self):
+        """Enforce `max_workspaces` (it may have been lowered): least recently used shapes go first, with their graphs."""
+        ws = self._workspaces
+        while len(ws) > max(int(self.max_workspaces), 1):
+            _, old = ws.popitem(last=False)
+            self._drop_graphs(old)
 
     def _drop_graphs(self, buf=None):
         """Forget the CUDA graphs captured over workspace `buf` (all graphs for None)."""
@@ -263,6 +268,7 @@ class _DenoiserBase(torch.nn.Module):
         graph, static, out, n_launch, buf = g
         ws_key = next(k for k, b in self._workspaces.items() if b is buf)
         self._workspaces.move_to_end(ws_key)
+        self._trim_workspaces()
         self._buf = buf
         for k, v in staged.items():
             if v is not None:
