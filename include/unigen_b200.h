@@ -251,7 +251,7 @@ int ug_gemv(const float* x, int64_t x_stride, const void* w, const void* bias, f
  * computes: the whole list on one GPU, rank r's 1/world share under sequence parallelism — there `peers` is the pool table and
  * every job's `out` is a BYTE OFFSET into the pools: each result is stored into every rank's pool, which all-gathers the table
  * (follow with ug_peer_barrier). n_j, k_j multiples of 8; x rows 16-byte aligned; batch <= 8. */
-#define UG_MAX_GEMV_JOBS 256
+#define UG_MAX_GEMV_JOBS 1024
 struct ug_peer_table;
 typedef struct ug_gemv_job {
   const void* w;      /* bf16 [n, k], contiguous */
@@ -261,7 +261,8 @@ typedef struct ug_gemv_job {
   int64_t x_stride, out_stride; /* elements */
   int32_t n, k;
   int32_t first_group;
-  int32_t flags;      /* bit 0: f = SiLU */
+  int32_t flags;      /* bit 0: f = SiLU; bit 1: out += result (with peers: added to this rank's own copy, so every copy must
+                         already hold the same value — issue a ug_peer_barrier after the launch that produced it) */
 } ug_gemv_job;
 int ug_gemv_grouped(const ug_gemv_job* jobs_dev, int32_t n_jobs, int32_t total_groups, int32_t batch, int32_t group_begin,
                     int32_t group_end, const struct ug_peer_table* peers_or_null, void* stream);

@@ -54,7 +54,7 @@ class QkvScatterArgs(C.Structure):
                 ("dst_offset", C.c_int64), ("seq_total", C.c_int32), ("dst_row0", C.c_int32)]
 
 
-UG_MAX_GEMV_JOBS = 256
+UG_MAX_GEMV_JOBS = 1024
 
 
 class GemvJob(C.Structure):

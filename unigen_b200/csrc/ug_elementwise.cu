@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, 
 // each compute 1/P of the groups and the table is all-gathered by the stores themselves.
 // ---------------------------------------------------------------------------------------------------
 struct GemvPeers {
-  int world;
+  int world, rank;
   uint8_t* base[UG_MAX_PEERS];
 };
 
@@ -526,6 +526,7 @@ __global__ void __launch_bounds__(256, 2) gemv_grouped_kernel(const ug_gemv_job*
     const float* x = J->x;
     const long long x_stride = J->x_stride;
     const bool silu_in = (J->flags & 1) != 0;
+    const bool accumulate = (J->flags & 2) != 0;
     float acc[kRows][kB];
 #pragma unroll
     for (int i = 0; i < kRows; ++i)
@@ -548,12 +549,15 @@ __global__ void __launch_bounds__(256, 2) gemv_grouped_kernel(const ug_gemv_job*
 #pragma unroll
         for (int b = 0; b < kB; ++b) {
           if (b >= batch) continue;
-          const float v = acc[i][b] + bv;
+          float v = acc[i][b] + bv;
           const long long off = (long long)b * out_stride + n0 + i;
           if (peers.world == 0) {
+            if (accumulate) v += J->out[off];
             J->out[off] = v;
           } else {
             const long long byte_off = (long long)reinterpret_cast<uintptr_t>(J->out);
+            // accumulate: the running value is this rank's OWN copy (every copy is identical after the preceding barrier)
+            if (accumulate) v += reinterpret_cast<const float*>(peers.base[peers.rank] + byte_off)[off];
 #pragma unroll
             for (int r = 0; r < UG_MAX_PEERS; ++r)  // constant indices: the table stays in the parameter bank
               if (r < peers.world) reinterpret_cast<float*>(peers.base[r] + byte_off)[off] = v;
@@ -826,10 +830,13 @@ extern "C" int ug_gemv_grouped(const ug_gemv_job* jobs_dev, int32_t n_jobs, int3
   if (group_begin == group_end) return UG_OK;
   ug::GemvPeers pp;
   pp.world = 0;
+  pp.rank = 0;
   for (int i = 0; i < UG_MAX_PEERS; ++i) pp.base[i] = nullptr;
   if (peers) {
     UG_CHECK_ARG(peers->world >= 1 && peers->world <= UG_MAX_PEERS, "gemv_grouped: bad peer world %d", peers->world);
+    UG_CHECK_ARG(peers->rank >= 0 && peers->rank < peers->world, "gemv_grouped: bad peer rank %d", peers->rank);
     pp.world = peers->world;
+    pp.rank = peers->rank;
     for (int i = 0; i < peers->world; ++i) {
       UG_CHECK_ARG(peers->base[i], "gemv_grouped: null peer base %d", i);
       pp.base[i] = reinterpret_cast<uint8_t*>(peers->base[i]);

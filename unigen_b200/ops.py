@@ -410,7 +410,7 @@ def gemv(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: Op
 
 class GemvPlan:
     """Device-resident job table of `gemv_grouped` (ug_gemv_job[]): built once per workspace, launched every step.
-    jobs: sequence of (w bf16 [n, k], bias bf16 [n] | None, x fp32 [B, k], out fp32 [B, n] view, silu_in). With `pool` (a
+    jobs: sequence of (w bf16 [n, k], bias bf16 [n] | None, x fp32 [B, k], out fp32 [B, n] view, silu_in[, accumulate]). With `pool` (a
     parallel.PeerPool) every `out` must be a view INTO that pool: its byte offset is stored instead of the pointer and the
     launch writes each result into every rank's pool."""
 
@@ -420,11 +420,13 @@ class GemvPlan:
         self.more = None
         B_all = jobs[0][2].shape[0]
         if B_all > 8:  # the kernel holds <= 8 batch rows in registers per weight pass: further rows are a second plan
-            self.more = GemvPlan([(w, b, x[8:], out[8:], s_) for w, b, x, out, s_ in jobs], device, pool)
-            jobs = [(w, b, x[:8], out[:8], s_) for w, b, x, out, s_ in jobs]
+            self.more = GemvPlan([(j[0], j[1], j[2][8:], j[3][8:]) + tuple(j[4:]) for j in jobs], device, pool)
+            jobs = [(j[0], j[1], j[2][:8], j[3][:8]) + tuple(j[4:]) for j in jobs]
         arr = (_lib.GemvJob * len(jobs))()
         self.keep, self.pool, g, self.batch = [], pool, 0, None
-        for j, (w, bias, x, out, silu_in) in enumerate(jobs):
+        for j, job in enumerate(jobs):
+            w, bias, x, out, silu_in = job[:5]
+            accumulate = bool(job[5]) if len(job) > 5 else False
             _dev(w, "gemv_grouped.w", BF16), _dev(x, "gemv_grouped.x", torch.float32), _dev(out, "gemv_grouped.out", torch.float32)
             n, k = w.shape
             B = x.shape[0]
@@ -444,13 +446,13 @@ class GemvPlan:
                 a.out = off
             else:
                 a.out = out.data_ptr()
-            a.x_stride, a.out_stride, a.n, a.k, a.first_group, a.flags = x.stride(0), out.stride(0), n, k, g, int(bool(silu_in))
+            a.x_stride, a.out_stride, a.n, a.k, a.first_group, a.flags = x.stride(0), out.stride(0), n, k, g, int(bool(silu_in)) | (2 if accumulate else 0)
             g += (n + 3) // 4
             self.keep.append((w, bias, x, out))
         self.n_jobs, self.total_groups = len(jobs), g
         raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
         self.table = raw.to(device)
-        self.weight_bytes = sum(w.numel() * 2 for w, _, _, _ in self.keep)
+        self.weight_bytes = sum(k_[0].numel() * 2 for k_ in self.keep)
 
 
 def gemv_grouped(plan: GemvPlan, rank: int = 0, world: int = 1) -> None:

@@ -597,13 +597,35 @@ class SequenceParallelUniCombineFlux(UniCombineFlux):
                 self._graphs.clear()  # captured graphs hold pointers into the old pool
                 self._pool.close()
             n_max = S  # velocity rows <= S
-            sizes = [("RECV", 3 * S * (D // P) * 2), ("AO", S_loc * D * 2), ("CAT", S_loc * 5 * D * 2), ("OUTF", n_max * a.in_channels * 2)]
+            sizes = [("RECV", 3 * S * (D // P) * 2), ("AO", S_loc * D * 2), ("CAT", S_loc * 5 * D * 2), ("OUTF", n_max * a.in_channels * 2),
+                     ("PMOD", self._mod_layout(B, self.groups - 1)[-1] * 4)]  # AdaLN tables: every rank computes 1/P, stores to all
             self._off, total = pool_layout(sizes)
             self._pool = PeerPool(self.sp_group, total, self.device_)
             self._pool_key = S_loc
             self._recv = self._pool.view(self._off["RECV"], (3, 1, S, D // P))
         buf.AO, buf.CAT = self._pool.view(self._off["AO"], (1, S_loc, D)), self._pool.view(self._off["CAT"], (1, S_loc, 5 * D))
         return buf
+
+    def _mods(self, buf, B: int, n: int):
+        """AdaLN tables SHARDED over the ranks: each rank runs 1/P of every grouped-GEMV launch and stores its results into every
+        rank's peer-mapped table (the all-gather is the stores themselves); a barrier before the accumulating LoRA launch (it
+        reads the down-projections and the running table values other ranks produced) and one after it."""
+        if not self.sp_enabled:
+            return super()._mods(buf, B, n)
+        P, r, pool = self.sp_world, self.sp_rank, self._pool
+        total = self._mod_layout(B, n)[-1]
+        flat = pool.view(self._off["PMOD"], (total,), dtype=torch.float32)
+        mp = self._mod_plans(buf, B, n, flat=flat, pool=pool)
+        mp.tembs[0].copy_(buf.temb)
+        for j in range(n):
+            mp.tembs[1 + j].copy_(buf.ctemb)
+        ops.silu(mp.tembs, mp.stembs)
+        ops.gemv_grouped(mp.main, r, P)
+        ops.gemv_grouped(mp.ctx, r, P)
+        pool.barrier()
+        ops.gemv_grouped(mp.lora, r, P)
+        pool.barrier()
+        return mp
 
     def _attention(self, buf, parts, out_name: str, bounds, vis):
         if not self.sp_enabled:

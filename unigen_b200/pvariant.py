@@ -237,7 +237,7 @@ class UniCombineFlux(torch.nn.Module):
         self._buf = self._bufs[key] = types.SimpleNamespace(
             X=z(B, S, D), NX=z(B, S, D), QKV=z(B, S, 3 * D), AO=z(B, S, D), FF=z(B, S, 4 * D), CAT=z(B, S, 5 * D),
             LT=z(B, S, 3 * self.R, dt=torch.float32), LTW=z(B, S, self.groups * LORA_BLOCK), temb=z(B, D, dt=torch.float32), ctemb=z(B, D, dt=torch.float32),
-            tmp=z(B, D, dt=torch.float32), ltmp=z(B, 16, dt=torch.float32), ltmp2=z(B, 16, dt=torch.float32), NO=None,
+            tmp=z(B, D, dt=torch.float32), NO=None, mod_plans={},
             rope=z(S, self.arch.attention_head_dim, dt=torch.float32))
         return self._buf
 
@@ -252,21 +252,84 @@ class UniCombineFlux(torch.nn.Module):
         ops.gemv(pooled, w.p1[0], w.p1[1], out=tmp, silu_out=True)
         ops.gemv(tmp, w.p2[0], w.p2[1], out=out, accumulate=True)
 
-    def _mod_table(self, w, lora: Optional[_LoraPair], tembs: torch.Tensor, n_chunks: int, ltmp: torch.Tensor,
-                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """AdaLN `linear(silu(temb))` of ALL streams of one block in one pass over the weights: tembs fp32 [G, B, D] (row 0 =
-        temb for the denoising group, rows 1.. = cond_temb for the condition groups) -> fp32 [G, B, n_chunks * D]; group g
-        additionally gets its switched LoRA update (enable_lora on norm1.linear / norm.linear, pyc L154-156, L168-170, L251-253)."""
-        G, B, D = tembs.shape
-        if out is None:
-            out = torch.empty(G, B, n_chunks * D, device=self.device_, dtype=torch.float32)
-        ops.gemv(tembs.view(G * B, D), w[0], w[1], out=out.view(G * B, n_chunks * D), silu_in=True)
-        if lora is not None:
-            t = ltmp[:B, :lora.rank]
+    def _mod_layout(self, B: int, n: int):
+        """fp32 element offsets of the per-block AdaLN tables inside one flat buffer: double block i -> [2 + n, B, 6D] (row 0 =
+        text stream / norm1_context, row 1 = image, rows 2.. = conditions), single block i -> [1 + n, B, 3D]; then the LoRA
+        down-projections t_g [jobs, B, Rp] and the [1 + n, B, D] conditioning vectors with their SiLU."""
+        D, G = self.inner_dim, 1 + n
+        off, dbl, sgl = 0, [], []
+        for _ in self.double:
+            dbl.append(off)
+            off += (2 + n) * B * 6 * D
+        for _ in self.single:
+            sgl.append(off)
+            off += G * B * 3 * D
+        n_lt = (len(self.double) + len(self.single)) * G
+        lt = off
+        off += n_lt * B * 16
+        tembs = off
+        off += G * B * D
+        stembs = off
+        off += G * B * D
+        return dbl, sgl, lt, tembs, stembs, off
+
+    def _mod_plans(self, buf, B: int, n: int, flat: Optional[torch.Tensor] = None, pool=None):
+        """Every AdaLN `linear(silu(temb))` of the step — all blocks, all streams, with the switched LoRA update of norm1.linear /
+        norm.linear (enable_lora per stream, pyc L154-156, L168-170, L251-253) — as THREE grouped-GEMV launches over
+        device-resident job tables instead of ~4 GEMVs per block and adapter group:
+          main : W silu(tembs) + b for the image / condition rows of every block (batch (1 + n) B: one weight pass serves all streams)
+          ctx  : norm1_context for the text rows (batch B) + the LoRA down-projections t_g = A_g silu(temb_g)
+          lora : table[g] += B_g t_g  (accumulating jobs; runs after `ctx`)
+        With `pool` (sequence parallelism) the flat buffer lives in the peer pool and every rank computes 1/P of each launch."""
+        key = (B, n, id(pool), flat.data_ptr() if flat is not None else 0)
+        mp = buf.mod_plans.get(key)
+        if mp is not None:
+            return mp
+        D, G, dev, L = self.inner_dim, 1 + n, self.device_, self.lora
+        dbl_off, sgl_off, lt_off, t_off, st_off, total = self._mod_layout(B, n)
+        if flat is None:
+            flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        mp = types.SimpleNamespace(flat=flat)
+        mp.tembs = flat[t_off:t_off + G * B * D].view(G, B, D)
+        mp.stembs = flat[st_off:st_off + G * B * D].view(G, B, D)
+        main, ctx, lora = [], [], []
+        lt_i = [0]
+
+        def lora_jobs(pair: _LoraPair, rows_of_group):
             for g in range(G):
-                ops.gemv(tembs[g], lora.a[g], None, out=t, silu_in=True)
-                ops.gemv(t, lora.b[g], None, out=out[g], accumulate=True)
-        return out
+                t = flat[lt_off + lt_i[0] * B * 16:lt_off + (lt_i[0] + 1) * B * 16].view(B, 16)[:, :pair.rank]
+                lt_i[0] += 1
+                ctx.append((pair.a[g], None, mp.stembs[g], t, False))
+                lora.append((pair.b[g], None, t, rows_of_group(g), False, True))
+
+        mp.dbl, mp.sgl = [], []
+        for i, w in enumerate(self.double):
+            tab = flat[dbl_off[i]:dbl_off[i] + (2 + n) * B * 6 * D].view(2 + n, B, 6 * D)
+            ctx.append((w.norm1_ctx[0], w.norm1_ctx[1], mp.stembs[0], tab[0], False))
+            main.append((w.norm1[0], w.norm1[1], mp.stembs.view(G * B, D), tab[1:].view(G * B, 6 * D), False))
+            lora_jobs(L[f"transformer_blocks.{i}.norm1"], lambda g, tab=tab: tab[1 + g])
+            mp.dbl.append((tab[0], tab[1:]))
+        for i, w in enumerate(self.single):
+            tab = flat[sgl_off[i]:sgl_off[i] + G * B * 3 * D].view(G, B, 3 * D)
+            main.append((w.norm[0], w.norm[1], mp.stembs.view(G * B, D), tab.view(G * B, 3 * D), False))
+            lora_jobs(L[f"single_transformer_blocks.{i}.norm"], lambda g, tab=tab: tab[g])
+            mp.sgl.append(tab)
+        mp.main, mp.ctx, mp.lora = (ops.GemvPlan(j, dev, pool=pool) for j in (main, ctx, lora))
+        buf.mod_plans[key] = mp
+        return mp
+
+    def _mods(self, buf, B: int, n: int):
+        """Fill the conditioning vectors' SiLU and launch the AdaLN job tables (see _mod_plans); returns the plan record with the
+        per-block tables. The sequence-parallel subclass shards the launches and all-gathers through the peer pool."""
+        mp = self._mod_plans(buf, B, n)
+        mp.tembs[0].copy_(buf.temb)
+        for j in range(n):
+            mp.tembs[1 + j].copy_(buf.ctemb)
+        ops.silu(mp.tembs, mp.stembs)
+        ops.gemv_grouped(mp.main)
+        ops.gemv_grouped(mp.ctx)
+        ops.gemv_grouped(mp.lora)
+        return mp
 
     @staticmethod
     def _chunks(row: torch.Tensor, n_chunks: int) -> List[torch.Tensor]:
@@ -351,45 +414,13 @@ class UniCombineFlux(torch.nn.Module):
         all_bounds = [0, T + N] + bounds[3:]                   # single blocks: [txt|img] share the denoising adapters
         all_groups = list(range(0, 1 + n))
 
-        # ---- AdaLN vectors of every block and stream (temb / cond_temb are step constants): block 0 on the main stream, the
-        # rest — HBM-bound weight streaming — on a side stream under the tensor-core-bound blocks ----
+        # ---- AdaLN vectors of every block and stream (temb / cond_temb are step constants): three grouped-GEMV launches ----
         L = self.lora
-        tembs = torch.empty(1 + n, B, D, device=dev, dtype=torch.float32)
-        tembs[0].copy_(buf.temb)
-        for j in range(n):
-            tembs[1 + j].copy_(buf.ctemb)
-        dbl_mods, sgl_mods = [None] * len(self.double), [None] * len(self.single)
-
-        def mods_double(i, ltmp):
-            w, p = self.double[i], f"transformer_blocks.{i}"
-            # ONE [2 + n, B, 6D] table per block: row 0 = text stream (norm1_context), row 1 = image, rows 2.. = conditions, so
-            # that ug_ln_modulate_segs / the gated GEMMs address every stream's vectors with a constant row stride
-            tab = torch.empty(2 + n, B, 6 * D, device=dev, dtype=torch.float32)
-            self._mod_table(w.norm1_ctx, None, tembs[:1], 6, ltmp, out=tab[:1])
-            self._mod_table(w.norm1, L[p + ".norm1"], tembs, 6, ltmp, out=tab[1:])
-            dbl_mods[i] = (tab[0], tab[1:])
-
-        def mods_single(i, ltmp):
-            w, p = self.single[i], f"single_transformer_blocks.{i}"
-            sgl_mods[i] = self._mod_table(w.norm, L[p + ".norm"], tembs, 3, ltmp)
-
-        mods_double(0, buf.ltmp)
-        main_stream = torch.cuda.current_stream()
-        side = self._side_stream if self.overlap_mod_gemv else None
-        if side is not None:
-            side.wait_stream(main_stream)
-        with torch.cuda.stream(side if side is not None else main_stream):
-            for i in range(1, len(self.double)):
-                mods_double(i, buf.ltmp2)
-            for i in range(len(self.single)):
-                mods_single(i, buf.ltmp2)
-        mods_joined = side is None
+        mp = self._mods(buf, B, n)
+        dbl_mods, sgl_mods = mp.dbl, mp.sgl
 
         for i, w in enumerate(self.double):  # ---- block_forward ----
             p = f"transformer_blocks.{i}"
-            if i == 1 and not mods_joined:
-                main_stream.wait_stream(side)
-                mods_joined = True
             # the image / condition streams' AdaLN vectors live in ONE [1+n, B, 6D] table so that the gated GEMMs below can
             # cover all of them in a single launch (ug_gemm_args.gate_seg_stride)
             m_txt = self._chunks(dbl_mods[i][0], 6)
@@ -428,8 +459,6 @@ class UniCombineFlux(torch.nn.Module):
             for j in range(n):
                 self._rec(f"double.{i}.cond{j}", seg(2 + j))
 
-        if not mods_joined:
-            main_stream.wait_stream(side)
         for i, w in enumerate(self.single):  # ---- single_block_forward ----
             p = f"single_transformer_blocks.{i}"
             m_x = self._chunks(sgl_mods[i][0], 3)
