@@ -226,6 +226,8 @@ def run_native(args):
     model.gemm_variant, model.attn_variant = args.gemm_variant, args.attn_variant
     model.use_cuda_graph = not args.no_graph
     model.overlap_text_stream = not args.no_text_overlap
+    if args.fuse_qk_norm is not None:
+        model.fuse_qk_norm = bool(args.fuse_qk_norm)
     E = model.expert_nums
 
     # synthetic inputs of the named shape, one distinct set per rank, resident in pinned host memory
@@ -674,6 +676,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-text-overlap", action="store_true", help="text-stream GEMMs on the main stream (A/B of the two-stream double block)")
+    ap.add_argument("--fuse-qk-norm", type=int, default=None, help="1 / 0: QK-RMSNorm + RoPE in the projection GEMM epilogue / as a separate pass "
+                                                                     "(default: the model's default)")
     ap.add_argument("--no-sp", action="store_true", help="N > 1: skip the sequence-parallel legs (data-parallel measurement only)")
     ap.add_argument("--sp-timeout", type=float, default=420.0, help="N > 1: seconds before the sequence-parallel legs are abandoned")
     ap.add_argument("--no-sp-pvariant", action="store_true", help="N > 1: skip the cfg4 P-variant sequence-parallel leg")

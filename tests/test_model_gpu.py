@@ -322,3 +322,24 @@ def test_use_shared_expert_false_and_use_transformer_params():
     assert torch.equal(v["control_joint_trans_blocks.0.attn.to_q.weight"], v["transformer_blocks.0.attn.to_q.weight"])
     assert torch.equal(v["control_single_trans_blocks.1.proj_mlp.weight"], v["single_transformer_blocks.1.proj_mlp.weight"])
     assert torch.equal(v["control_condition_embed.text_embedder.linear_2.weight"], v["time_text_embed.text_embedder.linear_2.weight"])
+
+
+def test_fused_qk_norm_epilogue_forward_matches_oracle():
+    """`fuse_qk_norm=True`: QK-RMSNorm + RoPE inside the projection GEMM epilogue instead of the separate in-place pass — same
+    per-block parity bar against the oracle, and a different (not bit-identical) rounding path than the default."""
+    cfg, sd, inp, oracle, model = _setup()
+    want = oracle.forward(**inp)[0]
+    dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()}
+    base = model(**dev)[0].clone()
+    model.fuse_qk_norm = True
+    model.trace = {}
+    got = model(**dev)[0]
+    bad = {k: rel_l2(model.trace[k], v) for k, v in oracle.trace.items()
+           if k in model.trace and not k.startswith("moe.") and rel_l2(model.trace[k], v) > 1e-2}
+    assert not bad, bad
+    assert rel_l2(got, want) < 1e-2 and rel_l2(got, base) < 1e-2
+    model.trace = None
+    model.use_cuda_graph = True
+    for _ in range(2):
+        graphed = model(**dev)[0]
+    assert torch.equal(graphed, got)

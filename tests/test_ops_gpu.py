@@ -433,3 +433,33 @@ def test_gemv_grouped_one_launch_equals_per_job_gemv(ug, B):
         assert torch.equal(pools[r][4096:].view(torch.float32).view(B, total), out)
     y = torch.empty_like(xs[2])
     assert torch.allclose(ug.silu(xs[2], y), torch.nn.functional.silu(xs[2]), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 5])
+@pytest.mark.parametrize("H,dh,rows", [(3, 128, 300), (6, 64, 333), (24, 128, 640)])
+def test_gemm_fused_qk_rmsnorm_rope_epilogue(ug, variant, H, dh, rows):
+    """north_star subsystem (1) "QK-RMSNorm and RoPE fused into the Q/K load": the q|k|v projection GEMM normalises every q / k
+    head from the fp32 accumulator and rotates it in its epilogue (direct epilogue: variants 1 / 2; smem-staged TMA-store
+    epilogue: 4 / 5, the default) == plain projection followed by the separate in-place pass, up to the bf16 rounding the
+    separate pass applies BEFORE normalising. v columns are bit-identical to the plain projection."""
+    from oracle import unigen_oracle as O
+    D, K = H * dh, 256
+    axes = (16, 56, 56) if dh == 128 else (8, 28, 28)
+    x, w, bias = rnd(2, rows, K), rnd(3 * D, K, scale=K ** -0.5), rnd(3 * D)
+    nw = (1 + 0.1 * torch.randn(2, dh)).to(torch.bfloat16).cuda()
+    ids = torch.stack([torch.zeros(rows), torch.arange(rows) // 20, torch.arange(rows) % 20], 1).float().cuda()
+    table = ug.rope_table(ids, axes)
+    fused = ug.gemm(x, w, bias=bias, variant=variant, qk_norm=dict(weight=nw, head_dim=dh, d=D, cos_sin=table, eps=1e-6))
+    plain = ug.gemm(x, w, bias=bias, variant=1)
+    assert torch.equal(fused[:, :, 2 * D:], plain[:, :, 2 * D:])
+    # fp32 reference straight from the definition (diffusers RMSNorm + apply_rotary_emb on the fp32 projection)
+    y = (x.float() @ w.float().t() + bias.float())[:, :, :2 * D].reshape(2, rows, 2, H, dh)
+    y = y * torch.rsqrt(y.pow(2).mean(-1, keepdim=True) + 1e-6) * nw.float()[None, None, :, None, :]
+    cs = table.view(rows, dh // 2, 2)
+    c, s_ = cs[None, :, None, None, :, 0], cs[None, :, None, None, :, 1]
+    y0, y1 = y[..., 0::2], y[..., 1::2]
+    want = torch.stack([y0 * c - y1 * s_, y1 * c + y0 * s_], -1).reshape(2, rows, 2 * D)
+    assert rel_l2(fused[:, :, :2 * D], want) < 4e-3
+    sep = plain.clone()
+    ug.qk_rmsnorm_rope(sep[:, :, :2 * D], 2 * H, dh, nw, table, heads_per_weight=H)
+    assert rel_l2(sep[:, :, :2 * D], want) < 6e-3  # the separate pass starts from bf16-rounded projections

@@ -214,6 +214,42 @@ __device__ __forceinline__ uint4 epilogue_group8(const GemmParams& p, const uint
   return o;
 }
 
+// Fused QK-RMSNorm + RoPE of 8 consecutive q / k columns starting at c: (acc + bias) * rstd * norm_weight, then the interleaved-
+// pair rotation with the (cos, sin) table row of token row r. `which` 0 / 1 = q / k head (selects norm_q / norm_k).
+__device__ __forceinline__ uint4 epilogue_qk_group8(const GemmParams& p, const uint32_t* v8, int b, int r, int c, int which, float rstd) {
+  const int c_in_head = c % p.qk_dh;
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v8[i]);
+  if (p.bias) {
+    const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + (long long)b * p.bias_bs + c);
+    const float2 f0 = unpack_bf16x2(bv.x), f1 = unpack_bf16x2(bv.y), f2 = unpack_bf16x2(bv.z), f3 = unpack_bf16x2(bv.w);
+    x[0] += f0.x; x[1] += f0.y; x[2] += f1.x; x[3] += f1.y;
+    x[4] += f2.x; x[5] += f2.y; x[6] += f3.x; x[7] += f3.y;
+  }
+  const uint4 wv = *reinterpret_cast<const uint4*>(p.qk_w + which * p.qk_dh + c_in_head);
+  const float2 w0 = unpack_bf16x2(wv.x), w1 = unpack_bf16x2(wv.y), w2 = unpack_bf16x2(wv.z), w3 = unpack_bf16x2(wv.w);
+  x[0] *= rstd * w0.x; x[1] *= rstd * w0.y; x[2] *= rstd * w1.x; x[3] *= rstd * w1.y;
+  x[4] *= rstd * w2.x; x[5] *= rstd * w2.y; x[6] *= rstd * w3.x; x[7] *= rstd * w3.y;
+  if (p.qk_cos_sin) {
+    const float* cs = p.qk_cos_sin + (long long)r * p.qk_dh + c_in_head;
+    const float4 t0 = __ldg(reinterpret_cast<const float4*>(cs)), t1 = __ldg(reinterpret_cast<const float4*>(cs + 4));
+    const float co[4] = {t0.x, t0.z, t1.x, t1.z}, si[4] = {t0.y, t0.w, t1.y, t1.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float a0 = x[2 * q], a1 = x[2 * q + 1];
+      x[2 * q] = a0 * co[q] - a1 * si[q];
+      x[2 * q + 1] = a1 * co[q] + a0 * si[q];
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16x2(x[0], x[1]);
+  o.y = pack_bf16x2(x[2], x[3]);
+  o.z = pack_bf16x2(x[4], x[5]);
+  o.w = pack_bf16x2(x[6], x[7]);
+  return o;
+}
+
 // bias (+ per-head RMSNorm weight * rstd + interleaved-pair RoPE for q / k columns) -> bf16.  c_in_head = column of the
 // first element of this 32-column chunk inside its head; `which` 0/1 = q/k head (normalised), 2 = v head (plain).
 __device__ __forceinline__ void epilogue_qkv_chunk(const GemmParams& p, const uint32_t (&v)[32], int b, int r, int col0,
@@ -477,6 +513,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         tc_fence_after();
         constexpr int kChunksPerWarp = (BN / 32) / (kEpiWarps / 4);
         const int ch0 = col_half * kChunksPerWarp;
+        // fused QK-RMSNorm + RoPE (q|k|v projections, BN = 256 tiles): this warp's 128 columns are ONE head (dh = 128) or two
+        // (dh = 64) of q, k or v; a first pass over the accumulator gives the per-row 1 / rms of each head, the second pass below
+        // normalises, rotates and stages — the separate in-place pass over the QKV buffer disappears
+        int qk_which = 2;
+        float qk_rstd[2] = {1.f, 1.f};
+        if constexpr (BN == 256) {
+          if (p.qk_w && cw0 < p.n) qk_which = cw0 / p.qk_d;
+          if (qk_which < 2) {
+            float ss[2] = {0.f, 0.f};
+#pragma unroll
+            for (int ch = 0; ch < kChunksPerWarp; ++ch) {
+              uint32_t v[32];
+              tmem_ld_32x32(taddr + (ch0 + ch) * 32, v);
+              tmem_ld_wait();
+              if (cw0 + 32 * ch < p.n) ss[(p.qk_dh == 64) ? (ch >> 1) : 0] += chunk_sumsq(p, v, b, cw0 + 32 * ch);
+            }
+            if (p.qk_dh != 64) ss[1] = ss[0];
+            qk_rstd[0] = rsqrtf(ss[0] / (float)p.qk_dh + p.qk_eps);
+            qk_rstd[1] = rsqrtf(ss[1] / (float)p.qk_dh + p.qk_eps);
+          }
+        }
 #pragma unroll 1
         for (int sl = 0; sl < Cfg::EPI_SLABS; ++sl) {
           const int cs0 = cw0 + 64 * sl;
@@ -498,7 +555,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 const int c = cs0 + 32 * h + 8 * j;
                 // row `lane` of the slab, 16-byte chunk (4 h + j) XOR-swizzled by the row's position in its 8-row atom
                 uint4* cell = reinterpret_cast<uint4*>(slab + lane * 128 + (((4 * h + j) ^ (lane & 7)) << 4));
-                if (c < p.n) *cell = epilogue_group8(p, &v[8 * j], b, c, gate_row, p.res ? *cell : make_uint4(0, 0, 0, 0));
+                if (c < p.n) {
+                  if (qk_which < 2) *cell = epilogue_qk_group8(p, &v[8 * j], b, r, c, qk_which, sl == 0 ? qk_rstd[0] : qk_rstd[1]);
+                  else *cell = epilogue_group8(p, &v[8 * j], b, c, gate_row, p.res ? *cell : make_uint4(0, 0, 0, 0));
+                }
               }
             }
           }
@@ -787,11 +847,23 @@ extern "C" int ug_gemm_bf16(const ug_gemm_args* args, void* stream) {
     if (a.n <= 128) variant = 3;
   }
   // epilogue flavour: variants 4 / 5 / 6 = tiles of 2 / 1 / 3 with the smem-staged TMA-store epilogue. The LoRA-in-epilogue,
-  // column-mask and fused QK-norm modes keep the direct epilogue (they need per-row state the staged path does not carry).
-  const bool special = a.lora_t || a.colmask_block || a.qk_norm_weight;
-  if (a.variant == 0 && !special && staged_epilogue_default()) variant = variant == 2 ? 4 : (variant == 1 ? 5 : 6);
+  // and column-mask modes keep the direct epilogue (they need per-row state the staged path does not carry).
+  const bool special = a.lora_t || a.colmask_block;
+  if (a.variant == 0 && !special && staged_epilogue_default()) {
+    if (a.qk_norm_weight && variant == 3) {
+      // the fused QK-norm epilogue needs a whole head inside one warp's 128 columns: BN = 256 tiles only
+      const int sms = num_sms();
+      const long long t2 = (long long)a.batch * ((a.rows + 255) / 256) * ((a.n + 255) / 256);
+      const long long t1 = (long long)a.batch * ((a.rows + 127) / 128) * ((a.n + 255) / 256);
+      const double c2 = (double)((t2 + sms / 2 - 1) / (sms / 2)) * 256 * 256 / 2.0, c1 = (double)((t1 + sms - 1) / sms) * 128 * 256 / 0.98;
+      variant = c2 <= c1 ? 2 : 1;
+    }
+    variant = variant == 2 ? 4 : (variant == 1 ? 5 : 6);
+  }
   if (variant >= 4 && variant <= 6) {
-    UG_CHECK_ARG(!special, "gemm: variants 4-6 (staged epilogue) do not compose with lora_t / colmask_block / qk_norm_weight");
+    UG_CHECK_ARG(!special, "gemm: variants 4-6 (staged epilogue) do not compose with lora_t / colmask_block");
+    UG_CHECK_ARG(!a.qk_norm_weight || (variant != 6 && a.qk_d % 128 == 0),
+                 "gemm: the staged fused QK-norm epilogue needs a 256-column tile (variants 4 / 5) and qk_d a multiple of 128");
     UG_CHECK_ARG(!a.residual || a.res_batch_stride % 8 == 0 || a.batch == 1, "gemm: residual batch stride must be a multiple of 8");
   }
   switch (variant) {
