@@ -310,7 +310,8 @@ struct Step {
   }
 
   int gemm(cudaStream_t s, View a, int k, Lin w, int n, View c, const float* gate = nullptr, const View* res = nullptr, int act = UG_ACT_NONE,
-           float alpha = 1.0f, int batch = -1, int64_t w_batch_stride = 0, int64_t bias_batch_stride = 0) const {
+           float alpha = 1.0f, int batch = -1, int64_t w_batch_stride = 0, int64_t bias_batch_stride = 0, const void* qk_rms = nullptr,
+           const float* qk_cos_sin = nullptr) const {
     ug_gemm_args g;
     memset(&g, 0, sizeof(g));
     g.a = a.p; g.a_row_stride = a.rs; g.a_batch_stride = a.bs;
@@ -321,6 +322,9 @@ struct Step {
     g.gate = gate; g.gate_batch_stride = gate ? mod_bs() : 0;
     g.alpha = alpha; g.act = act;
     if (res) { g.residual = res->p; g.res_row_stride = res->rs; g.res_batch_stride = res->bs; }
+    if (qk_rms) {  // q|k|v projection: per-head RMSNorm + RoPE in the GEMM epilogue (model.py: fuse_qk_norm, the default)
+      g.qk_norm_weight = qk_rms; g.qk_cos_sin = qk_cos_sin; g.qk_head_dim = dh; g.qk_d = D; g.qk_eps = 1e-6f;
+    }
     return ug_gemm_bf16(&g, s);
   }
   int ln(cudaStream_t s, View x, View o, const float* shift, const float* scale) const {
@@ -361,11 +365,6 @@ struct Step {
     a.scale = (float)(1.0 / sqrt((double)dh));  // the double-precision 1 / sqrt(head_dim) of the reference, rounded once
     return ug_attention_bf16(&a, main);
   }
-  int qk_norm(int row0, int rows, const void* rms, const float* rope_rows) const {
-    const int64_t rs = 3 * (int64_t)D, bs = (int64_t)(T + 2 * N) * rs;
-    return ug_qk_rmsnorm_rope(bf(L.QKV) + (int64_t)row0 * rs, rs, bs, B, rows, 2 * H, dh, rms, H, 1e-6f, rope_rows, main);
-  }
-
   // diffusers FluxTransformerBlock over [ctx (n_ctx rows) | smp (n_smp rows)] (model.py::_double_block)
   int double_block(const DoubleW& w, int slot_smp, int slot_ctx, View smp_in, View ctx_in, View smp_out, const View* ctx_out, size_t rope_off) const {
     const int n_ctx = ctx_in.rows, n_smp = smp_in.rows, Sq = n_ctx + n_smp;
@@ -381,14 +380,12 @@ struct Step {
     const bool fork = ctx_out != nullptr;  // text-stream GEMMs beside the image stream's (disjoint rows)
     cudaStream_t ts = fork ? h->text : main;
     if (fork) { cudaEventRecord(h->ev_t0, main); cudaStreamWaitEvent(ts, h->ev_t0, 0); }
-    UG_TRY(ln(ts, ctx_in, nx_c, csh_a, csc_a));
-    UG_TRY(gemm(ts, nx_c, D, w.add_qkv, 3 * D, qkv_c));
-    UG_TRY(ln(main, smp_in, nx_s, sh_a, sc_a));
-    UG_TRY(gemm(main, nx_s, D, w.qkv, 3 * D, qkv_s));
-    if (fork) { cudaEventRecord(h->ev_t1, ts); cudaStreamWaitEvent(main, h->ev_t1, 0); }
     const float* rp = f32(rope_off);
-    UG_TRY(qk_norm(0, n_ctx, w.rms_ctx, rp));
-    UG_TRY(qk_norm(n_ctx, n_smp, w.rms, rp + (size_t)n_ctx * dh));
+    UG_TRY(ln(ts, ctx_in, nx_c, csh_a, csc_a));
+    UG_TRY(gemm(ts, nx_c, D, w.add_qkv, 3 * D, qkv_c, nullptr, nullptr, UG_ACT_NONE, 1.0f, -1, 0, 0, w.rms_ctx, rp));
+    UG_TRY(ln(main, smp_in, nx_s, sh_a, sc_a));
+    UG_TRY(gemm(main, nx_s, D, w.qkv, 3 * D, qkv_s, nullptr, nullptr, UG_ACT_NONE, 1.0f, -1, 0, 0, w.rms, rp + (size_t)n_ctx * dh));
+    if (fork) { cudaEventRecord(h->ev_t1, ts); cudaStreamWaitEvent(main, h->ev_t1, 0); }
     UG_TRY(attention(Sq, ao));
     if (fork) {
       cudaEventRecord(h->ev_t0, main); cudaStreamWaitEvent(ts, h->ev_t0, 0);
@@ -413,9 +410,8 @@ struct Step {
     View cat_attn = cat, cat_mlp = cat;
     cat_mlp.p = bf(L.CAT) + D;
     UG_TRY(ln(main, x_in, nx, mod(slot), mod(slot + 1)));
-    UG_TRY(gemm(main, nx, D, w.qkv, 3 * D, qkv));
+    UG_TRY(gemm(main, nx, D, w.qkv, 3 * D, qkv, nullptr, nullptr, UG_ACT_NONE, 1.0f, -1, 0, 0, w.rms, f32(L.rope)));
     UG_TRY(gemm(main, nx, D, w.mlp, 4 * D, cat_mlp, nullptr, nullptr, UG_ACT_GELU_TANH));
-    UG_TRY(qk_norm(0, S, w.rms, f32(L.rope)));
     UG_TRY(attention(S, cat_attn));
     return gemm(main, cat, 5 * D, w.out, D, x_out, mod(slot + 2), &x_in);
   }

@@ -849,7 +849,7 @@ extern "C" int ug_gemm_bf16(const ug_gemm_args* args, void* stream) {
   // epilogue flavour: variants 4 / 5 / 6 = tiles of 2 / 1 / 3 with the smem-staged TMA-store epilogue. The LoRA-in-epilogue,
   // and column-mask modes keep the direct epilogue (they need per-row state the staged path does not carry).
   const bool special = a.lora_t || a.colmask_block;
-  if (a.variant == 0 && !special && staged_epilogue_default()) {
+  if (a.variant == 0 && !special && staged_epilogue_default() && !(a.qk_norm_weight && a.qk_d % 128 != 0)) {
     if (a.qk_norm_weight && variant == 3) {
       // the fused QK-norm epilogue needs a whole head inside one warp's 128 columns: BN = 256 tiles only
       const int sms = num_sms();

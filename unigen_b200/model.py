@@ -135,6 +135,9 @@ class _DenoiserBase(torch.nn.Module):
         self._side_stream = torch.cuda.Stream(device=self.device_)
         self.overlap_text_stream = True  # text-stream GEMMs of the double blocks on a second stream beside the image stream's
         self._text_stream = torch.cuda.Stream(device=self.device_)
+        # QK-RMSNorm + RoPE inside the q|k|v projection GEMM's (staged) epilogue — north_star "fused into the Q/K load" — instead
+        # of a separate in-place pass over the QKV buffer (-1.1 % per cfg3 step, same-box A/B in profiles/r02_ab_fuse_qk_norm.txt)
+        self.fuse_qk_norm = True
         self.trace: Optional[Dict[str, torch.Tensor]] = None  # set to {} to record per-block intermediates
         self.clone_outputs = True  # forward returns copies, not views of the workspace / graph-static buffers
 
@@ -302,7 +305,6 @@ class UniGenFlux(_DenoiserBase):
         self.norm_out_w = ws.linear("norm_out.linear", 2 * D, D)
         # proj_out has only in_channels (64) output features: keep it as is, the GEMM masks the partial N tile
         self.proj_out_w = ws.linear("proj_out", a.in_channels, D)
-        self.fuse_qk_norm = False  # QK-RMSNorm + RoPE inside the q|k|v projection GEMM epilogue (False: separate in-place pass)
 
     # ---------------------------------------------------------------------------------------------------------
     # reference API: construction

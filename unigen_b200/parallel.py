@@ -316,6 +316,8 @@ class SequenceParallelUniGenFlux(UniGenFlux):
     def _scatter(self, qkv_rows: torch.Tensor, rms, rope_rows, local_row0: int):
         a = self.arch
         row0, _, S = self._sp_rows
+        if self.fuse_qk_norm:  # q / k were normalised and rotated in the projection GEMM's epilogue: the scatter only moves heads
+            rms, rope_rows = None, None
         ops.qkv_scatter(self._pool.table, qkv_rows, a.num_attention_heads, a.attention_head_dim, rms, rope_rows, self._off["RECV"], S,
                         row0 + local_row0)
 

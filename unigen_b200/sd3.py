@@ -297,6 +297,11 @@ class UniGenSD3(_DenoiserBase):
     def _attn_qkv(self, x, aw_qkv, rms, qkv_rows):
         """q|k|v projection of one stream into its rows of a fused QKV buffer + in-place per-head RMSNorm (no RoPE)."""
         a = self.arch
+        if rms is not None and self.fuse_qk_norm and x.dim() == 3 and aw_qkv[0].dim() == 2:
+            # per-head RMSNorm of q / k inside the projection GEMM's epilogue (fp32 accumulator, no second pass over the buffer)
+            ops.gemm(x, aw_qkv[0], out=qkv_rows, bias=aw_qkv[1], variant=self.gemm_variant,
+                     qk_norm=dict(weight=rms, head_dim=a.attention_head_dim, d=self.inner_dim, cos_sin=None, eps=1e-6))
+            return
         ops.gemm(x, aw_qkv[0], out=qkv_rows, bias=aw_qkv[1], variant=self.gemm_variant)
         if rms is not None:
             ops.qk_rmsnorm_rope(qkv_rows[:, :, :2 * self.inner_dim], 2 * a.num_attention_heads, a.attention_head_dim, rms, None,
