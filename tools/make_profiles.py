@@ -125,7 +125,8 @@ def main():
             "(warm-up steps included; cold-cache, serialised launches: compare SHARES, not absolute times)\n" + summ)
     S, D, N = 4608, 3072, 4096
     cfg3 = [("grouped AdaLN GEMV (late table)", {"bytes": 9.157e9}), ("LN-modulate 4608 x 3072", {"bytes": 4.0 * S * D}),
-            ("q|k|v GEMM 4608x3072->9216", {"flops": 2.0 * S * D * 3 * D}), ("QK-RMSNorm+RoPE in place 4608x6144", {"bytes": 4.0 * S * 2 * D}),
+            ("q|k|v GEMM 4608x3072->9216", {"flops": 2.0 * S * D * 3 * D}), ("q|k|v GEMM + fused QK-norm+RoPE", {"flops": 2.0 * S * D * 3 * D}),
+            ("q|k|v GEMM (repeat, plain)", {"flops": 2.0 * S * D * 3 * D}), ("QK-RMSNorm+RoPE separate pass 4608x6144", {"bytes": 4.0 * S * 2 * D}),
             ("attention S=4608 H=24 dh=128", {"flops": 4.0 * S * S * D}), ("proj_mlp GEMM + GELU 4608x3072->12288", {"flops": 2.0 * S * D * 4 * D}),
             ("proj_out GEMM 4608x15360->3072 gate+res", {"flops": 2.0 * S * 5 * D * D}), ("ff2 GEMM 4096x12288->3072 gate+res", {"flops": 2.0 * N * 4 * D * D})]
     S5, D5 = 4096 + 333, 1536

@@ -4,7 +4,7 @@
       python tools/ncu_targets.py [--workload cfg3|cfg5]
 
 cfg3 (Flux, D = 3072, dh = 128, S = 4608):  grouped AdaLN GEMV (the step's `late` job table, ~9 GB of weights), LN-modulate
-(4608 x 3072), q|k|v projection GEMM (N = 9216), QK-RMSNorm + RoPE (in place, 4608 x 6144), joint attention (24 heads),
+(4608 x 3072), q|k|v projection GEMM (N = 9216) with the plain and with the fused QK-norm epilogue, the separate QK-RMSNorm + RoPE pass (in place, 4608 x 6144), joint attention (24 heads),
 proj_mlp GEMM with the GELU epilogue (N = 12288), ff2-shaped GEMM with the gated-residual epilogue (K = 12288), proj_out of the
 single blocks (K = 15360). cfg5 (SD3.5-medium, D = 1536, dh = 64): attention at dh = 64 and the K = 1536 GEMMs.
 The model is built exactly as bench.py builds it, one warm-up forward allocates the workspace and job tables, and the window
@@ -87,7 +87,10 @@ def main():
     prof.start()
     ops.gemv_grouped(mp.late)                                                                   # AdaLN weights, HBM-bound
     ops.ln_modulate(x, nx, shift, scale)                                                        # HBM-bound
-    ops.gemm(nx, w.qkv[0], out=buf.QKV[:, :S], bias=w.qkv[1])                                   # N = 3D
+    ops.gemm(nx, w.qkv[0], out=buf.QKV[:, :S], bias=w.qkv[1])                                   # N = 3D, plain epilogue
+    ops.gemm(nx, w.qkv[0], out=buf.QKV[:, :S], bias=w.qkv[1],                                   # the default: QK-norm + RoPE fused
+             qk_norm=dict(weight=w.rms, head_dim=dh, d=D, cos_sin=buf.rope[:S], eps=1e-6))
+    ops.gemm(nx, w.qkv[0], out=buf.QKV[:, :S], bias=w.qkv[1])                                   # (restore un-normalised q | k)
     ops.qk_rmsnorm_rope(buf.QKV[:, :S, :2 * D], 2 * H, dh, w.rms, buf.rope[:S], heads_per_weight=H)  # HBM-bound, in place
     ops.attention(buf.QKV[:, :S, 0:D], buf.QKV[:, :S, D:2 * D], buf.QKV[:, :S, 2 * D:3 * D], cat[:, :, :D], H, dh)
     ops.gemm(nx, w.mlp[0], out=cat[:, :, D:], bias=w.mlp[1], act=UG_ACT_GELU_TANH)              # N = 4D, GELU epilogue
