@@ -232,7 +232,8 @@ __device__ __forceinline__ uint4 epilogue_qk_group8(const GemmParams& p, const u
   x[0] *= rstd * w0.x; x[1] *= rstd * w0.y; x[2] *= rstd * w1.x; x[3] *= rstd * w1.y;
   x[4] *= rstd * w2.x; x[5] *= rstd * w2.y; x[6] *= rstd * w3.x; x[7] *= rstd * w3.y;
   if (p.qk_cos_sin) {
-    const float* cs = p.qk_cos_sin + (long long)r * p.qk_dh + c_in_head;
+    // rows past the matrix edge are computed (and clipped by the TMA store): keep their table reads inside the table
+    const float* cs = p.qk_cos_sin + (long long)min(r, p.rows - 1) * p.qk_dh + c_in_head;
     const float4 t0 = __ldg(reinterpret_cast<const float4*>(cs)), t1 = __ldg(reinterpret_cast<const float4*>(cs + 4));
     const float co[4] = {t0.x, t0.z, t1.x, t1.z}, si[4] = {t0.y, t0.w, t1.y, t1.w};
 #pragma unroll
