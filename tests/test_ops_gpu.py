@@ -132,7 +132,7 @@ def _sdpa_ref(qkv, H, dh, mask=None):
     return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, S, H * dh)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 5])
 @pytest.mark.parametrize("shape", [(1, 128, 1, 128), (1, 300, 3, 128), (2, 333, 2, 64), (1, 1024, 6, 64), (1, 1536, 4, 128)])
 def test_attention_full(ug, variant, shape):
     B, S, H, dh = shape
@@ -142,7 +142,7 @@ def test_attention_full(ug, variant, shape):
     assert rel_l2(out, _sdpa_ref(qkv, H, dh)) < 6e-3
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 5])
 @pytest.mark.parametrize("strict", [False, True])
 def test_attention_segment_mask_and_bit_exact_mask(ug, variant, strict):
     """[txt | img | c1 | c2] with the reference's visibility rule and the north-star's stricter one."""
@@ -463,3 +463,18 @@ def test_gemm_fused_qk_rmsnorm_rope_epilogue(ug, variant, H, dh, rows):
     sep = plain.clone()
     ug.qk_rmsnorm_rope(sep[:, :, :2 * D], 2 * H, dh, nw, table, heads_per_weight=H)
     assert rel_l2(sep[:, :, :2 * D], want) < 6e-3  # the separate pass starts from bf16-rounded projections
+
+
+@pytest.mark.parametrize("dh,H", [(128, 24), (64, 24)])
+def test_attention_split_p_variant_is_bit_identical_at_full_size(ug, dh, H):
+    """Variant 5 (P published in two 64-key halves, PV started on the first) issues the same MMAs on the same operands in the
+    same order as variant 3: bit-identical output at the cfg3 / cfg5 sequence lengths."""
+    S = 4608 if dh == 128 else 4429
+    qkv = rnd(1, S, 3, H * dh)
+    outs = []
+    for variant in (3, 5):
+        out = torch.zeros(1, S, H * dh, device="cuda", dtype=torch.bfloat16)
+        ug.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out, H, dh, variant=variant)
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    assert rel_l2(outs[1][:, :512], _sdpa_ref(qkv, H, dh)[:, :512]) < 6e-3

@@ -1,0 +1,19 @@
+#!/bin/bash
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_ops_gpu.py -m gpu -q -p no:cacheprovider -k "attention" > gpurun_out/r02h_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/r02h_pytest.log
+tail -4 gpurun_out/r02h_pytest.log
+B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-eager-baseline"
+for arm in 0 5 0 5; do
+  timeout 300 $B --attn-variant $arm > gpurun_out/r02h_ab_attn${arm}_$RANDOM.json 2>> gpurun_out/r02h_ab.err; echo "arm $arm exit $?"
+done
+for f in gpurun_out/r02h_ab_*.json; do python - "$f" <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); r=d["roofline"]
+    print(sys.argv[1].split("/")[-1], "ms/step %.2f"%d["ms_per_step"], "gemm %.2f ms"%r["ms_per_step_in_kernel"], "attn %.1f TF %.2f ms"%(r["attention"]["achieved"], r["attention"]["ms_per_step_in_kernel"]), "clk", d["clocks"]["sm_mhz"])
+except Exception as e: print(sys.argv[1], "FAILED", e)
+PY
+done
+tail -5 gpurun_out/r02h_ab.err

@@ -429,13 +429,17 @@ struct Attn2Cfg {
   static constexpr int TILE_BYTES = SLABS * SLAB_BYTES;
   static constexpr int KV_STAGES = 2;
   static constexpr int SMEM_TILES = TILE_BYTES * (2 + 2 * KV_STAGES);
-  static constexpr int NUM_BARS = 1 + 4 * KV_STAGES + 6;
+  static constexpr int NUM_BARS = 1 + 4 * KV_STAGES + 8;
   static constexpr int SMEM_BYTES = SMEM_TILES + NUM_BARS * 8 + 16 + kMaxTiles * 2 + 1024;
   static constexpr int TMEM_COLS = 512;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <int kDh, int kPolyMod>
+// kSplitP: the softmax groups publish P in two 64-key halves (p_ready / p_ready2) and the MMA warp issues the first four PV
+// MMAs as soon as the first half is in TMEM, so half of the PV work overlaps the exponentials of the second half instead of
+// waiting behind them (the per-group chain softmax -> PV -> S(next) -> softmax is what bounds this kernel: ncu shows tensor
+// pipe and MUFU ~53 % active each, i.e. mostly taking turns).
+template <int kDh, int kPolyMod, bool kSplitP>
 __global__ void __launch_bounds__(384, 1)
 attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                   const __grid_constant__ CUtensorMap tma_v, const AttnParams p) {
@@ -456,7 +460,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
   uint64_t* s_full = v_empty + KS;   // [2] per softmax group
   uint64_t* p_ready = s_full + 2;    // [2]
   uint64_t* pv_done = p_ready + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* p_ready2 = pv_done + 2;  // [2] second half of P (kSplitP)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_ready2 + 2);
   int* n_tiles_smem = reinterpret_cast<int*>(tmem_slot + 1);
   uint16_t* tile_list = reinterpret_cast<uint16_t*>(tmem_slot + 4);
 
@@ -476,6 +481,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
       mbar_init(&p_ready[s], 128);
+      mbar_init(&p_ready2[s], 128);
       mbar_init(&pv_done[s], 1);
     }
     fence_mbar_init();
@@ -541,10 +547,11 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
           umma_ss<1>(d, a_desc, b_desc, idesc_s, k != 0 ? 1u : 0u);
         }
       };
-      auto issue_pv = [&](int w, int stage, bool accumulate) {
+      auto issue_pv = [&](int w, int stage, bool accumulate, int k0 = 0, int k1 = kBlockKV / 16) {
         const uint32_t d = tmem_base + 256 + w * 128;
 #pragma unroll
         for (int k = 0; k < kBlockKV / 16; ++k) {
+          if (k < k0 || k >= k1) continue;
           const uint64_t b_desc =
               make_sdesc_sw128(smem_u32(smem_v + stage * Cfg::TILE_BYTES) + k * 2048, Cfg::SLAB_BYTES, 1024);
           umma_ts(d, tmem_base + w * 128 + k * 8, b_desc, idesc_o, (accumulate || k != 0) ? 1u : 0u);
@@ -572,8 +579,15 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
           mbar_wait(&v_full[stage], phase);
           if (more) mbar_wait(&k_full[nstage], ((i + 1) / KS) & 1);
           tc_fence_after();
+          if constexpr (kSplitP) {
+            if (lane == 0) issue_pv(0, stage, i > 0, 0, kBlockKV / 32);
+            __syncwarp();
+            mbar_wait(&p_ready2[0], i & 1);
+            tc_fence_after();
+          }
           if (lane == 0) {
-            issue_pv(0, stage, i > 0);
+            if constexpr (kSplitP) issue_pv(0, stage, true, kBlockKV / 32, kBlockKV / 16);
+            else issue_pv(0, stage, i > 0);
             umma_commit(&pv_done[0]);
             if (more) {
               issue_s(0, nstage);
@@ -584,8 +598,15 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
           // ---- group 1 ----
           mbar_wait(&p_ready[1], i & 1);
           tc_fence_after();
+          if constexpr (kSplitP) {
+            if (lane == 0) issue_pv(1, stage, i > 0, 0, kBlockKV / 32);
+            __syncwarp();
+            mbar_wait(&p_ready2[1], i & 1);
+            tc_fence_after();
+          }
           if (lane == 0) {
-            issue_pv(1, stage, i > 0);
+            if constexpr (kSplitP) issue_pv(1, stage, true, kBlockKV / 32, kBlockKV / 16);
+            else issue_pv(1, stage, i > 0);
             umma_commit(&pv_done[1]);
             umma_commit(&v_empty[stage]);
             if (more) {
@@ -687,11 +708,18 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
           pk[c] = pack_bf16x2(p0, p1);
         }
         tmem_st_32x32(s_addr + 32 * half, pk);
+        if constexpr (kSplitP) {
+          if (half == 0) {  // publish the first 64 keys of P: the MMA warp starts PV on them while the rest is exponentiated
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&p_ready[w]);
+          }
+        }
       }
       l = l * alpha + (((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7])));
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_ready[w]);
+      mbar_arrive(kSplitP ? &p_ready2[w] : &p_ready[w]);
       m = m_new;
     }
     if (n_tiles > 0) {
@@ -806,10 +834,10 @@ static int launch_attention(const ug_attn_args& a, const PeerO* peer, cudaStream
 }
 
 
-template <int kDh, int kPolyMod>
+template <int kDh, int kPolyMod, bool kSplitP = false>
 static int launch_attention2(const ug_attn_args& a, const PeerO* peer, cudaStream_t stream) {
   using Cfg = Attn2Cfg<kDh>;
-  auto kern = attention2_kernel<kDh, kPolyMod>;
+  auto kern = attention2_kernel<kDh, kPolyMod, kSplitP>;
   static bool attr_done[64] = {false};
   if (int st = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done, "attention2"); st != UG_OK) return st;
   CUtensorMap maps[3];
@@ -864,11 +892,13 @@ static int attention_dispatch(const ug_attn_args* args, const PeerO* peer, void*
     if (variant == 2) return launch_attention<128, false>(a, peer, s);
     if (variant == 3) return launch_attention2<128, 0>(a, peer, s);
     if (variant == 4) return launch_attention2<128, 4>(a, peer, s);
+    if (variant == 5) return launch_attention2<128, 0, true>(a, peer, s);
   } else if (a.head_dim == 64) {
     if (variant == 1) return launch_attention<64, true>(a, peer, s);
     if (variant == 2) return launch_attention<64, false>(a, peer, s);
     if (variant == 3) return launch_attention2<64, 0>(a, peer, s);
     if (variant == 4) return launch_attention2<64, 4>(a, peer, s);
+    if (variant == 5) return launch_attention2<64, 0, true>(a, peer, s);
   } else {
     set_error("attention: head_dim %d not supported (64 or 128)", a.head_dim);
     return UG_ERR_UNSUPPORTED;
