@@ -1036,11 +1036,9 @@ attention3_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       tmem_st_32x32(s_addr, pk);
       l = l * alpha + (((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7])));
       tmem_st_wait();
-      // (before the arrive: once P_w(j) is published the MMA warp may issue and retire PV_w(j), and a later wait for phase j-1
-      // would alias with phase j+1)
-      if (!pv_seen) mbar_wait(&pv_done[w], (j - 1) & 1);
       tc_fence_before();
       mbar_arrive(&p_ready[w]);
+      if (!pv_seen) mbar_wait(&pv_done[w], (j - 1) & 1);
       m = m_new;
     }
     if (n_tiles > 0) {
