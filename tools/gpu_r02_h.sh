@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_ops_gpu.py -m gpu -q -p no:cacheprovider -k "attention" > gpurun_out/r02h_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/r02h_pytest.log
 tail -4 gpurun_out/r02h_pytest.log
 B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-eager-baseline"
-for arm in 0 6 0 6; do
+for arm in 0 5 0 5; do
   timeout 300 $B --attn-variant $arm > gpurun_out/r02h_ab_attn${arm}_$RANDOM.json 2>> gpurun_out/r02h_ab.err; echo "arm $arm exit $?"
 done
 for f in gpurun_out/r02h_ab_*.json; do python - "$f" <<'PY'

@@ -73,9 +73,9 @@ struct AttnCfg {
 
 // Is key tile `kt` needed by query tile `qt` (any visible (query segment, key segment) pair)?  flags bit0 = needed,
 // bit1 = per-element masking required (some pair invisible, or the tile holds the sequence tail).
-__device__ __forceinline__ int classify_tile(const AttnParams& p, int qt, int kt, int block_q = kBlockQ, int block_kv = kBlockKV) {
+__device__ __forceinline__ int classify_tile(const AttnParams& p, int qt, int kt, int block_q = kBlockQ) {
   const int q_lo = qt * block_q, q_hi = min(q_lo + block_q, p.seq);
-  const int k_lo = kt * block_kv, k_hi_full = k_lo + block_kv, k_hi = min(k_hi_full, p.seq);
+  const int k_lo = kt * kBlockKV, k_hi_full = k_lo + kBlockKV, k_hi = min(k_hi_full, p.seq);
   int needed = 0, partial = (k_hi_full > p.seq) ? 1 : 0;
   if (p.n_seg == 0) return 1 | (partial << 1);
   for (int sq = 0; sq < p.n_seg; ++sq) {
@@ -91,13 +91,12 @@ __device__ __forceinline__ int classify_tile(const AttnParams& p, int qt, int kt
 // Key tiles a query tile has to visit, built by all 32 lanes of one warp (lane l classifies tiles l, l + 32, ...; a ballot
 // + prefix count compacts them in order). A single thread doing this serially cost tens of microseconds per CTA at 132 key
 // tiles x 5 segments — a large fraction of a short (condition-row) CTA's lifetime.
-__device__ __forceinline__ int build_tile_list(const AttnParams& p, int qt, int block_q, uint16_t* tile_list, int lane,
-                                               int block_kv = kBlockKV) {
-  const int total = (p.seq + block_kv - 1) / block_kv;
+__device__ __forceinline__ int build_tile_list(const AttnParams& p, int qt, int block_q, uint16_t* tile_list, int lane) {
+  const int total = (p.seq + kBlockKV - 1) / kBlockKV;
   int n = 0;
   for (int k0 = 0; k0 < total; k0 += 32) {
     const int kt = k0 + lane;
-    const int f = kt < total ? classify_tile(p, qt, kt, block_q, block_kv) : 0;
+    const int f = kt < total ? classify_tile(p, qt, kt, block_q) : 0;
     const unsigned int m = __ballot_sync(0xffffffffu, f & 1);
     if (f & 1) tile_list[n + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(kt | ((f >> 1) << 15));
     n += __popc(m);
@@ -762,324 +761,6 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
 }
 
 
-// =====================================================================================================================
-// v6: the v3 layout (two 128-row query tiles per CTA, one softmax warpgroup each) with 64-KEY sub-tiles and the score
-// accumulator of every group DOUBLE-BUFFERED in TMEM: S_w(j+1) (and S_w(j+2) right behind PV_w(j)) is issued before the
-// softmax of tile j has finished, so a group's softmax never waits for its own PV — in v3 the chain
-//   softmax(j) -> PV(j) -> S(j+1) -> softmax(j+1)
-// is serial per group (S aliases P) and ncu shows the tensor pipe and the MUFU unit ~53 % active each, i.e. taking turns.
-// TMEM (512 columns): group w: S_w[0] / S_w[1] at columns w*128 + {0, 64} (P_w(j) = bf16 pairs over the first 32 columns of
-// S_w[j & 1]), O_w at 256 + w*128.  K and V ride separate smem rings (K tile j is consumed two iterations before V tile j).
-// MMA issue order:  S0(0) S1(0) S0(1) S1(1)  then per j:  PV0(j) S0(j+2) PV1(j) S1(j+2).
-// =====================================================================================================================
-template <int kDh>
-struct Attn3Cfg {
-  static constexpr int BKV = 64;                          // keys per sub-tile
-  static constexpr int SLABS = kDh / 64;                  // 64-column (128-byte) slabs per row
-  static constexpr int Q_SLAB_BYTES = 128 * 128;          // 128 query rows x 128 B
-  static constexpr int Q_TILE_BYTES = SLABS * Q_SLAB_BYTES;
-  static constexpr int KV_SLAB_BYTES = BKV * 128;         // 64 keys x 128 B
-  static constexpr int KV_TILE_BYTES = SLABS * KV_SLAB_BYTES;
-  static constexpr int K_STAGES = 4, V_STAGES = 3;
-  static constexpr int SMEM_TILES = 2 * Q_TILE_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES;
-  static constexpr int NUM_BARS = 1 + 2 * K_STAGES + 2 * V_STAGES + 4 + 2 + 2;
-  static constexpr int SMEM_BYTES = SMEM_TILES + NUM_BARS * 8 + 16 + kMaxTiles * 2 + 1024;
-  static constexpr int TMEM_COLS = 512;
-  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-};
-
-template <int kDh>
-__global__ void __launch_bounds__(384, 1)
-attention3_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
-                  const __grid_constant__ CUtensorMap tma_v, const AttnParams p) {
-  using Cfg = Attn3Cfg<kDh>;
-  constexpr int KS = Cfg::K_STAGES, VS = Cfg::V_STAGES, BKV = Cfg::BKV;
-  constexpr int kBlockQ2 = 256;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* smem_q = smem;
-  uint8_t* smem_k = smem_q + 2 * Cfg::Q_TILE_BYTES;
-  uint8_t* smem_v = smem_k + KS * Cfg::KV_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::SMEM_TILES);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = q_full + 1;
-  uint64_t* k_empty = k_full + KS;
-  uint64_t* v_full = k_empty + KS;
-  uint64_t* v_empty = v_full + VS;
-  uint64_t* s_full = v_empty + VS;   // [group][buffer]
-  uint64_t* p_ready = s_full + 4;    // [group]
-  uint64_t* pv_done = p_ready + 2;   // [group]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
-  int* n_tiles_smem = reinterpret_cast<int*>(tmem_slot + 1);
-  uint16_t* tile_list = reinterpret_cast<uint16_t*>(tmem_slot + 4);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int qt = p.head_fastest ? blockIdx.y : blockIdx.x, head = p.head_fastest ? blockIdx.x : blockIdx.y, b = blockIdx.z;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tma_q);
-    tma_prefetch_desc(&tma_k);
-    tma_prefetch_desc(&tma_v);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
-    for (int s = 0; s < VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-    for (int s = 0; s < 4; ++s) mbar_init(&s_full[s], 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&p_ready[s], 128); mbar_init(&pv_done[s], 1); }
-    fence_mbar_init();
-  }
-  if (warp == 0) {
-    const int n = build_tile_list(p, qt, kBlockQ2, tile_list, lane, BKV);
-    if (lane == 0) *n_tiles_smem = n;
-  }
-  if (warp == 1) tmem_alloc<1>(tmem_slot, Cfg::TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int n_tiles = *n_tiles_smem;
-
-  if (warp < 4) {
-    setmaxnreg_dec<72>();
-    if (warp == 0) {
-      // ------------------------------ TMA producer: K0 K1, then V(j), K(j+2) ------------------------------
-      if (lane == 0) {
-        mbar_arrive_expect_tx(q_full, 2 * Cfg::Q_TILE_BYTES);
-#pragma unroll
-        for (int t = 0; t < 2; ++t)
-#pragma unroll
-          for (int s = 0; s < Cfg::SLABS; ++s)
-            tma_load_4d(smem_q + t * Cfg::Q_TILE_BYTES + s * Cfg::Q_SLAB_BYTES, &tma_q, q_full, s * 64, head, qt * kBlockQ2 + t * 128, b);
-      }
-      auto load_k = [&](int t) {
-        const int stage = t % KS;
-        mbar_wait(&k_empty[stage], ((t / KS) & 1) ^ 1);
-        if (lane == 0) {
-          const int kt = tile_list[t] & 0x7fff;
-          mbar_arrive_expect_tx(&k_full[stage], Cfg::KV_TILE_BYTES);
-#pragma unroll
-          for (int s = 0; s < Cfg::SLABS; ++s)
-            tma_load_4d(smem_k + stage * Cfg::KV_TILE_BYTES + s * Cfg::KV_SLAB_BYTES, &tma_k, &k_full[stage], s * 64, head, kt * BKV, b);
-        }
-        __syncwarp();
-      };
-      auto load_v = [&](int t) {
-        const int stage = t % VS;
-        mbar_wait(&v_empty[stage], ((t / VS) & 1) ^ 1);
-        if (lane == 0) {
-          const int kt = tile_list[t] & 0x7fff;
-          mbar_arrive_expect_tx(&v_full[stage], Cfg::KV_TILE_BYTES);
-#pragma unroll
-          for (int s = 0; s < Cfg::SLABS; ++s)
-            tma_load_4d(smem_v + stage * Cfg::KV_TILE_BYTES + s * Cfg::KV_SLAB_BYTES, &tma_v, &v_full[stage], s * 64, head, kt * BKV, b);
-        }
-        __syncwarp();
-      };
-      for (int t = 0; t < min(2, n_tiles); ++t) load_k(t);
-      for (int j = 0; j < n_tiles; ++j) {
-        load_v(j);
-        if (j + 2 < n_tiles) load_k(j + 2);
-      }
-    } else if (warp == 1) {
-      // ------------------------------ MMA issuer ------------------------------
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, false, false);   // S = Q K^T : 128 x 64, K = dh
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, kDh, false, true);    // O += P V : 128 x dh, K = 64 keys, V MN-major
-      auto issue_s = [&](int w, int t) {
-        const int stage = t % KS;
-        const uint32_t d = tmem_base + w * 128 + (t & 1) * 64;
-#pragma unroll
-        for (int k = 0; k < kDh / 16; ++k) {
-          const uint64_t a_desc = make_sdesc_sw128(smem_u32(smem_q + w * Cfg::Q_TILE_BYTES) + (k >> 2) * Cfg::Q_SLAB_BYTES + (k & 3) * 32, 16, 1024);
-          const uint64_t b_desc = make_sdesc_sw128(smem_u32(smem_k + stage * Cfg::KV_TILE_BYTES) + (k >> 2) * Cfg::KV_SLAB_BYTES + (k & 3) * 32, 16, 1024);
-          umma_ss<1>(d, a_desc, b_desc, idesc_s, k != 0 ? 1u : 0u);
-        }
-      };
-      auto issue_pv = [&](int w, int t, bool accumulate) {
-        const int stage = t % VS;
-        const uint32_t d = tmem_base + 256 + w * 128;
-        const uint32_t p_tmem = tmem_base + w * 128 + (t & 1) * 64;
-#pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          const uint64_t b_desc = make_sdesc_sw128(smem_u32(smem_v + stage * Cfg::KV_TILE_BYTES) + k * 2048, Cfg::KV_SLAB_BYTES, 1024);
-          umma_ts(d, p_tmem + k * 8, b_desc, idesc_o, (accumulate || k != 0) ? 1u : 0u);
-        }
-      };
-      if (n_tiles > 0) {
-        mbar_wait(q_full, 0);
-        for (int t = 0; t < min(2, n_tiles); ++t) {
-          mbar_wait(&k_full[t % KS], (t / KS) & 1);
-          tc_fence_after();
-          if (lane == 0) {
-            issue_s(0, t);
-            umma_commit(&s_full[0 * 2 + (t & 1)]);
-            issue_s(1, t);
-            umma_commit(&s_full[1 * 2 + (t & 1)]);
-            umma_commit(&k_empty[t % KS]);
-          }
-          __syncwarp();
-        }
-        for (int j = 0; j < n_tiles; ++j) {
-          const bool more = j + 2 < n_tiles;
-#pragma unroll
-          for (int w = 0; w < 2; ++w) {
-            mbar_wait(&p_ready[w], j & 1);
-            if (w == 0) {
-              mbar_wait(&v_full[j % VS], (j / VS) & 1);
-              if (more) mbar_wait(&k_full[(j + 2) % KS], ((j + 2) / KS) & 1);
-            }
-            tc_fence_after();
-            if (lane == 0) {
-              issue_pv(w, j, j > 0);
-              umma_commit(&pv_done[w]);
-              if (more) {
-                issue_s(w, j + 2);
-                umma_commit(&s_full[w * 2 + (j & 1)]);
-              }
-              if (w == 1) {
-                umma_commit(&v_empty[j % VS]);
-                if (more) umma_commit(&k_empty[(j + 2) % KS]);
-              }
-            }
-            __syncwarp();
-          }
-        }
-      }
-    }
-  } else {
-    // ------------------------------ softmax groups ------------------------------
-    setmaxnreg_inc<208>();
-    const int w = (warp - 4) >> 2;
-    const int qd = warp & 3;
-    const int row_local = qd * 32 + lane;
-    const int q_row = qt * kBlockQ2 + w * 128 + row_local;
-    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-    const uint32_t o_addr = tmem_base + lane_off + 256 + w * 128;
-    unsigned int vis = 0xffffffffu;
-    if (p.n_seg > 0) {
-      int sq = p.n_seg - 1;
-      for (int s = 0; s < p.n_seg; ++s)
-        if (q_row >= p.bounds[s] && q_row < p.bounds[s + 1]) sq = s;
-      vis = p.visible[sq];
-    }
-    float m = -INFINITY, l = 0.f;
-    for (int j = 0; j < n_tiles; ++j) {
-      const int entry = tile_list[j];
-      const int kt = entry & 0x7fff;
-      const uint32_t s_addr = tmem_base + lane_off + w * 128 + (j & 1) * 64;
-      mbar_wait(&s_full[w * 2 + (j & 1)], (j >> 1) & 1);
-      tc_fence_after();
-      uint32_t s[64];
-      tmem_ld_32x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-      tmem_ld_32x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-      tmem_ld_wait();
-      if (entry & 0x8000) {
-        unsigned int mw[2] = {0u, 0u};
-        const int k_lo = kt * BKV;
-        auto mask_range = [&](int lo, int hi) {
-          lo = max(lo, 0); hi = min(hi, BKV);
-          for (int ww = 0; ww < 2; ++ww) {
-            const int a = max(lo - 32 * ww, 0), e = min(hi - 32 * ww, 32);
-            if (a < e) mw[ww] |= (e - a == 32) ? 0xffffffffu : (((1u << (e - a)) - 1u) << a);
-          }
-        };
-        if (p.seq < k_lo + BKV) mask_range(p.seq - k_lo, BKV);
-        for (int sk = 0; sk < p.n_seg; ++sk)
-          if (!((vis >> sk) & 1u)) mask_range(p.bounds[sk] - k_lo, p.bounds[sk + 1] - k_lo);
-#pragma unroll
-        for (int c = 0; c < 64; ++c)
-          if ((mw[c >> 5] >> (c & 31)) & 1u) s[c] = 0xff800000u;
-      }
-      float rm[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) rm[c] = fmaxf(__uint_as_float(s[c]), __uint_as_float(s[c + 8]));
-#pragma unroll
-      for (int c = 16; c < 64; c += 16) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rm[i] = fmaxf(rm[i], fmaxf(__uint_as_float(s[c + i]), __uint_as_float(s[c + i + 8])));
-      }
-      const float rmax = fmaxf(fmaxf(fmaxf(rm[0], rm[1]), fmaxf(rm[2], rm[3])), fmaxf(fmaxf(rm[4], rm[5]), fmaxf(rm[6], rm[7])));
-      const float m_cand = fmaxf(m, rmax);
-      const bool grow = (m_cand - m) * p.scale_log2 > kRescaleLog2;  // lazy rescaling, see attention_kernel
-      const bool rescale = __any_sync(0xffffffffu, grow);
-      const float m_new = rescale ? m_cand : m;
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = rescale ? ex2_ftz((m - m_use) * p.scale_log2) : 1.f;
-      const float neg_ms = -m_use * p.scale_log2;
-      // pv_done[w] is observed ONCE PER TILE, in order (phase j-1 at tile j), so a wait can never alias a phase two steps back:
-      // before touching O when it must be rescaled (S_w(j) was issued BEFORE PV_w(j-1) here, so s_full no longer implies a
-      // quiescent O_w), otherwise at the end of the tile where PV_w(j-1) has long retired
-      bool pv_seen = j == 0;
-      if (j > 0 && rescale) {
-        mbar_wait(&pv_done[w], (j - 1) & 1);
-        pv_seen = true;
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < kDh / 32; ++c) {
-          uint32_t o[32];
-          tmem_ld_32x32(o_addr + 32 * c, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_32x32(o_addr + 32 * c, o);
-        }
-      }
-      float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      uint32_t pk[32];
-#pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float p0 = ex2_ftz(fmaf(__uint_as_float(s[2 * c]), p.scale_log2, neg_ms));
-        const float p1 = ex2_ftz(fmaf(__uint_as_float(s[2 * c + 1]), p.scale_log2, neg_ms));
-        rs[(2 * c) & 7] += p0;
-        rs[(2 * c + 1) & 7] += p1;
-        pk[c] = pack_bf16x2(p0, p1);
-      }
-      tmem_st_32x32(s_addr, pk);
-      l = l * alpha + (((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7])));
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_ready[w]);
-      if (!pv_seen) mbar_wait(&pv_done[w], (j - 1) & 1);
-      m = m_new;
-    }
-    if (n_tiles > 0) {
-      mbar_wait(&pv_done[w], (n_tiles - 1) & 1);
-      tc_fence_after();
-    }
-    const float inv_l = l > 0.f ? 1.f / l : 0.f;
-    __nv_bfloat16* orow = q_row < p.seq ? o_row_ptr(p, b, q_row, head, kDh) : p.o;
-#pragma unroll
-    for (int c = 0; c < kDh / 32; ++c) {
-      uint32_t o[32];
-      if (n_tiles > 0) {
-        tmem_ld_32x32(o_addr + 32 * c, o);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0u;
-      }
-      if (q_row < p.seq) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[8 * i]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
-          u.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
-          u.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
-          u.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + 32 * c + 8 * i) = u;
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<1>(tmem_base, Cfg::TMEM_COLS);
-  }
-}
-
-
 __global__ void expand_mask_kernel(int seq, int n_seg, AttnParams p, uint8_t* __restrict__ mask) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)seq * seq) return;
@@ -1186,40 +867,6 @@ static int launch_attention2(const ug_attn_args& a, const PeerO* peer, cudaStrea
   return UG_OK;
 }
 
-template <int kDh>
-static int launch_attention3(const ug_attn_args& a, const PeerO* peer, cudaStream_t stream) {
-  using Cfg = Attn3Cfg<kDh>;
-  auto kern = attention3_kernel<kDh>;
-  static bool attr_done[64] = {false};
-  if (int st = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done, "attention3"); st != UG_OK) return st;
-  UG_CHECK_ARG(a.seq <= kMaxTiles * Cfg::BKV, "attention (64-key sub-tile kernel): seq %d exceeds %d", a.seq, kMaxTiles * Cfg::BKV);
-  CUtensorMap maps[3];
-  const void* ptrs[3] = {a.q, a.k, a.v};
-  const int64_t rs[3] = {a.q_row_stride, a.k_row_stride, a.v_row_stride};
-  const int64_t bs[3] = {a.q_batch_stride, a.k_batch_stride, a.v_batch_stride};
-  for (int i = 0; i < 3; ++i) {
-    uint64_t dims[4] = {(uint64_t)kDh, (uint64_t)a.heads, (uint64_t)a.seq, (uint64_t)a.batch};
-    uint64_t bstride = a.batch > 1 ? (uint64_t)bs[i] : (uint64_t)a.seq * rs[i];
-    uint64_t strides[3] = {(uint64_t)kDh * 2, (uint64_t)rs[i] * 2, bstride * 2};
-    uint32_t box[4] = {64, 1, (uint32_t)(i == 0 ? 128 : Cfg::BKV), 1};  // Q: 128-row tiles; K / V: 64-key sub-tiles
-    int st = encode_tmap_bf16(&maps[i], ptrs[i], 4, dims, strides, box);
-    if (st != UG_OK) return st;
-  }
-  AttnParams p;
-  p.o = (__nv_bfloat16*)a.o; p.o_rs = a.o_row_stride; p.o_bs = a.o_batch_stride;
-  p.seq = a.seq; p.heads = a.heads; p.batch = a.batch;
-  set_peer(p, peer);
-  p.scale_log2 = a.scale * 1.4426950408889634f;
-  int st = fill_segments(p, a.seq, a.n_seg, a.seg_bounds, a.seg_visible);
-  if (st != UG_OK) return st;
-  const int q_tiles = (a.seq + 255) / 256;
-  p.head_fastest = ((long long)q_tiles * a.heads * a.batch < 4LL * num_sms()) ? 1 : 0;
-  dim3 grid(p.head_fastest ? a.heads : q_tiles, p.head_fastest ? q_tiles : a.heads, a.batch);
-  kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], p);
-  UG_CHECK_LAUNCH("attention3");
-  return UG_OK;
-}
-
 }  // namespace ug
 
 using namespace ug;
@@ -1246,14 +893,12 @@ static int attention_dispatch(const ug_attn_args* args, const PeerO* peer, void*
     if (variant == 3) return launch_attention2<128, 0>(a, peer, s);
     if (variant == 4) return launch_attention2<128, 4>(a, peer, s);
     if (variant == 5) return launch_attention2<128, 0, true>(a, peer, s);
-    if (variant == 6) return launch_attention3<128>(a, peer, s);
   } else if (a.head_dim == 64) {
     if (variant == 1) return launch_attention<64, true>(a, peer, s);
     if (variant == 2) return launch_attention<64, false>(a, peer, s);
     if (variant == 3) return launch_attention2<64, 0>(a, peer, s);
     if (variant == 4) return launch_attention2<64, 4>(a, peer, s);
     if (variant == 5) return launch_attention2<64, 0, true>(a, peer, s);
-    if (variant == 6) return launch_attention3<64>(a, peer, s);
   } else {
     set_error("attention: head_dim %d not supported (64 or 128)", a.head_dim);
     return UG_ERR_UNSUPPORTED;
