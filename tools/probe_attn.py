@@ -125,7 +125,8 @@ def run_variant(variant: int) -> None:
                           "ok": bool(torch.equal(m.bool(), dense_mask(S, segs, vis)))}), flush=True)
     if not ok:
         return
-    for (B, S, H, dh) in [(1, 4608, 24, 128), (1, 8704, 24, 128), (1, 1536, 24, 128), (2, 4608, 24, 128)]:
+    for (B, S, H, dh) in [(1, 4608, 24, 128), (1, 8704, 24, 128), (1, 1536, 24, 128), (2, 4608, 24, 128), (2, 4429, 24, 64),
+                          (1, 4608, 3, 128), (1, 16896, 24, 128)]:
         qkv = mk(B, S, H, dh)
         for _ in range(3):
             attn(qkv, H, dh)

@@ -162,7 +162,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(q_full, Cfg::TILE_BYTES);
 #pragma unroll
       for (int s = 0; s < Cfg::SLABS; ++s)
@@ -173,7 +173,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     for (int i = 0; i < n_tiles; ++i) {
       const int kt = tile_list[i] & 0x7fff;
       mbar_wait(&k_empty[stage], phase ^ 1);
-      if (lane == 0) {
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&k_full[stage], Cfg::TILE_BYTES);
 #pragma unroll
         for (int s = 0; s < Cfg::SLABS; ++s)
@@ -181,7 +181,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
                       kt * kBlockKV, b);
       }
       mbar_wait(&v_empty[stage], phase ^ 1);
-      if (lane == 0) {
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&v_full[stage], Cfg::TILE_BYTES);
 #pragma unroll
         for (int s = 0; s < Cfg::SLABS; ++s)
@@ -228,7 +228,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one_sync()) {
         issue_s(0, 0);
         umma_commit(&k_empty[0]);
         umma_commit(&s_full[0]);
@@ -241,7 +241,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
           const int nstage = (i + 1) % KS;
           mbar_wait(&k_full[nstage], ((i + 1) / KS) & 1);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one_sync()) {
             issue_s(nstage, (i + 1) & 1);
             umma_commit(&k_empty[nstage]);
             umma_commit(&s_full[(i + 1) & 1]);
@@ -251,7 +251,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         mbar_wait(&p_ready[i & 1], (i >> 1) & 1);
         mbar_wait(&v_full[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one_sync()) {
           issue_pv(stage, i & 1, i > 0);
           umma_commit(&v_empty[stage]);
           umma_commit(&pv_done[i & 1]);
@@ -322,16 +322,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = rescale ? ex2_ftz((m - m_use) * p.scale_log2) : 1.f;  // m = -inf -> 0
       const float neg_ms = -m_use * p.scale_log2;
-      float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      // packed fp32x2 scale-subtract and row sums (FFMA2 / FADD2): see attention2_kernel
+      float rs[8];
+      uint64_t rs2[4] = {0ull, 0ull, 0ull, 0ull};
+      const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(neg_ms, neg_ms);
       uint32_t pk[64];
 #pragma unroll
       for (int c = 0; c < 64; ++c) {
-        const float p0 = ex2_ftz(fmaf(__uint_as_float(s[2 * c]), p.scale_log2, neg_ms));
-        const float p1 = ex2_ftz(fmaf(__uint_as_float(s[2 * c + 1]), p.scale_log2, neg_ms));
-        rs[(2 * c) & 7] += p0;
-        rs[(2 * c + 1) & 7] += p1;
+        float a0, a1;
+        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(s[2 * c]), __uint_as_float(s[2 * c + 1])), sc2, nm2), a0, a1);
+        const float p0 = ex2_ftz(a0), p1 = ex2_ftz(a1);
+        rs2[c & 3] = add_f32x2(rs2[c & 3], pack_f32x2(p0, p1));
         pk[c] = pack_bf16x2(p0, p1);
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) unpack_f32x2(rs2[j], rs[2 * j], rs[2 * j + 1]);
       l = l * alpha + (((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7])));
       if constexpr (kPInTmem) {
         tmem_st_32x32(s_addr, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
@@ -468,7 +473,6 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int qt = p.head_fastest ? blockIdx.y : blockIdx.x, head = p.head_fastest ? blockIdx.x : blockIdx.y, b = blockIdx.z;
-
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_k);
@@ -501,7 +505,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     setmaxnreg_dec<72>();  // 168*384 = 64512 registers per CTA: 72*128 + 208*256 = 62464 fits
     if (warp == 0) {
       // ------------------------------ TMA producer ------------------------------
-      if (lane == 0) {
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES);
 #pragma unroll
         for (int t = 0; t < 2; ++t)
@@ -515,7 +519,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       for (int i = 0; i < n_tiles; ++i) {
         const int kt = tile_list[i] & 0x7fff;
         mbar_wait(&k_empty[stage], phase ^ 1);
-        if (lane == 0) {
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&k_full[stage], Cfg::TILE_BYTES);
 #pragma unroll
           for (int s = 0; s < Cfg::SLABS; ++s)
@@ -523,7 +527,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
                         kt * kBlockKV, b);
         }
         mbar_wait(&v_empty[stage], phase ^ 1);
-        if (lane == 0) {
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&v_full[stage], Cfg::TILE_BYTES);
 #pragma unroll
           for (int s = 0; s < Cfg::SLABS; ++s)
@@ -537,31 +541,45 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       // ------------------------------ MMA issuer ------------------------------
       constexpr uint32_t idesc_s = make_idesc_bf16(128, kBlockKV, false, false);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, kDh, false, true);
+      // Descriptors are built ONCE: per MMA only the 14-bit start-address field moves (+2 per 32 bytes along K inside a
+      // 128-byte swizzle row, + a slab / 2 KB step otherwise), so each tcgen05.mma costs the issuing thread one add per
+      // operand instead of re-encoding the descriptor (the issue thread, not the tensor pipe, was the bottleneck:
+      // ~85 cycles of scalar work per 64-cycle 128x128x16 MMA).
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const int nt = __shfl_sync(0xffffffffu, n_tiles, 0);
+      const uint64_t q_desc0 = make_sdesc_sw128(smem_u32(smem_q), 16, 1024);
+      const uint64_t k_desc0 = make_sdesc_sw128(smem_u32(smem_k), 16, 1024);
+      const uint64_t v_desc0 = make_sdesc_sw128(smem_u32(smem_v), Cfg::SLAB_BYTES, 1024);
+      // (the empty asm keeps ptxas from hoisting the 8 + 8 per-MMA addresses of every call site out of the tile loop: it
+      // would park ~50 loop-invariant values in registers, spill them, and reload them on the issue path)
       auto issue_s = [&](int w, int stage) {
-        const uint32_t d = tmem_base + w * 128;
+        uint32_t tbl = tb;
+        asm volatile("" : "+r"(tbl));
+        const uint32_t d = tbl + w * 128;
+        const uint64_t a0 = q_desc0 + (uint64_t)((w * Cfg::TILE_BYTES) >> 4);
+        const uint64_t b0 = k_desc0 + (uint64_t)((stage * Cfg::TILE_BYTES) >> 4);
 #pragma unroll
         for (int k = 0; k < kDh / 16; ++k) {
-          const uint32_t off = (k >> 2) * Cfg::SLAB_BYTES + (k & 3) * 32;
-          const uint64_t a_desc = make_sdesc_sw128(smem_u32(smem_q + w * Cfg::TILE_BYTES) + off, 16, 1024);
-          const uint64_t b_desc = make_sdesc_sw128(smem_u32(smem_k + stage * Cfg::TILE_BYTES) + off, 16, 1024);
-          umma_ss<1>(d, a_desc, b_desc, idesc_s, k != 0 ? 1u : 0u);
+          const uint32_t off = ((k >> 2) * Cfg::SLAB_BYTES + (k & 3) * 32) >> 4;
+          umma_ss<1>(d, a0 + off, b0 + off, idesc_s, k != 0 ? 1u : 0u);
         }
       };
       auto issue_pv = [&](int w, int stage, bool accumulate, int k0 = 0, int k1 = kBlockKV / 16) {
-        const uint32_t d = tmem_base + 256 + w * 128;
+        uint32_t tbl = tb;
+        asm volatile("" : "+r"(tbl));
+        const uint32_t d = tbl + 256 + w * 128;
+        const uint64_t b0 = v_desc0 + (uint64_t)((stage * Cfg::TILE_BYTES) >> 4);
 #pragma unroll
         for (int k = 0; k < kBlockKV / 16; ++k) {
           if (k < k0 || k >= k1) continue;
-          const uint64_t b_desc =
-              make_sdesc_sw128(smem_u32(smem_v + stage * Cfg::TILE_BYTES) + k * 2048, Cfg::SLAB_BYTES, 1024);
-          umma_ts(d, tmem_base + w * 128 + k * 8, b_desc, idesc_o, (accumulate || k != 0) ? 1u : 0u);
+          umma_ts(d, tbl + w * 128 + k * 8, b0 + (uint64_t)((k * 2048) >> 4), idesc_o, (accumulate || k != 0) ? 1u : 0u);
         }
       };
-      if (n_tiles > 0) {
+      if (nt > 0) {
         mbar_wait(q_full, 0);
         mbar_wait(&k_full[0], 0);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one_sync()) {
           issue_s(0, 0);
           umma_commit(&s_full[0]);
           issue_s(1, 0);
@@ -569,23 +587,22 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
           umma_commit(&k_empty[0]);
         }
         __syncwarp();
-        for (int i = 0; i < n_tiles; ++i) {
-          const int stage = i % KS;
-          const uint32_t phase = (i / KS) & 1;
-          const bool more = i + 1 < n_tiles;
-          const int nstage = (i + 1) % KS;
+        int stage = 0, nstage = 1 % KS;
+        uint32_t phase = 0, nphase = (1 / KS) & 1;
+        for (int i = 0; i < nt; ++i) {
+          const bool more = i + 1 < nt;
           // ---- group 0 ----
           mbar_wait(&p_ready[0], i & 1);
           mbar_wait(&v_full[stage], phase);
-          if (more) mbar_wait(&k_full[nstage], ((i + 1) / KS) & 1);
+          if (more) mbar_wait(&k_full[nstage], nphase);
           tc_fence_after();
           if constexpr (kSplitP) {
-            if (lane == 0) issue_pv(0, stage, i > 0, 0, kBlockKV / 32);
+            if (elect_one_sync()) issue_pv(0, stage, i > 0, 0, kBlockKV / 32);
             __syncwarp();
             mbar_wait(&p_ready2[0], i & 1);
             tc_fence_after();
           }
-          if (lane == 0) {
+          if (elect_one_sync()) {
             if constexpr (kSplitP) issue_pv(0, stage, true, kBlockKV / 32, kBlockKV / 16);
             else issue_pv(0, stage, i > 0);
             umma_commit(&pv_done[0]);
@@ -599,12 +616,12 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
           mbar_wait(&p_ready[1], i & 1);
           tc_fence_after();
           if constexpr (kSplitP) {
-            if (lane == 0) issue_pv(1, stage, i > 0, 0, kBlockKV / 32);
+            if (elect_one_sync()) issue_pv(1, stage, i > 0, 0, kBlockKV / 32);
             __syncwarp();
             mbar_wait(&p_ready2[1], i & 1);
             tc_fence_after();
           }
-          if (lane == 0) {
+          if (elect_one_sync()) {
             if constexpr (kSplitP) issue_pv(1, stage, true, kBlockKV / 32, kBlockKV / 16);
             else issue_pv(1, stage, i > 0);
             umma_commit(&pv_done[1]);
@@ -616,6 +633,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
             }
           }
           __syncwarp();
+          stage = nstage; phase = nphase;
+          if (++nstage == KS) { nstage = 0; nphase ^= 1; }
         }
       }
     }
@@ -640,6 +659,23 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     for (int i = 0; i < n_tiles; ++i) {
       const int entry = tile_list[i];
       const int kt = entry & 0x7fff;
+      // the column mask of a partially visible tile does not depend on S: build it while the S MMA is still in flight and
+      // register pressure is low (with the 128 score registers live, ptxas spilled a quarter of them around this branch)
+      unsigned int mw0 = 0u, mw1 = 0u, mw2 = 0u, mw3 = 0u;
+      if (entry & 0x8000) {
+        const int k_lo = kt * kBlockKV;
+        auto mask_range = [&](int lo, int hi) {
+          lo = max(lo, 0); hi = min(hi, kBlockKV);
+          auto word = [&](int ww) -> unsigned int {
+            const int a = max(lo - 32 * ww, 0), e = min(hi - 32 * ww, 32);
+            return a < e ? ((e - a == 32) ? 0xffffffffu : (((1u << (e - a)) - 1u) << a)) : 0u;
+          };
+          mw0 |= word(0); mw1 |= word(1); mw2 |= word(2); mw3 |= word(3);
+        };
+        if (p.seq < k_lo + kBlockKV) mask_range(p.seq - k_lo, kBlockKV);
+        for (int sk = 0; sk < p.n_seg; ++sk)
+          if (!((vis >> sk) & 1u)) mask_range(p.bounds[sk] - k_lo, p.bounds[sk + 1] - k_lo);
+      }
       mbar_wait(&s_full[w], i & 1);
       tc_fence_after();
       uint32_t s[128];
@@ -647,21 +683,11 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       for (int c = 0; c < 4; ++c) tmem_ld_32x32(s_addr + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
       tmem_ld_wait();
       if (entry & 0x8000) {
-        unsigned int mw[4] = {0u, 0u, 0u, 0u};
-        const int k_lo = kt * kBlockKV;
-        auto mask_range = [&](int lo, int hi) {
-          lo = max(lo, 0); hi = min(hi, kBlockKV);
-          for (int ww = 0; ww < 4; ++ww) {
-            const int a = max(lo - 32 * ww, 0), e = min(hi - 32 * ww, 32);
-            if (a < e) mw[ww] |= (e - a == 32) ? 0xffffffffu : (((1u << (e - a)) - 1u) << a);
-          }
-        };
-        if (p.seq < k_lo + kBlockKV) mask_range(p.seq - k_lo, kBlockKV);
-        for (int sk = 0; sk < p.n_seg; ++sk)
-          if (!((vis >> sk) & 1u)) mask_range(p.bounds[sk] - k_lo, p.bounds[sk + 1] - k_lo);
 #pragma unroll
-        for (int c = 0; c < 128; ++c)
-          if ((mw[c >> 5] >> (c & 31)) & 1u) s[c] = 0xff800000u;
+        for (int c = 0; c < 128; ++c) {
+          const unsigned int mwc = (c < 32) ? mw0 : (c < 64) ? mw1 : (c < 96) ? mw2 : mw3;
+          if ((mwc >> (c & 31)) & 1u) s[c] = 0xff800000u;
+        }
       }
       // 8 independent max chains (3-input FMNMX3), then a short tree: the row reduction is latency-, not issue-bound
       float rm[8];
@@ -681,41 +707,66 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       const float alpha = rescale ? ex2_ftz((m - m_use) * p.scale_log2) : 1.f;
       const float neg_ms = -m_use * p.scale_log2;
       // O_w is quiescent here (s_full(i) is committed after PV_w(i-1)): rescale it when the reference max moved
+      // (8-column chunks: with the 128 score registers live there is no room for 32-column round trips; ptxas spilled a
+      // quarter of the scores on the hot path to make room for this rare branch)
       if (i > 0 && rescale) {
-#pragma unroll
-        for (int c = 0; c < kDh / 32; ++c) {
-          uint32_t o[32];
-          tmem_ld_32x32(o_addr + 32 * c, o);
+#pragma unroll 1
+        for (int c = 0; c < kDh / 8; ++c) {
+          uint32_t o[8];
+          tmem_ld_32x8(o_addr + 8 * c, o);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-          tmem_st_32x32(o_addr + 32 * c, o);
+          for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+          tmem_st_32x8(o_addr + 8 * c, o);
         }
       }
-      float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      // The scale-subtract and the row sums run as packed fp32x2 instructions (FFMA2 / FADD2: the same IEEE operations, half
+      // the issue slots): a softmax warp that is alone on its scheduler has to hide everything else under its 128 MUFU.EX2
+      // (8 issue cycles each); with scalar FFMA / FADD ptxas left ~45 % of the loop's cycles outside the MUFU shadow.
+      float rs[8];
+      uint64_t rs2[4] = {0ull, 0ull, 0ull, 0ull};
+      const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(neg_ms, neg_ms);
+      // Software-pipelined over the 64 column pairs, in SOURCE order (ptxas keeps the order of independent instructions):
+      // the scale-subtract of pair t runs kDA pairs ahead of its two exponentials and the row-sum / bf16 pack kDC pairs
+      // behind them, so a softmax warp that is alone on its scheduler (the two groups are staggered) never waits on the
+      // MUFU result latency: consumers directly behind their MUFU.EX2 cost ~20 cycles per pair, as much as the MUFU itself.
+      {
+        constexpr int kDA = 2, kDC = 3;
+        uint64_t av[64];
+        float pv0[64], pv1[64];
+        uint32_t pk[64];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t pk[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          // every kPolyMod-th element takes the polynomial path (FMA pipe) instead of MUFU.EX2
-          const float a0 = fmaf(__uint_as_float(s[64 * half + 2 * c]), p.scale_log2, neg_ms);
-          const float a1 = fmaf(__uint_as_float(s[64 * half + 2 * c + 1]), p.scale_log2, neg_ms);
-          const float p0 = (kPolyMod > 0 && ((2 * c) % kPolyMod) == 0) ? ex2_poly(a0) : ex2_ftz(a0);
-          const float p1 = (kPolyMod > 0 && ((2 * c + 1) % kPolyMod) == 0) ? ex2_poly(a1) : ex2_ftz(a1);
-          rs[(2 * c) & 7] += p0;
-          rs[(2 * c + 1) & 7] += p1;
-          pk[c] = pack_bf16x2(p0, p1);
-        }
-        tmem_st_32x32(s_addr + 32 * half, pk);
-        if constexpr (kSplitP) {
-          if (half == 0) {  // publish the first 64 keys of P: the MMA warp starts PV on them while the rest is exponentiated
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&p_ready[w]);
+        for (int t = 0; t < 64 + kDA + kDC; ++t) {
+          const int cm = t - kDA, cc = t - kDA - kDC;
+          if (t < 64) av[t] = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * t]), __uint_as_float(s[2 * t + 1])), sc2, nm2);
+          if (cm >= 0 && cm < 64) {
+            if (kPolyMod > 0 && (cm % kPolyMod) == kPolyMod - 1) {
+              // every kPolyMod-th PAIR takes the polynomial (FMA-pipe) exp2 on both lanes instead of two MUFU.EX2
+              ex2_poly_x2(av[cm], pv0[cm], pv1[cm]);
+            } else {
+              float a0, a1;
+              unpack_f32x2(av[cm], a0, a1);
+              pv0[cm] = ex2_ftz(a0);
+              pv1[cm] = ex2_ftz(a1);
+            }
+          }
+          if (cc >= 0 && cc < 64) {
+            rs2[cc & 3] = add_f32x2(rs2[cc & 3], pack_f32x2(pv0[cc], pv1[cc]));
+            pk[cc] = pack_bf16x2(pv0[cc], pv1[cc]);
+            if (cc == 31) {
+              tmem_st_32x32(s_addr, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
+              if constexpr (kSplitP) {  // publish the first 64 keys of P: the MMA warp starts PV on them meanwhile
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&p_ready[w]);
+              }
+            }
+            if (cc == 63) tmem_st_32x32(s_addr + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
           }
         }
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) unpack_f32x2(rs2[j], rs[2 * j], rs[2 * j + 1]);
       l = l * alpha + (((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7])));
       tmem_st_wait();
       tc_fence_before();
@@ -893,12 +944,14 @@ static int attention_dispatch(const ug_attn_args* args, const PeerO* peer, void*
     if (variant == 3) return launch_attention2<128, 0>(a, peer, s);
     if (variant == 4) return launch_attention2<128, 4>(a, peer, s);
     if (variant == 5) return launch_attention2<128, 0, true>(a, peer, s);
+    if (variant == 6) return launch_attention2<128, 3>(a, peer, s);
   } else if (a.head_dim == 64) {
     if (variant == 1) return launch_attention<64, true>(a, peer, s);
     if (variant == 2) return launch_attention<64, false>(a, peer, s);
     if (variant == 3) return launch_attention2<64, 0>(a, peer, s);
     if (variant == 4) return launch_attention2<64, 4>(a, peer, s);
     if (variant == 5) return launch_attention2<64, 0, true>(a, peer, s);
+    if (variant == 6) return launch_attention2<64, 3>(a, peer, s);
   } else {
     set_error("attention: head_dim %d not supported (64 or 128)", a.head_dim);
     return UG_ERR_UNSUPPORTED;

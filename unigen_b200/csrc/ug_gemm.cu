@@ -396,7 +396,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int wb = p.w_batched ? b : 0;
       for (int kb = 0; kb < p.k_blocks; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
-        if (lane == 0) {
+        if (elect_one_sync()) {
           void* sa = smem_a + stage * Cfg::A_BYTES;
           void* sb = smem_b + stage * Cfg::B_BYTES;
           // second operand pair (K extension: C += A2 @ W2^T accumulates into the same TMEM tile)
@@ -434,7 +434,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
+          // elect.sync, not `lane == 0`: ptxas then knows the block is single-threaded and keeps the descriptors in uniform
+          // registers; with a lane test every tcgen05.mma was wrapped in an R2UR + ELECT / BRA.U.ANY loop
+          if (elect_one_sync()) {
             const uint64_t a_desc = make_sdesc_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES), 16, 1024);
             const uint64_t b_desc = make_sdesc_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES), 16, 1024);
 #pragma unroll

@@ -192,6 +192,16 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
          | ((uint32_t)(N >> 3) << 17)           //
          | ((uint32_t)(M >> 4) << 24);
 }
+// One lane of the (converged) warp: ptxas knows the region guarded by elect.sync is single-threaded, so the operands of the
+// tcgen05 instructions issued there stay in uniform registers. Under `if (lane == 0)` it cannot prove that and wraps every
+// tcgen05.mma in an R2UR + ELECT / BRA.U.ANY loop (~12 scalar instructions per MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
 template <int kCtaGroup>
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -245,6 +255,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // registers -> TMEM (32 lanes x 32 columns)
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
@@ -293,6 +314,30 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 // single MUFU.EX2 (flush-to-zero): exp2f() without the denormal-range fix-up sequence
+// Packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2, two IEEE fp32 operations per issue slot on a 64-bit register pair)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ float ex2_ftz(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -310,6 +355,23 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, f, 0.69328293f);
   p = fmaf(p, f, 1.0f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
+// the same polynomial on a packed pair (FFMA2 / FADD2: 6 packed + 2 clamps + 2 shift-adds for two exponentials)
+__device__ __forceinline__ void ex2_poly_x2(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  unpack_f32x2(x2, x0, x1);
+  x2 = pack_f32x2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+  const uint64_t xr2 = add_f32x2(x2, pack_f32x2(12582912.0f, 12582912.0f));
+  const uint64_t t2 = add_f32x2(xr2, pack_f32x2(-12582912.0f, -12582912.0f));
+  const uint64_t f2 = fma_f32x2(t2, pack_f32x2(-1.0f, -1.0f), x2);
+  uint64_t q2 = fma_f32x2(f2, pack_f32x2(0.05500893f, 0.05500893f), pack_f32x2(0.24221096f, 0.24221096f));
+  q2 = fma_f32x2(q2, f2, pack_f32x2(0.69328293f, 0.69328293f));
+  q2 = fma_f32x2(q2, f2, pack_f32x2(1.0f, 1.0f));
+  float q0, q1, r0, r1;
+  unpack_f32x2(q2, q0, q1);
+  unpack_f32x2(xr2, r0, r1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(r0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23));
 }
 // register budget hand-off between warp roles (whole warpgroups of 4 warps, values multiple of 8)
 template <int kRegs>
