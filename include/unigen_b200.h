@@ -174,9 +174,9 @@ typedef struct ug_attn_args {
   int32_t n_seg;
   const int32_t* seg_bounds;   /* host, n_seg + 1 entries, seg_bounds[0] = 0, seg_bounds[n_seg] = seq */
   const uint32_t* seg_visible; /* host, n_seg entries */
-  int32_t variant;             /* 0 = auto; 1 = 128-row tile, P in TMEM; 2 = 128-row tile, P staged in smem; 3 = two 128-row tiles ping-pong;
-                                * 4 / 6 = as 3 with every 4th / 3rd pair of exponentials on the FMA pipe (packed polynomial) instead of
-                                * MUFU.EX2; 5 = as 3 with P published in two 64-key halves */
+  int32_t variant;             /* 0 = auto (5 when the 256-row tiles fill the SMs, else 1); 1 = 128-row tile, P in TMEM; 2 = 128-row tile, P
+                                * staged in smem; 3 = two 128-row tiles ping-pong; 4 / 6 = as 3 with every 4th / 3rd pair of exponentials
+                                * on the FMA pipe (packed polynomial) instead of MUFU.EX2; 5 = as 3 with P published in two 64-key halves */
   int32_t reserved;
 } ug_attn_args;
 

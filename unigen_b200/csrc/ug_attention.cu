@@ -502,7 +502,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
   const int n_tiles = *n_tiles_smem;
 
   if (warp < 4) {
-    setmaxnreg_dec<72>();  // 168*384 = 64512 registers per CTA: 72*128 + 208*256 = 62464 fits
+setmaxnreg_dec<72>();  // 168*384 = 64512 registers per CTA: 72*128 + 208*256 = 62464 fits
     if (warp == 0) {
       // ------------------------------ TMA producer ------------------------------
       if (elect_one_sync()) {
@@ -591,10 +591,11 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         uint32_t phase = 0, nphase = (1 / KS) & 1;
         for (int i = 0; i < nt; ++i) {
           const bool more = i + 1 < nt;
-          // ---- group 0 ----
-          mbar_wait(&p_ready[0], i & 1);
+          // ---- group 0 ---- (K / V arrive long before P: poll them first so that nothing but the issue itself follows the
+          // wake-up on p_ready; measured 225 cycles between "P seen" and the first MMA with the waits in the other order)
           mbar_wait(&v_full[stage], phase);
           if (more) mbar_wait(&k_full[nstage], nphase);
+          mbar_wait(&p_ready[0], i & 1);
           tc_fence_after();
           if constexpr (kSplitP) {
             if (elect_one_sync()) issue_pv(0, stage, i > 0, 0, kBlockKV / 32);
@@ -643,6 +644,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
     setmaxnreg_inc<208>();
     const int w = (warp - 4) >> 2;            // group
     const int qd = warp & 3;                  // TMEM lane quarter
+    constexpr int NC = 128;                   // score columns per thread (one query row)
+    constexpr int NP = NC / 2;                // column pairs = packed P columns
     const int row_local = qd * 32 + lane;
     const int q_row = qt * kBlockQ2 + w * 128 + row_local;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
@@ -660,41 +663,41 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       const int entry = tile_list[i];
       const int kt = entry & 0x7fff;
       // the column mask of a partially visible tile does not depend on S: build it while the S MMA is still in flight and
-      // register pressure is low (with the 128 score registers live, ptxas spilled a quarter of them around this branch)
-      unsigned int mw0 = 0u, mw1 = 0u, mw2 = 0u, mw3 = 0u;
+      // register pressure is low (with the score registers live, ptxas spilled a quarter of them around this branch)
+      unsigned int mw[NC / 32];
+#pragma unroll
+      for (int ww = 0; ww < NC / 32; ++ww) mw[ww] = 0u;
       if (entry & 0x8000) {
         const int k_lo = kt * kBlockKV;
         auto mask_range = [&](int lo, int hi) {
-          lo = max(lo, 0); hi = min(hi, kBlockKV);
-          auto word = [&](int ww) -> unsigned int {
+          lo = max(lo, 0); hi = min(hi, NC);
+#pragma unroll
+          for (int ww = 0; ww < NC / 32; ++ww) {
             const int a = max(lo - 32 * ww, 0), e = min(hi - 32 * ww, 32);
-            return a < e ? ((e - a == 32) ? 0xffffffffu : (((1u << (e - a)) - 1u) << a)) : 0u;
-          };
-          mw0 |= word(0); mw1 |= word(1); mw2 |= word(2); mw3 |= word(3);
+            mw[ww] |= a < e ? ((e - a == 32) ? 0xffffffffu : (((1u << (e - a)) - 1u) << a)) : 0u;
+          }
         };
-        if (p.seq < k_lo + kBlockKV) mask_range(p.seq - k_lo, kBlockKV);
+        if (p.seq < k_lo + NC) mask_range(p.seq - k_lo, NC);
         for (int sk = 0; sk < p.n_seg; ++sk)
           if (!((vis >> sk) & 1u)) mask_range(p.bounds[sk] - k_lo, p.bounds[sk + 1] - k_lo);
       }
       mbar_wait(&s_full[w], i & 1);
       tc_fence_after();
-      uint32_t s[128];
+      uint32_t s[NC];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32(s_addr + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
+      for (int c = 0; c < NC / 32; ++c) tmem_ld_32x32(s_addr + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));
       tmem_ld_wait();
       if (entry & 0x8000) {
 #pragma unroll
-        for (int c = 0; c < 128; ++c) {
-          const unsigned int mwc = (c < 32) ? mw0 : (c < 64) ? mw1 : (c < 96) ? mw2 : mw3;
-          if ((mwc >> (c & 31)) & 1u) s[c] = 0xff800000u;
-        }
+        for (int c = 0; c < NC; ++c)
+          if ((mw[c >> 5] >> (c & 31)) & 1u) s[c] = 0xff800000u;
       }
       // 8 independent max chains (3-input FMNMX3), then a short tree: the row reduction is latency-, not issue-bound
       float rm[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) rm[c] = fmaxf(__uint_as_float(s[c]), __uint_as_float(s[c + 8]));
 #pragma unroll
-      for (int c = 16; c < 128; c += 16) {
+      for (int c = 16; c < NC; c += 16) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) rm[j] = fmaxf(rm[j], fmaxf(__uint_as_float(s[c + j]), __uint_as_float(s[c + j + 8])));
       }
@@ -707,7 +710,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       const float alpha = rescale ? ex2_ftz((m - m_use) * p.scale_log2) : 1.f;
       const float neg_ms = -m_use * p.scale_log2;
       // O_w is quiescent here (s_full(i) is committed after PV_w(i-1)): rescale it when the reference max moved
-      // (8-column chunks: with the 128 score registers live there is no room for 32-column round trips; ptxas spilled a
+      // (8-column chunks: with the score registers live there is no room for 32-column round trips; ptxas spilled a
       // quarter of the scores on the hot path to make room for this rare branch)
       if (i > 0 && rescale) {
 #pragma unroll 1
@@ -721,47 +724,36 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
         }
       }
       // The scale-subtract and the row sums run as packed fp32x2 instructions (FFMA2 / FADD2: the same IEEE operations, half
-      // the issue slots): a softmax warp that is alone on its scheduler has to hide everything else under its 128 MUFU.EX2
-      // (8 issue cycles each); with scalar FFMA / FADD ptxas left ~45 % of the loop's cycles outside the MUFU shadow.
+      // the issue slots).
       float rs[8];
       uint64_t rs2[4] = {0ull, 0ull, 0ull, 0ull};
       const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(neg_ms, neg_ms);
-      // Software-pipelined over the 64 column pairs, in SOURCE order (ptxas keeps the order of independent instructions):
-      // the scale-subtract of pair t runs kDA pairs ahead of its two exponentials and the row-sum / bf16 pack kDC pairs
-      // behind them, so a softmax warp that is alone on its scheduler (the two groups are staggered) never waits on the
-      // MUFU result latency: consumers directly behind their MUFU.EX2 cost ~20 cycles per pair, as much as the MUFU itself.
       {
-        constexpr int kDA = 2, kDC = 3;
-        uint64_t av[64];
-        float pv0[64], pv1[64];
-        uint32_t pk[64];
+        uint32_t pk[NP];
 #pragma unroll
-        for (int t = 0; t < 64 + kDA + kDC; ++t) {
-          const int cm = t - kDA, cc = t - kDA - kDC;
-          if (t < 64) av[t] = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * t]), __uint_as_float(s[2 * t + 1])), sc2, nm2);
-          if (cm >= 0 && cm < 64) {
-            if (kPolyMod > 0 && (cm % kPolyMod) == kPolyMod - 1) {
-              // every kPolyMod-th PAIR takes the polynomial (FMA-pipe) exp2 on both lanes instead of two MUFU.EX2
-              ex2_poly_x2(av[cm], pv0[cm], pv1[cm]);
-            } else {
-              float a0, a1;
-              unpack_f32x2(av[cm], a0, a1);
-              pv0[cm] = ex2_ftz(a0);
-              pv1[cm] = ex2_ftz(a1);
-            }
+        for (int c = 0; c < NP; ++c) {
+          float p0, p1;
+          const uint64_t a2 = fma_f32x2(pack_f32x2(__uint_as_float(s[2 * c]), __uint_as_float(s[2 * c + 1])), sc2, nm2);
+          if (kPolyMod > 0 && (c % kPolyMod) == kPolyMod - 1) {
+            // every kPolyMod-th PAIR takes the polynomial (FMA-pipe) exp2 on both lanes instead of two MUFU.EX2
+            ex2_poly_x2(a2, p0, p1);
+          } else {
+            float a0, a1;
+            unpack_f32x2(a2, a0, a1);
+            p0 = ex2_ftz(a0);
+            p1 = ex2_ftz(a1);
           }
-          if (cc >= 0 && cc < 64) {
-            rs2[cc & 3] = add_f32x2(rs2[cc & 3], pack_f32x2(pv0[cc], pv1[cc]));
-            pk[cc] = pack_bf16x2(pv0[cc], pv1[cc]);
-            if (cc == 31) {
-              tmem_st_32x32(s_addr, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
-              if constexpr (kSplitP) {  // publish the first 64 keys of P: the MMA warp starts PV on them meanwhile
+          rs2[c & 3] = add_f32x2(rs2[c & 3], pack_f32x2(p0, p1));
+          pk[c] = pack_bf16x2(p0, p1);
+          if (c % 32 == 31) {
+            tmem_st_32x32(s_addr + (c - 31), *reinterpret_cast<const uint32_t(*)[32]>(&pk[c - 31]));
+            if constexpr (kSplitP) {  // publish the first 64 keys of P: the MMA warp starts PV on them meanwhile
+              if (c == 31) {
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&p_ready[w]);
               }
             }
-            if (cc == 63) tmem_st_32x32(s_addr + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
           }
         }
       }
@@ -935,9 +927,10 @@ static int attention_dispatch(const ug_attn_args* args, const PeerO* peer, void*
                                 a.o_batch_stride % 8 == 0),
                "attention: batch strides must be multiples of 8 elements");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  // auto: the two-tile ping-pong kernel once there are enough 256-row query tiles to fill the machine
+  // auto: the two-tile ping-pong kernel once there are enough 256-row query tiles to fill the machine, with P published in two
+  // halves (bit-identical to variant 3; -0.4 % per cfg3 step once the MMA issue stopped being the bottleneck)
   int variant = a.variant;
-  if (variant == 0) variant = ((long long)((a.seq + 255) / 256) * a.heads * a.batch >= num_sms()) ? 3 : 1;
+  if (variant == 0) variant = ((long long)((a.seq + 255) / 256) * a.heads * a.batch >= num_sms()) ? 5 : 1;
   if (a.head_dim == 128) {
     if (variant == 1) return launch_attention<128, true>(a, peer, s);
     if (variant == 2) return launch_attention<128, false>(a, peer, s);
