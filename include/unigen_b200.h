@@ -176,7 +176,9 @@ typedef struct ug_attn_args {
   const uint32_t* seg_visible; /* host, n_seg entries */
   int32_t variant;             /* 0 = auto (5 when the 256-row tiles fill the SMs, else 1); 1 = 128-row tile, P in TMEM; 2 = 128-row tile, P
                                 * staged in smem; 3 = two 128-row tiles ping-pong; 4 / 6 = as 3 with every 4th / 3rd pair of exponentials
-                                * on the FMA pipe (packed polynomial) instead of MUFU.EX2; 5 = as 3 with P published in two 64-key halves */
+                                * on the FMA pipe (packed polynomial) instead of MUFU.EX2; 5 = as 3 with P published in two 64-key halves;
+                                * 7 = 5 as a persistent grid (one CTA per SM walks the (query tile, head) units, next unit's Q / K / V
+                                * prefetched, epilogue overlapped with the next unit's first MMAs; bit-identical, measured 2-3 % slower) */
   int32_t reserved;
 } ug_attn_args;
 

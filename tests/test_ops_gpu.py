@@ -132,7 +132,7 @@ def _sdpa_ref(qkv, H, dh, mask=None):
     return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, S, H * dh)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
 @pytest.mark.parametrize("shape", [(1, 128, 1, 128), (1, 300, 3, 128), (2, 333, 2, 64), (1, 1024, 6, 64), (1, 1536, 4, 128)])
 def test_attention_full(ug, variant, shape):
     B, S, H, dh = shape
@@ -142,7 +142,7 @@ def test_attention_full(ug, variant, shape):
     assert rel_l2(out, _sdpa_ref(qkv, H, dh)) < 6e-3
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
 @pytest.mark.parametrize("strict", [False, True])
 def test_attention_segment_mask_and_bit_exact_mask(ug, variant, strict):
     """[txt | img | c1 | c2] with the reference's visibility rule and the north-star's stricter one."""
@@ -472,9 +472,27 @@ def test_attention_split_p_variant_is_bit_identical_at_full_size(ug, dh, H):
     S = 4608 if dh == 128 else 4429
     qkv = rnd(1, S, 3, H * dh)
     outs = []
-    for variant in (3, 5):
+    for variant in (3, 5, 7):  # 7 = the persistent form of 5 (one CTA per SM walking the (query tile, head) units)
         out = torch.zeros(1, S, H * dh, device="cuda", dtype=torch.bfloat16)
         ug.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out, H, dh, variant=variant)
         outs.append(out)
-    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     assert rel_l2(outs[1][:, :512], _sdpa_ref(qkv, H, dh)[:, :512]) < 6e-3
+
+
+def test_attention_persistent_segment_mask_many_units(ug):
+    """Persistent two-tile kernel with more work units than SMs AND a segment mask (units of different length, tile lists built
+    one unit ahead): bit-identical to the one-unit-per-CTA kernel."""
+    from oracle import unigen_oracle as O
+    bounds = [0, 512, 2560, 3584, 4608]
+    vis = O.pvariant_visibility(2)
+    S, H, dh = bounds[-1], 12, 128
+    qkv = rnd(2, S, 3, H * dh)
+    outs = []
+    for variant in (5, 7):
+        out = torch.zeros(2, S, H * dh, device="cuda", dtype=torch.bfloat16)
+        ug.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out, H, dh, seg_bounds=bounds, seg_visible=vis, variant=variant)
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    mask = O.segment_mask(bounds, vis)
+    assert rel_l2(outs[1][:, ::7], _sdpa_ref(qkv, H, dh, mask.cuda())[:, ::7]) < 6e-3

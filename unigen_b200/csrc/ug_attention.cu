@@ -8,6 +8,8 @@
 // column mask on tiles that straddle a segment boundary; it is the same rule ug_expand_segment_mask materialises.
 //
 // Replaces F.scaled_dot_product_attention in diffusers FluxAttnProcessor2_0.
+#include <algorithm>
+
 #include "ug_host.h"
 #include "ug_ptx.cuh"
 
@@ -35,6 +37,7 @@ struct AttnParams {
   // 1 = head fastest (grid = (heads, q_tiles, batch)): with few CTAs per SM and a segment mask, the query tiles with the
   // most visible keys (text / image rows come first) all start in the first wave instead of trailing in the last one
   int head_fastest;
+  int q_tiles2, n_units;  // persistent two-tile kernel: 256-row query tiles and work units (= q_tiles2 * heads * batch)
 };
 
 __device__ __forceinline__ __nv_bfloat16* o_row_ptr(const AttnParams& p, int b, int q_row, int head, int dh) {
@@ -434,8 +437,8 @@ struct Attn2Cfg {
   static constexpr int TILE_BYTES = SLABS * SLAB_BYTES;
   static constexpr int KV_STAGES = 2;
   static constexpr int SMEM_TILES = TILE_BYTES * (2 + 2 * KV_STAGES);
-  static constexpr int NUM_BARS = 1 + 4 * KV_STAGES + 8;
-  static constexpr int SMEM_BYTES = SMEM_TILES + NUM_BARS * 8 + 16 + kMaxTiles * 2 + 1024;
+  static constexpr int NUM_BARS = 1 + 4 * KV_STAGES + 8 + 5;   // + q_empty, list_full[2], list_empty[2] (persistent mode)
+  static constexpr int SMEM_BYTES = SMEM_TILES + NUM_BARS * 8 + 16 + 2 * kMaxTiles * 2 + 1024;
   static constexpr int TMEM_COLS = 512;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
@@ -444,7 +447,14 @@ struct Attn2Cfg {
 // MMAs as soon as the first half is in TMEM, so half of the PV work overlaps the exponentials of the second half instead of
 // waiting behind them (the per-group chain softmax -> PV -> S(next) -> softmax is what bounds this kernel: ncu shows tensor
 // pipe and MUFU ~53 % active each, i.e. mostly taking turns).
-template <int kDh, int kPolyMod, bool kSplitP>
+// kPersist: grid = min(units, SMs); every CTA walks the work units u = blockIdx.x, + gridDim.x, ... (unit = one 256-row query
+// tile of one head). The K / V ring, the MMA issue stream and the barrier phases simply continue across units: the producer
+// prefetches the next unit's Q (as soon as the last S MMAs of the current one have retired) and its first K / V tiles, the
+// MMA warp issues S(0) of the next unit behind the last PV of the current one, so the O epilogue of one unit overlaps the
+// first MMAs of the next, and TMEM allocation / barrier init / CTA launch are paid once. Per-unit key-tile lists are built
+// one unit ahead by warp 2 into a double buffer. (Cycle stamps of the one-unit-per-CTA form at S = 4608: ~9 of 83 us per
+// CTA were prologue, epilogue, the tail where one group idles, and the relaunch gap.)
+template <int kDh, int kPolyMod, bool kSplitP, bool kPersist>
 __global__ void __launch_bounds__(384, 1)
 attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                   const __grid_constant__ CUtensorMap tma_v, const AttnParams p) {
@@ -466,13 +476,31 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
   uint64_t* p_ready = s_full + 2;    // [2]
   uint64_t* pv_done = p_ready + 2;   // [2]
   uint64_t* p_ready2 = pv_done + 2;  // [2] second half of P (kSplitP)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_ready2 + 2);
-  int* n_tiles_smem = reinterpret_cast<int*>(tmem_slot + 1);
-  uint16_t* tile_list = reinterpret_cast<uint16_t*>(tmem_slot + 4);
+  uint64_t* q_empty = p_ready2 + 2;    // persistent mode: the unit's last S MMAs retired, Q may be overwritten
+  uint64_t* list_full = q_empty + 1;   // [2] tile list of unit k is in buffer k & 1
+  uint64_t* list_empty = list_full + 2;  // [2] every consumer is done with it (10 arrivals: producer, MMA, 8 softmax warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(list_empty + 2);
+  int* n_tiles_smem = reinterpret_cast<int*>(tmem_slot + 1);  // [2]
+  uint16_t* tile_lists = reinterpret_cast<uint16_t*>(tmem_slot + 4);  // [2][kMaxTiles]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = p.head_fastest ? blockIdx.y : blockIdx.x, head = p.head_fastest ? blockIdx.x : blockIdx.y, b = blockIdx.z;
+  const int n_units = kPersist ? p.n_units : 1;
+  const int u_first = kPersist ? (int)blockIdx.x : 0, u_step = kPersist ? (int)gridDim.x : 1;
+  // work unit -> (256-row query tile, head, batch); same order as the one-unit-per-CTA grid
+  auto decode = [&](int u, int& qt, int& head, int& b) {
+    if constexpr (kPersist) {
+      const int fast = p.head_fastest ? p.heads : p.q_tiles2, slow = p.head_fastest ? p.q_tiles2 : p.heads;
+      const int x = u % fast, y = (u / fast) % slow;
+      b = u / (fast * slow);
+      qt = p.head_fastest ? y : x;
+      head = p.head_fastest ? x : y;
+    } else {
+      qt = p.head_fastest ? blockIdx.y : blockIdx.x;
+      head = p.head_fastest ? blockIdx.x : blockIdx.y;
+      b = blockIdx.z;
+    }
+  };
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_k);
@@ -487,55 +515,80 @@ attention2_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_consta
       mbar_init(&p_ready[s], 128);
       mbar_init(&p_ready2[s], 128);
       mbar_init(&pv_done[s], 1);
+      mbar_init(&list_full[s], 1);
+      mbar_init(&list_empty[s], 10);
     }
+    mbar_init(q_empty, 1);
     fence_mbar_init();
   }
-  if (warp == 0) {
-    const int n = build_tile_list(p, qt, kBlockQ2, tile_list, lane);
-    if (lane == 0) *n_tiles_smem = n;
+  if constexpr (!kPersist) {
+    if (warp == 0) {
+      int qt, head, b;
+      decode(0, qt, head, b);
+      const int n = build_tile_list(p, qt, kBlockQ2, tile_lists, lane);
+      if (lane == 0) n_tiles_smem[0] = n;
+    }
   }
   if (warp == 1) tmem_alloc<1>(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_tiles = *n_tiles_smem;
+  // tile list of the k-th unit of this CTA (persistent: wait until warp 2 has built it)
+  auto acquire_list = [&](int k, const uint16_t*& tile_list) -> int {
+    if constexpr (kPersist) mbar_wait(&list_full[k & 1], (k >> 1) & 1);
+    tile_list = tile_lists + (k & 1) * kMaxTiles;
+    return n_tiles_smem[k & 1];
+  };
+  auto release_list = [&](int k) {  // by ONE lane per consumer warp
+    if constexpr (kPersist) mbar_arrive(&list_empty[k & 1]);
+  };
 
   if (warp < 4) {
 setmaxnreg_dec<72>();  // 168*384 = 64512 registers per CTA: 72*128 + 208*256 = 62464 fits
     if (warp == 0) {
       // ------------------------------ TMA producer ------------------------------
-      if (elect_one_sync()) {
-        mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES);
-#pragma unroll
-        for (int t = 0; t < 2; ++t)
-#pragma unroll
-          for (int s = 0; s < Cfg::SLABS; ++s)
-            tma_load_4d(smem_q + t * Cfg::TILE_BYTES + s * Cfg::SLAB_BYTES, &tma_q, q_full, s * 64, head,
-                        qt * kBlockQ2 + t * 128, b);
-      }
       int stage = 0;
       uint32_t phase = 0;
-      for (int i = 0; i < n_tiles; ++i) {
-        const int kt = tile_list[i] & 0x7fff;
-        mbar_wait(&k_empty[stage], phase ^ 1);
+      int k = 0;
+      for (int u = u_first; u < n_units; u += u_step, ++k) {
+        int qt, head, b;
+        decode(u, qt, head, b);
+        const uint16_t* tile_list;
+        const int n_tiles = acquire_list(k, tile_list);
+        if constexpr (kPersist) mbar_wait(q_empty, (k & 1) ^ 1);  // the previous unit's S MMAs have all read Q
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&k_full[stage], Cfg::TILE_BYTES);
+          mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES);
 #pragma unroll
-          for (int s = 0; s < Cfg::SLABS; ++s)
-            tma_load_4d(smem_k + stage * Cfg::TILE_BYTES + s * Cfg::SLAB_BYTES, &tma_k, &k_full[stage], s * 64, head,
-                        kt * kBlockKV, b);
-        }
-        mbar_wait(&v_empty[stage], phase ^ 1);
-        if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&v_full[stage], Cfg::TILE_BYTES);
+          for (int t = 0; t < 2; ++t)
 #pragma unroll
-          for (int s = 0; s < Cfg::SLABS; ++s)
-            tma_load_4d(smem_v + stage * Cfg::TILE_BYTES + s * Cfg::SLAB_BYTES, &tma_v, &v_full[stage], s * 64, head,
-                        kt * kBlockKV, b);
+            for (int s = 0; s < Cfg::SLABS; ++s)
+              tma_load_4d(smem_q + t * Cfg::TILE_BYTES + s * Cfg::SLAB_BYTES, &tma_q, q_full, s * 64, head,
+                          qt * kBlockQ2 + t * 128, b);
         }
+        for (int i = 0; i < n_tiles; ++i) {
+          const int kt = tile_list[i] & 0x7fff;
+          mbar_wait(&k_empty[stage], phase ^ 1);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&k_full[stage], Cfg::TILE_BYTES);
+#pragma unroll
+            for (int s = 0; s < Cfg::SLABS; ++s)
+              tma_load_4d(smem_k + stage * Cfg::TILE_BYTES + s * Cfg::SLAB_BYTES, &tma_k, &k_full[stage], s * 64, head,
+                          kt * kBlockKV, b);
+          }
+          mbar_wait(&v_empty[stage], phase ^ 1);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&v_full[stage], Cfg::TILE_BYTES);
+#pragma unroll
+            for (int s = 0; s < Cfg::SLABS; ++s)
+              tma_load_4d(smem_v + stage * Cfg::TILE_BYTES + s * Cfg::SLAB_BYTES, &tma_v, &v_full[stage], s * 64, head,
+                          kt * kBlockKV, b);
+          }
+          __syncwarp();
+          if (++stage == KS) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one_sync()) release_list(k);
         __syncwarp();
-        if (++stage == KS) { stage = 0; phase ^= 1; }
       }
     } else if (warp == 1) {
       // ------------------------------ MMA issuer ------------------------------
@@ -546,7 +599,6 @@ setmaxnreg_dec<72>();  // 168*384 = 64512 registers per CTA: 72*128 + 208*256 = 
       // operand instead of re-encoding the descriptor (the issue thread, not the tensor pipe, was the bottleneck:
       // ~85 cycles of scalar work per 64-cycle 128x128x16 MMA).
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const int nt = __shfl_sync(0xffffffffu, n_tiles, 0);
       const uint64_t q_desc0 = make_sdesc_sw128(smem_u32(smem_q), 16, 1024);
       const uint64_t k_desc0 = make_sdesc_sw128(smem_u32(smem_k), 16, 1024);
       const uint64_t v_desc0 = make_sdesc_sw128(smem_u32(smem_v), Cfg::SLAB_BYTES, 1024);
@@ -575,6 +627,14 @@ setmaxnreg_dec<72>();  // 168*384 = 64512 registers per CTA: 72*128 + 208*256 = 
           umma_ts(d, tbl + w * 128 + k * 8, b0 + (uint64_t)((k * 2048) >> 4), idesc_o, (accumulate || k != 0) ? 1u : 0u);
         }
       };
+      // One continuous stream of tiles over all units of this CTA. g counts tiles (barrier parities), the K / V ring runs on.
+      int stage = 0, nstage = 1 % KS;
+      uint32_t phase = 0, nphase = (1 / KS) & 1;
+      uint32_t g = 0;
+      int k = 0;
+      const uint16_t* unused_list;
+      int nt = u_first < n_units ? __shfl_sync(0xffffffffu, acquire_list(0, unused_list), 0) : 0;
+      // S of the first tile of the first unit
       if (nt > 0) {
         mbar_wait(q_full, 0);
         mbar_wait(&k_full[0], 0);
@@ -585,41 +645,53 @@ setmaxnreg_dec<72>();  // 168*384 = 64512 registers per CTA: 72*128 + 208*256 = 
           issue_s(1, 0);
           umma_commit(&s_full[1]);
           umma_commit(&k_empty[0]);
+          if (kPersist && nt == 1) umma_commit(q_empty);
         }
         __syncwarp();
-        int stage = 0, nstage = 1 % KS;
-        uint32_t phase = 0, nphase = (1 / KS) & 1;
-        for (int i = 0; i < nt; ++i) {
-          const bool more = i + 1 < nt;
-          // ---- group 0 ---- (K / V arrive long before P: poll them first so that nothing but the issue itself follows the
-          // wake-up on p_ready; measured 225 cycles between "P seen" and the first MMA with the waits in the other order)
+      }
+      for (int u = u_first; u < n_units; u += u_step, ++k) {
+        const bool next_unit = kPersist && (u + u_step < n_units);
+        int nt_next = 0;
+        for (int i = 0; i < nt; ++i, ++g) {
+          const bool last = i + 1 == nt;
+          // `more`: there is a next tile whose S is issued behind this tile's PV (the first tile of the next unit included)
+          const bool more = !last || next_unit;
+          // K / V arrive long before P: poll them first so that nothing but the issue itself follows the wake-up on p_ready
+          // (measured 225 cycles between "P seen" and the first MMA the other way round). At a unit boundary the next unit's
+          // S(0) is issued AFTER both PVs of this unit's last tile (`cross`): its Q is still on its way (it could only be
+          // requested once this unit's last S MMAs had retired), and this unit's epilogue must not wait for it.
+          const bool cross = last && next_unit;
+          const bool s_now = more && !cross;
           mbar_wait(&v_full[stage], phase);
-          if (more) mbar_wait(&k_full[nstage], nphase);
-          mbar_wait(&p_ready[0], i & 1);
+          if (s_now) mbar_wait(&k_full[nstage], nphase);
+          // the next tile is the last one of its unit: once its S MMAs have been issued, Q is no longer needed
+          const bool q_done = kPersist && s_now && i + 2 == nt;
+          // ---- group 0 ----
+          mbar_wait(&p_ready[0], g & 1);
           tc_fence_after();
           if constexpr (kSplitP) {
             if (elect_one_sync()) issue_pv(0, stage, i > 0, 0, kBlockKV / 32);
             __syncwarp();
-            mbar_wait(&p_ready2[0], i & 1);
+            mbar_wait(&p_ready2[0], g & 1);
             tc_fence_after();
           }
           if (elect_one_sync()) {
             if constexpr (kSplitP) issue_pv(0, stage, true, kBlockKV / 32, kBlockKV / 16);
             else issue_pv(0, stage, i > 0);
             umma_commit(&pv_done[0]);
-            if (more) {
+            if (s_now) {
               issue_s(0, nstage);
               umma_commit(&s_full[0]);
             }
           }
           __syncwarp();
           // ---- group 1 ----
-          mbar_wait(&p_ready[1], i & 1);
+          mbar_wait(&p_ready[1], g & 1);
           tc_fence_after();
           if constexpr (kSplitP) {
             if (elect_one_sync()) issue_pv(1, stage, i > 0, 0, kBlockKV / 32);
             __syncwarp();
-            mbar_wait(&p_ready2[1], i & 1);
+            mbar_wait(&p_ready2[1], g & 1);
             tc_fence_after();
           }
           if (elect_one_sync()) {
@@ -627,15 +699,48 @@ setmaxnreg_dec<72>();  // 168*384 = 64512 registers per CTA: 72*128 + 208*256 = 
             else issue_pv(1, stage, i > 0);
             umma_commit(&pv_done[1]);
             umma_commit(&v_empty[stage]);
-            if (more) {
+            if (s_now) {
               issue_s(1, nstage);
               umma_commit(&s_full[1]);
               umma_commit(&k_empty[nstage]);
+              if (q_done) umma_commit(q_empty);
             }
           }
           __syncwarp();
+          if (cross) {
+            nt_next = __shfl_sync(0xffffffffu, acquire_list(k + 1, unused_list), 0);
+            mbar_wait(q_full, (k + 1) & 1);
+            mbar_wait(&k_full[nstage], nphase);
+            tc_fence_after();
+            if (elect_one_sync()) {
+              issue_s(0, nstage);
+              umma_commit(&s_full[0]);
+              issue_s(1, nstage);
+              umma_commit(&s_full[1]);
+              umma_commit(&k_empty[nstage]);
+              if (nt_next == 1) umma_commit(q_empty);
+            }
+            __syncwarp();
+          }
           stage = nstage; phase = nphase;
           if (++nstage == KS) { nstage = 0; nphase ^= 1; }
+        }
+        if (elect_one_sync()) release_list(k);
+        __syncwarp();
+        nt = nt_next;
+      }
+    } else if (warp == 2) {
+      // ------------------------------ tile lists, one unit ahead (persistent mode) ------------------------------
+      if constexpr (kPersist) {
+        int k = 0;
+        for (int u = u_first; u < n_units; u += u_step, ++k) {
+          int qt, head, b;
+          decode(u, qt, head, b);
+          mbar_wait(&list_empty[k & 1], ((k >> 1) & 1) ^ 1);
+          const int n = build_tile_list(p, qt, kBlockQ2, tile_lists + (k & 1) * kMaxTiles, lane);
+          if (lane == 0) n_tiles_smem[k & 1] = n;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&list_full[k & 1]);
         }
       }
     }
@@ -647,10 +752,17 @@ setmaxnreg_dec<72>();  // 168*384 = 64512 registers per CTA: 72*128 + 208*256 = 
     constexpr int NC = 128;                   // score columns per thread (one query row)
     constexpr int NP = NC / 2;                // column pairs = packed P columns
     const int row_local = qd * 32 + lane;
-    const int q_row = qt * kBlockQ2 + w * 128 + row_local;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_off + w * 128;
     const uint32_t o_addr = tmem_base + lane_off + 256 + w * 128;
+    uint32_t g = 0;  // tiles processed so far (barrier parities run on across units)
+    int k = 0;
+    for (int u = u_first; u < n_units; u += u_step, ++k) {
+    int qt, head, b;
+    decode(u, qt, head, b);
+    const uint16_t* tile_list;
+    const int n_tiles = acquire_list(k, tile_list);
+    const int q_row = qt * kBlockQ2 + w * 128 + row_local;
     unsigned int vis = 0xffffffffu;
     if (p.n_seg > 0) {
       int sq = p.n_seg - 1;
@@ -659,7 +771,7 @@ setmaxnreg_dec<72>();  // 168*384 = 64512 registers per CTA: 72*128 + 208*256 = 
       vis = p.visible[sq];
     }
     float m = -INFINITY, l = 0.f;
-    for (int i = 0; i < n_tiles; ++i) {
+    for (int i = 0; i < n_tiles; ++i, ++g) {
       const int entry = tile_list[i];
       const int kt = entry & 0x7fff;
       // the column mask of a partially visible tile does not depend on S: build it while the S MMA is still in flight and
@@ -681,7 +793,7 @@ setmaxnreg_dec<72>();  // 168*384 = 64512 registers per CTA: 72*128 + 208*256 = 
         for (int sk = 0; sk < p.n_seg; ++sk)
           if (!((vis >> sk) & 1u)) mask_range(p.bounds[sk] - k_lo, p.bounds[sk + 1] - k_lo);
       }
-      mbar_wait(&s_full[w], i & 1);
+      mbar_wait(&s_full[w], g & 1);
       tc_fence_after();
       uint32_t s[NC];
 #pragma unroll
@@ -766,7 +878,7 @@ setmaxnreg_dec<72>();  // 168*384 = 64512 registers per CTA: 72*128 + 208*256 = 
       m = m_new;
     }
     if (n_tiles > 0) {
-      mbar_wait(&pv_done[w], (n_tiles - 1) & 1);
+      mbar_wait(&pv_done[w], (g - 1) & 1);
       tc_fence_after();
     }
     const float inv_l = l > 0.f ? 1.f / l : 0.f;
@@ -793,6 +905,9 @@ setmaxnreg_dec<72>();  // 168*384 = 64512 registers per CTA: 72*128 + 208*256 = 
         }
       }
     }
+    __syncwarp();
+    if (lane == 0) release_list(k);
+    }  // units
   }
 
   tc_fence_before();
@@ -877,10 +992,10 @@ static int launch_attention(const ug_attn_args& a, const PeerO* peer, cudaStream
 }
 
 
-template <int kDh, int kPolyMod, bool kSplitP = false>
+template <int kDh, int kPolyMod, bool kSplitP = false, bool kPersist = false>
 static int launch_attention2(const ug_attn_args& a, const PeerO* peer, cudaStream_t stream) {
   using Cfg = Attn2Cfg<kDh>;
-  auto kern = attention2_kernel<kDh, kPolyMod, kSplitP>;
+  auto kern = attention2_kernel<kDh, kPolyMod, kSplitP, kPersist>;
   static bool attr_done[64] = {false};
   if (int st = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done, "attention2"); st != UG_OK) return st;
   CUtensorMap maps[3];
@@ -904,8 +1019,22 @@ static int launch_attention2(const ug_attn_args& a, const PeerO* peer, cudaStrea
   if (st != UG_OK) return st;
   const int q_tiles = (a.seq + 255) / 256;
   p.head_fastest = ((long long)q_tiles * a.heads * a.batch < 4LL * num_sms()) ? 1 : 0;
-  dim3 grid(p.head_fastest ? a.heads : q_tiles, p.head_fastest ? q_tiles : a.heads, a.batch);
-  kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], p);
+  p.q_tiles2 = q_tiles;
+  p.n_units = q_tiles * a.heads * a.batch;
+  if constexpr (kPersist) {
+    // the persistent stream issues S(0) of a unit behind the last PV of the previous one: every unit needs >= 1 key tile,
+    // i.e. every non-empty segment must see a non-empty segment (always true for the reference's visibility rules)
+    for (int sq = 0; sq < p.n_seg; ++sq) {
+      if (p.bounds[sq + 1] <= p.bounds[sq]) continue;
+      bool sees = false;
+      for (int sk = 0; sk < p.n_seg; ++sk) sees |= ((p.visible[sq] >> sk) & 1u) && p.bounds[sk + 1] > p.bounds[sk];
+      if (!sees) return launch_attention2<kDh, kPolyMod, kSplitP, false>(a, peer, stream);
+    }
+    kern<<<dim3(std::min(p.n_units, num_sms())), 384, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], p);
+  } else {
+    dim3 grid(p.head_fastest ? a.heads : q_tiles, p.head_fastest ? q_tiles : a.heads, a.batch);
+    kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], p);
+  }
   UG_CHECK_LAUNCH("attention2");
   return UG_OK;
 }
@@ -938,6 +1067,7 @@ static int attention_dispatch(const ug_attn_args* args, const PeerO* peer, void*
     if (variant == 4) return launch_attention2<128, 4>(a, peer, s);
     if (variant == 5) return launch_attention2<128, 0, true>(a, peer, s);
     if (variant == 6) return launch_attention2<128, 3>(a, peer, s);
+    if (variant == 7) return launch_attention2<128, 0, true, true>(a, peer, s);
   } else if (a.head_dim == 64) {
     if (variant == 1) return launch_attention<64, true>(a, peer, s);
     if (variant == 2) return launch_attention<64, false>(a, peer, s);
@@ -945,6 +1075,7 @@ static int attention_dispatch(const ug_attn_args* args, const PeerO* peer, void*
     if (variant == 4) return launch_attention2<64, 4>(a, peer, s);
     if (variant == 5) return launch_attention2<64, 0, true>(a, peer, s);
     if (variant == 6) return launch_attention2<64, 3>(a, peer, s);
+    if (variant == 7) return launch_attention2<64, 0, true, true>(a, peer, s);
   } else {
     set_error("attention: head_dim %d not supported (64 or 128)", a.head_dim);
     return UG_ERR_UNSUPPORTED;
