@@ -55,6 +55,7 @@ class FluxConfig:
     single_block_control_method: str = "overall_add"
     use_pooled_prompt_embeds: bool = True
     use_shared_expert: bool = True
+    use_consis_module: bool = False  # src/UniGenTransformer.py:893-923 (V2: two joint blocks, the first one used twice)
 
     @property
     def inner_dim(self) -> int:
@@ -482,18 +483,36 @@ class UniGenFluxOracle:
         expert_cond = moe_combine(combine, ec.reshape(E, C, D), choice)
         self._rec("moe.expert_hidden", expert_hidden); self._rec("moe.expert_cond", expert_cond)
 
+        expert_hidden, expert_cond = self.post_experts(hidden, cond, expert_hidden, expert_cond, enc_ctrl, temb_ctrl, cond_temb, ids)
+        return expert_hidden, expert_cond, l_aux, exp_counts
+
+    # --- src/UniGenTransformer.py:982-1024: what moe_forward does with the routed experts' (combined) outputs ---
+    def post_experts(self, hidden, cond, expert_hidden, expert_cond, enc_ctrl, temb_ctrl, cond_temb, ids):
+        cfg, sd = self.cfg, self.sd
+        N = hidden.shape[1]
+        H = cfg.num_attention_heads
+        img_ids, txt_ids, cond_ids = ids
+        rope_of = lambda *parts: flux_pos_embed(torch.cat(parts, 0), cfg.axes_dims_rope, cfg.theta)  # noqa: E731 (encoder ids first)
+        # `expert_output` is the tuple the MoE layer returned (:979); the consis branch only rebinds the two LOCAL names (:1002-1003)
+        # and only the shared-expert branch builds a new tuple from them (:1024). So with use_shared_expert=False the consis
+        # module's result never reaches the return value (:1026) — restated as is (pinned by tests/golden: moe_wiring).
+        expert_output = (expert_hidden, expert_cond)
+        if cfg.use_consis_module and cfg.use_shared_expert:  # :982-1003, V2 — consis_module[0] is called TWICE, consis_module[1] never
+            # hidden = the experts' condition output, encoder = the embedded condition tokens, temb = THIS condition's temb
+            _, consis_cond = flux_double_block(sd, "consis_module.0", H, expert_cond, cond, cond_temb, rope_of(cond_ids, cond_ids))
+            # hidden = [experts' image output | the block's condition output], encoder = the image tokens, temb = control temb
+            _, hc = flux_double_block(sd, "consis_module.0", H, torch.cat([expert_hidden, consis_cond], dim=1), hidden, temb_ctrl,
+                                      rope_of(img_ids, img_ids, cond_ids))
+            self._rec("moe.consis_hidden", hc[:, :N]); self._rec("moe.consis_cond", hc[:, N:])
+            expert_hidden, expert_cond = expert_hidden + hc[:, :N], expert_cond + hc[:, N:]
         if cfg.use_shared_expert:  # :1005-1024, V2
-            img_ids, txt_ids, cond_ids = ids
-            H = cfg.num_attention_heads
-            rope0 = flux_pos_embed(torch.cat([cond_ids, img_ids], 0), cfg.axes_dims_rope, cfg.theta)
-            cond_states, hid = flux_double_block(sd, "shared_expert.0", H, hidden, cond, cond_temb, rope0)
-            rope1 = flux_pos_embed(torch.cat([txt_ids, img_ids, cond_ids], 0), cfg.axes_dims_rope, cfg.theta)
+            cond_states, hid = flux_double_block(sd, "shared_expert.0", H, hidden, cond, cond_temb, rope_of(cond_ids, img_ids))
             hc = torch.cat([hid, cond_states], dim=1)
-            _, hc = flux_double_block(sd, "shared_expert.1", H, hc, enc_ctrl, temb_ctrl, rope1)
+            _, hc = flux_double_block(sd, "shared_expert.1", H, hc, enc_ctrl, temb_ctrl, rope_of(txt_ids, img_ids, cond_ids))
             hid, cond_states = hc[:, :N], hc[:, N:]
             self._rec("moe.shared_hidden", hid); self._rec("moe.shared_cond", cond_states)
-            expert_hidden, expert_cond = hid + expert_hidden, cond_states + expert_cond
-        return expert_hidden, expert_cond, l_aux, exp_counts
+            expert_output = (hid + expert_hidden, cond_states + expert_cond)
+        return expert_output
 
     # --- src/UniGenTransformer.py:1028-1068 ---
     def preprocess_moe_forward(self, hidden, cond_tokens, enc, pooled, cond_pooled, timestep, guidance, ids,
@@ -661,6 +680,9 @@ def init_state_dict(cfg: FluxConfig, seed: int = 0, zero_linear_std: Optional[fl
             _lin(sd, f"{p}.{br}.1", D, cfg.pooled_projection_dim, gen)
     for s in (0, 1):
         _double_block(sd, f"shared_expert.{s}", D, dh, gen)
+    if cfg.use_consis_module:  # both exist in the reference's state dict; only consis_module.0 is ever called (:994, :998)
+        for s in (0, 1):
+            _double_block(sd, f"consis_module.{s}", D, dh, gen)
     return sd
 
 

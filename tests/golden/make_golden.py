@@ -281,6 +281,58 @@ def main():
     gold["weave"] = [run_weave(19, 38, 2, "overall_add"), run_weave(2, 4, 2, "overall_add"),
                      run_weave(5, 6, 2, "single_add")]
 
+    # 3b. moe_forward wiring: the REAL UniGenFlux.moe_forward (src/UniGenTransformer.py:969-1026) with the MoE layer and the
+    # joint blocks (consis_module / shared_expert) replaced by affine stand-ins that fold their ids into the result -----------
+    def run_moe_wiring(consis, shared):
+        Dm, Nm, Tm = 4, 5, 3
+        gg = torch.Generator().manual_seed(31 + 2 * int(consis) + int(shared))
+        calls = []
+        coef = dict(consis0=0.3, consis1=0.7, shared0=-0.2, shared1=0.45)
+
+        def mk_block(tag):
+            def blk(hidden_states, encoder_hidden_states, temb=None, joint_attention_kwargs=None):
+                jk = joint_attention_kwargs
+                calls.append((tag, tuple(hidden_states.shape), tuple(encoder_hidden_states.shape)))
+                hid_sig = jk["hd_ids"].float().sum(-1)
+                enc_sig = jk["encoder_hd_ids"].float().sum(-1)
+                out_enc = (encoder_hidden_states * 0.9 + temb[:, None] * 0.01 + enc_sig[None, :, None] * 1e-3
+                           + hidden_states.mean(1, keepdim=True) * 0.02 + coef[tag])
+                out_hid = (hidden_states * 1.1 + temb[:, None] * 0.02 + hid_sig[None, :, None] * 2e-3
+                           + encoder_hidden_states.mean(1, keepdim=True) * 0.05 - coef[tag])
+                return out_enc, out_hid
+            return blk
+
+        eh, ec = torch.randn(1, Nm, Dm, generator=gg), torch.randn(1, Nm, Dm, generator=gg)
+
+        class Layer:
+            l_aux = torch.tensor(0.125)
+            exp_counts = torch.tensor([3, 2])
+
+            def __call__(self, **kw):
+                return eh, ec
+
+        fs = types.SimpleNamespace(use_rope=True, pos_embed="pos_embed", use_consis_module=consis, use_shared_expert=shared,
+                                   consis_module=[mk_block("consis0"), mk_block("consis1")],
+                                   shared_expert=[mk_block("shared0"), mk_block("shared1")],
+                                   moe=types.SimpleNamespace(moe_layer=Layer()))
+        h, c = torch.randn(1, Nm, Dm, generator=gg), torch.randn(1, Nm, Dm, generator=gg)
+        enc = torch.randn(1, Tm, Dm, generator=gg)
+        temb, ctemb = torch.randn(1, Dm, generator=gg), torch.randn(1, Dm, generator=gg)
+        img_ids = torch.randint(0, 9, (Nm, 3), generator=gg).float()
+        txt_ids = torch.randint(0, 9, (Tm, 3), generator=gg).float()
+        cond_ids = torch.randint(0, 9, (Nm, 3), generator=gg).float()
+        with torch.no_grad():
+            (oh, oc), l_aux, counts = T.UniGenFlux.moe_forward(
+                fs, hidden_states=h, condition_hidden_states=c, encoder_hidden_states=enc, temb=temb, condition_temb=ctemb,
+                condition_pooled_projections=None, pooled_projections=None,
+                joint_attention_kwargs=dict(img_ids=img_ids, prompt_ids=txt_ids, condition_ids=cond_ids, rope_embed="rope"))
+        return dict(consis=consis, shared=shared, hidden=h, cond=c, enc=enc, temb=temb, ctemb=ctemb, expert_hidden=eh,
+                    expert_cond=ec, img_ids=img_ids, txt_ids=txt_ids, cond_ids=cond_ids, coef=coef, calls=calls,
+                    out_hidden=oh.detach(), out_cond=oc.detach(), l_aux=l_aux, exp_counts=counts)
+
+    gold["moe_wiring"] = [run_moe_wiring(True, True), run_moe_wiring(True, False), run_moe_wiring(False, True),
+                          run_moe_wiring(False, False)]
+
     # 4. enable_lora ----------------------------------------------------------------------------------------
     Base = sys.modules["peft.tuners.tuners_utils"].BaseTunerLayer
 

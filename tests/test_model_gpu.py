@@ -324,6 +324,53 @@ def test_use_shared_expert_false_and_use_transformer_params():
     assert torch.equal(v["control_condition_embed.text_embedder.linear_2.weight"], v["time_text_embed.text_embedder.linear_2.weight"])
 
 
+def test_use_consis_module_matches_oracle_per_stage():
+    """`use_consis_module=True` (src/UniGenTransformer.py:893-923, 982-1003, V2): consis_module[0] runs twice — over (experts'
+    condition output | condition tokens) with the condition's temb / ids and over ([experts' image output | that result] | image
+    tokens) with control_temb — and its halves are added to the experts' outputs before the shared experts join. Wiring pinned
+    by the reference's own moe_forward (tests/golden: moe_wiring); here the native pre-stage against the oracle, stage by stage.
+    With use_shared_expert=False the module's result never reaches the output (reference :1024): weights only."""
+    from oracle import unigen_oracle as O
+    from unigen_b200.model import FluxArch, UniGenFlux, canonical_control_params
+    cfg = O.FluxConfig.tiny()
+    cfg.use_consis_module = True
+    sd = O.init_state_dict(cfg, seed=11)
+    assert "consis_module.1.attn.to_q.weight" in sd
+    sd = {k: (v if k.endswith("gate.wg.weight") else v.to(torch.bfloat16).float()) for k, v in sd.items()}
+    inp = O.make_inputs(cfg, 256, 256, text_len=512)
+    for k in ("hidden_states", "condition_hidden_states", "encoder_hidden_states"):
+        inp[k] = inp[k].to(torch.bfloat16).float()
+    oracle = O.UniGenFluxOracle(cfg, sd)
+    oracle.record = True
+    want = oracle.forward(**inp)[0]
+    model = UniGenFlux(FluxArch.tiny(), device="cuda")
+    model.init_condition_block(condition_nums=1, control_params=dict(canonical_control_params(), use_consis_module=True))
+    assert "consis_module" in model.trainable_control_modules
+    model.load_state_dict(sd, strict=True)
+    model.trace = {}
+    dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()}
+    got = model(**dev)[0]
+    for name in ("moe.expert_hidden", "moe.expert_cond", "moe.consis_hidden", "moe.consis_cond", "moe.shared_hidden", "moe.ctrl_in"):
+        assert rel_l2(model.trace[name], oracle.trace[name]) < 1e-2, name
+    assert rel_l2(got, want) < 1e-2
+    # the module changes the result (it is not a no-op at random init) ...
+    plain = UniGenFlux(FluxArch.tiny(), device="cuda")
+    plain.init_condition_block(condition_nums=1, control_params=canonical_control_params())
+    plain.load_state_dict({k: v for k, v in sd.items() if not k.startswith("consis_module")}, strict=True)
+    assert rel_l2(plain(**dev)[0], got) > 1e-3
+    # ... graph replay == eager, and without the shared experts it holds weights but contributes nothing (reference :1024)
+    model.trace = None
+    model.use_cuda_graph = True
+    assert torch.equal(model(**dev)[0], got) and torch.equal(model(**dev)[0], got)
+    cfg2 = O.FluxConfig.tiny()
+    cfg2.use_consis_module, cfg2.use_shared_expert = True, False
+    sd2 = {k: v for k, v in sd.items() if not k.startswith("shared_expert")}
+    m2 = UniGenFlux(FluxArch.tiny(), device="cuda")
+    m2.init_condition_block(condition_nums=1, control_params=dict(canonical_control_params(), use_consis_module=True, use_shared_expert=False))
+    m2.load_state_dict(sd2, strict=True)
+    assert rel_l2(m2(**dev)[0], O.UniGenFluxOracle(cfg2, sd2).forward(**inp)[0]) < 1e-2
+
+
 def test_fused_qk_norm_epilogue_forward_matches_oracle():
     """`fuse_qk_norm=True`: QK-RMSNorm + RoPE inside the projection GEMM epilogue instead of the separate in-place pass — same
     per-block parity bar against the oracle, and a different (not bit-identical) rounding path than the default."""

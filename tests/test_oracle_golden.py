@@ -84,6 +84,44 @@ def test_weave_matches_reference_base_forward(golden):
         assert [tuple(c) for c in case["calls"]] == want
 
 
+def test_moe_forward_wiring_consis_and_shared_experts(golden, monkeypatch):
+    """The reference's own moe_forward (src/UniGenTransformer.py:969-1026) ran with affine stand-in joint blocks that fold
+    their (hidden, encoder) ids into the result; the oracle's post_experts() must hand the same tensors, the same temb and the
+    same id tables to the same blocks in the same order — with use_consis_module on / off and use_shared_expert on / off."""
+    tag_of = {"consis_module.0": "consis0", "consis_module.1": "consis1", "shared_expert.0": "shared0", "shared_expert.1": "shared1"}
+    for case in golden["moe_wiring"]:
+        calls = []
+
+        def stub_block(sd, prefix, H, h, c, temb, rope, trace=None, case=case, calls=calls):
+            tag = tag_of[prefix]
+            calls.append((tag, tuple(h.shape), tuple(c.shape)))
+            n_enc = c.shape[1]
+            enc_sig, hid_sig = rope[:n_enc].float().sum(-1), rope[n_enc:].float().sum(-1)  # encoder ids come first
+            k = case["coef"][tag]
+            out_enc = c * 0.9 + temb[:, None] * 0.01 + enc_sig[None, :, None] * 1e-3 + h.mean(1, keepdim=True) * 0.02 + k
+            out_hid = h * 1.1 + temb[:, None] * 0.02 + hid_sig[None, :, None] * 2e-3 + c.mean(1, keepdim=True) * 0.05 - k
+            return out_enc, out_hid
+
+        monkeypatch.setattr(O, "flux_double_block", stub_block)
+        monkeypatch.setattr(O, "flux_pos_embed", lambda ids, axes, theta: ids)  # the stand-ins consume the raw id tables
+        D = case["hidden"].shape[-1]
+        cfg = O.FluxConfig(num_attention_heads=1, attention_head_dim=D, use_shared_expert=case["shared"],
+                           use_consis_module=case["consis"])
+        m = O.UniGenFluxOracle(cfg, {})
+        oh, oc = m.post_experts(case["hidden"], case["cond"], case["expert_hidden"], case["expert_cond"], case["enc"], case["temb"],
+                                case["ctemb"], (case["img_ids"], case["txt_ids"], case["cond_ids"]))
+        want_calls = [tuple(c) for c in case["calls"]]
+        if case["consis"] and not case["shared"]:
+            # the reference still RUNS the consis block there, but its result never reaches the return value (the tuple is only
+            # rebuilt inside the shared-expert branch, :1024): the oracle skips the dead calls
+            assert [c[0] for c in want_calls] == ["consis0", "consis0"] and calls == []
+            torch.testing.assert_close(case["out_hidden"], case["expert_hidden"], rtol=0, atol=0)
+        else:
+            assert calls == want_calls
+        torch.testing.assert_close(oh, case["out_hidden"], rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(oc, case["out_cond"], rtol=1e-6, atol=1e-6)
+
+
 def test_weave_schedule_integer_exact():
     assert O.weave_schedule(19, 9) == [0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8]  # SURVEY.md §8 A2
     assert O.weave_schedule(38, 19) == [i // 2 for i in range(38)]

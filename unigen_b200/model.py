@@ -378,9 +378,11 @@ class UniGenFlux(_DenoiserBase):
             # the predecessor forbids it outright (MoeCombineTransformer.pyc L557-570) and the shipped transformer-block
             # experts are shape-broken with a per-token temb
             raise ValueError("Warning: please use rope or modulated")
-        if get("use_consis_module", False):
-            raise ops.UgError("use_consis_module is not supported by the B200-native path (SURVEY.md §A.1: left off)")
         self.use_shared_expert = bool(get("use_shared_expert", False))  # :863 (False: the routed experts alone, :1024 skipped)
+        # :893-923 (V2): two joint blocks; moe_forward calls consis_module[0] twice and consis_module[1] never (:994, :998). Its
+        # result only reaches the output through the tuple the shared-expert branch builds (:1024), so with
+        # use_shared_expert=False the blocks hold weights but contribute nothing (tests/golden: moe_wiring).
+        self.use_consis_module = bool(get("use_consis_module", False))
         dev = get("single_control_dev", 2)
         self.cn_joint_layers, self.cn_single_joint_layers = a.num_layers // dev, a.num_single_layers // dev
         self.single_block_control_method = get("single_block_control_method", "overall_add")
@@ -417,10 +419,12 @@ class UniGenFlux(_DenoiserBase):
                 ws.views[p + ".1.weight"] = self.exp_mod_w[br][e * D:(e + 1) * D]
                 ws.views[p + ".1.bias"] = self.exp_mod_b[br][e * D:(e + 1) * D]
         self.shared = [_DoubleBlockW(ws, f"shared_expert.{s}", D, dh) for s in (0, 1)] if self.use_shared_expert else []
+        self.consis = [_DoubleBlockW(ws, f"consis_module.{s}", D, dh) for s in (0, 1)] if self.use_consis_module else []
         self.trainable_control_modules = {k: None for k in (
             "control_pos_embed_input", "control_time_text_embed", "control_condition_embed", "control_context_embedder",
             "control_x_embedder", "control_joint_trans_blocks", "controlnet_add_joint_blocks", "control_single_trans_blocks",
-            "controlnet_add_single_blocks", "moe") + (("shared_expert",) if self.use_shared_expert else ())}
+            "controlnet_add_single_blocks", "moe") + (("shared_expert",) if self.use_shared_expert else ())
+            + (("consis_module",) if self.use_consis_module else ())}
         self._control_ready = True
         if get("use_transformer_params", False):
             self.init_control_param()
@@ -456,10 +460,15 @@ class UniGenFlux(_DenoiserBase):
         D, dev = self.inner_dim, self.device_
         S = T + N
         Smax = T + 2 * N  # shared_expert[1] runs over [txt | img | cond]
+        consis = self.use_consis_module and self.use_shared_expert
+        if consis:
+            Smax = max(Smax, 3 * N)  # consis_module[0], second call: [img | experts' img | consis cond]
         E = self.expert_nums
         C = ops.moe_capacity(B * N, E)
         z = lambda *s, dt=BF16: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
         n_mod = (6 * 2 * (self.arch.num_layers + self.cn_joint_layers + 1 + self.condition_nums) + 3 * (self.arch.num_single_layers + len(self.ctrl_single)) + 2)
+        if consis:
+            n_mod += 6 * 2 * (1 + self.condition_nums)
         b = types.SimpleNamespace(
             X=z(B, S, D), NX=z(B, Smax, D), QKV=z(B, Smax, 3 * D), AO=z(B, Smax, D), FF=z(B, Smax, 4 * D),
             CAT=z(B, S, 5 * D), CH=z(B, N, D), CS=z(B, S, D), CENC=z(B, T, D), COND=z(B, N, D), HC=z(B, 2 * N, D),
@@ -475,6 +484,10 @@ class UniGenFlux(_DenoiserBase):
         b.temb, b.ctemb, b.cdtemb = b.TEMBS[0], b.TEMBS[1], b.TEMBS[2]
         b.cdtemb_c = [b.TEMBS[3 + c] for c in range(self.condition_nums)]
         b.mod_plans = None
+        if consis:  # [experts' image output | consis condition output] and the id tables of the two consis_module[0] calls
+            b.CONS = z(B, 2 * N, D)
+            b.ropek0 = z(2 * N, self.arch.attention_head_dim, dt=torch.float32)
+            b.ropek1 = z(3 * N, self.arch.attention_head_dim, dt=torch.float32)
         return b
 
     # ---------------------------------------------------------------------------------------------------------
@@ -526,6 +539,13 @@ class UniGenFlux(_DenoiserBase):
             mp.mods_s0 = [(job(self.shared[0].norm1, buf.STEMBS[3 + c], 6, early), job(self.shared[0].norm1_ctx, buf.STEMBS[3 + c], 6, early))
                           for c in range(n_cond)]
             mp.mods_s1 = (job(self.shared[1].norm1, s_ctemb, 6, early), job(self.shared[1].norm1_ctx, s_ctemb, 6, early))
+        mp.mods_k0, mp.mods_k1 = [None] * n_cond, None
+        if self.use_consis_module and self.use_shared_expert:
+            # consis_module[0]: first call modulated by THIS condition's temb, second call by control_temb (:994, :998)
+            k0 = self.consis[0]
+            mp.mods_k0 = [(job(k0.norm1, buf.STEMBS[3 + c], 6, early), job(k0.norm1_ctx, buf.STEMBS[3 + c], 6, early))
+                          for c in range(n_cond)]
+            mp.mods_k1 = (job(k0.norm1, s_ctemb, 6, early), job(k0.norm1_ctx, s_ctemb, 6, early))
         mp.m_out = job(self.norm_out_w, s_temb, 2, late)  # AdaLayerNormContinuous: (scale, shift)
         assert slot[0] <= buf.n_mod, (slot[0], buf.n_mod)
         dev = self.device_
@@ -650,7 +670,7 @@ class UniGenFlux(_DenoiserBase):
     # expert_forward :925-967) — runs once per step at the first control call
     # ---------------------------------------------------------------------------------------------------------
     def _prestage(self, buf, B, N, T, h_img, cond_tokens, pooled, cond_pooled, rts_uniform, mods_s0, mods_s1, cond_index,
-                  txt_ids, img_ids, cond_ids):
+                  txt_ids, img_ids, cond_ids, mods_k0=None, mods_k1=None):
         """One CoMoE pass for one condition; the control stream `CIN` accumulates over conditions
         (MultiCondtionUniGenFlux: merged_hidden_states = sum_c (expert_hidden + expert_cond), :1313-1316)."""
         a = self.arch
@@ -687,6 +707,20 @@ class UniGenFlux(_DenoiserBase):
         ops.moe_combine(buf.YH, route, C, buf.EH)
         ops.moe_combine(buf.YC, route, C, buf.EC)
         self._rec(tag + ".expert_hidden", buf.EH.view(B, N, D)); self._rec(tag + ".expert_cond", buf.EC.view(B, N, D))
+        if self.use_consis_module and self.use_shared_expert:
+            # --- consis module (V2, :982-1003): consis_module[0] over (hidden = experts' cond output, encoder = cond tokens) with
+            # the condition's temb and ids, then over (hidden = [experts' image output | that result], encoder = image tokens)
+            # with control_temb; its two halves are ADDED to the experts' outputs. The encoder-side results are discarded
+            # (`_, x = block(...)`), so the context streams' post-attention halves are never computed (ctx_out=None).
+            eh, ec = buf.EH.view(B, N, D), buf.EC.view(B, N, D)
+            self._rope(buf.ropek0, cond_ids, cond_ids)
+            self._rope(buf.ropek1, img_ids, img_ids, cond_ids)
+            ops.copy(eh, buf.CONS[:, :N])
+            self._double_block(buf, self.consis[0], mods_k0[0], mods_k0[1], ec, buf.COND, buf.CONS[:, N:], None, buf.ropek0)
+            self._double_block(buf, self.consis[0], mods_k1[0], mods_k1[1], buf.CONS, h_img, buf.CONS, None, buf.ropek1)
+            self._rec(tag + ".consis_hidden", buf.CONS[:, :N]); self._rec(tag + ".consis_cond", buf.CONS[:, N:])
+            ops.add(eh, buf.CONS[:, :N], eh)
+            ops.add(ec, buf.CONS[:, N:], ec)
         if not self.use_shared_expert:  # use_shared_expert=False (:1005): the control stream is the routed experts' output alone
             if cond_index == 0:
                 ops.add(buf.EH.view(B, N, D), buf.EC.view(B, N, D), buf.CIN)
@@ -819,7 +853,7 @@ class UniGenFlux(_DenoiserBase):
                 self._rec("moe.control_context", buf.CENC)
                 for c in range(n_cond):
                     route = self._prestage(buf, B, N, T, x_img, cs[c], pooled, cond_pooled[c], rts_uniform[c], mods_s0[c],
-                                           mods_s1, c, txt_ids, img_ids, condition_ids[c])
+                                           mods_s1, c, txt_ids, img_ids, condition_ids[c], mp.mods_k0[c], mp.mods_k1)
                 self._rec("moe.ctrl_in", buf.CIN)
                 ctrl_in = buf.CIN
             else:               # later calls: the control block reads the base stream

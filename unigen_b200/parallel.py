@@ -230,6 +230,8 @@ class SequenceParallelUniGenFlux(UniGenFlux):
     def _run_staged(self, key, staged, *args):
         if not self.sp_enabled:
             return super()._run_staged((key, "local"), staged, *args)
+        if self.use_consis_module and self.use_shared_expert:
+            raise ops.UgError("use_consis_module is not sharded: run with sp_enabled=False (the pre-stage is a small part of the step)")
         if self.exchange != "peer":  # NCCL collectives stay out of graph capture: the staged-exchange baseline runs eagerly
             return self._forward_impl(*args, **staged)
         if self._pool is not None:
