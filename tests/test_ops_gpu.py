@@ -169,6 +169,22 @@ def test_ln_modulate(ug):
         assert rel_l2(out, want) < 4e-3
 
 
+def test_ln_modulate_persistent_kernel_many_rows(ug):
+    """Enough row groups to take the persistent prefetching kernel (two blocks per SM walking the groups, next group's rows in
+    flight), ragged last group, batch 2 and strided input rows."""
+    from oracle import unigen_oracle as O
+    D = 3072
+    for B, R in ((1, 4608), (2, 1501)):
+        xx = rnd(B, R, 2 * D, scale=2.0)
+        x = xx[:, :, :D]  # row stride 2 D
+        shift, scale = torch.randn(B, D, device="cuda"), torch.randn(B, D, device="cuda")
+        out = torch.full((B, R + 1, D), 7.0, device="cuda", dtype=torch.bfloat16)
+        ug.ln_modulate(x, out[:, :R], shift, scale)
+        want = O.layer_norm(x.float()) * (1 + scale[:, None]) + shift[:, None]
+        assert rel_l2(out[:, :R], want) < 4e-3
+        assert torch.all(out[:, R] == 7.0)  # nothing written past the last row
+
+
 @pytest.mark.parametrize("dh", [64, 128])
 def test_qk_rmsnorm_rope(ug, dh):
     from oracle import unigen_oracle as O

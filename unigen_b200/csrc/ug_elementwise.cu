@@ -4,6 +4,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <algorithm>
+
 #include "ug_host.h"
 #include "ug_ptx.cuh"
 
@@ -281,6 +283,116 @@ __global__ void __launch_bounds__(kThreads) ln_modulate_rows_kernel(const __nv_b
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean[r]) * rstd[r] * (1.f + s[j]) + h[j];
       op[t + kThreads * i] = pack8(f);
+    }
+  }
+}
+
+// Persistent form of the same kernel (same thread -> column mapping and reduction order: bit-identical results). A block keeps
+// its (1 + scale, shift) column chunks in registers and walks the row groups g = blockIdx.x, + gridDim.x, ...; the rows of group
+// g + gridDim.x are requested BEFORE group g is reduced, so after the first group the load latency hides behind the two
+// reductions and the stores, and the modulation vectors (as many bytes as the kR rows of a group) are fetched once per block
+// instead of once per group. The one-group-per-block kernel was wave-latency-bound: 2.6 waves of (load -> 2 syncs -> store).
+template <int kThreads, int kChunks, int kR>
+__global__ void __launch_bounds__(kThreads) ln_modulate_stream_kernel(const __nv_bfloat16* __restrict__ x, long long x_rs, long long x_bs,
+                                                                      __nv_bfloat16* __restrict__ out, long long o_rs, long long o_bs,
+                                                                      const float* __restrict__ shift, const float* __restrict__ scale,
+                                                                      long long mod_bs, int rows, int d, float eps) {
+  constexpr int kWarps = kThreads / 32;
+  __shared__ float red[2][kR][kWarps];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int b = blockIdx.y;
+  const int groups = (rows + kR - 1) / kR;
+  const __nv_bfloat16* xb = x + (long long)b * x_bs;
+  __nv_bfloat16* ob = out + (long long)b * o_bs;
+  auto load_group = [&](int g, uint4 (&dst)[kR][kChunks]) {
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      const int row = min(g * kR + r, rows - 1);  // a ragged last group re-reads the last row; only rows < `rows` are stored
+      const uint4* xp = reinterpret_cast<const uint4*>(xb + (long long)row * x_rs);
+#pragma unroll
+      for (int i = 0; i < kChunks; ++i) dst[r][i] = xp[t + kThreads * i];
+    }
+  };
+  int g = blockIdx.x;
+  if (g >= groups) return;
+  uint4 buf[kR][kChunks];
+  load_group(g, buf);
+  // this thread's column chunks of (scale, shift), parked in shared memory (each thread reads back only what it wrote: no
+  // barrier, conflict-free) — in registers they would not fit next to two groups of rows
+  __shared__ float4 smod[2][kChunks * 2][kThreads];
+  const float* scp = scale + (long long)b * mod_bs;
+  const float* shp = shift + (long long)b * mod_bs;
+#pragma unroll
+  for (int i = 0; i < kChunks; ++i) {
+    const int c = 8 * (t + kThreads * i);
+    smod[0][2 * i][t] = *reinterpret_cast<const float4*>(scp + c); smod[0][2 * i + 1][t] = *reinterpret_cast<const float4*>(scp + c + 4);
+    smod[1][2 * i][t] = *reinterpret_cast<const float4*>(shp + c); smod[1][2 * i + 1][t] = *reinterpret_cast<const float4*>(shp + c + 4);
+  }
+  for (; g < groups; g += gridDim.x) {
+    const int gn = g + gridDim.x;
+    uint4 nxt[kR][kChunks];
+    if (gn < groups) load_group(gn, nxt);
+    float mean[kR], rstd[kR];
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < kChunks; ++i) {
+        float f[8];
+        unpack8(buf[r][i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += f[j];
+      }
+      s = warp_sum(s);
+      if (lane == 0) red[0][r][warp] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) s += red[0][r][w];
+      mean[r] = s / (float)d;
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < kChunks; ++i) {
+        float f[8];
+        unpack8(buf[r][i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float u = f[j] - mean[r]; v += u * u; }
+      }
+      v = warp_sum(v);
+      if (lane == 0) red[1][r][warp] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) v += red[1][r][w];
+      rstd[r] = rsqrtf(v / (float)d + eps);
+    }
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      if (g * kR + r >= rows) break;
+      uint4* op = reinterpret_cast<uint4*>(ob + (long long)(g * kR + r) * o_rs);
+#pragma unroll
+      for (int i = 0; i < kChunks; ++i) {
+        float f[8];
+        unpack8(buf[r][i], f);
+        const float4 c0 = smod[0][2 * i][t], c1 = smod[0][2 * i + 1][t], h0 = smod[1][2 * i][t], h1 = smod[1][2 * i + 1][t];
+        const float s8[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        const float h8[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean[r]) * rstd[r] * (1.f + s8[j]) + h8[j];
+        op[t + kThreads * i] = pack8(f);
+      }
+    }
+    if (gn < groups) {
+#pragma unroll
+      for (int r = 0; r < kR; ++r)
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i) buf[r][i] = nxt[r][i];
     }
   }
 }
@@ -648,15 +760,17 @@ __global__ void __launch_bounds__(256) gated_add_slots_kernel(__nv_bfloat16* __r
   }
 }
 
-// UG_LN_KERNEL=rows|warp: A/B switch between the kR-rows-per-block LayerNorm kernel and the one / two-warps-per-row kernels
-static inline bool ln_rows_kernel_enabled() {
+// UG_LN_KERNEL=stream|rows|warp: A/B switch between the persistent prefetching kernel (default), the one-group-per-block kernel
+// (bit-identical to it) and the one / two-warps-per-row kernels
+static inline int ln_kernel_choice() {
   static int cached = -1;
   if (cached < 0) {
     const char* e = getenv("UG_LN_KERNEL");
-    cached = (e && strcmp(e, "warp") == 0) ? 0 : 1;
+    cached = (e && strcmp(e, "warp") == 0) ? 0 : (e && strcmp(e, "rows") == 0) ? 1 : 2;
   }
-  return cached == 1;
+  return cached;
 }
+static inline bool ln_rows_kernel_enabled() { return ln_kernel_choice() >= 1; }
 
 static inline int grid_for(long long threads, int block) {
   long long g = (threads + block - 1) / block;
@@ -695,6 +809,11 @@ static int launch_ln_modulate(const void* x, int64_t x_rs, int64_t x_bs, void* o
     const dim3 g((unsigned)((rows + kR - 1) / kR), (unsigned)batch);
     const int nvec = d >> 3;
     bool done = true;
+    if (ln_kernel_choice() == 2 && nvec == 3 * 128 && (long long)g.x * batch > 2LL * num_sms()) {
+      // persistent: two blocks per SM over all samples, each walking its row groups with the next group's rows in flight
+      const dim3 gp((unsigned)std::max(1, std::min((int)g.x, (2 * num_sms() + batch - 1) / batch)), (unsigned)batch);
+      ln_modulate_stream_kernel<128, 3, kR><<<gp, 128, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, rows, d, eps);
+    } else
     if (nvec == 3 * 128) ln_modulate_rows_kernel<128, 3, kR><<<g, 128, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, rows, d, eps);
     else if (nvec == 3 * 64) ln_modulate_rows_kernel<64, 3, kR><<<g, 64, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, rows, d, eps);
     else if (nvec == 2 * 128) ln_modulate_rows_kernel<128, 2, kR><<<g, 128, 0, s>>>(xp, x_rs, x_bs, op, o_rs, o_bs, shift, scale, mod_bs, rows, d, eps);
