@@ -827,7 +827,6 @@ extern "C" int ug_gemm_bf16(const ug_gemm_args* args, void* stream) {
     UG_CHECK_ARG(a.a2_row_stride % 8 == 0 && a.w2_row_stride % 8 == 0 && a.a2_row_stride >= a.k2 && a.w2_row_stride >= a.k2 &&
                      (a.batch == 1 || a.a2_batch_stride % 8 == 0),
                  "gemm: second operand pair strides must be multiples of 8 elements and cover k2");
-    UG_CHECK_ARG(!a.qk_norm_weight, "gemm: the second operand pair does not compose with the fused QK-norm epilogue");
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int variant = a.variant;

@@ -644,8 +644,9 @@ class SequenceParallelUniCombineFlux(UniCombineFlux):
             if hi == lo:
                 continue
             rms = next(w for plo, phi, w in parts if plo <= lo and hi <= phi)
-            ops.qkv_scatter(pool.table, qkv[lo:hi], H, dh, rms, buf.rope[lo:hi], self._off["RECV"], S,
-                            gbounds[s] + self.sp_rank * (hi - lo))
+            fused = self._fused_qk()  # q / k already normalised and rotated by the projection GEMM: the scatter only moves heads
+            ops.qkv_scatter(pool.table, qkv[lo:hi], H, dh, None if fused else rms, None if fused else buf.rope[lo:hi],
+                            self._off["RECV"], S, gbounds[s] + self.sp_rank * (hi - lo))
         pool.barrier()
         ops.attention_peer(pool.table, self._recv[0], self._recv[1], self._recv[2], H // P, dh, self._off[out_name],
                            D if out_name == "AO" else 5 * D, 0, seg_bounds=gbounds, seg_visible=vis, variant=self.attn_variant)

@@ -94,6 +94,7 @@ class UniCombineFlux(torch.nn.Module):
         self._bufs: Dict[Any, Any] = {}
         self.gemm_variant = 0
         self.attn_variant = 0
+        self.fuse_qk_norm = True  # QK-RMSNorm + RoPE in the projection GEMMs' epilogue (lora_mode "mma"), see _fused_qk
         # "mma": the switched low-rank update rides the main GEMM's tensor-core loop as a K extension (A2 / W2 operand pair);
         # "epilogue": it is applied per output element on the CUDA cores in the epilogue (kept for comparison)
         self.lora_mode = "mma"
@@ -354,14 +355,26 @@ class UniCombineFlux(torch.nn.Module):
                         lora=dict(t=t, b=pair.b, rank=pair.rank, block_n=pair.n_each, seg_bounds=seg_bounds,
                                   seg_group=seg_group), **kw)
 
+    def _fused_qk(self) -> bool:
+        """QK-RMSNorm + RoPE inside the projection GEMMs' epilogue (as in the S-variant); the LoRA-in-epilogue mode keeps the
+        separate pass (its epilogue carries per-row LoRA state instead)."""
+        return self.fuse_qk_norm and self.lora_mode == "mma"
+
+    def _qk_norm(self, buf, rms, lo: int, hi: int):
+        if not self._fused_qk():
+            return None
+        return dict(weight=rms, head_dim=self.arch.attention_head_dim, d=self.inner_dim, cos_sin=buf.rope[lo:hi], eps=1e-6)
+
     def _attention(self, buf, parts, out_name: str, bounds, vis):
-        """QK-RMSNorm + RoPE in place on the q|k columns of row ranges `parts` = [(lo, hi, rms_weight)], then the joint
-        attention with the segment-visibility rule -> buf.AO, or the first D columns of buf.CAT (single blocks).
+        """QK-RMSNorm + RoPE on the q|k columns of row ranges `parts` = [(lo, hi, rms_weight)] (in place here unless the
+        projection GEMMs already did it in their epilogue), then the joint attention with the segment-visibility rule ->
+        buf.AO, or the first D columns of buf.CAT (single blocks).
         The sequence-parallel subclass (parallel.py) fuses both steps with the Ulysses exchange over peer memory."""
         a, D = self.arch, self.inner_dim
         H, dh = a.num_attention_heads, a.attention_head_dim
-        for lo, hi, rms in parts:
-            ops.qk_rmsnorm_rope(buf.QKV[:, lo:hi, :2 * D], 2 * H, dh, rms, buf.rope[lo:hi], heads_per_weight=H)
+        if not self._fused_qk():
+            for lo, hi, rms in parts:
+                ops.qk_rmsnorm_rope(buf.QKV[:, lo:hi, :2 * D], 2 * H, dh, rms, buf.rope[lo:hi], heads_per_weight=H)
         out = buf.AO if out_name == "AO" else buf.CAT[:, :, :D]
         ops.attention(buf.QKV[:, :, 0:D], buf.QKV[:, :, D:2 * D], buf.QKV[:, :, 2 * D:], out, H, dh,
                       seg_bounds=bounds, seg_visible=vis, variant=self.attn_variant)
@@ -428,8 +441,9 @@ class UniCombineFlux(torch.nn.Module):
             m_c = [self._chunks(dbl_mods[i][1][1 + j], 6) for j in range(n)]
             mods = [m_txt, m_img] + m_c
             ops.ln_modulate_segs(buf.X, buf.NX, m_txt[0], m_txt[1], bounds, B * 6 * D)
-            ops.gemm(buf.NX[:, :T], w.add_qkv[0], out=buf.QKV[:, :T], bias=w.add_qkv[1], variant=gv)
-            self._lora_gemm(buf, buf.NX[:, T:], w.qkv, L[p + ".qkv"], img_cond_bounds, img_cond_groups, buf.QKV[:, T:])
+            ops.gemm(buf.NX[:, :T], w.add_qkv[0], out=buf.QKV[:, :T], bias=w.add_qkv[1], variant=gv, qk_norm=self._qk_norm(buf, w.rms_ctx, 0, T))
+            self._lora_gemm(buf, buf.NX[:, T:], w.qkv, L[p + ".qkv"], img_cond_bounds, img_cond_groups, buf.QKV[:, T:],
+                            qk_norm=self._qk_norm(buf, w.rms, T, S))
             self._attention(buf, [(0, T, w.rms_ctx), (T, S, w.rms)], "AO", bounds, vis)
             ops.gemm(buf.AO[:, :T], w.to_add_out[0], out=seg(0), bias=w.to_add_out[1], gate=m_txt[2], residual=seg(0), variant=gv)
             # to_out[0]: LoRA group AND gate switched per stream inside one launch over [img | c_1 .. c_n]
@@ -465,7 +479,7 @@ class UniCombineFlux(torch.nn.Module):
             m_c = [self._chunks(sgl_mods[i][1 + j], 3) for j in range(n)]
             mods = [m_x] + m_c
             ops.ln_modulate_segs(buf.X, buf.NX, m_x[0], m_x[1], all_bounds, B * 3 * D)
-            self._lora_gemm(buf, buf.NX, w.qkv, L[p + ".qkv"], all_bounds, all_groups, buf.QKV)
+            self._lora_gemm(buf, buf.NX, w.qkv, L[p + ".qkv"], all_bounds, all_groups, buf.QKV, qk_norm=self._qk_norm(buf, w.rms, 0, S))
             self._lora_gemm(buf, buf.NX, w.mlp, L[p + ".mlp"], all_bounds, all_groups, buf.CAT[:, :, D:], act=UG_ACT_GELU_TANH)
             self._attention(buf, [(0, S, w.rms)], "CAT", bounds, vis)
             self._lora_gemm(buf, buf.CAT, w.out, L[p + ".out"], all_bounds, all_groups, buf.X, gate=m_x[2],
