@@ -10,6 +10,12 @@ Configuration restated: the SHIPPED control_params (config/unigen.yaml:3-11: `us
 `SD3SingleTransformerBlock`s (src/UniGenTransformer.py:184-195) run on the dispatched `(1, C, D)` capacity buffers
 with a PER-TOKEN `(1, C, D)` temb (src/UniGenUtils.py:375-414), the shared experts are
 `JointTransformerBlock(context_pre_only=False)` and `JointTransformerBlock(context_pre_only=True, dual)` (:205-222).
+Also restated: `use_modulate: True` (:171-183, :252-258 — the experts are the condition-modulated linear pairs of the
+Flux class: `modulated_flatten` over `Linear(D, D)` weights scaled by `Linear(pooled_dim, D)` of the pooled
+projections) and `use_shared_expert: False` (:203, :279 — the routed experts' outputs alone). NOT restated:
+`use_rope: True` — unreachable as shipped: `UniGenSD3.forward` calls `prepare_latent_image_ids` (:657-659), a name
+that is neither defined nor imported anywhere in the reference (`src/UniGenUtils.py` has no such function, the only
+import of it, :2055, fails), so the first forward raises NameError.
 
 Parity pinning status
   * reference-owned arithmetic — the three AdaLN forwards (src/UniGenUtils.py:340-373), `JointTransformerBlock.forward`
@@ -33,7 +39,7 @@ import torch
 import torch.nn.functional as F
 
 from .unigen_oracle import (_heads, _lin, _time_text, combined_timestep_text_embed, feed_forward, layer_norm, linear,
-                            moe_capacity, moe_combine, moe_dispatch, rms_norm, sdpa, top1gating)
+                            moe_capacity, moe_combine, moe_dispatch, modulated_flatten, rms_norm, sdpa, top1gating)
 
 Tensor = torch.Tensor
 
@@ -57,6 +63,7 @@ class SD3Config:
     expert_num_each_condition: int = 3
     use_pooled_prompt_embeds: bool = True
     use_shared_expert: bool = True
+    use_modulate: bool = False  # src/UniGenTransformer.py:171: modulated-linear experts instead of transformer blocks
 
     @property
     def inner_dim(self) -> int:
@@ -227,19 +234,29 @@ class UniGenSD3Oracle:
             self.trace[name] = t.detach().clone()
 
     # --- src/UniGenTransformer.py:222-262, transformer-block branch (:256-258) ---
-    def expert_forward(self, hidden, cond, temb, cond_temb) -> Tuple[Tensor, Tensor]:
+    def expert_forward(self, hidden, cond, temb, cond_temb, pooled=None, cond_pooled=None) -> Tuple[Tensor, Tensor]:
         """Dispatched (1,E,C,D) tensors in, stacked (1,E,C,D) out. Every expert sees its C capacity slots as ONE
-        sequence of a batch-1 sample: empty slots (all-zero rows, zero temb) take part in the self-attention."""
+        sequence of a batch-1 sample: empty slots (all-zero rows, zero temb) take part in the self-attention.
+        `use_modulate` (:252-255): expert[0] modulates the condition rows by the dispatched condition pooled projection,
+        expert[1] modulates (hidden + that result) by the dispatched pooled projection; temb is not used."""
         H = self.cfg.num_attention_heads
         outs_h, outs_c = [], []
         for e in range(self.cfg.expert_nums):
             p = f"moe.moe_layer.experts.deepspeed_experts.{e}"
+            if self.cfg.use_modulate:
+                s_c = linear(self.sd, f"{p}.0.1", cond_pooled[:, e])
+                cc = modulated_flatten(cond[:, e], self.sd[f"{p}.0.0.weight"], s_c) + self.sd[f"{p}.0.0.bias"][None]
+                s_h = linear(self.sd, f"{p}.1.1", pooled[:, e])
+                hc = modulated_flatten(hidden[:, e] + cc, self.sd[f"{p}.1.0.weight"], s_h) + self.sd[f"{p}.1.0.bias"][None]
+                outs_h.append(hc)
+                outs_c.append(cc)
+                continue
             outs_h.append(sd3_single_block(self.sd, p + ".0", H, hidden[:, e], temb[:, e]))
             outs_c.append(sd3_single_block(self.sd, p + ".1", H, cond[:, e], cond_temb[:, e]))
         return torch.stack(outs_h, dim=1), torch.stack(outs_c, dim=1)
 
     # --- src/UniGenUtils.py:74-134 + src/UniGenTransformer.py:264-296 ---
-    def moe_forward(self, hidden, cond, enc_ctrl, temb_ctrl, cond_temb, rts_uniform):
+    def moe_forward(self, hidden, cond, enc_ctrl, temb_ctrl, cond_temb, rts_uniform, pooled=None, cond_pooled=None):
         cfg, sd = self.cfg, self.sd
         B, N, D = hidden.shape
         E, H = cfg.expert_nums, cfg.num_attention_heads
@@ -257,7 +274,10 @@ class UniGenSD3Oracle:
                 v = v.reshape(-1, v.shape[-1])
             return moe_dispatch(dispatch, v)[None]
 
-        eh, ec = self.expert_forward(disp(hidden), disp(cond), disp(temb_ctrl), disp(cond_temb))
+        if cfg.use_modulate:  # the pooled projections are dispatched like every other 2-D kwarg (src/UniGenUtils.py:104-110)
+            eh, ec = self.expert_forward(disp(hidden), disp(cond), None, None, disp(pooled), disp(cond_pooled))
+        else:
+            eh, ec = self.expert_forward(disp(hidden), disp(cond), disp(temb_ctrl), disp(cond_temb))
         expert_hidden = moe_combine(combine, eh.reshape(E, C, D), choice)
         expert_cond = moe_combine(combine, ec.reshape(E, C, D), choice)
         self._rec("moe.expert_hidden", expert_hidden); self._rec("moe.expert_cond", expert_cond)
@@ -279,7 +299,8 @@ class UniGenSD3Oracle:
         condition_temb = combined_timestep_text_embed(sd, "control_condition_embed", timestep, cond_pooled)
         enc_ctrl = linear(sd, "control_context_embedder", enc)  # Linear(D, D) on the BASE text stream (:493)
         self._rec("moe.cond_embed", cond); self._rec("moe.enc_ctrl", enc_ctrl)
-        eh, ec, l_aux, exp_counts = self.moe_forward(hidden, cond, enc_ctrl, control_temb, condition_temb, rts_uniform)
+        eh, ec, l_aux, exp_counts = self.moe_forward(hidden, cond, enc_ctrl, control_temb, condition_temb, rts_uniform,
+                                                     pooled, cond_pooled)
         return dict(expert_hidden_states=eh, expert_condition_hidden_states=ec, control_encoder_hidden_states=enc_ctrl,
                     control_temb=control_temb, condition_temb=condition_temb, exp_count=exp_counts, moe_loss=l_aux)
 
@@ -393,11 +414,16 @@ def init_state_dict(cfg: SD3Config, seed: int = 0, zero_linear_std: Optional[flo
     for e in range(cfg.expert_nums):
         for br in (0, 1):
             p = f"moe.moe_layer.experts.deepspeed_experts.{e}.{br}"
+            if cfg.use_modulate:  # ModuleList([Linear(D, D), Linear(pooled_dim, D)]) (:173-182)
+                _lin(sd, p + ".0", D, D, gen)
+                _lin(sd, p + ".1", D, cfg.pooled_projection_dim, gen)
+                continue
             _lin(sd, p + ".norm1.linear", 6 * D, D, gen)
             _attn(sd, p + ".attn", D, dh, gen, False, False, False)
             _ff(sd, p + ".ff", D, gen)
-    _joint_block_init(sd, "shared_expert.0", D, dh, gen, False, False, qk)
-    _joint_block_init(sd, "shared_expert.1", D, dh, gen, True, True, qk)
+    if cfg.use_shared_expert:
+        _joint_block_init(sd, "shared_expert.0", D, dh, gen, False, False, qk)
+        _joint_block_init(sd, "shared_expert.1", D, dh, gen, True, True, qk)
     return sd
 
 

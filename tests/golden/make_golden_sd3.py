@@ -12,6 +12,8 @@ functions with real tensors).  Pinned here:
   * `UniGenSD3.preprocess_moe_forward` / `control_forward` / `base_forward`   src/UniGenTransformer.py:498-623
     with affine stand-in blocks (weave order, first-call substitution, which tensors reach the MoE)
   * `UniGenSD3.forward` embedding order + un-patchify                         src/UniGenTransformer.py:625-710
+  * `use_modulate=True`: `UniGenBase.expert_forward` modulated-linear branch (:252-255, real `modulated_flatten`)
+    through the real `MOELayer`, `moe_forward` with `use_shared_expert` True / False (:279)
 
 The attention / feed-forward / gate sub-modules those functions call are third-party (diffusers `Attention` +
 `JointAttnProcessor2_0`, `FeedForward`, deepspeed `top1gating`): stand-ins written from the published algorithm are
@@ -293,6 +295,47 @@ def main():
                                                 pooled_projections=torch.zeros(Bf, 4), condition_pooled_projections=torch.zeros(Bf, 4),
                                                 timestep=torch.tensor([1.0, 1.0]))
     gold["unpatchify"] = dict(tokens=tok, h=Hh // p, w=Ww // p, p=p, c=Cc, out=out.detach(), moe_loss=losses["moe_loss"])
+
+    # 6. use_modulate=True: modulated-linear experts through the real MOELayer + UniGenBase.expert_forward (:252-255) and
+    #    moe_forward with and without the shared experts (:279) ---------------------------------------------------------
+    g6 = torch.Generator().manual_seed(3636)
+    mod_cases = []
+    for use_shared in (True, False):
+        hidden6, cond6 = torch.randn(B, N, D, generator=g6), torch.randn(B, N, D, generator=g6)
+        enc6 = torch.randn(B, Tn, D, generator=g6)
+        temb6, ctemb6 = torch.randn(B, D, generator=g6), torch.randn(B, D, generator=g6)
+        pooled6, cpooled6 = torch.randn(B, P, generator=g6), torch.randn(B, P, generator=g6)
+        rts6 = torch.rand(B * N, E, generator=g6)
+        wg6 = torch.randn(E, D, generator=g6) * 0.5
+        experts6 = nn.ModuleList([nn.ModuleList([randomize(nn.ModuleList([nn.Linear(D, D), nn.Linear(P, D)]), g6)
+                                                 for _ in range(2)]) for _ in range(E)])
+        shared6 = [make_joint(False, False), make_joint(True, True)]  # consumes g (after every earlier section)
+
+        class Gate6(nn.Module):
+            def forward(self, reshaped_input, used_token=None, wg_=wg6, rts_=rts6):
+                l_aux, combine, dispatch, counts, _ = top1gating(F.linear(reshaped_input.float(), wg_), C, rts_)
+                return l_aux, combine, dispatch, counts
+
+        fake6 = types.SimpleNamespace(num_local_experts=E, use_modulate=True, use_rope=False, use_shared_expert=use_shared,
+                                      shared_expert=[shared6[0].forward, shared6[1].forward])
+
+        class ExpertsFn6(nn.Module):
+            def forward(self, fake_=fake6, **kw):
+                return T.UniGenBase.expert_forward(fake_, **kw)
+
+        layer6 = U.MOELayer(Gate6(), ExpertsFn6(), "ep_size_1", 1, E)
+        layer6.experts.deepspeed_experts = experts6
+        fake6.moe = types.SimpleNamespace(moe_layer=layer6)
+        with torch.no_grad():
+            (eh6, ec6), l_aux6, counts6 = T.UniGenBase.moe_forward(
+                fake6, hidden_states=hidden6, condition_hidden_states=cond6, encoder_hidden_states=enc6, temb=temb6,
+                condition_temb=ctemb6, condition_pooled_projections=cpooled6, pooled_projections=pooled6,
+                joint_attention_kwargs=dict())
+        mod_cases.append(dict(use_shared_expert=use_shared, hidden=hidden6, cond=cond6, enc=enc6, temb=temb6, ctemb=ctemb6,
+                              pooled=pooled6, cpooled=cpooled6, rts=rts6, wg=wg6, E=E, C=C, P=P,
+                              experts=[[sd_of(b) for b in pair] for pair in experts6], shared=[sd_of(s_) for s_ in shared6],
+                              out_hidden=eh6.detach(), out_cond=ec6.detach(), l_aux=l_aux6.detach(), counts=counts6.detach()))
+    gold["moe_modulate"] = mod_cases
 
     torch.save(gold, OUT)
     print("wrote", OUT, {k: (len(v) if isinstance(v, (list, dict)) else type(v)) for k, v in gold.items()})

@@ -74,6 +74,29 @@ def test_moe_with_transformer_block_experts_and_shared_experts(gold):
     assert torch.equal(counts, m["counts"])
 
 
+def test_moe_with_modulated_linear_experts_with_and_without_shared_experts(gold):
+    """use_modulate=True (src/UniGenTransformer.py:171-183, :252-255) x use_shared_expert True / False (:279)."""
+    assert [c["use_shared_expert"] for c in gold["moe_modulate"]] == [True, False]
+    for m in gold["moe_modulate"]:
+        E, D = m["E"], m["hidden"].shape[-1]
+        cfg = O.SD3Config(num_attention_heads=gold["heads"], attention_head_dim=D // gold["heads"], condition_nums=0,
+                          expert_num_each_condition=E, use_modulate=True, use_shared_expert=m["use_shared_expert"],
+                          pooled_projection_dim=m["P"])
+        sd = {"moe.moe_layer.gate.wg.weight": m["wg"]}
+        for e, pair in enumerate(m["experts"]):
+            for br, w in enumerate(pair):
+                sd.update(_pref(w, f"moe.moe_layer.experts.deepspeed_experts.{e}.{br}"))
+        for s, w in enumerate(m["shared"]):
+            sd.update(_pref(w, f"shared_expert.{s}"))
+        orc = O.UniGenSD3Oracle(cfg, sd)
+        eh, ec, l_aux, counts = orc.moe_forward(m["hidden"], m["cond"], m["enc"], m["temb"], m["ctemb"], m["rts"],
+                                                m["pooled"], m["cpooled"])
+        torch.testing.assert_close(eh, m["out_hidden"], **TOL)
+        torch.testing.assert_close(ec, m["out_cond"], **TOL)
+        torch.testing.assert_close(l_aux, m["l_aux"])
+        assert torch.equal(counts, m["counts"])
+
+
 def test_weave_matches_reference_call_order_and_values(gold):
     """UniGenSD3.base_forward / control_forward / preprocess_moe_forward (src/UniGenTransformer.py:498-623)."""
     for w in gold["weave"]:

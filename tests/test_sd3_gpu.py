@@ -18,7 +18,7 @@ def _round(sd):
     return {k: (v if k.endswith("gate.wg.weight") else v.to(torch.bfloat16).float()) for k, v in sd.items()}
 
 
-def _setup(height=256, width=256, text_len=77, batch=1, zero_linear_std=0.02, seed=0, cfg=None):
+def _setup(height=256, width=256, text_len=77, batch=1, zero_linear_std=0.02, seed=0, cfg=None, control_params=None):
     from oracle import unigen_sd3_oracle as O
     from unigen_b200.sd3 import SD3Arch, UniGenSD3, shipped_control_params
     cfg = cfg or O.SD3Config.tiny()
@@ -33,7 +33,7 @@ def _setup(height=256, width=256, text_len=77, batch=1, zero_linear_std=0.02, se
                    pooled_projection_dim=cfg.pooled_projection_dim, pos_embed_max_size=cfg.pos_embed_max_size,
                    qk_norm=cfg.qk_norm, dual_attention_layers=cfg.dual_attention_layers)
     model = UniGenSD3(arch, device="cuda")
-    model.init_condition_block(condition_nums=cfg.condition_nums, control_params=shipped_control_params())
+    model.init_condition_block(condition_nums=cfg.condition_nums, control_params=control_params or shipped_control_params())
     res = model.load_state_dict(sd, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
     return cfg, sd, inp, oracle, model
@@ -152,6 +152,60 @@ def test_slot_kernels_match_torch(ug):
     img = ug.unpatchify(tok, 6, 5, 2, 16)
     want = torch.einsum("nhwpqc->nchpwq", tok.reshape(2, 6, 5, 2, 2, 16)).reshape(2, 16, 12, 10)
     assert torch.equal(img, want)
+
+
+@pytest.mark.parametrize("use_modulate,use_shared", [(True, True), (True, False), (False, False)])
+def test_expert_variants_match_oracle_per_block(use_modulate, use_shared):
+    """control_params switches around the shipped configuration (src/UniGenTransformer.py:171-183, :203, :252-255, :279):
+    modulated-linear experts (`use_modulate`) and the routed experts alone (`use_shared_expert=False`); batch 2 so that the
+    per-sample modulation vectors differ inside an expert's capacity buffer."""
+    import dataclasses
+    from oracle import unigen_sd3_oracle as O
+    from unigen_b200.sd3 import shipped_control_params
+    cfg = dataclasses.replace(O.SD3Config.tiny(), use_modulate=use_modulate, use_shared_expert=use_shared)
+    params = dict(shipped_control_params(), use_modulate=use_modulate, use_shared_expert=use_shared)
+    cfg, sd, inp, oracle, model = _setup(batch=2, seed=7, cfg=cfg, control_params=params)
+    assert ("shared_expert.0.norm1.linear.weight" in sd) == use_shared
+    assert ("moe.moe_layer.experts.deepspeed_experts.0.0.1.weight" in sd) == use_modulate
+    want, want_losses, want_out = oracle.forward(**inp)
+    model.trace = {}
+    got, losses, outs = model(**_dev(inp))
+    torch.cuda.synchronize()
+    worst = {name: rel_l2(model.trace[name], ref) for name, ref in oracle.trace.items()
+             if name in model.trace and name.split(".")[-1] not in ("expert_idx", "slot", "prob")}
+    assert {"moe.expert_hidden", "moe.expert_cond", "moe.ctrl_in"} <= set(worst)
+    assert ("moe.shared_hidden" in worst) == use_shared
+    bad = {k: v for k, v in worst.items() if v > 1e-2}
+    assert not bad, f"per-block rel-L2 above 1e-2: {bad}"
+    cos = torch.nn.functional.cosine_similarity(got.float().cpu().flatten(), want.flatten(), dim=0).item()
+    assert cos >= 0.999, cos
+    idx = model._last_route["expert_idx"].cpu().long()
+    assert (idx == oracle.trace["moe.expert_idx"]).float().mean().item() >= 0.99
+    assert abs(losses["moe_loss"].item() - want_losses["moe_loss"].item()) < 2e-3
+    # CUDA-graph replay of the variant == eager, bit for bit
+    model.trace = None
+    eager = model(**_dev(inp))[0].clone()
+    model.use_cuda_graph = True
+    for _ in range(2):
+        replay = model(**_dev(inp))[0]
+    assert torch.equal(eager, replay)
+
+
+def test_use_transformer_params_copies_base_weights_into_the_control_branch():
+    """init_control_param (src/UniGenTransformer.py:144-158): control blocks / embedders start from the base model's weights;
+    keys whose shapes differ (the context_pre_only last block) are skipped."""
+    from unigen_b200.sd3 import SD3Arch, UniGenSD3, shipped_control_params
+    m = UniGenSD3(SD3Arch.tiny(), device="cuda")
+    m.init_random_(seed=3)
+    m.init_condition_block(condition_nums=1, control_params=shipped_control_params())
+    sd = m.state_dict()
+    for src, dst in (("transformer_blocks.1.attn.to_q.weight", "control_transformer_blocks.1.attn.to_q.weight"),
+                     ("transformer_blocks.0.ff.net.2.bias", "control_transformer_blocks.0.ff.net.2.bias"),
+                     ("time_text_embed.timestep_embedder.linear_1.weight", "control_condition_embed.timestep_embedder.linear_1.weight"),
+                     ("pos_embed.proj.weight", "control_pos_embed_input.proj.weight")):
+        assert torch.equal(sd[src], sd[dst]), dst
+    last = m.arch.num_layers - 1
+    assert sd[f"transformer_blocks.{last}.norm1_context.linear.weight"].shape != sd[f"control_transformer_blocks.{last}.norm1_context.linear.weight"].shape
 
 
 def test_rejects_unsupported_configurations():

@@ -10,7 +10,12 @@ libunigen_b200.so; there is no eager / CPU fallback.
 
 Configuration covered = the SHIPPED control_params (config/unigen.yaml): `use_modulate: False`, no `use_rope`,
 `use_shared_expert: True`, `use_encoder_hidden_states: True`, `cn2base_method: add` — experts are two
-`SD3SingleTransformerBlock`s per expert run on the dispatched capacity buffers with a per-token temb.
+`SD3SingleTransformerBlock`s per expert run on the dispatched capacity buffers with a per-token temb — plus the two
+reachable switches around it: `use_modulate: True` (:171-183, :252-255: the experts are the condition-modulated linear
+pairs of the Flux class, stacked [E, D, D] and run as two batched GEMMs over the capacity slots) and
+`use_shared_expert: False` (:203, :279: the routed experts' outputs alone feed the control stream).
+`use_rope: True` stays rejected: the reference's own forward raises NameError there (`prepare_latent_image_ids`, :657,
+is defined nowhere in the reference), so there is no behaviour to match.
 
 Data layout in HBM (bf16 unless noted)
   X     [B, N+T, D]  joint residual stream, SAMPLE ROWS FIRST (JointAttnProcessor2_0 concatenates sample | context)
@@ -193,14 +198,13 @@ class UniGenSD3(_DenoiserBase):
         self.use_pooled_prompt_embeds = get("use_pooled_prompt_embeds", True)
         self.use_encoder_hidden_states = get("use_encoder_hidden_states", True)
         assert self.use_encoder_hidden_states, ValueError("please use joint transformer block to enhance condition hidden states")
-        self.use_rope, self.use_modulate = get("use_rope", False), get("use_modulate", False)
-        if self.use_rope or self.use_modulate:
-            raise ops.UgError("UniGenSD3 (B200-native) covers the shipped configuration: transformer-block experts "
-                              "(use_rope=False, use_modulate=False); the RoPE / modulated-linear SD3 variants are not built")
+        self.use_rope, self.use_modulate = bool(get("use_rope", False)), bool(get("use_modulate", False))
+        if self.use_rope:
+            raise ops.UgError("UniGenSD3 use_rope=True: the reference forward raises NameError (prepare_latent_image_ids, "
+                              "src/UniGenTransformer.py:657, is defined nowhere) — there is no behaviour to reproduce")
         if get("use_pos_embed", False) or get("extra_conditioning_channels", 0):
             raise ops.UgError("use_pos_embed / extra_conditioning_channels are not covered by the B200-native SD3 path")
-        if not get("use_shared_expert", False):
-            raise ops.UgError("use_shared_expert=False is not covered by the B200-native path yet")
+        self.use_shared_expert = bool(get("use_shared_expert", False))  # :203 (False: the routed experts alone, :279 skipped)
         self.cn_method = get("cn2base_method", "add")
         if self.cn_method != "add":
             raise ops.UgError("cn2base_method='CrossAttn' needs attn.condition_k_proj, which nothing creates (SURVEY.md §2); unsupported")
@@ -222,13 +226,53 @@ class UniGenSD3(_DenoiserBase):
         E = self.expert_nums
         self.gate_wg = ws.alloc(E, D, dtype=torch.float32)
         ws.views["moe.moe_layer.gate.wg.weight"] = self.gate_wg
-        self.experts = [_ExpertStackW(ws, E, 0, D), _ExpertStackW(ws, E, 1, D)]
+        if self.use_modulate:
+            # :173-182: expert = [[Linear(D, D), Linear(pooled, D)] (condition), [Linear(D, D), Linear(pooled, D)] (hidden)],
+            # stacked over the experts exactly like the Flux class's (model.py)
+            P = a.pooled_projection_dim
+            self.experts = []
+            self.exp_w, self.exp_b = [ws.alloc(E, D, D), ws.alloc(E, D, D)], [ws.alloc(E, D), ws.alloc(E, D)]
+            self.exp_mod_w, self.exp_mod_b = [ws.alloc(E * D, P), ws.alloc(E * D, P)], [ws.alloc(E * D), ws.alloc(E * D)]
+            for e in range(E):
+                for br in (0, 1):
+                    p = f"moe.moe_layer.experts.deepspeed_experts.{e}.{br}"
+                    ws.views[p + ".0.weight"], ws.views[p + ".0.bias"] = self.exp_w[br][e], self.exp_b[br][e]
+                    ws.views[p + ".1.weight"] = self.exp_mod_w[br][e * D:(e + 1) * D]
+                    ws.views[p + ".1.bias"] = self.exp_mod_b[br][e * D:(e + 1) * D]
+        else:
+            self.experts = [_ExpertStackW(ws, E, 0, D), _ExpertStackW(ws, E, 1, D)]
         self.shared = [_JointBlockW(ws, "shared_expert.0", D, dh, False, False, qk),
-                       _JointBlockW(ws, "shared_expert.1", D, dh, True, True, qk)]
+                       _JointBlockW(ws, "shared_expert.1", D, dh, True, True, qk)] if self.use_shared_expert else []
         self.trainable_control_modules = {k: None for k in (
             "control_pos_embed_input", "control_time_text_embed", "control_condition_embed", "control_context_embedder",
-            "control_transformer_blocks", "controlnet_add_blocks", "moe", "shared_expert")}
+            "control_transformer_blocks", "controlnet_add_blocks", "moe") + (("shared_expert",) if self.use_shared_expert else ())}
         self._control_ready = True
+        if get("use_transformer_params", False):
+            self.init_control_param()
+
+    @torch.no_grad()
+    def init_control_param(self):
+        """reference src/UniGenTransformer.py:144-158: the control branch starts from the base model's weights —
+        `control_pos_embed_input` <- `pos_embed`, both control time-text embedders <- `time_text_embed`, control block j <-
+        base block j (`load_state_dict(..., strict=False)` over the ModuleLists). `control_context_embedder` is re-created
+        as a fresh Linear(D, D) right after (:493), so nothing is copied into it. Deviation, on purpose: the LAST base block is
+        context_pre_only (`norm1_context.linear` [2D, D], no `to_add_out` / `ff_context`) while its control twin is not
+        ([6D, D]) — `strict=False` does not forgive a size mismatch, so the reference call raises RuntimeError with the
+        shipped 24 + 24 layout; here keys whose shapes differ are skipped and the call succeeds."""
+        v = self._ws.views
+
+        def copy_prefix(dst: str, src: str):
+            for k in [k for k in v if k.startswith(src + ".")]:
+                kd = dst + k[len(src):]
+                if kd in v and v[kd].shape == v[k].shape:
+                    v[kd].copy_(v[k])
+
+        copy_prefix("control_pos_embed_input", "pos_embed")
+        copy_prefix("control_time_text_embed", "time_text_embed")
+        copy_prefix("control_condition_embed", "time_text_embed")
+        for j in range(min(self.control_blocks_num, self.arch.num_layers)):
+            copy_prefix(f"control_transformer_blocks.{j}", f"transformer_blocks.{j}")
+        self._weights_loaded()
 
     def _weights_loaded(self):
         self.pos_embed_w._crop.clear()
@@ -256,6 +300,8 @@ class UniGenSD3(_DenoiserBase):
             TE=[torch.zeros(B + 1, D, device=dev, dtype=torch.float32) for _ in (0, 1)],  # [temb rows | zero row]
             MOD=z(B, n_mod * D, dt=torch.float32), temb=z(B, D, dt=torch.float32), tmp=z(B, D, dt=torch.float32),
             PAT=z(B, N, kpe), NO=z(B, N, D), OUT=z(B, N, a.patch_size ** 2 * a.out_channels), capacity=C)
+        if self.use_modulate:  # per-sample, per-expert modulation vectors of the two linear experts
+            b.MODC, b.MODH = z(B, E, D, dt=torch.float32), z(B, E, D, dt=torch.float32)
         return b
 
     def _sd3_mod_plans(self, buf, B: int):
@@ -280,7 +326,9 @@ class UniGenSD3(_DenoiserBase):
         mp = types.SimpleNamespace()
         mp.m_base = [pair(w, buf.temb, early if i == 0 else late) for i, w in enumerate(self.blocks)]
         mp.m_ctrl = [pair(w, condition_temb, early if j == 0 else late) for j, w in enumerate(self.ctrl_blocks)]
-        mp.mods_s0, mp.mods_s1 = pair(self.shared[0], condition_temb, early), pair(self.shared[1], control_temb, early)
+        mp.mods_s0 = mp.mods_s1 = None
+        if self.use_shared_expert:
+            mp.mods_s0, mp.mods_s1 = pair(self.shared[0], condition_temb, early), pair(self.shared[1], control_temb, early)
         mp.m_out = job(self.norm_out_w, buf.temb, 2, late)  # AdaLayerNormContinuous: (scale, shift)
         mp.early, mp.late = ops.GemvPlan(early, self.device_), ops.GemvPlan(late, self.device_)
         buf.mod_plans = mp
@@ -372,28 +420,44 @@ class UniGenSD3(_DenoiserBase):
         ops.gated_add_slots(x, buf.STMP, chunk(5), st, E, C, N, B)
         return x
 
-    def _prestage(self, buf, B, N, T, x_img, x_txt, cond_latents, mods_s0, mods_s1, rts_uniform):
+    def _prestage(self, buf, B, N, T, x_img, x_txt, cond_latents, mods_s0, mods_s1, rts_uniform, pooled, cpooled):
         """preprocess_moe_forward (src/UniGenTransformer.py:498-540) + moe_forward (:264-296) + MOELayer.forward +
         expert_forward (:222-262): runs once per step after base block 0; leaves the control-stream input in buf.CIN."""
         D, E, C = self.inner_dim, self.expert_nums, buf.capacity
+        gv = self.gemm_variant
         self._patch_embed(buf, self.control_pos_embed_input_w, cond_latents, buf.COND)
         ops.gemm(x_txt, self.control_context_embedder_w[0], out=buf.CENC, bias=self.control_context_embedder_w[1], variant=self.gemm_variant)
         self._rec("moe.cond_embed", buf.COND); self._rec("moe.enc_ctrl", buf.CENC)
         ops.add(x_img, buf.COND, buf.G.view(B, N, D))
         route = ops.moe_route(buf.G, self.gate_wg, rts_uniform, C)
         ops.copy(x_img, buf.EH.view(B, N, D))  # contiguous token-major copy of the (strided) image rows for the gather
-        ops.moe_gather_modulate(buf.EH, route["slot_token"], None, E, C, N, out=buf.SL[0])
-        ops.moe_gather_modulate(buf.COND.view(B * N, D), route["slot_token"], None, E, C, N, out=buf.SL[1])
-        self._expert_branch(buf, 0, route, B, N)  # expert[0](hidden_chunk, temb_chunk)            temb = control_temb
-        self._expert_branch(buf, 1, route, B, N)  # expert[1](condition_chunk, condition_temb_chunk)
-        # shared experts (:281-294): [0] sample = hidden, context = condition, temb = condition_temb
+        if self.use_modulate:
+            # :252-255: cond' = Wc (s_c . cond) + bc ; hid' = Wh (s_h . (hid + cond')) + bh with s = Linear(pooled) per expert —
+            # the row scale rides in the gather, the (C, D, D) modulated weights of `modulated_flatten` never exist
+            ops.gemv(cpooled, self.exp_mod_w[0], self.exp_mod_b[0], out=buf.MODC.view(B, E * D))
+            ops.gemv(pooled, self.exp_mod_w[1], self.exp_mod_b[1], out=buf.MODH.view(B, E * D))
+            ops.moe_gather_modulate(buf.COND.view(B * N, D), route["slot_token"], buf.MODC, E, C, N, out=buf.SNX)
+            ops.gemm(buf.SNX.view(E, C, D), self.exp_w[0], out=buf.SL[1].view(E, C, D), bias=self.exp_b[0], variant=gv)
+            ops.moe_gather_modulate(buf.EH, route["slot_token"], buf.MODH, E, C, N, addend=buf.SL[1], out=buf.SNX)
+            ops.gemm(buf.SNX.view(E, C, D), self.exp_w[1], out=buf.SL[0].view(E, C, D), bias=self.exp_b[1], variant=gv)
+        else:
+            ops.moe_gather_modulate(buf.EH, route["slot_token"], None, E, C, N, out=buf.SL[0])
+            ops.moe_gather_modulate(buf.COND.view(B * N, D), route["slot_token"], None, E, C, N, out=buf.SL[1])
+            self._expert_branch(buf, 0, route, B, N)  # expert[0](hidden_chunk, temb_chunk)            temb = control_temb
+            self._expert_branch(buf, 1, route, B, N)  # expert[1](condition_chunk, condition_temb_chunk)
         hc_h, hc_c = buf.HC[:, :N], buf.HC[:, N:]
-        self._joint_block(buf, self.shared[0], mods_s0[0], mods_s0[1], x_img, buf.COND, hc_h, hc_c)
-        #                   [1] sample = [hidden | condition], context = control text, temb = control_temb, context_pre_only
-        self._joint_block(buf, self.shared[1], mods_s1[0], mods_s1[1], buf.HC, buf.CENC, buf.HC, None)
+        if self.use_shared_expert:
+            # shared experts (:281-294): [0] sample = hidden, context = condition, temb = condition_temb
+            self._joint_block(buf, self.shared[0], mods_s0[0], mods_s0[1], x_img, buf.COND, hc_h, hc_c)
+            #                   [1] sample = [hidden | condition], context = control text, temb = control_temb, context_pre_only
+            self._joint_block(buf, self.shared[1], mods_s1[0], mods_s1[1], buf.HC, buf.CENC, buf.HC, None)
         ops.moe_combine(buf.SL[0], route, C, buf.EH)
         ops.moe_combine(buf.SL[1], route, C, buf.EC)
         self._rec("moe.expert_hidden", buf.EH.view(B, N, D)); self._rec("moe.expert_cond", buf.EC.view(B, N, D))
+        if not self.use_shared_expert:  # :279 skipped: control stream := expert_hidden + expert_cond (:561)
+            ops.add(buf.EH.view(B, N, D), buf.EC.view(B, N, D), buf.CIN)
+            self._rec("moe.ctrl_in", buf.CIN)
+            return route
         self._rec("moe.shared_hidden", hc_h); self._rec("moe.shared_cond", hc_c)
         # control stream := (shared_hidden + expert_hidden) + (shared_cond + expert_cond)   (:294, :561)
         ops.add(hc_h, buf.EH.view(B, N, D), buf.CIN)
@@ -488,7 +552,7 @@ class UniGenSD3(_DenoiserBase):
             self._rec(f"block.{i}.base_hidden", x_img)
             j = int(i / (n_base / n_ctrl))
             if i == 0:   # first control call: CoMoE pre-stage on (hidden after block 0, base text after block 0) (:558-562)
-                route = self._prestage(buf, B, N, T, x_img, x_txt, cs, mods_s0, mods_s1, u)
+                route = self._prestage(buf, B, N, T, x_img, x_txt, cs, mods_s0, mods_s1, u, pooled, cpooled)
                 ctrl_in = buf.CIN
             else:
                 ctrl_in = x_img
