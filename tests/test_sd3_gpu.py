@@ -258,3 +258,58 @@ def test_sd3_cfg_loop_is_one_cuda_graph_and_equals_the_stepwise_loop():
         ops.euler_step(x, v, sig[i].item(), sig[i + 1].item())
     assert torch.equal(x, eager)
     assert not torch.equal(eager, lat)
+
+
+def test_sd3_pipeline_call_shaped_entry_and_control_guidance_window():
+    """`UniGenSD3Pipeline.__call__`-shaped entry (src/UniGenPipeline.py:145-449): embeddings + condition latents in, latents out;
+    `control_guidance_end` switches the control branch off for the late steps through `controlnet_keep` (:367-373, :387-391) —
+    checked against the loop stepped through the public forward with the per-step scale."""
+    from unigen_b200 import ops, pipeline as PL
+    from unigen_b200.ops import UgError
+    cfg, sd, inp, oracle, model = _setup()
+    d = _dev(inp)
+    steps, g_scale, c_scale = 4, 4.0, 0.8
+    gen = torch.Generator().manual_seed(11)
+    B, Cc, Hh, Ww = d["hidden_states"].shape
+    N = (Hh // 2) * (Ww // 2)
+    rts = [torch.rand(2 * B * N, cfg.expert_nums, generator=gen).cuda() for _ in range(steps)]
+    neg_es = torch.randn(d["encoder_hidden_states"].shape, generator=gen).to(torch.bfloat16).cuda()
+    neg_pool = torch.randn(d["pooled_projections"].shape, generator=gen).cuda()
+    lat = d["hidden_states"].to(torch.bfloat16)
+    pipe = PL.UniGenSD3Pipeline(model)
+    kw = dict(control_image=d["condition_hidden_states"], conditioning_scale=[c_scale], num_inference_steps=steps, guidance_scale=g_scale,
+              latents=lat, prompt_embeds=d["encoder_hidden_states"], negative_prompt_embeds=neg_es,
+              pooled_prompt_embeds=d["pooled_projections"], negative_pooled_prompt_embeds=neg_pool,
+              condition_pooled_prompt_embeds=d["condition_pooled_projections"], rts_uniform=rts)
+    full = pipe(**kw).images
+    direct = PL.denoise_sd3(model, lat, d["condition_hidden_states"], d["encoder_hidden_states"], d["pooled_projections"],
+                            d["condition_pooled_projections"], num_inference_steps=steps, guidance_scale=g_scale,
+                            negative_encoder_hidden_states=neg_es, negative_pooled_projections=neg_pool, conditioning_scale=c_scale,
+                            rts_uniform=rts)
+    assert torch.equal(full, direct) and full.shape == lat.shape
+    windowed, = pipe(control_guidance_end=[0.5], return_dict=False, **kw)
+    assert not torch.equal(windowed, full)
+    keep = [PL.sd3_controlnet_keep(i, steps, 0.0, 0.5) for i in range(steps)]
+    assert keep == [1.0, 1.0, 0.0, 0.0]
+    sig = torch.tensor(PL.flow_match_sigmas(steps, N, use_dynamic_shifting=False, shift=3.0), dtype=torch.float32)
+    x = lat.clone()
+    es2 = torch.cat([neg_es, d["encoder_hidden_states"].to(torch.bfloat16)], 0)
+    pool2 = torch.cat([neg_pool, d["pooled_projections"]], 0)
+    cs2 = torch.cat([d["condition_hidden_states"].to(torch.bfloat16)] * 2, 0)
+    cp2 = torch.cat([d["condition_pooled_projections"]] * 2, 0)
+    for i in range(steps):
+        t = (sig[i] * 1000.0).reshape(1).cuda()
+        out = model(hidden_states=torch.cat([x, x], 0), condition_hidden_states=cs2, conditioning_scale=c_scale * keep[i],
+                    encoder_hidden_states=es2, pooled_projections=pool2, condition_pooled_projections=cp2, timestep=t,
+                    rts_uniform=rts[i])[0]
+        v = ops.cfg_combine(out[:B], out[B:], g_scale)
+        ops.euler_step(x, v, sig[i].item(), sig[i + 1].item())
+    assert torch.equal(x, windowed)
+    with pytest.raises(UgError):
+        pipe(prompt="a photo", **{k: v for k, v in kw.items()})
+    with pytest.raises(ValueError):
+        pipe(**{k: v for k, v in kw.items() if k != "negative_prompt_embeds"})
+    # guidance_scale <= 1: no batch doubling, no negative embeddings needed
+    plain = pipe(**dict({k: v for k, v in kw.items() if not k.startswith("negative")}, guidance_scale=1.0,
+                        rts_uniform=[r[:B * N] for r in rts])).images
+    assert plain.shape == lat.shape and not torch.equal(plain, full)

@@ -182,18 +182,27 @@ def denoise(transformer, latents: torch.Tensor, condition_latents, encoder_hidde
     return out.clone()
 
 
+def sd3_controlnet_keep(i: int, n_steps: int, start: float = 0.0, end: float = 1.0) -> float:
+    """src/UniGenPipeline.py:367-373: `1.0 - float(i / len(timesteps) < s or (i + 1) / len(timesteps) > e)`."""
+    return 1.0 - float(i / n_steps < start or (i + 1) / n_steps > end)
+
+
 @torch.no_grad()
 def denoise_sd3(transformer, latents: torch.Tensor, condition_latents: torch.Tensor, encoder_hidden_states, pooled_projections,
                 condition_pooled_projections, num_inference_steps: int = 28, guidance_scale: float = 7.0,
                 negative_encoder_hidden_states=None, negative_pooled_projections=None, conditioning_scale: float = 1.0,
                 shift: float = 3.0, rts_uniform: Optional[Sequence] = None, sigmas: Optional[Sequence[float]] = None,
-                graph_loop: bool = True) -> torch.Tensor:
+                graph_loop: bool = True, control_guidance_start: float = 0.0, control_guidance_end: float = 1.0) -> torch.Tensor:
     """`UniGenSD3Pipeline.__call__` loop (src/UniGenPipeline.py:377-412) on latents (B, 16, H, W): with classifier-free guidance
     (`guidance_scale > 1` and negative embeddings) every step runs ONE batch-doubled forward over [uncond | text] (:380, prompt
     embeddings concatenated negative-first) and combines `uncond + g * (text - uncond)` (:405-407) on the device; Euler update
-    with the static-shift flow-match schedule (SD3.5: shift 3.0). Returns the final latents (bf16)."""
+    with the static-shift flow-match schedule (SD3.5: shift 3.0). `control_guidance_start / end` gate the control branch per
+    step exactly as `controlnet_keep` does (:367-373, :387-391: scale_i = conditioning_scale * keep_i). Returns the final
+    latents (bf16)."""
     dev = transformer.device
     n_steps = int(num_inference_steps)
+    scales = [float(conditioning_scale) * sd3_controlnet_keep(i, n_steps, control_guidance_start, control_guidance_end)
+              for i in range(n_steps)]
     x0 = ops.to_bf16(latents.to(dev).contiguous()).clone()
     B = x0.shape[0]
     p = transformer.arch.patch_size
@@ -226,7 +235,7 @@ def denoise_sd3(transformer, latents: torch.Tensor, condition_latents: torch.Ten
             ops.copy(xf, xi[:B])  # latent_model_input = cat([latents] * 2) (:380)
             if do_cfg:
                 ops.copy(xf, xi[B:])
-            out = transformer._forward_impl(float(conditioning_scale), st["xin"], st["cs"], st["es"], st["pooled"], st["cpooled"],
+            out = transformer._forward_impl(scales[i], st["xin"], st["cs"], st["es"], st["pooled"], st["cpooled"],
                                             st["timesteps"][i:i + 1], st["u"][i])[0]
             if do_cfg:  # noise_pred_uncond, noise_pred_text = noise_pred.chunk(2)
                 v = ops.cfg_combine(out[:B], out[B:], float(guidance_scale), out=st["v"])
@@ -235,7 +244,7 @@ def denoise_sd3(transformer, latents: torch.Tensor, condition_latents: torch.Ten
             ops.euler_step_table(x, v, st["sigmas"], i)
         return x
 
-    key = ("sd3", tuple(x0.shape), encoder_hidden_states.shape[1], n_steps, float(conditioning_scale), do_cfg, float(guidance_scale))
+    key = ("sd3", tuple(x0.shape), encoder_hidden_states.shape[1], n_steps, tuple(scales), do_cfg, float(guidance_scale))
     use_graph = bool(graph_loop) and getattr(transformer, "trace", None) is None
     return _loop_graphs(transformer).run(key, inputs, body, use_graph).clone()
 
@@ -348,4 +357,92 @@ class UniGenFLUXPipeline:
             if self.vae_decode is None:
                 raise ops.UgError("VAE decode is outside the B200-native path: use output_type='latent' or pass vae_decode=")
             image = self.vae_decode(self._unpack_latents(out, height, width, self.vae_scale_factor))
+        return types.SimpleNamespace(images=image) if return_dict else (image,)
+
+
+class UniGenSD3Pipeline:
+    """`UniGenSD3Pipeline`-shaped entry (src/UniGenPipeline.py:145-449) for the B200-native `UniGenSD3`. Same call-site keywords
+    for everything the denoise path consumes; what needs a text encoder / VAE must arrive pre-computed:
+
+      prompt_embeds, pooled_prompt_embeds (+ negative_*)   instead of prompt / prompt_2 / prompt_3 (a string prompt raises)
+      condition_pooled_prompt_embeds                        the pooled embedding of the condition prompt (:274-286)
+      control_image                                         condition LATENTS (B, 16, H/8, W/8), already `(vae.encode(x) - shift) *
+                                                            scaling` (:306-308), or pixels when `vae_encode=` is given
+      output_type="latent"                                  (or pass `vae_decode=` to get pixels from a caller-owned VAE)
+
+    Classifier-free guidance is on for `guidance_scale > 1` (`do_classifier_free_guidance`) and then needs the negative embeddings,
+    as the reference's `encode_prompt` would produce them. Returns `SimpleNamespace(images=latents)` or `(latents,)`."""
+
+    def __init__(self, transformer, vae_encode=None, vae_decode=None, vae_scale_factor: int = 8, default_sample_size: int = 128,
+                 shift: float = 3.0):
+        self.transformer = transformer
+        self.vae_encode, self.vae_decode = vae_encode, vae_decode
+        self.vae_scale_factor, self.default_sample_size, self.shift = vae_scale_factor, default_sample_size, shift
+        self.joint_attention_kwargs = None
+
+    @property
+    def device(self):
+        return self.transformer.device
+
+    @property
+    def dtype(self):
+        return self.transformer.dtype
+
+    def prepare_latents(self, batch_size, num_channels_latents, height, width, dtype, device, generator, latents=None):
+        """StableDiffusion3Pipeline.prepare_latents: noise (B, C, h // 8, w // 8) unless latents are given."""
+        if latents is not None:
+            return latents.to(device=device, dtype=dtype)
+        shape = (batch_size, num_channels_latents, int(height) // self.vae_scale_factor, int(width) // self.vae_scale_factor)
+        gdev = generator.device if generator is not None else device
+        return torch.randn(shape, generator=generator, device=gdev, dtype=torch.float32).to(device=device, dtype=dtype)
+
+    @torch.no_grad()
+    def __call__(self, prompt=None, prompt_2=None, prompt_3=None, condition_prompt=None, control_image=None,
+                 control_use_vae_shift_factor: bool = True, conditioning_scale=1.0, height: Optional[int] = None,
+                 width: Optional[int] = None, num_inference_steps: int = 28, sigmas: Optional[List[float]] = None,
+                 guidance_scale: float = 7.0, control_guidance_start=0.0, control_guidance_end=1.0, negative_prompt=None,
+                 negative_prompt_2=None, negative_prompt_3=None, condition_negative_prompt=None, num_images_per_prompt: int = 1,
+                 generator=None, latents=None, prompt_embeds=None, condition_prompt_embeds=None, negative_prompt_embeds=None,
+                 condition_negative_prompt_embeds=None, pooled_prompt_embeds=None, condition_pooled_prompt_embeds=None,
+                 negative_pooled_prompt_embeds=None, condition_negative_pooled_prompt_embeds=None, ip_adapter_image=None,
+                 ip_adapter_image_embeds=None, output_type: str = "latent", return_dict: bool = True, joint_attention_kwargs=None,
+                 rts_uniform=None, graph_loop: bool = True, **kwargs):
+        if any(p is not None for p in (prompt, prompt_2, prompt_3, negative_prompt, negative_prompt_2, negative_prompt_3)):
+            raise ops.UgError("text encoders are outside the B200-native path: pass prompt_embeds / pooled_prompt_embeds "
+                              "(and the negative_* embeddings for classifier-free guidance)")
+        if ip_adapter_image is not None or ip_adapter_image_embeds is not None:
+            raise ops.UgError("ip_adapter_image(_embeds) is not covered by the B200-native path")
+        if prompt_embeds is None or pooled_prompt_embeds is None or control_image is None or condition_pooled_prompt_embeds is None:
+            raise ValueError("prompt_embeds, pooled_prompt_embeds, control_image and condition_pooled_prompt_embeds are required")
+        first = lambda v: v[0] if isinstance(v, (list, tuple)) else v  # noqa: E731  (:226-236: lists collapse to their first entry)
+        conditioning_scale = first(conditioning_scale)
+        start, end = float(first(control_guidance_start)), float(first(control_guidance_end))
+        tr, dev = self.transformer, self.device
+        do_cfg = guidance_scale > 1  # do_classifier_free_guidance
+        if do_cfg and (negative_prompt_embeds is None or negative_pooled_prompt_embeds is None):
+            raise ValueError("guidance_scale > 1 needs negative_prompt_embeds and negative_pooled_prompt_embeds")
+        B = prompt_embeds.shape[0] * num_images_per_prompt
+        rep = lambda t: t.repeat_interleave(num_images_per_prompt, 0) if num_images_per_prompt > 1 else t  # noqa: E731
+        if self.vae_encode is not None and control_image.shape[1] != tr.config.in_channels:
+            control_image = self.vae_encode(control_image)  # caller-owned VAE: returns the shifted / scaled latents (:306-308)
+        cond_latents = control_image if control_image.shape[0] == B else rep(control_image)
+        if cond_latents.dim() != 4 or cond_latents.shape[1] != tr.config.in_channels:
+            raise ops.UgError("control_image must be condition latents (B, in_channels, H/8, W/8): VAE encode is outside the "
+                              "B200-native path (or pass vae_encode=)")
+        # the reference takes height / width from the prepared control image (:304); here from its latents
+        height, width = cond_latents.shape[2] * self.vae_scale_factor, cond_latents.shape[3] * self.vae_scale_factor
+        latents = self.prepare_latents(B, tr.config.in_channels, height, width, torch.bfloat16, dev, generator, latents)
+        cpool = condition_pooled_prompt_embeds if condition_pooled_prompt_embeds.shape[0] == B else rep(condition_pooled_prompt_embeds)
+        out = denoise_sd3(tr, latents, cond_latents, rep(prompt_embeds), rep(pooled_prompt_embeds), cpool,
+                          num_inference_steps=num_inference_steps, guidance_scale=float(guidance_scale),
+                          negative_encoder_hidden_states=rep(negative_prompt_embeds) if do_cfg else None,
+                          negative_pooled_projections=rep(negative_pooled_prompt_embeds) if do_cfg else None,
+                          conditioning_scale=float(conditioning_scale), shift=self.shift, rts_uniform=rts_uniform, sigmas=sigmas,
+                          graph_loop=graph_loop, control_guidance_start=start, control_guidance_end=end)
+        if output_type == "latent":
+            image = out
+        else:
+            if self.vae_decode is None:
+                raise ops.UgError("VAE decode is outside the B200-native path: use output_type='latent' or pass vae_decode=")
+            image = self.vae_decode(out)  # caller-owned: `latents / scaling_factor + shift_factor` -> vae.decode (:430-433)
         return types.SimpleNamespace(images=image) if return_dict else (image,)
