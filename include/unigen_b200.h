@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define UG_ABI_VERSION 8
+#define UG_ABI_VERSION 9
 
 typedef enum {
   UG_OK = 0,
@@ -463,6 +463,64 @@ int ug_flux_bind_weight(ug_flux* handle, const char* name, const void* dev_ptr, 
 size_t ug_flux_workspace_bytes(const ug_flux* handle, int32_t batch, int32_t n_img, int32_t n_txt);
 int ug_flux_forward(ug_flux* handle, const ug_flux_inputs* inputs, const ug_flux_outputs* outputs, void* workspace,
                     size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * AutoencoderKL (VAE) ops — SURVEY.md §8 (f)4 tail: the condition image is VAE-encoded before the denoise loop
+ * (`vae.encode(control_image).latent_dist.sample()`, src/UniGenPipeline.py:306-308; Flux: `Condition._encode_image`
+ * src/condition.py:90-99) and the final latents are VAE-decoded after it (:430-433, :1120-1124). Activations are NHWC bf16
+ * ([batch, h, w, c] contiguous; a "pixel row" is one (b, y, x) with c channels), so every convolution is a GEMM over pixel rows.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct ug_conv2d_args {
+  const void* x;            /* bf16 NHWC [batch, h, w_px, c_in], contiguous */
+  const void* w;            /* bf16 [c_out, 9 * c_in]: column (ky * 3 + kx) * c_in + c  (nn.Conv2d weight permuted to [co, ky, kx, ci]) */
+  const void* bias;         /* bf16 [c_out] or NULL */
+  const void* residual;     /* bf16 NHWC [batch, h, w_px, res_pixel_stride] or NULL; may alias y */
+  int64_t res_pixel_stride;
+  void* y;                  /* bf16 NHWC [batch, h, w_px, y_pixel_stride] */
+  int64_t y_pixel_stride;   /* elements between output pixels (>= c_out, multiple of 8) */
+  int32_t batch, h, w_px, c_in, c_out;
+  float alpha;              /* y = alpha * (conv + bias) + residual; 0 is read as 1 */
+  int32_t variant;          /* 0 = auto (GEMM tile variants 1-6 of ug_gemm_args) */
+  int32_t reserved;
+} ug_conv2d_args;
+/* nn.Conv2d(c_in, c_out, kernel_size=3, stride=1, padding=1) as an IMPLICIT GEMM on the tcgen05 path: the TMA unit assembles
+ * each [128 pixels x 64 channels] A tile from the image at the filter tap's offset (zero fill outside the image), no im2col
+ * buffer. Needs c_in % 64 == 0 and w_px a multiple of 128 or a divisor of 128; other shapes: ug_im2col_bf16 + ug_gemm_bf16. */
+int ug_conv3x3_bf16(const ug_conv2d_args* args, void* stream);
+
+/* Patch gather for the convolutions the implicit path does not take (stride 2 `Downsample2D` with its (0,1,0,1) padding,
+ * c_in = 3 / 16 stems): cols[(b, yo, xo), (ky * kw + kx) * c + ch] = x[b, yo * stride + ky - pad_top, xo * stride + kx - pad_left, ch]
+ * (0 outside the image, 0 in columns [kh * kw * c, k_pad)). x is addressed through element strides, so NCHW fp32 / bf16 inputs
+ * (the pixel-space image, the latents) and NHWC bf16 activations are all accepted. In-image values pass through
+ * alpha * x + beta (the `latents / scaling_factor + shift_factor` in front of the decoder's first convolution, whose zero
+ * padding must stay zero; alpha = 1, beta = 0 otherwise). cols: bf16 [batch * h_out * w_out, k_pad]. */
+int ug_im2col_bf16(const void* x, int32_t x_is_f32, int64_t sb, int64_t sy, int64_t sx, int64_t sc, void* cols, int32_t batch,
+                   int32_t h, int32_t w, int32_t c, int32_t kh, int32_t kw, int32_t stride, int32_t pad_top, int32_t pad_left,
+                   int32_t h_out, int32_t w_out, int32_t k_pad, float alpha, float beta, void* stream);
+
+/* GroupNorm(groups, c, eps, affine) [+ SiLU] over NHWC bf16 [batch, pixels, c]: statistics in fp32, deterministic (no atomics):
+ * per-block partial sums -> fixed-order fold -> normalise / scale / shift / activate (three launches). `stats`: fp32 scratch of
+ * batch * groups * 2 * (1 + UG_GROUPNORM_MAX_CHUNKS) elements. y may alias x. */
+#define UG_GROUPNORM_MAX_CHUNKS 1024
+int ug_groupnorm_bf16(const void* x, void* y, const void* gamma, const void* beta, float* stats, int32_t batch, int32_t pixels,
+                      int32_t c, int32_t groups, float eps, int32_t silu, void* stream);
+
+/* F.interpolate(scale_factor=2, mode="nearest") over NHWC bf16: [batch, h, w, c] -> [batch, 2h, 2w, c] (`Upsample2D`). */
+int ug_upsample2x_nhwc_bf16(const void* x, void* y, int32_t batch, int32_t h, int32_t w, int32_t c, void* stream);
+
+/* In-place row softmax of bf16 scores (fp32 arithmetic): x[r, :cols] <- softmax(x[r, :cols]); the single-head, 512-wide
+ * attention of the VAE mid block runs as GEMM (scaled q k^T) -> this -> GEMM (p v). */
+int ug_softmax_rows_bf16(void* x, int64_t row_stride, int32_t rows, int32_t cols, void* stream);
+
+/* NHWC bf16 (pixel stride >= c) -> NCHW (bf16, or fp32 when y_is_f32): the first c channels of every pixel. */
+int ug_nhwc_to_nchw(const void* x, int64_t pixel_stride, void* y, int32_t y_is_f32, int32_t batch, int32_t c, int32_t h, int32_t w,
+                    void* stream);
+
+/* DiagonalGaussianDistribution over the encoder's moments (NHWC bf16 [batch, pixels, 2 * c]: mean | logvar):
+ * z = mean + exp(0.5 * clamp(logvar, -30, 20)) * noise  (noise fp32 NCHW [batch, c, pixels]; NULL = `.mode()`), then
+ * latents = (z - shift) * scale — NCHW bf16 [batch, c, pixels]. */
+int ug_vae_sample(const void* moments, int64_t pixel_stride, const float* noise, void* latents, int32_t batch, int32_t c,
+                  int32_t pixels, float shift, float scale, void* stream);
 
 #ifdef __cplusplus
 }

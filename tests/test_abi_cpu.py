@@ -35,7 +35,8 @@ def test_struct_layouts_match_header_field_order():
     from unigen_b200 import _lib
     text = HEADER.read_text()
     for struct, cls in (("ug_gemm_args", _lib.GemmArgs), ("ug_attn_args", _lib.AttnArgs), ("ug_gemv_job", _lib.GemvJob),
-                        ("ug_flux_desc", _lib.FluxDesc), ("ug_flux_inputs", _lib.FluxInputs), ("ug_flux_outputs", _lib.FluxOutputs)):
+                        ("ug_flux_desc", _lib.FluxDesc), ("ug_flux_inputs", _lib.FluxInputs), ("ug_flux_outputs", _lib.FluxOutputs),
+                        ("ug_conv2d_args", _lib.Conv2dArgs)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), text, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []
@@ -78,7 +79,7 @@ def test_struct_offsets_match_a_compiled_probe(tmp_path):
     if shutil.which("gcc") is None:
         pytest.skip("gcc not available")
     structs = {"ug_gemm_args": _lib.GemmArgs, "ug_attn_args": _lib.AttnArgs, "ug_peer_table": _lib.PeerTable,
-               "ug_qkv_scatter_args": _lib.QkvScatterArgs}
+               "ug_qkv_scatter_args": _lib.QkvScatterArgs, "ug_conv2d_args": _lib.Conv2dArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
     for name, cls in structs.items():
         lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')

@@ -11,7 +11,8 @@ LIB_PATH = PKG_DIR / "libunigen_b200.so"
 UG_ACT_NONE = 0
 UG_ACT_GELU_TANH = 1
 UG_MAX_SEGMENTS = 8
-UG_ABI_VERSION = 8  # include/unigen_b200.h; checked against ug_abi_version() of the loaded library
+UG_GROUPNORM_MAX_CHUNKS = 1024
+UG_ABI_VERSION = 9  # include/unigen_b200.h; checked against ug_abi_version() of the loaded library
 
 
 class UgError(RuntimeError):
@@ -37,6 +38,12 @@ class GemmArgs(C.Structure):
         ("a2", C.c_void_p), ("a2_row_stride", C.c_int64), ("a2_batch_stride", C.c_int64),
         ("w2", C.c_void_p), ("w2_row_stride", C.c_int64), ("k2", C.c_int32), ("colmask_block", C.c_int32),
     ]
+
+
+class Conv2dArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("residual", C.c_void_p), ("res_pixel_stride", C.c_int64),
+                ("y", C.c_void_p), ("y_pixel_stride", C.c_int64), ("batch", C.c_int32), ("h", C.c_int32), ("w_px", C.c_int32),
+                ("c_in", C.c_int32), ("c_out", C.c_int32), ("alpha", C.c_float), ("variant", C.c_int32), ("reserved", C.c_int32)]
 
 
 UG_MAX_PEERS = 8
@@ -156,6 +163,14 @@ SIGNATURES = {
     "ug_attention_bf16_peer": (C.c_int, [C.POINTER(AttnArgs), C.POINTER(PeerTable), _I64, _I32, _VP]),
     "ug_peer_bcast_rows": (C.c_int, [C.POINTER(PeerTable), _VP, _I64, _I32, _I32, _I64, _I64, _I32, _VP]),
     "ug_unpatchify": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "ug_conv3x3_bf16": (C.c_int, [C.POINTER(Conv2dArgs), _VP]),
+    "ug_im2col_bf16": (C.c_int, [_VP, _I32, _I64, _I64, _I64, _I64, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32,
+                                 _I32, _F32, _F32, _VP]),
+    "ug_groupnorm_bf16": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _F32, _I32, _VP]),
+    "ug_upsample2x_nhwc_bf16": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _VP]),
+    "ug_softmax_rows_bf16": (C.c_int, [_VP, _I64, _I32, _I32, _VP]),
+    "ug_nhwc_to_nchw": (C.c_int, [_VP, _I64, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "ug_vae_sample": (C.c_int, [_VP, _I64, _VP, _VP, _I32, _I32, _I32, _F32, _F32, _VP]),
 }
 
 _lib = None

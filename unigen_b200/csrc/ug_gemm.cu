@@ -50,6 +50,17 @@ struct GemmParams {
   const float* qk_cos_sin;    // fp32 [rows, qk_dh]: (cos, sin) per rotation pair, row = row of the C view (NULL = no RoPE)
   int qk_dh, qk_d;
   float qk_eps;
+  // implicit-GEMM 3x3 convolution (stride 1, zero padding 1) over an NHWC image: the A operand is a 4-D tensor map
+  // (channel, x, y, image); K block kb = filter tap kb / conv_cblocks, channel block kb % conv_cblocks, and the A tile of that
+  // block is the box of the tile's 128 output pixels shifted by the tap offset (out-of-image pixels arrive as zeros from the
+  // TMA unit: the padding costs nothing). conv_cblocks == 0: plain GEMM.
+  int conv_cblocks, conv_w;
+};
+
+// host-side description of the convolution a GEMM launch computes (ug_conv3x3_bf16)
+struct ConvDesc {
+  const void* x;
+  int batch, h, w, c_in;
 };
 
 template <int kCta, int BN, int kStages, bool kTmaEpi = false>
@@ -394,26 +405,45 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int row0 = mt * (Cfg::BM * kCta) + (int)cta_rank * Cfg::BM;
       const int wrow0 = nt * BN + (int)cta_rank * Cfg::BN_LOAD;
       const int wb = p.w_batched ? b : 0;
+      int conv_y0 = 0, conv_x0 = 0, conv_tap = 0, conv_cb = 0;
+      if (p.conv_cblocks) {
+        conv_y0 = row0 / p.conv_w;
+        conv_x0 = row0 - conv_y0 * p.conv_w;
+      }
       for (int kb = 0; kb < p.k_blocks; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one_sync()) {
           void* sa = smem_a + stage * Cfg::A_BYTES;
           void* sb = smem_b + stage * Cfg::B_BYTES;
-          // second operand pair (K extension: C += A2 @ W2^T accumulates into the same TMEM tile)
-          const bool second = kb >= p.k1_blocks;
-          const CUtensorMap* ma = second ? &tma_a2 : &tma_a;
-          const CUtensorMap* mw = second ? &tma_w2 : &tma_w;
-          const int kc = (second ? kb - p.k1_blocks : kb) * Cfg::BK;
-          if constexpr (kCta == 1) {
-            mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-            tma_load_3d(sa, ma, &full[stage], kc, row0, b);
-            tma_load_3d(sb, mw, &full[stage], kc, wrow0, second ? 0 : wb);
+          if (p.conv_cblocks) {
+            const int dy = conv_tap / 3, dx = conv_tap - 3 * dy;
+            if constexpr (kCta == 1) {
+              mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+              tma_load_4d(sa, &tma_a, &full[stage], conv_cb * Cfg::BK, conv_x0 + dx - 1, conv_y0 + dy - 1, b);
+              tma_load_3d(sb, &tma_w, &full[stage], kb * Cfg::BK, wrow0, 0);
+            } else {
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+              tma_load_4d_2sm(sa, &tma_a, &full[stage], conv_cb * Cfg::BK, conv_x0 + dx - 1, conv_y0 + dy - 1, b);
+              tma_load_3d_2sm(sb, &tma_w, &full[stage], kb * Cfg::BK, wrow0, 0);
+            }
           } else {
-            if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
-            tma_load_3d_2sm(sa, ma, &full[stage], kc, row0, b);
-            tma_load_3d_2sm(sb, mw, &full[stage], kc, wrow0, second ? 0 : wb);
+            // second operand pair (K extension: C += A2 @ W2^T accumulates into the same TMEM tile)
+            const bool second = kb >= p.k1_blocks;
+            const CUtensorMap* ma = second ? &tma_a2 : &tma_a;
+            const CUtensorMap* mw = second ? &tma_w2 : &tma_w;
+            const int kc = (second ? kb - p.k1_blocks : kb) * Cfg::BK;
+            if constexpr (kCta == 1) {
+              mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+              tma_load_3d(sa, ma, &full[stage], kc, row0, b);
+              tma_load_3d(sb, mw, &full[stage], kc, wrow0, second ? 0 : wb);
+            } else {
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+              tma_load_3d_2sm(sa, ma, &full[stage], kc, row0, b);
+              tma_load_3d_2sm(sb, mw, &full[stage], kc, wrow0, second ? 0 : wb);
+            }
           }
         }
+        if (p.conv_cblocks && ++conv_cb == p.conv_cblocks) { conv_cb = 0; ++conv_tap; }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
@@ -643,13 +673,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 }
 
 template <int kCta, int BN, int kStages, bool kTmaEpi = false>
-static int launch_gemm(const ug_gemm_args& a, cudaStream_t stream) {
+static int launch_gemm(const ug_gemm_args& a, cudaStream_t stream, const ConvDesc* conv = nullptr) {
   using Cfg = GemmCfg<kCta, BN, kStages, kTmaEpi>;
   auto kern = gemm_bf16_kernel<kCta, BN, kStages, kTmaEpi>;
   static bool attr_done[64] = {false};
   if (int st = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, attr_done, "gemm"); st != UG_OK) return st;
   CUtensorMap tma_a, tma_w;
-  {
+  if (conv) {
+    // NHWC image as (channel, x, y, image); box = 64 channels x the 128 output pixels of one CTA's row tile (a run of a row
+    // when the width is a multiple of 128, else 128 / width whole rows)
+    const uint32_t bw = conv->w % Cfg::BM == 0 ? (uint32_t)Cfg::BM : (uint32_t)conv->w;
+    uint64_t dims[4] = {(uint64_t)conv->c_in, (uint64_t)conv->w, (uint64_t)conv->h, (uint64_t)conv->batch};
+    uint64_t strides[3] = {(uint64_t)conv->c_in * 2, (uint64_t)conv->w * conv->c_in * 2, (uint64_t)conv->h * conv->w * conv->c_in * 2};
+    uint32_t box[4] = {(uint32_t)Cfg::BK, bw, (uint32_t)Cfg::BM / bw, 1};
+    int st = encode_tmap_bf16(&tma_a, conv->x, 4, dims, strides, box);
+    if (st != UG_OK) return st;
+  } else {
     uint64_t dims[3] = {(uint64_t)a.k, (uint64_t)a.rows, (uint64_t)a.batch};
     uint64_t bs = a.batch > 1 ? (uint64_t)a.a_batch_stride : (uint64_t)a.rows * a.a_row_stride;
     uint64_t strides[2] = {(uint64_t)a.a_row_stride * 2, bs * 2};
@@ -733,6 +772,8 @@ static int launch_gemm(const ug_gemm_args& a, cudaStream_t stream) {
   p.w_batched = w_batched ? 1 : 0;
   p.qk_w = (const __nv_bfloat16*)a.qk_norm_weight; p.qk_cos_sin = a.qk_cos_sin; p.qk_dh = a.qk_head_dim;
   p.qk_d = a.qk_d; p.qk_eps = a.qk_eps;
+  p.conv_cblocks = conv ? conv->c_in / Cfg::BK : 0;
+  p.conv_w = conv ? conv->w : 0;
   p.lora_t = a.lora_t; p.lora_t_rs = a.lora_t_row_stride; p.lora_t_bs = a.lora_t_batch_stride;
   p.lora_b = (const __nv_bfloat16*)a.lora_b;
   p.lora_r = a.lora_rank; p.lora_block_n = a.lora_block_n > 0 ? a.lora_block_n : a.n; p.lora_nseg = a.lora_nseg;
@@ -772,6 +813,23 @@ static bool staged_epilogue_default() {
     cached = (e && strcmp(e, "direct") == 0) ? 0 : 1;
   }
   return cached == 1;
+}
+
+// auto tile choice: estimate each variant's time as  waves x tile area / (SMs per tile x relative tile efficiency)
+static int pick_tile_variant(int batch, int rows, int n) {
+  const int sms = num_sms();
+  struct Cand { int v, tm, tn; double rate; int units; };
+  // relative per-SM tile throughput from profiles/r01_probe_gemm_v1.log (large problems: 1371 / 1349 / ~900 TFLOP/s)
+  const Cand cands[3] = {{2, 256, 256, 2.0, sms / 2}, {1, 128, 256, 0.98, sms}, {3, 128, 128, 0.67, sms}};
+  double best = 0.0;
+  int variant = 0;
+  for (const Cand& c : cands) {
+    const long long tiles = (long long)batch * ((rows + c.tm - 1) / c.tm) * ((n + c.tn - 1) / c.tn);
+    const long long waves = (tiles + c.units - 1) / c.units;
+    const double t = (double)waves * c.tm * c.tn / c.rate;
+    if (variant == 0 || t < best) { best = t; variant = c.v; }
+  }
+  return variant;
 }
 
 }  // namespace ug
@@ -835,17 +893,7 @@ extern "C" int ug_gemm_bf16(const ug_gemm_args* args, void* stream) {
     // smallest — wave quantisation and the padding of a partial last row tile decide for small M (text stream, per-rank
     // shards of sequence parallelism: M = 576 at P = 8), the 2-CTA pair tile (half the per-SM W traffic, measured 2 % faster per
     // cfg3 step under the 1 kW power cap) wins whenever the grid fills the machine
-    const int sms = num_sms();
-    struct Cand { int v, tm, tn; double rate; int units; };
-    // relative per-SM tile throughput from profiles/r01_probe_gemm_v1.log (large problems: 1371 / 1349 / ~900 TFLOP/s)
-    const Cand cands[3] = {{2, 256, 256, 2.0, sms / 2}, {1, 128, 256, 0.98, sms}, {3, 128, 128, 0.67, sms}};
-    double best = 0.0;
-    for (const Cand& c : cands) {
-      const long long tiles = (long long)a.batch * ((a.rows + c.tm - 1) / c.tm) * ((a.n + c.tn - 1) / c.tn);
-      const long long waves = (tiles + c.units - 1) / c.units;
-      const double t = (double)waves * c.tm * c.tn / c.rate;
-      if (variant == 0 || t < best) { best = t; variant = c.v; }
-    }
+    variant = pick_tile_variant(a.batch, a.rows, a.n);
     if (a.n <= 128) variant = 3;
   }
   // epilogue flavour: variants 4 / 5 / 6 = tiles of 2 / 1 / 3 with the smem-staged TMA-store epilogue. The LoRA-in-epilogue,
@@ -877,6 +925,57 @@ extern "C" int ug_gemm_bf16(const ug_gemm_args* args, void* stream) {
     case 6: return launch_gemm<1, 128, 6, true>(a, s);
     default:
       set_error("gemm: unknown variant %d", a.variant);
+      return UG_ERR_INVALID;
+  }
+}
+
+// 3x3 convolution, stride 1, zero padding 1, over NHWC bf16 images as an implicit GEMM on the tcgen05 path above: no im2col
+// buffer exists — the TMA unit assembles every A tile from the image with the filter tap's offset and fills the halo with zeros.
+// Replaces the nn.Conv2d(k=3, p=1) calls of the AutoencoderKL the reference pipelines run around the denoiser
+// (vae.encode src/UniGenPipeline.py:306-308, vae.decode :430-433, :1120-1124) — SURVEY.md §8 (f)4.
+extern "C" int ug_conv3x3_bf16(const ug_conv2d_args* args, void* stream) {
+  using namespace ug;
+  UG_CHECK_ARG(args != nullptr, "conv3x3: null args");
+  const ug_conv2d_args& c = *args;
+  UG_CHECK_ARG(c.x && c.w && c.y, "conv3x3: null operand pointer");
+  UG_CHECK_ARG(c.batch >= 1 && c.h >= 1 && c.w_px >= 1, "conv3x3: empty image");
+  UG_CHECK_ARG(c.c_in >= 64 && c.c_in % 64 == 0, "conv3x3: c_in (%d) must be a multiple of 64 (use ug_im2col_bf16 + ug_gemm_bf16 otherwise)", c.c_in);
+  UG_CHECK_ARG(c.c_out >= 8 && c.c_out % 8 == 0 && c.y_pixel_stride >= c.c_out && c.y_pixel_stride % 8 == 0,
+               "conv3x3: c_out (%d) and the output pixel stride (%d) must be multiples of 8", c.c_out, (int)c.y_pixel_stride);
+  UG_CHECK_ARG(c.w_px % 128 == 0 || (c.w_px <= 128 && 128 % c.w_px == 0),
+               "conv3x3: image width %d must be a multiple of 128 or divide 128 (use ug_im2col_bf16 + ug_gemm_bf16 otherwise)", c.w_px);
+  UG_CHECK_ARG((reinterpret_cast<uintptr_t>(c.y) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.x) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(c.w) & 15) == 0, "conv3x3: operands must be 16-byte aligned");
+  if (c.bias) UG_CHECK_ARG((reinterpret_cast<uintptr_t>(c.bias) & 15) == 0, "conv3x3: bias alignment");
+  if (c.residual)
+    UG_CHECK_ARG((reinterpret_cast<uintptr_t>(c.residual) & 15) == 0 && c.res_pixel_stride >= c.c_out && c.res_pixel_stride % 8 == 0,
+                 "conv3x3: residual alignment / pixel stride");
+  ug_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  const int rows = c.h * c.w_px;
+  g.a = c.x; g.a_row_stride = c.c_in; g.a_batch_stride = (int64_t)rows * c.c_in;
+  g.w = c.w; g.w_row_stride = 9 * c.c_in;
+  g.c = c.y; g.c_row_stride = c.y_pixel_stride; g.c_batch_stride = (int64_t)rows * c.y_pixel_stride;
+  g.batch = c.batch; g.rows = rows; g.n = c.c_out; g.k = 9 * c.c_in;
+  g.bias = c.bias; g.alpha = c.alpha == 0.0f ? 1.0f : c.alpha; g.act = UG_ACT_NONE;
+  g.residual = c.residual; g.res_row_stride = c.res_pixel_stride; g.res_batch_stride = (int64_t)rows * c.res_pixel_stride;
+  const ConvDesc cd{c.x, c.batch, c.h, c.w_px, c.c_in};
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int variant = c.variant;
+  if (variant == 0) {
+    variant = pick_tile_variant(c.batch, rows, c.c_out);
+    if (c.c_out <= 128) variant = 3;
+    variant = variant == 2 ? 4 : (variant == 1 ? 5 : 6);  // smem-staged TMA-store epilogue
+  }
+  switch (variant) {
+    case 1: return launch_gemm<1, 256, 4>(g, s, &cd);
+    case 2: return launch_gemm<2, 256, 6>(g, s, &cd);
+    case 3: return launch_gemm<1, 128, 6>(g, s, &cd);
+    case 4: return launch_gemm<2, 256, 5, true>(g, s, &cd);
+    case 5: return launch_gemm<1, 256, 3, true>(g, s, &cd);
+    case 6: return launch_gemm<1, 128, 6, true>(g, s, &cd);
+    default:
+      set_error("conv3x3: unknown variant %d", c.variant);
       return UG_ERR_INVALID;
   }
 }

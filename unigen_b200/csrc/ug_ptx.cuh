@@ -110,6 +110,14 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, ui
       "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                int c2, int c3) {
+  uint32_t bar_addr = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 
 // TMA store (shared::cta -> global, tile mode, bulk-group completion). OOB rows / columns of the box are clipped by the
 // hardware. The smem source must be made visible to the async proxy first (fence_proxy_async_smem after the writes).

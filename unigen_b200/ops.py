@@ -14,7 +14,7 @@ from ._lib import UG_ACT_GELU_TANH, UG_ACT_NONE, AttnArgs, GemmArgs, QkvScatterA
 
 __all__ = ["gemm", "lora_down", "lora_down_wide", "attention", "attention_peer", "qkv_scatter", "peer_bcast_rows", "peer_barrier", "expand_segment_mask", "ln_modulate", "qk_rmsnorm_rope", "rope_table", "gemv", "GemvPlan", "gemv_grouped", "silu",
            "timestep_embedding", "add", "copy", "to_bf16", "to_f32", "moe_route", "moe_gather_modulate",
-           "moe_combine", "ln_modulate_segs", "ln_modulate_slots", "gated_add_slots", "unpatchify", "euler_step", "euler_step_table", "cfg_combine", "pack_latents", "unpack_latents", "launch_count", "reset_launch_count", "UG_ACT_NONE", "UG_ACT_GELU_TANH", "UgError"]
+           "moe_combine", "ln_modulate_segs", "ln_modulate_slots", "gated_add_slots", "unpatchify", "euler_step", "euler_step_table", "cfg_combine", "pack_latents", "unpack_latents", "conv3x3", "conv3x3_implicit_ok", "im2col", "groupnorm", "upsample2x", "softmax_rows_", "nhwc_to_nchw", "vae_sample", "launch_count", "reset_launch_count", "UG_ACT_NONE", "UG_ACT_GELU_TANH", "UgError"]
 
 BF16 = torch.bfloat16
 
@@ -645,4 +645,156 @@ def unpatchify(tokens: torch.Tensor, h: int, w: int, p: int, channels: int, out:
     if out is None:
         out = torch.empty(B, channels, h * p, w * p, device=tokens.device, dtype=BF16)
     check(_lib.load().ug_unpatchify(tokens.data_ptr(), out.data_ptr(), B, h, w, p, channels, _stream()), "ug_unpatchify")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# AutoencoderKL (VAE) ops: NHWC bf16 activations [B, H, W, C] (SURVEY.md §8 (f)4 tail)
+# ------------------------------------------------------------------------------------------------------------------
+def _nhwc(t: torch.Tensor, name: str) -> torch.Tensor:
+    _dev(t, name, BF16)
+    if t.dim() != 4 or not t.is_contiguous():
+        raise UgError(f"{name}: expected a contiguous NHWC [B, H, W, C] bf16 tensor, got shape {tuple(t.shape)} strides {t.stride()}")
+    return t
+
+
+def conv3x3_implicit_ok(c_in: int, width: int) -> bool:
+    """Shapes the implicit-GEMM convolution takes (others go through im2col + gemm)."""
+    return c_in % 64 == 0 and (width % 128 == 0 or (width <= 128 and 128 % width == 0))
+
+
+def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+            out: Optional[torch.Tensor] = None, alpha: float = 1.0, variant: int = 0) -> torch.Tensor:
+    """nn.Conv2d(k=3, s=1, p=1) over NHWC: x [B, H, W, Ci], w [Co, 9 * Ci] (column (ky*3+kx)*Ci + c), out [B, H, W, Co'] with
+    Co' >= Co (the first Co channels of every pixel are written). Implicit GEMM: no im2col buffer."""
+    from ._lib import Conv2dArgs
+    _nhwc(x, "conv3x3.x")
+    _dev(w, "conv3x3.w", BF16)
+    B, H, W, Ci = x.shape
+    Co = w.shape[0]
+    if w.dim() != 2 or w.shape[1] != 9 * Ci or not w.is_contiguous():
+        raise UgError(f"conv3x3: weight must be a contiguous [c_out, 9 * c_in] matrix, got {tuple(w.shape)} for c_in {Ci}")
+    if out is None:
+        out = torch.empty(B, H, W, Co, device=x.device, dtype=BF16)
+    _nhwc(out, "conv3x3.out")
+    if out.shape[:3] != x.shape[:3] or out.shape[3] < Co:
+        raise UgError(f"conv3x3: out {tuple(out.shape)} does not match x {tuple(x.shape)} / c_out {Co}")
+    a = Conv2dArgs()
+    a.x, a.w, a.y, a.y_pixel_stride = x.data_ptr(), w.data_ptr(), out.data_ptr(), out.shape[3]
+    a.batch, a.h, a.w_px, a.c_in, a.c_out = B, H, W, Ci, Co
+    a.alpha, a.variant = float(alpha), int(variant)
+    if bias is not None:
+        a.bias = _dev(bias, "conv3x3.bias", BF16).data_ptr()
+    if residual is not None:
+        _nhwc(residual, "conv3x3.residual")
+        if residual.shape[:3] != x.shape[:3] or residual.shape[3] < Co:
+            raise UgError("conv3x3: residual shape mismatch")
+        a.residual, a.res_pixel_stride = residual.data_ptr(), residual.shape[3]
+    check(_lib.load().ug_conv3x3_bf16(C.byref(a), _stream()), "ug_conv3x3_bf16")
+    return out
+
+
+def im2col(x: torch.Tensor, layout: str, kh: int, kw: int, stride: int, pad_top: int, pad_left: int, h_out: int, w_out: int,
+           k_pad: Optional[int] = None, out: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 0.0) -> torch.Tensor:
+    """Patch gather -> bf16 [B * h_out * w_out, k_pad]; layout "nhwc" ([B, H, W, C]) or "nchw" ([B, C, H, W]), bf16 or fp32;
+    in-image values pass through alpha * x + beta (padding stays zero)."""
+    if not x.is_cuda or x.dim() != 4 or x.dtype not in (BF16, torch.float32):
+        raise UgError("im2col: expected a 4-D CUDA bf16 / fp32 tensor — the UniGen hot path has no CPU fallback")
+    if layout == "nhwc":
+        B, H, W, Cc = x.shape
+        sb, sy, sx, sc = x.stride()
+    elif layout == "nchw":
+        B, Cc, H, W = x.shape
+        sb, sc, sy, sx = x.stride()
+    else:
+        raise UgError(f"im2col: unknown layout {layout!r}")
+    k = kh * kw * Cc
+    k_pad = k_pad or (k + 7) // 8 * 8
+    rows = B * h_out * w_out
+    if out is None:
+        out = torch.empty(rows, k_pad, device=x.device, dtype=BF16)
+    _dev(out, "im2col.out", BF16)
+    if out.numel() < rows * k_pad or not out.is_contiguous():
+        raise UgError("im2col: out too small / not contiguous")
+    check(_lib.load().ug_im2col_bf16(x.data_ptr(), int(x.dtype == torch.float32), sb, sy, sx, sc, out.data_ptr(), B, H, W, Cc, kh, kw,
+                                     stride, pad_top, pad_left, h_out, w_out, k_pad, float(alpha), float(beta), _stream()),
+          "ug_im2col_bf16")
+    return out.view(-1)[:rows * k_pad].view(rows, k_pad)
+
+
+def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float = 1e-6, silu_act: bool = False,
+              out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(groups, C, eps) (+ SiLU) over NHWC bf16 [B, H, W, C]; out may be x."""
+    _nhwc(x, "groupnorm.x")
+    B, H, W, Cc = x.shape
+    _dev(gamma, "groupnorm.weight", BF16), _dev(beta, "groupnorm.bias", BF16)
+    if out is None:
+        out = torch.empty_like(x)
+    _nhwc(out, "groupnorm.out")
+    need = B * groups * 2 * (1 + _lib.UG_GROUPNORM_MAX_CHUNKS)
+    if stats is None:
+        stats = torch.empty(need, device=x.device, dtype=torch.float32)
+    _dev(stats, "groupnorm.stats", torch.float32)
+    if stats.numel() < need:
+        raise UgError("groupnorm: stats scratch too small")
+    check(_lib.load().ug_groupnorm_bf16(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(), B, H * W, Cc,
+                                        int(groups), float(eps), int(bool(silu_act)), _stream()), "ug_groupnorm_bf16")
+    return out
+
+
+def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _nhwc(x, "upsample2x.x")
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty(B, 2 * H, 2 * W, Cc, device=x.device, dtype=BF16)
+    _nhwc(out, "upsample2x.out")
+    if tuple(out.shape) != (B, 2 * H, 2 * W, Cc):
+        raise UgError("upsample2x: out shape mismatch")
+    check(_lib.load().ug_upsample2x_nhwc_bf16(x.data_ptr(), out.data_ptr(), B, H, W, Cc, _stream()), "ug_upsample2x_nhwc_bf16")
+    return out
+
+
+def softmax_rows_(x: torch.Tensor) -> torch.Tensor:
+    """In-place softmax over the last dim of a bf16 [rows, cols] view (unit inner stride)."""
+    _dev(x, "softmax_rows.x", BF16)
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise UgError("softmax_rows: expected a [rows, cols] view with contiguous cols")
+    check(_lib.load().ug_softmax_rows_bf16(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], _stream()), "ug_softmax_rows_bf16")
+    return x
+
+
+def nhwc_to_nchw(x: torch.Tensor, channels: int, dtype=BF16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """First `channels` channels of NHWC bf16 [B, H, W, C'] -> NCHW [B, channels, H, W] (bf16 or fp32)."""
+    _nhwc(x, "nhwc_to_nchw.x")
+    B, H, W, Cs = x.shape
+    if dtype not in (BF16, torch.float32) or channels > Cs:
+        raise UgError("nhwc_to_nchw: dtype must be bf16 / fp32 and channels <= C")
+    if out is None:
+        out = torch.empty(B, channels, H, W, device=x.device, dtype=dtype)
+    _dev(out, "nhwc_to_nchw.out", dtype)
+    if tuple(out.shape) != (B, channels, H, W) or not out.is_contiguous():
+        raise UgError("nhwc_to_nchw: out shape mismatch / not contiguous")
+    check(_lib.load().ug_nhwc_to_nchw(x.data_ptr(), Cs, out.data_ptr(), int(dtype == torch.float32), B, channels, H, W, _stream()),
+          "ug_nhwc_to_nchw")
+    return out
+
+
+def vae_sample(moments: torch.Tensor, latent_channels: int, noise: Optional[torch.Tensor], shift: float = 0.0, scale: float = 1.0,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """moments: NHWC bf16 [B, h, w, >= 2 * c] (mean | logvar) -> NCHW bf16 latents (mean + std * noise - shift) * scale;
+    noise: fp32 NCHW [B, c, h, w] or None (the distribution's mode)."""
+    _nhwc(moments, "vae_sample.moments")
+    B, H, W, Cs = moments.shape
+    c = int(latent_channels)
+    if Cs < 2 * c:
+        raise UgError("vae_sample: moments need 2 * latent_channels channels")
+    if noise is not None:
+        _dev(noise, "vae_sample.noise", torch.float32)
+        if tuple(noise.shape) != (B, c, H, W) or not noise.is_contiguous():
+            raise UgError("vae_sample: noise must be a contiguous fp32 [B, c, h, w] tensor")
+    if out is None:
+        out = torch.empty(B, c, H, W, device=moments.device, dtype=BF16)
+    _dev(out, "vae_sample.out", BF16)
+    check(_lib.load().ug_vae_sample(moments.data_ptr(), Cs, noise.data_ptr() if noise is not None else None, out.data_ptr(), B, c, H * W,
+                                    float(shift), float(scale), _stream()), "ug_vae_sample")
     return out
