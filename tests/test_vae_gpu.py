@@ -252,3 +252,41 @@ def test_flux_vae_full_size_decode_and_encode_match_fp32_oracle_on_gpu():
                                image_rel_l2=rel_l2(got_img, want_img), latent_rel_l2=rel_l2(got_lat, want_lat)), f, indent=1)
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def test_flux_pipeline_encodes_the_condition_image_and_decodes_the_latents_through_the_native_vae():
+    """`UniGenFLUXPipeline.__call__` with pixels on both sides (src/UniGenPipeline.py:954-961 vae.encode -> sample -> shift / scale ->
+    pack; :1123-1125 unpack -> latents / scaling + shift -> vae.decode) == the same steps done by hand around the latent-space call."""
+    from oracle import unigen_oracle as FO
+    from unigen_b200 import ops
+    from unigen_b200.condition import Condition
+    from unigen_b200.model import FluxArch, UniGenFlux, canonical_control_params
+    from unigen_b200.pipeline import UniGenFLUXPipeline
+    cfg, sd, oracle, vae = _setup()
+    tr = UniGenFlux(FluxArch.tiny(), device="cuda")
+    tr.init_condition_block(condition_nums=1, control_params=canonical_control_params())
+    tr.init_random_(seed=2)
+    E = tr.expert_nums
+    H = W = 64  # pixels: latents 8 x 8 (the tiny VAE has one down-sampling level: factor 2) -> use vae_scale_factor = 2
+    g = torch.Generator().manual_seed(9)
+    img = _bf(torch.rand(1, 3, H, W, generator=g) * 2 - 1).float().cuda()
+    pe, pp, cp = torch.randn(1, 32, 4096, generator=g).cuda(), torch.randn(1, 768, generator=g).cuda(), torch.randn(1, 768, generator=g).cuda()
+    lat0 = _bf(torch.randn(1, 16, H // 2, W // 2, generator=g)).cuda()
+    N = (H // 4) * (W // 4)
+    rts = [torch.rand(N, E, generator=g).cuda() for _ in range(2)]
+    pipe = UniGenFLUXPipeline(tr, vae=vae, vae_scale_factor=2)
+    kw = dict(prompt_embeds=pe, pooled_prompt_embeds=pp, condition_pooled_prompt_embeds=cp, height=H, width=W, num_inference_steps=2,
+              latents=ops.pack_latents(lat0), rts_uniform=rts)
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    image = pipe(control_image=img, condition_types=["canny"], generator=gen, output_type="pt", **kw).images
+    assert image.shape == (1, 3, H, W)
+    # by hand: encode -> pack, latent-space pipeline call, unpack -> decode
+    gen.manual_seed(4)
+    tokens, ids, type_id = Condition("canny", img).encode(pipe, gen)
+    assert tokens.shape == (1, N, 64) and ids.shape == (N, 3) and int(type_id[0, 0]) == 1
+    assert torch.equal(ids.cpu(), FO.prepare_latent_image_ids(H // 4, W // 4))
+    lat_out = pipe(control_image=tokens, condition_ids=ids, output_type="latent", **kw).images
+    want = vae.decode_latents(ops.unpack_latents(lat_out, H // 2, W // 2))
+    assert torch.equal(image, want)
+    sub_tokens, sub_ids, _ = Condition("subject", img).encode(pipe, gen)
+    assert torch.equal(sub_ids[:, 2].cpu(), ids[:, 2].cpu() + (H // 2) // 2)  # :109-110

@@ -59,8 +59,23 @@ class Condition:
     def type_id(self) -> int:
         return condition_dict[self.condition_type]
 
-    def encode(self, pipe=None):
+    def _encode_image(self, pipe, cond_img: torch.Tensor, generator=None):
+        """src/condition.py:90-111: VAE-encode the (already preprocessed, [-1, 1]) condition image, shift / scale, pack into
+        tokens, build the position ids of the latent grid (`subject`: column 2 offset by the latent height // 2)."""
+        vae = getattr(pipe, "vae", None)
+        if vae is None:
+            raise ValueError("Condition holds a pixel image: the pipeline needs a `vae` (unigen_b200.vae.AutoencoderKL) to encode it")
+        lat = vae.encode_condition(cond_img, generator=generator)
+        tokens = pipe._pack_latents(lat)
+        ids = prepare_latent_image_ids(lat.shape[2] // 2, lat.shape[3] // 2, device=lat.device, dtype=torch.float32)
+        if self.condition_type == "subject":
+            ids[:, 2] += lat.shape[2] // 2
+        return tokens, ids
+
+    def encode(self, pipe=None, generator=None):
         tokens, ids = self.condition, self.condition_ids
+        if ids is None and tokens.dim() == 4:  # a pixel image (B, 3, H, W), not packed tokens (B, Nc, 64): way (2) of the reference
+            tokens, ids = self._encode_image(pipe, tokens, generator)
         if ids is None:
             if self.height is None or self.width is None:
                 raise ValueError("Condition needs either condition_ids or the pixel height / width of the condition image")

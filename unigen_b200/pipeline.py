@@ -3,8 +3,10 @@
 `UniGenFLUXPipeline.__call__` mirrors the part of the reference `UniGenFLUXPipeline.__call__` (src/UniGenPipeline.py:810-1134)
 between prompt encoding and VAE decode: latent preparation (:978-987), the sigma schedule (:989-1006), the loop body
 (:1050-1116: transformer call with `timestep / 1000`, optional true-CFG second call + combine, Euler flow-match step) and the
-`output_type="latent"` exit (:1120-1121). Text encoders, the VAE and image pre-processing are callers of the path and stay out
-of scope: prompts arrive as embeddings, condition images as packed latents (`unigen_b200.condition.Condition`).
+`output_type="latent"` exit (:1120-1121) or, with `vae=` (the native `unigen_b200.vae.AutoencoderKL`), the VAE encode of the
+condition image (:954-961) and the decode of the final latents (:1123-1125). Text encoders and image pre-processing (PIL ->
+[-1, 1] tensors) are callers of the path and stay out of scope: prompts arrive as embeddings, condition images as packed latents
+(`unigen_b200.condition.Condition`) or pre-processed pixel tensors.
 
 The whole loop is ONE CUDA graph (`graph_loop=True`, default): the sigma / timestep tables live in device memory
 (`ug_timestep_embedding` reads entry i, `ug_euler_step_table` reads entries i, i+1), the per-step RTS uniform draws are a
@@ -255,13 +257,18 @@ class UniGenFLUXPipeline:
 
       prompt_embeds, pooled_prompt_embeds         instead of prompt / prompt_2 (a string prompt raises: no text encoder here)
       condition_pooled_prompt_embeds              (tensor, or a list with one entry per condition)
-      control_image                               packed condition latents (B, Nc, 64), a `condition.Condition`, or a list of either
-      output_type="latent"                        (or pass `vae_decode=` to get pixels from a caller-owned VAE)
+      control_image                               packed condition latents (B, Nc, 64), a `condition.Condition`, or a list of either;
+                                                  with `vae=` also preprocessed pixel images (B, 3, H, W) in [-1, 1]
+      output_type="latent"                        or "pt" with `vae=` (unigen_b200.vae.AutoencoderKL: native encode / decode) or a
+                                                  caller-owned `vae_decode=` callable
 
     Returns `SimpleNamespace(images=latents)` (FluxPipelineOutput-shaped) or `(latents,)` with return_dict=False."""
 
-    def __init__(self, transformer, vae_decode=None, vae_scale_factor: int = 8, default_sample_size: int = 128):
+    def __init__(self, transformer, vae_decode=None, vae_scale_factor: int = 8, default_sample_size: int = 128, vae=None):
         self.transformer = transformer
+        self.vae = vae
+        if vae_decode is None and vae is not None:  # :1123-1125: latents / scaling_factor + shift_factor -> vae.decode
+            vae_decode = vae.decode_latents
         self.vae_decode = vae_decode
         self.vae_scale_factor, self.default_sample_size = vae_scale_factor, default_sample_size
         self.joint_attention_kwargs = None
@@ -328,7 +335,10 @@ class UniGenFLUXPipeline:
         cond_tokens, cond_ids = [], []
         for im, ty, gi in zip(imgs, types_, given_ids):
             if isinstance(im, cond_mod.Condition):
-                tok, ids, _ = im.encode(self)
+                tok, ids, _ = im.encode(self, generator)
+            elif im.dim() == 4:  # pixel image: :954-961 (vae.encode -> sample -> shift / scale -> pack)
+                tok, ids, _ = cond_mod.Condition(ty or "depth", im).encode(self, generator)
+                ids = gi if gi is not None else ids
             else:
                 tok = im
                 ids = gi if gi is not None else (cond_mod.condition_ids(ty, height, width)[0] if ty is not None else
@@ -355,7 +365,7 @@ class UniGenFLUXPipeline:
             image = out
         else:
             if self.vae_decode is None:
-                raise ops.UgError("VAE decode is outside the B200-native path: use output_type='latent' or pass vae_decode=")
+                raise ops.UgError("no VAE bound: use output_type='latent', or pass vae= (unigen_b200.vae.AutoencoderKL) / vae_decode=")
             image = self.vae_decode(self._unpack_latents(out, height, width, self.vae_scale_factor))
         return types.SimpleNamespace(images=image) if return_dict else (image,)
 
@@ -367,15 +377,18 @@ class UniGenSD3Pipeline:
       prompt_embeds, pooled_prompt_embeds (+ negative_*)   instead of prompt / prompt_2 / prompt_3 (a string prompt raises)
       condition_pooled_prompt_embeds                        the pooled embedding of the condition prompt (:274-286)
       control_image                                         condition LATENTS (B, 16, H/8, W/8), already `(vae.encode(x) - shift) *
-                                                            scaling` (:306-308), or pixels when `vae_encode=` is given
-      output_type="latent"                                  (or pass `vae_decode=` to get pixels from a caller-owned VAE)
+                                                            scaling` (:306-308), or pixels when `vae=` / `vae_encode=` is given
+      output_type="latent"                                  or "pt" with `vae=` (unigen_b200.vae.AutoencoderKL, native) / `vae_decode=`
 
     Classifier-free guidance is on for `guidance_scale > 1` (`do_classifier_free_guidance`) and then needs the negative embeddings,
     as the reference's `encode_prompt` would produce them. Returns `SimpleNamespace(images=latents)` or `(latents,)`."""
 
     def __init__(self, transformer, vae_encode=None, vae_decode=None, vae_scale_factor: int = 8, default_sample_size: int = 128,
-                 shift: float = 3.0):
+                 shift: float = 3.0, vae=None):
         self.transformer = transformer
+        self.vae = vae  # unigen_b200.vae.AutoencoderKL: native encode of the condition image / decode of the final latents
+        if vae is not None and vae_decode is None:
+            vae_decode = vae.decode_latents
         self.vae_encode, self.vae_decode = vae_encode, vae_decode
         self.vae_scale_factor, self.default_sample_size, self.shift = vae_scale_factor, default_sample_size, shift
         self.joint_attention_kwargs = None
@@ -423,8 +436,11 @@ class UniGenSD3Pipeline:
             raise ValueError("guidance_scale > 1 needs negative_prompt_embeds and negative_pooled_prompt_embeds")
         B = prompt_embeds.shape[0] * num_images_per_prompt
         rep = lambda t: t.repeat_interleave(num_images_per_prompt, 0) if num_images_per_prompt > 1 else t  # noqa: E731
-        if self.vae_encode is not None and control_image.shape[1] != tr.config.in_channels:
-            control_image = self.vae_encode(control_image)  # caller-owned VAE: returns the shifted / scaled latents (:306-308)
+        if control_image.dim() == 4 and control_image.shape[1] != tr.config.in_channels:
+            if self.vae_encode is not None:
+                control_image = self.vae_encode(control_image)  # caller-owned VAE: returns the shifted / scaled latents (:306-308)
+            elif self.vae is not None:
+                control_image = self.vae.encode_condition(control_image, generator=generator, use_shift_factor=control_use_vae_shift_factor)
         cond_latents = control_image if control_image.shape[0] == B else rep(control_image)
         if cond_latents.dim() != 4 or cond_latents.shape[1] != tr.config.in_channels:
             raise ops.UgError("control_image must be condition latents (B, in_channels, H/8, W/8): VAE encode is outside the "
@@ -443,6 +459,6 @@ class UniGenSD3Pipeline:
             image = out
         else:
             if self.vae_decode is None:
-                raise ops.UgError("VAE decode is outside the B200-native path: use output_type='latent' or pass vae_decode=")
+                raise ops.UgError("no VAE bound: use output_type='latent', or pass vae= (unigen_b200.vae.AutoencoderKL) / vae_decode=")
             image = self.vae_decode(out)  # caller-owned: `latents / scaling_factor + shift_factor` -> vae.decode (:430-433)
         return types.SimpleNamespace(images=image) if return_dict else (image,)
