@@ -44,7 +44,24 @@ __global__ void __launch_bounds__(256) groupnorm_partial_kernel(const __nv_bfloa
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (sub < lanes_px) {
     const __nv_bfloat16* base = x + ((long long)b * pixels) * c + o * 8;
-    for (int p = p0 + sub; p < p1; p += lanes_px) {
+    int p = p0 + sub;
+    // four pixels per trip: four independent 16-byte loads in flight per thread (the pass is a pure HBM stream)
+    for (; p + 3 * lanes_px < p1; p += 4 * lanes_px) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(base + (long long)(p + u * lanes_px) * c);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += f[i];
+          q[i] = fmaf(f[i], f[i], q[i]);
+        }
+      }
+    }
+    for (; p < p1; p += lanes_px) {
       const uint4 v = *reinterpret_cast<const uint4*>(base + (long long)p * c);
       float f[8];
       unpack8(v, f);
@@ -103,6 +120,8 @@ __global__ void __launch_bounds__(32) groupnorm_finalize_kernel(const float* __r
   }
 }
 
+// Normalise + affine (+ SiLU). The grid stride is a multiple of c / 8, so a thread keeps ONE channel octet for its whole walk:
+// its eight (scale, shift) pairs  a = rstd * gamma, d = beta - mean * a  are rebuilt only when the walk crosses into the next image.
 template <bool kSilu>
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                               const __nv_bfloat16* __restrict__ gamma,
@@ -111,25 +130,52 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat1
   const int octets = c >> 3;
   const int cpg = c / groups;
   const float inv_n = 1.0f / ((float)pixels * (float)cpg);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_octets; i += (long long)gridDim.x * blockDim.x) {
-    const int o = (int)(i % octets);
-    const long long px = i / octets;
-    const int b = (int)(px / pixels);
-    float f[8], gm[8], bt[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + i * 8), f);
-    unpack8(*reinterpret_cast<const uint4*>(gamma + o * 8), gm);
-    unpack8(*reinterpret_cast<const uint4*>(beta + o * 8), bt);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long per_image = (long long)pixels * octets;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int o = (int)(i % octets);
+  float gm[8], bt[8], a[8], d[8];
+  unpack8(*reinterpret_cast<const uint4*>(gamma + o * 8), gm);
+  unpack8(*reinterpret_cast<const uint4*>(beta + o * 8), bt);
+  int cur_b = -1;
+  auto coeffs = [&](int b) {
     const float* st = stats + (long long)b * 2 * groups;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int g = (o * 8 + j) / cpg;
       const float mean = st[2 * g] * inv_n;
       const float var = fmaxf(st[2 * g + 1] * inv_n - mean * mean, 0.0f);
-      float v = (f[j] - mean) * rsqrtf(var + eps) * gm[j] + bt[j];
-      if (kSilu) v = silu(v);
-      f[j] = v;
+      a[j] = rsqrtf(var + eps) * gm[j];
+      d[j] = fmaf(-mean, a[j], bt[j]);
     }
-    *reinterpret_cast<uint4*>(y + i * 8) = pack8(f);
+    cur_b = b;
+  };
+  auto one = [&](long long idx, const uint4& v) {
+    float f[8];
+    unpack8(v, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float r = fmaf(f[j], a[j], d[j]);
+      if (kSilu) r = silu(r);
+      f[j] = r;
+    }
+    *reinterpret_cast<uint4*>(y + idx * 8) = pack8(f);
+  };
+  // two octets per trip (two independent loads in flight); both usually belong to the same image
+  for (; i + stride < total_octets; i += 2 * stride) {
+    const uint4 v0 = *reinterpret_cast<const uint4*>(x + i * 8);
+    const uint4 v1 = *reinterpret_cast<const uint4*>(x + (i + stride) * 8);
+    const int b0 = (int)(i / per_image), b1 = (int)((i + stride) / per_image);
+    if (b0 != cur_b) coeffs(b0);
+    one(i, v0);
+    if (b1 != cur_b) coeffs(b1);
+    one(i + stride, v1);
+  }
+  if (i < total_octets) {
+    const uint4 v0 = *reinterpret_cast<const uint4*>(x + i * 8);
+    const int b0 = (int)(i / per_image);
+    if (b0 != cur_b) coeffs(b0);
+    one(i, v0);
   }
 }
 
@@ -309,12 +355,17 @@ extern "C" int ug_groupnorm_bf16(const void* x, void* y, const void* gamma, cons
   groupnorm_finalize_kernel<<<batch * groups, 32, 0, s>>>(partial, stats, chunks, groups);
   UG_CHECK_LAUNCH("groupnorm_finalize");
   const long long total = (long long)batch * pixels * (c / 8);
+  // grid stride (blocks x 256 threads) must be a multiple of c / 8: a thread then keeps one channel octet for its whole walk
+  int mult = c / 8, g256 = 256;
+  while (g256 % 2 == 0 && mult % 2 == 0) { g256 /= 2; mult /= 2; }  // mult = (c / 8) / gcd(c / 8, 256)
+  int grid = grid_for((total + 1) / 2);
+  grid = (grid + mult - 1) / mult * mult;
   if (silu_act)
-    groupnorm_apply_kernel<true><<<grid_for(total), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, (const __nv_bfloat16*)gamma,
-                                                                (const __nv_bfloat16*)beta, stats, pixels, c, groups, eps, total);
+    groupnorm_apply_kernel<true><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, (const __nv_bfloat16*)gamma,
+                                                      (const __nv_bfloat16*)beta, stats, pixels, c, groups, eps, total);
   else
-    groupnorm_apply_kernel<false><<<grid_for(total), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, (const __nv_bfloat16*)gamma,
-                                                                 (const __nv_bfloat16*)beta, stats, pixels, c, groups, eps, total);
+    groupnorm_apply_kernel<false><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, (const __nv_bfloat16*)gamma,
+                                                       (const __nv_bfloat16*)beta, stats, pixels, c, groups, eps, total);
   UG_CHECK_LAUNCH("groupnorm_apply");
   return UG_OK;
 }
