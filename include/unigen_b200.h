@@ -480,7 +480,7 @@ typedef struct ug_conv2d_args {
   int64_t y_pixel_stride;   /* elements between output pixels (>= c_out, multiple of 8) */
   int32_t batch, h, w_px, c_in, c_out;
   float alpha;              /* y = alpha * (conv + bias) + residual; 0 is read as 1 */
-  int32_t variant;          /* 0 = auto (GEMM tile variants 1-6 of ug_gemm_args) */
+  int32_t variant;          /* 0 = auto; 1-6 = the GEMM tile variants of ug_gemm_args; 7 = 2-CTA pair on a 256 x 128 tile (c_out <= 128) */
   int32_t reserved;
 } ug_conv2d_args;
 /* nn.Conv2d(c_in, c_out, kernel_size=3, stride=1, padding=1) as an IMPLICIT GEMM on the tcgen05 path: the TMA unit assembles

@@ -24,7 +24,8 @@ def _bf(t):
 @pytest.mark.parametrize("B,H,W,Ci,Co,variant", [
     (2, 16, 32, 64, 128, 0), (1, 8, 128, 128, 64, 0), (1, 4, 256, 64, 64, 0), (1, 24, 64, 192, 256, 0), (1, 6, 16, 64, 64, 0),
     (1, 32, 128, 128, 256, 1), (1, 32, 128, 128, 256, 2), (1, 32, 128, 128, 256, 3), (1, 32, 128, 128, 256, 4),
-    (1, 32, 128, 128, 256, 5), (1, 32, 128, 128, 256, 6), (3, 10, 8, 64, 72, 0)])
+    (1, 32, 128, 128, 256, 5), (1, 32, 128, 128, 256, 6), (3, 10, 8, 64, 72, 0), (1, 32, 128, 128, 128, 7), (1, 48, 128, 64, 72, 7),
+    (1, 256, 256, 64, 128, 0)])
 def test_implicit_conv3x3_matches_conv2d(B, H, W, Ci, Co, variant):
     from unigen_b200 import ops
     g = torch.Generator().manual_seed(B * 1000 + H * 10 + W + Ci + Co + variant)

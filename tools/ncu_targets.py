@@ -22,12 +22,38 @@ sys.path.insert(0, str(ROOT))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5", "tiny"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5", "tiny", "vae"])
     args = ap.parse_args()
     from unigen_b200 import ops
     from unigen_b200.ops import UG_ACT_GELU_TANH
     dev = torch.device("cuda")
     prof = torch.cuda.profiler
+    if args.workload == "vae":
+        # FLUX.1 VAE decoder at 1024 x 1024, top level (128 channels) and the level below (256 channels at 512 x 512): the implicit
+        # 3x3 convolution, GroupNorm + SiLU (statistics, fold, apply), nearest x2 up-sampling, the mid attention's row softmax
+        bf = torch.bfloat16
+        g = torch.Generator(device=dev).manual_seed(0)
+        x1 = torch.randn(1, 1024, 1024, 128, device=dev, generator=g).to(bf)
+        x2 = torch.randn(1, 512, 512, 256, device=dev, generator=g).to(bf)
+        w1 = (torch.randn(128, 9 * 128, device=dev, generator=g) / 34).to(bf)
+        w2 = (torch.randn(256, 9 * 256, device=dev, generator=g) / 48).to(bf)
+        b1, b2 = torch.zeros(128, device=dev, dtype=bf), torch.zeros(256, device=dev, dtype=bf)
+        gm, bt = torch.ones(128, device=dev, dtype=bf), torch.zeros(128, device=dev, dtype=bf)
+        y1, y2, n1 = torch.empty_like(x1), torch.empty_like(x2), torch.empty_like(x1)
+        up = torch.empty(1, 1024, 1024, 256, device=dev, dtype=bf)
+        s = torch.randn(16384, 16384, device=dev, generator=g).to(bf)
+        for _ in range(2):
+            ops.conv3x3(x1, w1, bias=b1, residual=x1, out=y1)
+        torch.cuda.synchronize()
+        prof.start()
+        ops.conv3x3(x1, w1, bias=b1, residual=x1, out=y1)
+        ops.conv3x3(x2, w2, bias=b2, out=y2)
+        ops.groupnorm(x1, gm, bt, 32, silu_act=True, out=n1)
+        ops.upsample2x(x2, out=up)
+        ops.softmax_rows_(s)
+        torch.cuda.synchronize()
+        prof.stop()
+        return
     if args.workload == "cfg5":
         from unigen_b200.sd3 import SD3Arch, UniGenSD3, shipped_control_params
         model = UniGenSD3(SD3Arch(), device=dev)

@@ -964,8 +964,14 @@ extern "C" int ug_conv3x3_bf16(const ug_conv2d_args* args, void* stream) {
   int variant = c.variant;
   if (variant == 0) {
     variant = pick_tile_variant(c.batch, rows, c.c_out);
-    if (c.c_out <= 128) variant = 3;
     variant = variant == 2 ? 4 : (variant == 1 ? 5 : 6);  // smem-staged TMA-store epilogue
+    if (c.c_out <= 128) {
+      // 128 output channels (the full-resolution level of the VAE): a 2-CTA pair on a 256-pixel x 128-channel tile — each CTA
+      // stages its own 128 pixels and HALF of the filter block, 3/4 of the shared-memory operand traffic of a 128 x 128 CTA tile,
+      // whose SS MMAs sit on the smem-bandwidth limit (ncu: 52 % tensor-pipe active at 1024^2 x 128)
+      const long long pairs = (long long)c.batch * ((rows + 255) / 256);
+      variant = pairs >= num_sms() / 2 ? 7 : 6;
+    }
   }
   switch (variant) {
     case 1: return launch_gemm<1, 256, 4>(g, s, &cd);
@@ -974,6 +980,7 @@ extern "C" int ug_conv3x3_bf16(const ug_conv2d_args* args, void* stream) {
     case 4: return launch_gemm<2, 256, 5, true>(g, s, &cd);
     case 5: return launch_gemm<1, 256, 3, true>(g, s, &cd);
     case 6: return launch_gemm<1, 128, 6, true>(g, s, &cd);
+    case 7: return launch_gemm<2, 128, 7, true>(g, s, &cd);
     default:
       set_error("conv3x3: unknown variant %d", c.variant);
       return UG_ERR_INVALID;
