@@ -35,12 +35,21 @@ def calculate_shift(image_seq_len: int, base_seq_len: int = 256, max_seq_len: in
 
 
 def flow_match_sigmas(num_inference_steps: int, image_seq_len: int, use_dynamic_shifting: bool = True,
-                      sigmas: Optional[Sequence[float]] = None, shift: float = 1.0) -> List[float]:
-    """sigmas = linspace(1, 1/n, n) (src/UniGenPipeline.py:989) -> FlowMatchEulerDiscreteScheduler.set_timesteps: dynamic
-    (exponential) time shifting with mu = calculate_shift(seq_len) (Flux), or the static `shift` (SD3.5: 3.0); a terminal 0 is
-    appended. timestep_i = 1000 sigma_i."""
+                      sigmas: Optional[Sequence[float]] = None, shift: float = 1.0, num_train_timesteps: int = 1000) -> List[float]:
+    """FlowMatchEulerDiscreteScheduler.set_timesteps. Flux (dynamic shifting): the pipeline passes sigmas = linspace(1, 1/n, n)
+    (src/UniGenPipeline.py:989) and the scheduler applies the exponential time shift with mu = calculate_shift(seq_len). SD3.5 (static
+    `shift`, 3.0): the pipeline passes NO sigmas (:345-351), so the scheduler starts from linspace(sigma_max, sigma_min, n) with
+    sigma_max / sigma_min the ends of its ALREADY shifted training schedule (1 and shift / 1000 / (1 + (shift - 1) / 1000)) and
+    shifts once more. A terminal 0 is appended; timestep_i = 1000 sigma_i."""
     n = num_inference_steps
-    sig = list(sigmas) if sigmas is not None else [1.0 + (1.0 / n - 1.0) * i / max(n - 1, 1) for i in range(n)]
+    if sigmas is not None:
+        sig = list(sigmas)
+    elif use_dynamic_shifting:
+        sig = [1.0 + (1.0 / n - 1.0) * i / max(n - 1, 1) for i in range(n)]
+    else:
+        lo = 1.0 / num_train_timesteps
+        s_min = shift * lo / (1.0 + (shift - 1.0) * lo)
+        sig = [1.0 + (s_min - 1.0) * i / max(n - 1, 1) for i in range(n)]
     if use_dynamic_shifting:
         mu = calculate_shift(image_seq_len)
         sig = [math.exp(mu) / (math.exp(mu) + (1.0 / s - 1.0)) for s in sig]
