@@ -355,9 +355,15 @@ def run_native(args):
         try:
             step_resident()
             torch.cuda.synchronize()
-            # what an event pair measures around a kernel that does (almost) nothing, launched the same way into the same busy
-            # stream: the part of every per-launch duration below that is not the kernel's own work
+            # what an event pair measures around a kernel that does (almost) nothing when, as in the instrumented step, the stream
+            # is backed up (the CPU runs ahead of the GPU): ~5 ms of GEMMs are queued first, so the 96 probe launches below execute
+            # back to back on the device and the pair reports the device-side floor, not the host's launch latency
             tiny_in, tiny_out = torch.zeros(32, device=dev, dtype=torch.float32), torch.zeros(32, device=dev, dtype=torch.float32)
+            fa = torch.zeros(1, 4608, 3072, device=dev, dtype=torch.bfloat16)
+            fw = torch.zeros(12288, 3072, device=dev, dtype=torch.bfloat16)
+            fo = torch.empty(1, 4608, 12288, device=dev, dtype=torch.bfloat16)
+            for _ in range(24):
+                orig_gemm(fa, fw, out=fo)
             pairs = []
             for _ in range(96):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -366,6 +372,7 @@ def run_native(args):
                 e1.record()
                 pairs.append((e0, e1))
             torch.cuda.synchronize()
+            del fa, fw, fo
             floor_us = sorted(e0.elapsed_time(e1) for e0, e1 in pairs[32:])[32] * 1e3
         finally:
             ops.gemm, ops.attention = orig_gemm, orig_attn
@@ -399,8 +406,8 @@ def run_native(args):
         elementwise["event_floor_us"] = floor_us
         elementwise["note"] = ("in situ (inside the step, CUDA events on one stream, no profiler): LN / QK-norm inputs were just written by "
                                f"the producing GEMM and are largely L2-resident; peak = MEASURED_PEAKS.json hbm_gbs ({hbm_peak:.0f} GB/s copy); "
-                               "event_floor_us = median duration an event pair reports around a 1-block kernel launched the same way "
-                               "(the ~10-16 us LayerNorm launches are mostly that floor; *_net_of_event_floor subtracts it per launch)")
+                               "event_floor_us = median duration an event pair reports around a 1-block kernel launched the same way into a "
+                               "backed-up stream (device-side floor of every per-launch figure; *_net_of_event_floor subtracts it per launch)")
         roof = {"bound": "tensor", "kernel": "ug::gemm_bf16_kernel (tcgen05)", "achieved": gm["tflops"], "peak": peak,
                 "unit": "TFLOP/s", "frac": gm["tflops"] / peak, "traffic": ncu_traffic()[0],
                 "traffic_note": ncu_traffic()[1], "peak_source": peak_src,
