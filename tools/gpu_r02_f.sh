@@ -16,6 +16,7 @@ timeout 300 python bench.py --workload cfg2 --steps 8 --warmup 3 --loop 4 --no-c
 timeout 300 python bench.py --workload cfg4 --steps 5 --warmup 3 --no-cpu-baseline --no-eager-baseline > gpurun_out/${T}_bench_cfg4_svariant.json 2> gpurun_out/${T}_bench_cfg4.err; echo "bench cfg4 exit $?"
 timeout 300 python tools/bench_pvariant.py --steps 4 > gpurun_out/${T}_bench_cfg4_pvariant.json 2> gpurun_out/${T}_bench_pv.err; echo "bench pv exit $?"
 timeout 300 python tools/bench_sd3.py --batch 4 --steps 5 > gpurun_out/${T}_bench_sd3_b4.json 2> gpurun_out/${T}_bench_sd3.err; echo "bench sd3 exit $?"
+timeout 300 python tools/bench_vae.py --side 1024 --eager > gpurun_out/${T}_bench_vae_1024.json 2> gpurun_out/${T}_bench_vae.err; echo "bench vae exit $?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:ug:: -c 4000 --csv \
   --log-file gpurun_out/${T}_launches_cfg3.csv python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline --no-eager-baseline > gpurun_out/${T}_ncu_launches.log 2>&1; echo "ncu launches exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/prof_r02_targets \
