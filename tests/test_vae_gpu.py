@@ -291,3 +291,34 @@ def test_flux_pipeline_encodes_the_condition_image_and_decodes_the_latents_throu
     assert torch.equal(image, want)
     sub_tokens, sub_ids, _ = Condition("subject", img).encode(pipe, gen)
     assert torch.equal(sub_ids[:, 2].cpu(), ids[:, 2].cpu() + (H // 2) // 2)  # :109-110
+
+
+def test_from_pretrained_reads_a_local_diffusers_vae_folder(tmp_path):
+    """`AutoencoderKL.from_pretrained(base, subfolder="vae")`: config.json + safetensors of a local diffusers folder; attention
+    projections stored as 1x1 convolutions (checkpoints converted from the LDM layout) are accepted."""
+    import json
+    from safetensors.torch import save_file
+    from unigen_b200 import ops
+    from unigen_b200.vae import AutoencoderKL
+    cfg, sd, oracle, model = _setup()
+    d = tmp_path / "base" / "vae"
+    d.mkdir(parents=True)
+    (d / "config.json").write_text(json.dumps(dict(
+        _class_name="AutoencoderKL", act_fn="silu", in_channels=3, out_channels=3, latent_channels=16,
+        block_out_channels=list(cfg.block_out_channels), layers_per_block=cfg.layers_per_block, norm_num_groups=32,
+        down_block_types=["DownEncoderBlock2D"] * 2, up_block_types=["UpDecoderBlock2D"] * 2, scaling_factor=cfg.scaling_factor,
+        shift_factor=cfg.shift_factor, use_quant_conv=False, use_post_quant_conv=False, sample_size=1024, force_upcast=True)))
+    as_conv = {k: (v[:, :, None, None] if ".attentions.0.to_" in k and k.endswith(".weight") else v) for k, v in sd.items()}
+    save_file({k: v.contiguous() for k, v in as_conv.items()}, str(d / "diffusion_pytorch_model.safetensors"))
+    m2 = AutoencoderKL.from_pretrained(str(tmp_path / "base"), subfolder="vae", torch_dtype=torch.bfloat16).to("cuda")
+    m2.requires_grad_(False).eval()
+    assert m2.config.block_out_channels == tuple(cfg.block_out_channels) and m2.config.scaling_factor == cfg.scaling_factor
+    lat = _bf(torch.randn(1, 16, 32, 32)).cuda()
+    assert torch.equal(m2.decode_latents(lat), model.decode_latents(lat))
+    with pytest.raises(OSError):
+        AutoencoderKL.from_pretrained(str(tmp_path / "nowhere"))
+    (d / "config.json").write_text(json.dumps(dict(block_out_channels=[64, 128], layers_per_block=1, act_fn="gelu")))
+    with pytest.raises(ops.UgError):
+        AutoencoderKL.from_pretrained(str(d))
+    with pytest.raises(ops.UgError):
+        m2.to("cpu")

@@ -143,6 +143,60 @@ class AutoencoderKL(_DenoiserBase):
         self.dec_out = _ConvW(ws, "decoder.conv_out", out_channels, rev[-1], 3)
         self.conv_variant = 0
 
+    _CONFIG_FIELDS = ("in_channels", "out_channels", "latent_channels", "block_out_channels", "layers_per_block", "norm_num_groups",
+                      "scaling_factor", "shift_factor", "use_quant_conv", "use_post_quant_conv", "mid_block_add_attention")
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, subfolder: Optional[str] = None, torch_dtype=None,
+                        device: Any = "cuda", variant: Optional[str] = None, trust_pickle: bool = False, **kwargs):
+        """`AutoencoderKL.from_pretrained(base, subfolder="vae")` — what the pipeline's own `from_pretrained(base, transformer=None)` does for its `vae` component (infer.py:146-149):
+        reads `config.json` (diffusers AutoencoderKL fields) and `diffusion_pytorch_model*.safetensors` of a LOCAL folder. No hub
+        download (this process has no network by design)."""
+        import json
+        import os
+        from . import checkpoint
+        path = os.path.join(pretrained_model_name_or_path, subfolder) if subfolder else pretrained_model_name_or_path
+        cfg_file = os.path.join(path, "config.json")
+        if not os.path.isfile(cfg_file):
+            raise OSError(f"{path} does not contain config.json: from_pretrained needs a local diffusers VAE folder")
+        with open(cfg_file) as f:
+            cfg = json.load(f)
+        if torch_dtype not in (None, BF16):
+            import warnings
+            warnings.warn(f"torch_dtype={torch_dtype}: the B200-native path stores weights and activations in bf16 (fp32 accumulate)")
+        fields = {k: cfg[k] for k in cls._CONFIG_FIELDS if k in cfg}
+        fields.update({k: v for k, v in kwargs.items() if k in cls._CONFIG_FIELDS})
+        for k, want in (("act_fn", "silu"), ("down_block_types", "DownEncoderBlock2D"), ("up_block_types", "UpDecoderBlock2D")):
+            got = cfg.get(k, want)
+            if any(g != want for g in (got if isinstance(got, (list, tuple)) else [got])):
+                raise ops.UgError(f"AutoencoderKL (B200-native): {k}={got!r} is not covered (only {want!r})")
+        model = cls(device=device, **fields)
+        sd = checkpoint.read_state_dict(path, trust_pickle=trust_pickle, variant=variant)
+        own = model._ws.views
+        # checkpoints converted from the original LDM layout keep the attention projections as 1x1 convolutions ([c, c, 1, 1])
+        sd = {k: (v.reshape(v.shape[0], v.shape[1]) if k in own and v.dim() == 4 and own[k].dim() == 2 else v) for k, v in sd.items()}
+        missing = [k for k in own if k not in sd]
+        if missing:
+            raise RuntimeError(f"{path} lacks {len(missing)} VAE keys, e.g. {missing[:4]}")
+        model.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
+        model.name_or_path = pretrained_model_name_or_path
+        return model
+
+    def to(self, *args, **kwargs):
+        """`vae.to(device, dtype=...)`: the weights already live on the CUDA device the model was built on, in bf16; another
+        device is an error (no fallback), a dtype is a no-op."""
+        for a in list(args) + [kwargs.get("device")]:
+            if isinstance(a, (str, torch.device)) and a is not None:
+                d = torch.device(a)
+                if d.type != "cuda" or (d.index is not None and d.index != (self.device_.index or 0)):
+                    raise ops.UgError(f"the B200-native VAE lives on {self.device_}; moving it to {d} is not supported")
+        return self
+
+    def requires_grad_(self, requires_grad: bool = True):  # the pipelines keep the VAE frozen (train.py:312 `vae.requires_grad_(False)`)
+        if requires_grad:
+            raise ops.UgError("the B200-native path is forward-only")
+        return self
+
     @torch.no_grad()
     def init_random_(self, seed: int = 0, zero_linear_std=None):
         """nn.Conv2d / nn.Linear default init on the device, GroupNorm affine = (1, 0) (bench / smoke: no checkpoint offline)."""
