@@ -322,3 +322,11 @@ def test_from_pretrained_reads_a_local_diffusers_vae_folder(tmp_path):
         AutoencoderKL.from_pretrained(str(d))
     with pytest.raises(ops.UgError):
         m2.to("cpu")
+
+
+def test_mid_attention_score_chunks_are_bit_identical_to_one_chunk():
+    cfg, sd, oracle, model = _setup()
+    lat = _bf(torch.randn(2, 16, 32, 32, generator=torch.Generator().manual_seed(2))).cuda()
+    whole = model.decode_latents(lat)
+    model.max_score_elems = 192 * 1024  # 1024 tokens -> chunks of 192 query rows (the last one ragged)
+    assert torch.equal(model.decode_latents(lat), whole)

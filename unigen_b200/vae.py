@@ -142,6 +142,7 @@ class AutoencoderKL(_DenoiserBase):
         self.dec_norm_out = _NormW(ws, "decoder.conv_norm_out", rev[-1])
         self.dec_out = _ConvW(ws, "decoder.conv_out", out_channels, rev[-1], 3)
         self.conv_variant = 0
+        self.max_score_elems = 1 << 30  # bf16 score elements per chunk of the mid-block attention (2 GB)
 
     _CONFIG_FIELDS = ("in_channels", "out_channels", "latent_channels", "block_out_channels", "layers_per_block", "norm_num_groups",
                       "scaling_factor", "shift_factor", "use_quant_conv", "use_post_quant_conv", "mid_block_add_attention")
@@ -252,13 +253,17 @@ class AutoencoderKL(_DenoiserBase):
             raise ops.UgError(f"VAE attention needs h * w ({T}) to be a multiple of 64")
         o = torch.empty(B, T, Cc, device=x.device, dtype=BF16)
         vt = torch.empty(Cc, T, device=x.device, dtype=BF16)
-        s = torch.empty(T, T, device=x.device, dtype=BF16)
+        # query rows in chunks so that the bf16 score matrix stays <= ~2 GB (T = 16 384 at 1024^2: one 512 MB chunk)
+        rows = min(T, max(64, (self.max_score_elems // T) // 64 * 64))
+        s = torch.empty(rows, T, device=x.device, dtype=BF16)
         for b in range(B):
             # v^T [C, T] straight out of a GEMM (A = W_v, "weights" = the tokens); its bias joins after the softmax (rows of p sum to 1)
             ops.gemm(w.v[0].unsqueeze(0), t[b], out=vt.unsqueeze(0), variant=gv)
-            ops.gemm(q[b:b + 1], k[b], out=s.unsqueeze(0), alpha=1.0 / math.sqrt(Cc), variant=gv)
-            ops.softmax_rows_(s)
-            ops.gemm(s.unsqueeze(0), vt, out=o[b:b + 1], bias=w.v[1], variant=gv)
+            for r0 in range(0, T, rows):
+                n = min(rows, T - r0)
+                ops.gemm(q[b:b + 1, r0:r0 + n], k[b], out=s[:n].unsqueeze(0), alpha=1.0 / math.sqrt(Cc), variant=gv)
+                ops.softmax_rows_(s[:n])
+                ops.gemm(s[:n].unsqueeze(0), vt, out=o[b:b + 1, r0:r0 + n], bias=w.v[1], variant=gv)
         out = torch.empty_like(x)
         ops.gemm(o, w.out[0], out=out.view(B, T, Cc), bias=w.out[1], residual=x.view(B, T, Cc), variant=gv)
         return out
