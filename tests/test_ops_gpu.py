@@ -132,7 +132,7 @@ def _sdpa_ref(qkv, H, dh, mask=None):
     return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, S, H * dh)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 9, 10])
 @pytest.mark.parametrize("shape", [(1, 128, 1, 128), (1, 300, 3, 128), (2, 333, 2, 64), (1, 1024, 6, 64), (1, 1536, 4, 128)])
 def test_attention_full(ug, variant, shape):
     B, S, H, dh = shape
@@ -142,7 +142,7 @@ def test_attention_full(ug, variant, shape):
     assert rel_l2(out, _sdpa_ref(qkv, H, dh)) < 6e-3
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 9, 10])
 @pytest.mark.parametrize("strict", [False, True])
 def test_attention_segment_mask_and_bit_exact_mask(ug, variant, strict):
     """[txt | img | c1 | c2] with the reference's visibility rule and the north-star's stricter one."""

@@ -1058,6 +1058,8 @@ static int attention_dispatch(const ug_attn_args* args, const PeerO* peer, void*
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   // auto: the two-tile ping-pong kernel once there are enough 256-row query tiles to fill the machine, with P published in two
   // halves (bit-identical to variant 3; -0.4 % per cfg3 step once the MMA issue stopped being the bottleneck)
+  // (variants 9 / 10 = split-P + packed polynomial exp2 on every 3rd / 2nd pair: 9 is +5 % in isolation at the SD3.5 head_dim-64 shape
+  // and +1 % at head_dim 128, but does not shorten the cfg5 step — 120.9 vs 119.3 ms, same box — so the MUFU path stays the default)
   int variant = a.variant;
   if (variant == 0) variant = ((long long)((a.seq + 255) / 256) * a.heads * a.batch >= num_sms()) ? 5 : 1;
   if (a.head_dim == 128) {
@@ -1068,6 +1070,8 @@ static int attention_dispatch(const ug_attn_args* args, const PeerO* peer, void*
     if (variant == 5) return launch_attention2<128, 0, true>(a, peer, s);
     if (variant == 6) return launch_attention2<128, 3>(a, peer, s);
     if (variant == 7) return launch_attention2<128, 0, true, true>(a, peer, s);
+    if (variant == 9) return launch_attention2<128, 3, true>(a, peer, s);
+    if (variant == 10) return launch_attention2<128, 2, true>(a, peer, s);
   } else if (a.head_dim == 64) {
     if (variant == 1) return launch_attention<64, true>(a, peer, s);
     if (variant == 2) return launch_attention<64, false>(a, peer, s);
@@ -1076,6 +1080,8 @@ static int attention_dispatch(const ug_attn_args* args, const PeerO* peer, void*
     if (variant == 5) return launch_attention2<64, 0, true>(a, peer, s);
     if (variant == 6) return launch_attention2<64, 3>(a, peer, s);
     if (variant == 7) return launch_attention2<64, 0, true, true>(a, peer, s);
+    if (variant == 9) return launch_attention2<64, 3, true>(a, peer, s);
+    if (variant == 10) return launch_attention2<64, 2, true>(a, peer, s);
   } else {
     set_error("attention: head_dim %d not supported (64 or 128)", a.head_dim);
     return UG_ERR_UNSUPPORTED;
