@@ -56,3 +56,57 @@ def test_vae_conv_weight_views_have_conv2d_shapes_over_the_gemm_layout():
     # column (ky * 3 + kx) * c_in + ci of the GEMM matrix holds weight[co, ci, ky, kx]; padding stays zero
     assert torch.equal(cw.w[:3, :144].float(), w.permute(0, 2, 3, 1).reshape(3, 144).to(torch.bfloat16).float())
     assert (cw.w[3:] == 0).all() and (cw.w[:, 144:] == 0).all() and (cw.b[3:] == 0).all()
+
+
+def test_condition_encode_image_builds_tokens_and_ids_like_the_reference():
+    """`Condition._encode_image` host logic (src/condition.py:90-111) with a stand-in pipe: VAE latents (already shifted / scaled) ->
+    packed tokens; ids of the latent grid // 2; `subject` offsets column 2 by the latent height // 2; type ids from condition_dict."""
+    import types
+    from unigen_b200.condition import Condition
+    lat = torch.arange(2 * 16 * 8 * 12, dtype=torch.float32).reshape(2, 16, 8, 12)
+    calls = {}
+
+    def encode_condition(img, generator=None):
+        calls["img"], calls["gen"] = img, generator
+        return lat
+
+    def pack(x):  # FluxPipeline._pack_latents
+        B, C, H, W = x.shape
+        return x.view(B, C, H // 2, 2, W // 2, 2).permute(0, 2, 4, 1, 3, 5).reshape(B, (H // 2) * (W // 2), C * 4)
+
+    pipe = types.SimpleNamespace(vae=types.SimpleNamespace(encode_condition=encode_condition), _pack_latents=pack)
+    img = torch.zeros(2, 3, 64, 96)
+    gen = torch.Generator().manual_seed(1)
+    tokens, ids, type_id = Condition("depth", img).encode(pipe, gen)
+    assert calls["img"] is img and calls["gen"] is gen
+    assert tokens.shape == (2, 24, 64) and torch.equal(tokens, O.pack_latents(lat))
+    assert torch.equal(ids, O.prepare_latent_image_ids(4, 6)) and torch.equal(type_id, torch.zeros(24, 1))
+    _, sub_ids, sub_type = Condition("subject", img).encode(pipe)
+    assert torch.equal(sub_ids[:, 2], ids[:, 2] + 4) and torch.equal(sub_ids[:, :2], ids[:, :2]) and int(sub_type[0, 0]) == 4
+    with pytest.raises(ValueError):
+        Condition("canny", img).encode(types.SimpleNamespace(vae=None))
+
+
+def test_sd3_modulated_experts_equal_the_flux_oracle_expert_path():
+    """Two independent restatements of the same reference arithmetic (`UniGenBase.expert_forward` :252-255 and `UniGenFlux.expert_forward`
+    :953-959 are the same lines): the SD3 oracle's `use_modulate` branch and the Flux oracle's expert path agree on shared weights."""
+    import dataclasses
+    from oracle import unigen_sd3_oracle as S
+    g = torch.Generator().manual_seed(5)
+    cfg3 = dataclasses.replace(S.SD3Config.tiny(), use_modulate=True, num_attention_heads=2, attention_head_dim=16, pooled_projection_dim=24,
+                               condition_nums=0, expert_num_each_condition=3)
+    D, E, C, P = cfg3.inner_dim, cfg3.expert_nums, 5, 24
+    sd = {}
+    for e in range(E):
+        for br in (0, 1):
+            p = f"moe.moe_layer.experts.deepspeed_experts.{e}.{br}"
+            sd[p + ".0.weight"], sd[p + ".0.bias"] = torch.randn(D, D, generator=g) / D ** 0.5, torch.randn(D, generator=g)
+            sd[p + ".1.weight"], sd[p + ".1.bias"] = torch.randn(D, P, generator=g) / P ** 0.5, torch.randn(D, generator=g)
+    hidden, cond = torch.randn(1, E, C, D, generator=g), torch.randn(1, E, C, D, generator=g)
+    pooled, cpooled = torch.randn(1, E, C, P, generator=g), torch.randn(1, E, C, P, generator=g)
+    eh3, ec3 = S.UniGenSD3Oracle(cfg3, sd).expert_forward(hidden, cond, None, None, pooled, cpooled)
+    fcfg = dataclasses.replace(O.FluxConfig.tiny(), condition_nums=0, expert_num_each_condition=3)
+    assert fcfg.expert_nums == E
+    ehf, ecf = O.UniGenFluxOracle(fcfg, sd).expert_forward(hidden, cond, pooled, cpooled)
+    torch.testing.assert_close(eh3, ehf)
+    torch.testing.assert_close(ec3, ecf)
